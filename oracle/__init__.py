@@ -1,0 +1,360 @@
+"""ctypes front-end of the CPU oracle (oracle/*.c).
+
+TEST INFRASTRUCTURE ONLY.  Importable from tests/, ``__graft_entry__.smoke()``
+and ``bench.py``'s cpu_baseline / ``--impl reference`` leg — never from
+``open3d_b200`` (the product).  See oracle/oracle.h for what each function
+restates (reference file:line) and its parity status.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liboracle.so")
+_SOURCES = ["icp_oracle.c", "tsdf_oracle.c", "oracle.h"]
+
+
+def build(force: bool = False) -> str:
+    """Compile liboracle.so with the committed Makefile if missing or stale."""
+    stale = force or not os.path.exists(_LIB_PATH)
+    if not stale:
+        t = os.path.getmtime(_LIB_PATH)
+        stale = any(os.path.getmtime(os.path.join(_HERE, s)) > t for s in _SOURCES)
+    if stale:
+        subprocess.run(["make", "-B", "-C", _HERE, "liboracle.so"], check=True,
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB_PATH)
+        _declare(_lib)
+    return _lib
+
+
+_f32p = C.POINTER(C.c_float)
+_f64p = C.POINTER(C.c_double)
+_i32p = C.POINTER(C.c_int32)
+_i64p = C.POINTER(C.c_int64)
+_u8p = C.POINTER(C.c_uint8)
+_u16p = C.POINTER(C.c_uint16)
+
+
+class _IcpResult(C.Structure):
+    _fields_ = [("num_iterations", C.c_int), ("converged", C.c_int),
+                ("fitness", C.c_double), ("inlier_rmse", C.c_double),
+                ("transformation", C.c_double * 16)]
+
+
+def _declare(L):
+    L.orc_minivec_hash_i32x3.restype = C.c_uint64
+    L.orc_minivec_hash_i32x3.argtypes = [C.c_int32] * 3
+    L.orc_spatial_hash.restype = C.c_uint64
+    L.orc_spatial_hash.argtypes = [C.c_int32] * 3
+    L.orc_compute_voxel_index_f32.restype = None
+    L.orc_compute_voxel_index_f32.argtypes = [_f32p, C.c_float, _i32p]
+    L.orc_robust_weight_f64.restype = C.c_double
+    L.orc_robust_weight_f64.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double]
+    L.orc_robust_weight_f32.restype = C.c_float
+    L.orc_robust_weight_f32.argtypes = [C.c_int, C.c_double, C.c_double, C.c_float]
+    for name in ("orc_hybrid_search_f32", "orc_hybrid_search_bruteforce_f32"):
+        f = getattr(L, name)
+        f.restype = None
+        f.argtypes = [_f32p, C.c_int64, _f32p, C.c_int64, C.c_double, C.c_int,
+                      _i32p, _f32p, _i32p]
+    L.orc_pose_p2plane_sums_f32.restype = None
+    L.orc_pose_p2plane_sums_f32.argtypes = [_f32p, _f32p, _f32p, _i64p, C.c_int64,
+                                            C.c_int, C.c_double, C.c_double,
+                                            _f64p, _f32p, _f64p]
+    L.orc_pose_p2plane_sums_f64.restype = None
+    L.orc_pose_p2plane_sums_f64.argtypes = [_f64p, _f64p, _f64p, _i64p, C.c_int64,
+                                            C.c_int, C.c_double, C.c_double, _f64p]
+    L.orc_pose_colored_sums_f32.restype = None
+    L.orc_pose_colored_sums_f32.argtypes = [_f32p] * 6 + [_i64p, C.c_int64, C.c_double,
+                                                         C.c_int, C.c_double, C.c_double,
+                                                         _f64p, _f64p]
+    L.orc_decode_and_solve_6x6.restype = C.c_int
+    L.orc_decode_and_solve_6x6.argtypes = [_f64p, _f64p, _f64p, C.POINTER(C.c_int)]
+    L.orc_pose_to_transformation.restype = None
+    L.orc_pose_to_transformation.argtypes = [_f64p, _f64p]
+    L.orc_transform_points_f32.restype = None
+    L.orc_transform_points_f32.argtypes = [_f64p, _f32p, C.c_int64]
+    L.orc_transform_normals_f32.restype = None
+    L.orc_transform_normals_f32.argtypes = [_f64p, _f32p, C.c_int64]
+    L.orc_rmse_p2plane_f32.restype = C.c_double
+    L.orc_rmse_p2plane_f32.argtypes = [_f32p, _f32p, _f32p, _i64p, C.c_int64]
+    L.orc_icp_p2plane_f32.restype = C.c_int
+    L.orc_icp_p2plane_f32.argtypes = [_f32p, C.c_int64, _f32p, _f32p, C.c_int64,
+                                      C.c_double, _f64p, C.c_int, C.c_double, C.c_double,
+                                      C.c_int, C.c_double, C.c_double, C.c_int,
+                                      C.POINTER(_IcpResult), _f64p, _i64p]
+    L.orc_inverse_transformation.restype = None
+    L.orc_inverse_transformation.argtypes = [_f64p, _f64p]
+    L.orc_depth_touch.restype = C.c_int64
+    L.orc_depth_touch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _f64p, _f64p,
+                                  C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
+                                  C.c_int, _i32p, C.c_int64]
+    L.orc_tsdf_integrate.restype = None
+    L.orc_tsdf_integrate.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                     _i32p, C.c_int64, _i32p, _f32p, _u16p, _u16p,
+                                     _f64p, _f64p, _f64p, C.c_int, C.c_float, C.c_float,
+                                     C.c_float, C.c_float]
+    L.orc_hashmap_activate.restype = C.c_int
+    L.orc_hashmap_activate.argtypes = [_i32p, C.c_int64, _i64p, _i32p, C.c_int64,
+                                       _i32p, _u8p]
+    L.orc_num_threads.restype = C.c_int
+    L.orc_num_threads.argtypes = []
+
+
+def _arr(a, dtype):
+    a = np.ascontiguousarray(a, dtype=dtype)
+    return a
+
+
+def _p(a, ptype):
+    return a.ctypes.data_as(ptype)
+
+
+ROBUST = {"L2Loss": 0, "L1Loss": 1, "HuberLoss": 2, "CauchyLoss": 3, "GMLoss": 4,
+          "TukeyLoss": 5, "GeneralizedLoss": 6}
+
+
+def num_threads() -> int:
+    return lib().orc_num_threads()
+
+
+def minivec_hash(keys) -> np.ndarray:
+    keys = _arr(keys, np.int32).reshape(-1, 3)
+    L = lib()
+    return np.array([L.orc_minivec_hash_i32x3(int(k[0]), int(k[1]), int(k[2])) for k in keys],
+                    dtype=np.uint64)
+
+
+def spatial_hash(cells) -> np.ndarray:
+    cells = _arr(cells, np.int32).reshape(-1, 3)
+    L = lib()
+    return np.array([L.orc_spatial_hash(int(k[0]), int(k[1]), int(k[2])) for k in cells],
+                    dtype=np.uint64)
+
+
+def compute_voxel_index(pos, inv_voxel_size) -> np.ndarray:
+    pos = _arr(pos, np.float32).reshape(3)
+    out = np.zeros(3, np.int32)
+    lib().orc_compute_voxel_index_f32(_p(pos, _f32p), float(inv_voxel_size), _p(out, _i32p))
+    return out
+
+
+def robust_weight(method, scale, shape, residual, f32=False) -> float:
+    m = ROBUST[method] if isinstance(method, str) else int(method)
+    if f32:
+        return float(lib().orc_robust_weight_f32(m, scale, shape, residual))
+    return float(lib().orc_robust_weight_f64(m, scale, shape, residual))
+
+
+def hybrid_search(points, queries, radius, max_knn=1, bruteforce=False):
+    """-> (idx [N,k] int32, dist2 [N,k] f32, counts [N] int32)."""
+    points = _arr(points, np.float32).reshape(-1, 3)
+    queries = _arr(queries, np.float32).reshape(-1, 3)
+    n = queries.shape[0]
+    idx = np.empty((n, max_knn), np.int32)
+    d2 = np.empty((n, max_knn), np.float32)
+    cnt = np.empty(n, np.int32)
+    f = lib().orc_hybrid_search_bruteforce_f32 if bruteforce else lib().orc_hybrid_search_f32
+    f(_p(points, _f32p), points.shape[0], _p(queries, _f32p), n, float(radius), int(max_knn),
+      _p(idx, _i32p), _p(d2, _f32p), _p(cnt, _i32p))
+    return idx, d2, cnt
+
+
+def pose_p2plane_sums(src, tgt, nrm, corr, robust=("L2Loss", 1.0, 1.0)):
+    """-> dict(sums64, sums32, abs64) for f32 clouds."""
+    src = _arr(src, np.float32).reshape(-1, 3)
+    tgt = _arr(tgt, np.float32).reshape(-1, 3)
+    nrm = _arr(nrm, np.float32).reshape(-1, 3)
+    corr = _arr(corr, np.int64).reshape(-1)
+    s64 = np.zeros(29, np.float64)
+    s32 = np.zeros(29, np.float32)
+    a64 = np.zeros(29, np.float64)
+    lib().orc_pose_p2plane_sums_f32(_p(src, _f32p), _p(tgt, _f32p), _p(nrm, _f32p),
+                                    _p(corr, _i64p), src.shape[0], ROBUST[robust[0]],
+                                    float(robust[1]), float(robust[2]),
+                                    _p(s64, _f64p), _p(s32, _f32p), _p(a64, _f64p))
+    return {"sums64": s64, "sums32": s32, "abs64": a64}
+
+
+def pose_p2plane_sums_f64(src, tgt, nrm, corr, robust=("L2Loss", 1.0, 1.0)):
+    src = _arr(src, np.float64).reshape(-1, 3)
+    tgt = _arr(tgt, np.float64).reshape(-1, 3)
+    nrm = _arr(nrm, np.float64).reshape(-1, 3)
+    corr = _arr(corr, np.int64).reshape(-1)
+    s64 = np.zeros(29, np.float64)
+    lib().orc_pose_p2plane_sums_f64(_p(src, _f64p), _p(tgt, _f64p), _p(nrm, _f64p),
+                                    _p(corr, _i64p), src.shape[0], ROBUST[robust[0]],
+                                    float(robust[1]), float(robust[2]), _p(s64, _f64p))
+    return s64
+
+
+def pose_colored_sums(src, src_colors, tgt, nrm, tgt_colors, tgt_grad, corr,
+                      lambda_geometric=0.968, robust=("L2Loss", 1.0, 1.0)):
+    a = [_arr(x, np.float32).reshape(-1, 3) for x in (src, src_colors, tgt, nrm, tgt_colors, tgt_grad)]
+    corr = _arr(corr, np.int64).reshape(-1)
+    s64 = np.zeros(29, np.float64)
+    a64 = np.zeros(29, np.float64)
+    lib().orc_pose_colored_sums_f32(*[_p(x, _f32p) for x in a], _p(corr, _i64p), a[0].shape[0],
+                                    float(lambda_geometric), ROBUST[robust[0]],
+                                    float(robust[1]), float(robust[2]),
+                                    _p(s64, _f64p), _p(a64, _f64p))
+    return {"sums64": s64, "abs64": a64}
+
+
+def decode_and_solve_6x6(sums29):
+    """-> (pose[6], residual, inlier_count, singular)."""
+    s = _arr(sums29, np.float64).reshape(29)
+    pose = np.zeros(6, np.float64)
+    res = C.c_double(0)
+    cnt = C.c_int(0)
+    rc = lib().orc_decode_and_solve_6x6(_p(s, _f64p), _p(pose, _f64p), C.byref(res), C.byref(cnt))
+    return pose, res.value, cnt.value, bool(rc)
+
+
+def pose_to_transformation(pose) -> np.ndarray:
+    p = _arr(pose, np.float64).reshape(6)
+    T = np.zeros(16, np.float64)
+    lib().orc_pose_to_transformation(_p(p, _f64p), _p(T, _f64p))
+    return T.reshape(4, 4)
+
+
+def transform_points(T, points) -> np.ndarray:
+    T = _arr(T, np.float64).reshape(16)
+    pts = np.array(points, dtype=np.float32, order="C", copy=True).reshape(-1, 3)
+    lib().orc_transform_points_f32(_p(T, _f64p), _p(pts, _f32p), pts.shape[0])
+    return pts
+
+
+def transform_normals(T, normals) -> np.ndarray:
+    T = _arr(T, np.float64).reshape(16)
+    nr = np.array(normals, dtype=np.float32, order="C", copy=True).reshape(-1, 3)
+    lib().orc_transform_normals_f32(_p(T, _f64p), _p(nr, _f32p), nr.shape[0])
+    return nr
+
+
+def rmse_p2plane(src, tgt, nrm, corr) -> float:
+    src = _arr(src, np.float32).reshape(-1, 3)
+    tgt = _arr(tgt, np.float32).reshape(-1, 3)
+    nrm = _arr(nrm, np.float32).reshape(-1, 3)
+    corr = _arr(corr, np.int64).reshape(-1)
+    return float(lib().orc_rmse_p2plane_f32(_p(src, _f32p), _p(tgt, _f32p), _p(nrm, _f32p),
+                                            _p(corr, _i64p), src.shape[0]))
+
+
+@dataclass
+class IcpResult:
+    transformation: np.ndarray
+    fitness: float
+    inlier_rmse: float
+    converged: bool
+    num_iterations: int
+    per_iteration: np.ndarray  # [num_iterations_executed, 2] (fitness, rmse)
+    correspondences: np.ndarray  # [N] int64
+    status: int  # 0 ok, 1 singular system (the reference raises)
+
+
+def icp_p2plane(source, target, target_normals, max_corr_dist, init=None, max_iteration=30,
+                relative_fitness=1e-6, relative_rmse=1e-6, robust=("L2Loss", 1.0, 1.0),
+                accumulate_f64=True) -> IcpResult:
+    src = _arr(source, np.float32).reshape(-1, 3)
+    tgt = _arr(target, np.float32).reshape(-1, 3)
+    nrm = _arr(target_normals, np.float32).reshape(-1, 3)
+    T0 = _arr(np.eye(4) if init is None else init, np.float64).reshape(16)
+    res = _IcpResult()
+    per = np.full((max(max_iteration, 1), 2), np.nan, np.float64)
+    corr = np.empty(src.shape[0], np.int64)
+    rc = lib().orc_icp_p2plane_f32(_p(src, _f32p), src.shape[0], _p(tgt, _f32p), _p(nrm, _f32p),
+                                   tgt.shape[0], float(max_corr_dist), _p(T0, _f64p),
+                                   int(max_iteration), float(relative_fitness),
+                                   float(relative_rmse), ROBUST[robust[0]], float(robust[1]),
+                                   float(robust[2]), int(bool(accumulate_f64)),
+                                   C.byref(res), _p(per, _f64p), _p(corr, _i64p))
+    executed = int(np.sum(~np.isnan(per[:, 0])))
+    return IcpResult(np.array(res.transformation, np.float64).reshape(4, 4), res.fitness,
+                     res.inlier_rmse, bool(res.converged), res.num_iterations,
+                     per[:executed].copy(), corr, rc)
+
+
+def inverse_transformation(T) -> np.ndarray:
+    T = _arr(T, np.float64).reshape(16)
+    Ti = np.zeros(16, np.float64)
+    lib().orc_inverse_transformation(_p(T, _f64p), _p(Ti, _f64p))
+    return Ti.reshape(4, 4)
+
+
+def depth_touch(depth, K, extrinsic, resolution=16, voxel_size=0.008, sdf_trunc=0.064,
+                depth_scale=1000.0, depth_max=3.0, stride=4) -> np.ndarray:
+    """-> unique block keys [B,3] int32, lexicographically sorted."""
+    depth = np.ascontiguousarray(depth)
+    assert depth.dtype in (np.uint16, np.float32)
+    depth = depth.reshape(depth.shape[0], depth.shape[1])
+    rows, cols = depth.shape
+    K = _arr(K, np.float64).reshape(9)
+    E = _arr(extrinsic, np.float64).reshape(16)
+    cap = (rows // stride) * (cols // stride) * 4 + 1
+    out = np.empty((cap, 3), np.int32)
+    n = lib().orc_depth_touch(depth.ctypes.data, int(depth.dtype == np.float32), rows, cols,
+                              _p(K, _f64p), _p(E, _f64p), int(resolution), float(voxel_size),
+                              float(sdf_trunc), float(depth_scale), float(depth_max),
+                              int(stride), _p(out, _i32p), cap)
+    assert n >= 0, n
+    return out[:n].copy()
+
+
+def tsdf_integrate(depth, color, buf_indices, block_keys, tsdf, weight, color_buf, depth_K,
+                   color_K, extrinsic, resolution=16, voxel_size=0.008, sdf_trunc=0.064,
+                   depth_scale=1000.0, depth_max=3.0) -> None:
+    """In-place update of tsdf/weight/color_buf numpy buffers (slam::Model layout)."""
+    depth = np.ascontiguousarray(depth)
+    f32 = depth.dtype == np.float32
+    assert f32 or depth.dtype == np.uint16
+    rows, cols = depth.shape[0], depth.shape[1]
+    if color is not None:
+        color = np.ascontiguousarray(color)
+        assert color.dtype == (np.float32 if f32 else np.uint8)
+        assert color.shape[0] == rows and color.shape[1] == cols
+    bi = _arr(buf_indices, np.int32).reshape(-1)
+    assert block_keys.dtype == np.int32 and block_keys.flags.c_contiguous
+    assert tsdf.dtype == np.float32 and tsdf.flags.c_contiguous
+    assert weight.dtype == np.uint16 and weight.flags.c_contiguous
+    if color_buf is not None:
+        assert color_buf.dtype == np.uint16 and color_buf.flags.c_contiguous
+    dK = _arr(depth_K, np.float64).reshape(9)
+    cK = _arr(color_K if color_K is not None else depth_K, np.float64).reshape(9)
+    E = _arr(extrinsic, np.float64).reshape(16)
+    lib().orc_tsdf_integrate(depth.ctypes.data, None if color is None else color.ctypes.data,
+                             int(f32), rows, cols, _p(bi, _i32p), bi.shape[0],
+                             _p(block_keys, _i32p), _p(tsdf, _f32p), _p(weight, _u16p),
+                             None if color_buf is None else _p(color_buf, _u16p),
+                             _p(dK, _f64p), _p(cK, _f64p), _p(E, _f64p), int(resolution),
+                             float(voxel_size), float(sdf_trunc), float(depth_scale),
+                             float(depth_max))
+
+
+def hashmap_activate(table_keys, size, keys):
+    """table_keys [cap,3] int32 (in place), size int -> (buf_indices, masks, new_size, rc)."""
+    assert table_keys.dtype == np.int32 and table_keys.flags.c_contiguous
+    keys = _arr(keys, np.int32).reshape(-1, 3)
+    n = keys.shape[0]
+    bi = np.empty(n, np.int32)
+    mk = np.empty(n, np.uint8)
+    sz = C.c_int64(int(size))
+    rc = lib().orc_hashmap_activate(_p(table_keys, _i32p), table_keys.shape[0], C.byref(sz),
+                                    _p(keys, _i32p), n, _p(bi, _i32p), _p(mk, _u8p))
+    return bi, mk.astype(bool), sz.value, rc

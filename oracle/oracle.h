@@ -1,0 +1,212 @@
+/*
+ * oracle.h — CPU restatement of the Open3D ICP + TSDF hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product.
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * `--impl reference` leg may load this library, and only as the checker or as
+ * the timed CPU baseline.  The product path (open3d_b200/csrc) never links,
+ * imports or calls it.
+ *
+ * Every function cites the reference file:line it restates (paths relative to
+ * the Open3D tree, cpp/open3d/...).  Parity status is stated per function:
+ * "pinned: <reference KAT>" or "parity unpinned".
+ *
+ * Plain C99 + OpenMP (the reference CPU path is TBB; TBB is absent here).
+ */
+#ifndef O3D_ORACLE_H_
+#define O3D_ORACLE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ hashes */
+
+/* core/hashmap/Dispatch.h:67-81 (MiniVecHash<int,3>), int32 sign-extended to
+ * uint64, FNV-1a style.  Pinned indirectly (set semantics) by
+ * tests/t/geometry/VoxelBlockGrid.cpp:211-219; the hash VALUE is pinned against
+ * the reference header itself through oracle/_ref (ref_shim). */
+uint64_t orc_minivec_hash_i32x3(int32_t x, int32_t y, int32_t z);
+
+/* core/nns/NeighborSearchCommon.h:31-37 SpatialHash: int arithmetic (wraps),
+ * widened to size_t. */
+uint64_t orc_spatial_hash(int32_t x, int32_t y, int32_t z);
+
+/* core/nns/NeighborSearchCommon.h:44-52 ComputeVoxelIndex (f32). */
+void orc_compute_voxel_index_f32(const float pos[3], float inv_voxel_size,
+                                 int32_t out[3]);
+
+/* ------------------------------------------------------------ robust kernel */
+
+/* t/pipelines/registration/RobustKernelImpl.h:35-115, enum order of
+ * RobustKernel.h:15-23: 0 L2, 1 L1, 2 Huber, 3 Cauchy, 4 GM, 5 Tukey,
+ * 6 Generalized.  Pinned: tests/t/pipelines/registration/Registration.cpp:411-490.
+ */
+double orc_robust_weight_f64(int method, double scale, double shape,
+                             double residual);
+float orc_robust_weight_f32(int method, double scale, double shape,
+                            float residual);
+
+/* ------------------------------------------------------------------- search */
+
+/* Hybrid search semantics (radius + max_knn), restating
+ * core/nns/FixedRadiusSearchImpl.cuh:514-631 (CUDA) and
+ * core/nns/NanoFlannImpl.h:306-370 (CPU, nanoflann v1.5.0 radiusSearch sorted,
+ * truncated to max_knn): for every query the max_knn nearest points with
+ * dist^2 <= radius^2, ascending; idx padded with -1, dist^2 with 0.
+ * dist^2 is computed in f32 as fma(dz,dz,fma(dy,dy,dx*dx)); exact ties go to
+ * the lower point index (the reference leaves tie order undefined).
+ * Uniform-grid accelerated, exact.  Pinned: tests/core/NearestNeighborSearch.cpp:321-383.
+ */
+void orc_hybrid_search_f32(const float* points, int64_t num_points,
+                           const float* queries, int64_t num_queries,
+                           double radius, int max_knn, int32_t* idx /*N*k*/,
+                           float* dist2 /*N*k*/, int32_t* counts /*N*/);
+
+/* O(N*M) brute force twin of the above; used to validate the grid version. */
+void orc_hybrid_search_bruteforce_f32(const float* points, int64_t num_points,
+                                      const float* queries,
+                                      int64_t num_queries, double radius,
+                                      int max_knn, int32_t* idx, float* dist2,
+                                      int32_t* counts);
+
+/* -------------------------------------------------------- pose estimation */
+
+/* t/pipelines/kernel/RegistrationImpl.h:251-287 (Jacobian, f32 per-term math)
+ * + t/pipelines/kernel/RegistrationCPU.cpp:30-90 (29-slot packing).
+ * sums64: accumulated in f64 (the precise target); sums32: accumulated in f32
+ * in index order (what a single-threaded reference build would produce);
+ * abs64: sum of |term| per slot (the natural error scale).  Any may be NULL.
+ * corr == -1 means "no correspondence".
+ * Pinned: tests/t/pipelines/registration/TransformationEstimation.cpp:33-84,148,176.
+ */
+void orc_pose_p2plane_sums_f32(const float* src, const float* tgt,
+                               const float* tgt_normals, const int64_t* corr,
+                               int64_t n, int robust_method,
+                               double robust_scale, double robust_shape,
+                               double sums64[29], float sums32[29],
+                               double abs64[29]);
+
+/* Same for f64 clouds (all math in f64). */
+void orc_pose_p2plane_sums_f64(const double* src, const double* tgt,
+                               const double* tgt_normals, const int64_t* corr,
+                               int64_t n, int robust_method,
+                               double robust_scale, double robust_shape,
+                               double sums64[29]);
+
+/* t/pipelines/kernel/RegistrationImpl.h:413-493 + RegistrationCPU.cpp
+ * (ComputePoseColoredICPKernelCPU): two residual rows per correspondence;
+ * slot 27 = sum(r_G^2 + r_I^2).  parity unpinned offline (the reference's
+ * ColoredICP tests need a downloaded dataset); validated against the reference
+ * header itself via oracle/_ref. */
+void orc_pose_colored_sums_f32(const float* src, const float* src_colors,
+                               const float* tgt, const float* tgt_normals,
+                               const float* tgt_colors,
+                               const float* tgt_color_gradients,
+                               const int64_t* corr, int64_t n,
+                               double lambda_geometric, int robust_method,
+                               double robust_scale, double robust_shape,
+                               double sums64[29], double abs64[29]);
+
+/* t/pipelines/kernel/TransformationConverter.cpp:189-226 DecodeAndSolve6x6:
+ * unpack lower-tri, solve AtA x = -Atb by LU with partial pivoting (LAPACK
+ * dgesv semantics).  Returns 0, or 1 if a pivot is exactly zero (singular). */
+int orc_decode_and_solve_6x6(const double sums[29], double pose[6],
+                             double* residual, int* inlier_count);
+
+/* t/pipelines/kernel/TransformationConverterImpl.h:22-42 + .cpp:81-104:
+ * pose (alpha,beta,gamma,tx,ty,tz) -> row-major 4x4 (f64). */
+void orc_pose_to_transformation(const double pose[6], double T[16]);
+
+/* t/geometry/kernel/TransformImpl.h:20-45: in-place p <- (T p)/w, f32, T cast
+ * to f32 first (kernel/Transform.cpp).  No FMA contraction. */
+void orc_transform_points_f32(const double T[16], float* points, int64_t n);
+/* TransformImpl.h:47-62 */
+void orc_transform_normals_f32(const double T[16], float* normals, int64_t n);
+
+/* TransformationEstimation.cpp:161-194 ComputeRMSE (point to plane). */
+double orc_rmse_p2plane_f32(const float* src, const float* tgt,
+                            const float* tgt_normals, const int64_t* corr,
+                            int64_t n);
+
+/* ---------------------------------------------------------------- ICP loop */
+
+typedef struct {
+    int num_iterations;    /* iterations executed (RegistrationResult::num_iterations_) */
+    int converged;         /* RegistrationResult::converged_ */
+    double fitness;        /* final fitness_ */
+    double inlier_rmse;    /* final inlier_rmse_ */
+    double transformation[16]; /* row-major 4x4 f64 */
+} orc_icp_result;
+
+/* t/pipelines/registration/Registration.cpp:24-62, 275-360, 362-444 for one
+ * scale, PointToPlane estimation, no down-sampling (voxel_size = -1).
+ * source/target are not modified (the reference clones the source).
+ * per_iter (may be NULL) receives 2*max_iteration doubles (fitness, rmse of
+ * every executed iteration, as seen by the callback at Registration.cpp:330-345);
+ * corr_out (may be NULL) receives the final N correspondences (int64).
+ * accumulate_f64 != 0: 29 sums accumulated in f64 (precise); 0: f32. */
+int orc_icp_p2plane_f32(const float* source, int64_t n, const float* target,
+                        const float* target_normals, int64_t m,
+                        double max_corr_dist, const double init_T[16],
+                        int max_iteration, double rel_fitness, double rel_rmse,
+                        int robust_method, double robust_scale,
+                        double robust_shape, int accumulate_f64,
+                        orc_icp_result* result, double* per_iter,
+                        int64_t* corr_out);
+
+/* ------------------------------------------------------------------- TSDF */
+
+/* t/geometry/kernel/GeometryIndexer.h:136-143 stores intrinsics/extrinsics as
+ * float; t/geometry/Utility.h:77-115 InverseTransformation in f64. */
+void orc_inverse_transformation(const double T[16], double Tinv[16]);
+
+/* t/geometry/kernel/VoxelBlockGridCPU.cpp:117-201 DepthTouchCPU.
+ * depth: H*W, u16 (is_f32 == 0) or f32.  Writes the UNIQUE block keys
+ * (int32 triples) sorted lexicographically (x,y,z) into keys_out (capacity
+ * max_keys triples) and returns their number, or -1 if capacity is exceeded.
+ * The reference's output order is undefined; sorted here for set comparison.
+ * parity unpinned offline (reference counts need the Redwood download). */
+int64_t orc_depth_touch(const void* depth, int is_f32, int rows, int cols,
+                        const double K[9], const double extrinsic[16],
+                        int resolution, float voxel_size, float sdf_trunc,
+                        float depth_scale, float depth_max, int stride,
+                        int32_t* keys_out, int64_t max_keys);
+
+/* t/geometry/kernel/VoxelBlockGridImpl.h:151-308 IntegrateCPU for the
+ * slam::Model layout (tsdf f32, weight u16, color u16x3;  Model.cpp:28-35) with
+ * u16 depth / u8 color or f32 depth / f32 color inputs.
+ * block_keys: capacity x 3 int32, buf_indices: n_blocks int32 into the value
+ * buffers (tsdf [cap][res^3], weight [cap][res^3], color [cap][res^3][3]).
+ * color / color_buf may be NULL (depth-only overload, VoxelBlockGrid.cpp:269-278).
+ * parity unpinned offline (see above); cross-checked against the reference
+ * header math via oracle/_ref where that compiles. */
+void orc_tsdf_integrate(const void* depth, const void* color, int inputs_f32,
+                        int rows, int cols, const int32_t* buf_indices,
+                        int64_t n_blocks, const int32_t* block_keys,
+                        float* tsdf_buf, uint16_t* weight_buf,
+                        uint16_t* color_buf, const double depth_K[9],
+                        const double color_K[9], const double extrinsic[16],
+                        int resolution, float voxel_size, float sdf_trunc,
+                        float depth_scale, float depth_max);
+
+/* Set-semantics activate, core/hashmap/HashMap.cpp:166-197 +
+ * CPU/TBBHashBackend.h:173-227: keys n x 3; masks[i] = 1 for exactly one
+ * inserter of every key not yet present; buf_indices[i] = slot of key i
+ * (slots assigned in first-seen order starting at *size).  Slot ORDER is
+ * implementation-defined in the reference (parity unpinned for buf values).
+ * table_keys: capacity x 3 key buffer; *size updated.  Returns 0 or -1 if
+ * capacity would be exceeded.  Pinned (set semantics):
+ * tests/t/geometry/VoxelBlockGrid.cpp:211-219, tests/core/HashMap.cpp:92-360. */
+int orc_hashmap_activate(int32_t* table_keys, int64_t capacity, int64_t* size,
+                         const int32_t* keys, int64_t n, int32_t* buf_indices,
+                         uint8_t* masks);
+
+int orc_num_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
