@@ -1,0 +1,302 @@
+/*
+ * open3d_b200.h — C ABI of the B200-native ICP + TSDF hot path.
+ *
+ * This is the drop-in boundary: a flat extern "C" surface (plain pointers and
+ * sizes, no torch / Open3D types) that Open3D's L2 "thin dispatch" functions
+ * (the *CUDA symbols of cpp/open3d/t/pipelines/kernel, t/geometry/kernel,
+ * core/nns and core/hashmap) can forward to.  Each entry point cites the
+ * reference interface it replaces (paths relative to cpp/open3d/).
+ * INTEGRATION.md shows the reference-side stubs.
+ *
+ * Conventions
+ *  - `*_dev` pointers are device memory on the CURRENT CUDA device, contiguous,
+ *    row-major; `*_host` pointers are host memory.  Kernels never free inputs.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *    Calls are asynchronous on `stream` unless they return values to the host,
+ *    in which case they synchronise that stream (never the device).
+ *  - Return value: O3DB_OK (0) or a negative o3db_status; o3db_last_error()
+ *    returns a thread-local message.  There is NO CPU fallback: without a CUDA
+ *    device every compute entry point fails with O3DB_ERR_CUDA.
+ *  - Thread safety: handles are not internally locked; use one handle per host
+ *    thread (the reference has the same rule, cf. core/CUDAUtils.cpp:149-172).
+ */
+#ifndef OPEN3D_B200_H_
+#define OPEN3D_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define O3DB_VERSION_MAJOR 0
+#define O3DB_VERSION_MINOR 1
+
+typedef enum {
+    O3DB_OK = 0,
+    O3DB_ERR_INVALID = -1,   /* bad argument (shape, null, range) */
+    O3DB_ERR_CUDA = -2,      /* CUDA runtime / launch failure, or no device */
+    O3DB_ERR_SINGULAR = -3,  /* singular 6x6 system (reference raises, TransformationConverter.cpp:219-225) */
+    O3DB_ERR_CAPACITY = -4,  /* hash map / buffer capacity exceeded */
+    O3DB_ERR_NO_BLOCKS = -5, /* "No block is touched in TSDF volume" (VoxelBlockGridCUDA.cu:193-198) */
+    O3DB_ERR_COMM = -6       /* NCCL not available / communicator failure */
+} o3db_status;
+
+const char* o3db_last_error(void);
+int o3db_version(void);
+/* Number of kernels launched by this library in this process (all threads). */
+uint64_t o3db_kernel_launch_count(void);
+
+/* ------------------------------------------------------------------------
+ * Robust kernels — t/pipelines/registration/RobustKernel.h:15-23 (enum order),
+ * RobustKernelImpl.h:35-115 (weights).
+ * ---------------------------------------------------------------------- */
+typedef enum {
+    O3DB_ROBUST_L2 = 0, O3DB_ROBUST_L1 = 1, O3DB_ROBUST_HUBER = 2, O3DB_ROBUST_CAUCHY = 3,
+    O3DB_ROBUST_GM = 4, O3DB_ROBUST_TUKEY = 5, O3DB_ROBUST_GENERALIZED = 6
+} o3db_robust_method;
+
+typedef struct {
+    int method;     /* o3db_robust_method */
+    double scale;   /* RobustKernel::scaling_parameter_ */
+    double shape;   /* RobustKernel::shape_parameter_ */
+} o3db_robust_kernel;
+
+/* ------------------------------------------------------------------------
+ * Correspondence search — replaces core::nns::BuildSpatialHashTableCUDA<float>
+ * (core/nns/FixedRadiusIndex.h:227, FixedRadiusSearchOps.cu:20-58) and
+ * core::nns::HybridSearchCUDA<float,int32> (FixedRadiusIndex.h:364,
+ * FixedRadiusSearchOps.cu:162-198), i.e. NearestNeighborSearch::HybridIndex /
+ * HybridSearch (core/nns/NearestNeighborSearch.cpp:66-91, 144-165).
+ * The index owns a cell-sorted float4 copy of the points; `points_dev` may be
+ * freed after creation.
+ * ---------------------------------------------------------------------- */
+typedef struct o3db_nns o3db_nns;
+
+int o3db_nns_create(const float* points_dev /* [M,3] */, int64_t num_points, double radius,
+                    void* stream, o3db_nns** out);
+void o3db_nns_destroy(o3db_nns* nns);
+
+/* Hybrid search: up to max_knn (1..32) nearest points with dist^2 <= radius^2,
+ * ascending; indices padded with -1, distances with 0 (FixedRadiusSearchImpl.cuh:514-631).
+ * Exact ties resolve to the lower point index.  `radius` must not exceed the
+ * radius the index was built for.  Any output may be NULL. */
+int o3db_nns_hybrid_search(const o3db_nns* nns, const float* queries_dev /* [N,3] */,
+                           int64_t num_queries, double radius, int max_knn,
+                           int32_t* indices_dev /* [N,max_knn] */, float* distances_dev /* [N,max_knn] */,
+                           int32_t* counts_dev /* [N] */, void* stream);
+
+/* Reference-layout CSR spatial hash (parity / interop only): exactly the tables
+ * BuildSpatialHashTableCUDA produces — cell = floor(p/(2r)), bucket =
+ * SpatialHash(cell) % hash_table_size (core/nns/NeighborSearchCommon.h:31-52),
+ * cell_splits = exclusive prefix sums (hash_table_size+1 entries), index table
+ * = point ids grouped by bucket (order inside a bucket undefined, as upstream). */
+int o3db_build_spatial_hash_table(const float* points_dev, int64_t num_points, double radius,
+                                  uint32_t hash_table_size, uint32_t* hash_table_index_dev /* [M] */,
+                                  uint32_t* hash_table_cell_splits_dev /* [size+1] */, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Pose estimation from given correspondences — replaces
+ * t::pipelines::kernel::ComputePosePointToPlaneCUDA (kernel/RegistrationImpl.h:93-102,
+ * RegistrationCUDA.cu:29-117) including DecodeAndSolve6x6
+ * (kernel/TransformationConverter.cpp:189-226).
+ *   sums29_dev (optional, device, 29 doubles): the reduction vector
+ *     [0..20] lower-tri JtWJ, [21..26] JtWr, [27] sum r, [28] inlier count.
+ *   pose_dev (optional, device, 6 doubles): solution of AtA x = -Atb.
+ *   residual_host / inlier_count_host (optional): as the reference's by-ref outputs
+ *     (forces a stream synchronise).
+ * Returns O3DB_ERR_SINGULAR if the system is singular (only detectable when a
+ * host output is requested; otherwise pose is zero-filled, as upstream's catch). */
+int o3db_compute_pose_point_to_plane(const float* source_dev, const float* target_dev,
+                                     const float* target_normals_dev,
+                                     const int64_t* correspondences_dev, int64_t n,
+                                     const o3db_robust_kernel* kernel, double* sums29_dev,
+                                     double* pose_dev, float* residual_host, int* inlier_count_host,
+                                     void* stream);
+
+/* ComputePoseColoredICPCUDA (kernel/RegistrationImpl.h:118-131, RegistrationCUDA.cu:119-230). */
+int o3db_compute_pose_colored_icp(const float* source_dev, const float* source_colors_dev,
+                                  const float* target_dev, const float* target_normals_dev,
+                                  const float* target_colors_dev, const float* target_color_gradients_dev,
+                                  const int64_t* correspondences_dev, int64_t n,
+                                  const o3db_robust_kernel* kernel, double lambda_geometric,
+                                  double* sums29_dev, double* pose_dev, float* residual_host,
+                                  int* inlier_count_host, void* stream);
+
+/* kernel::PoseToTransformation (kernel/TransformationConverter.cpp:81-104,
+ * TransformationConverterImpl.h:22-42); host math, f64. */
+void o3db_pose_to_transformation(const double pose_host[6], double transformation_host[16]);
+
+/* t::geometry::kernel::transform::TransformPointsCUDA / TransformNormalsCUDA
+ * (t/geometry/kernel/Transform.h:42-47, TransformImpl.h:20-62): in place,
+ * T (row-major 4x4, host f64) is cast to f32 first as upstream does. */
+int o3db_transform_points(const double transformation_host[16], float* points_dev, int64_t n, void* stream);
+int o3db_transform_normals(const double transformation_host[16], float* normals_dev, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Fused, device-resident ICP loop — replaces
+ * t::pipelines::registration::ICP / MultiScaleICP / DoSingleScaleICPIterations /
+ * ComputeRegistrationResult (registration/Registration.cpp:24-62, 93-106, 275-444)
+ * for TransformationEstimationPointToPlane (TransformationEstimation.cpp:196-227)
+ * on one scale without down-sampling.
+ * ---------------------------------------------------------------------- */
+typedef struct {
+    double max_correspondence_distance;
+    int max_iteration;          /* ICPConvergenceCriteria::max_iteration_ (Registration.h:43-48) */
+    double relative_fitness;    /* ICPConvergenceCriteria::relative_fitness_ */
+    double relative_rmse;       /* ICPConvergenceCriteria::relative_rmse_ */
+    o3db_robust_kernel kernel;  /* TransformationEstimationPointToPlane::kernel_ */
+    double cell_scale;          /* search-grid cell = cell_scale * radius (0 => default) */
+    int search_variant;         /* 0 = default; see DESIGN.md (1 = direct global, 2 = TMA-staged tiles) */
+} o3db_icp_options;
+
+typedef struct {
+    double transformation[16];  /* RegistrationResult::transformation_ (row-major 4x4 f64) */
+    double fitness;             /* RegistrationResult::fitness_ */
+    double inlier_rmse;         /* RegistrationResult::inlier_rmse_ */
+    int converged;              /* RegistrationResult::converged_ */
+    int num_iterations;         /* RegistrationResult::num_iterations_ */
+    int status;                 /* O3DB_OK or O3DB_ERR_SINGULAR */
+    int64_t num_correspondences;
+} o3db_icp_result;
+
+typedef struct o3db_icp o3db_icp;
+typedef struct o3db_comm o3db_comm;
+
+/* Builds the target index, clones + cell-sorts the source (the caller's arrays
+ * are never modified, as Registration.cpp:398-404 clones) and applies
+ * init_source_to_target.  `comm` may be NULL (single GPU); with a communicator
+ * the source arrays are this rank's shard, the target is replicated, and every
+ * iteration all-reduces the 30-double system. */
+int o3db_icp_create(const float* source_dev, int64_t n, const float* target_dev,
+                    const float* target_normals_dev, int64_t m,
+                    const double init_source_to_target_host[16], const o3db_icp_options* options,
+                    o3db_comm* comm, void* stream, o3db_icp** out);
+/* Restore the state right after o3db_icp_create (source re-gathered, T = init). */
+int o3db_icp_reset(o3db_icp* icp, void* stream);
+/* Enqueue up to `iterations` ICP iterations (asynchronous, no host sync). */
+int o3db_icp_iterate(o3db_icp* icp, int iterations, void* stream);
+/* Final ComputeRegistrationResult (Registration.cpp:424-431) + read-back.
+ * correspondences_dev (optional, [N] int64, -1 = none) in the caller's source order;
+ * per_iteration_host (optional): 2 doubles (fitness, inlier_rmse) per executed iteration. */
+int o3db_icp_finish(o3db_icp* icp, o3db_icp_result* result_host, int64_t* correspondences_dev,
+                    double* per_iteration_host, void* stream);
+void o3db_icp_destroy(o3db_icp* icp);
+
+/* One-shot convenience: create + iterate(max_iteration) + finish + destroy. */
+int o3db_icp_point_to_plane(const float* source_dev, int64_t n, const float* target_dev,
+                            const float* target_normals_dev, int64_t m,
+                            const double init_source_to_target_host[16],
+                            const o3db_icp_options* options, o3db_icp_result* result_host,
+                            int64_t* correspondences_dev, double* per_iteration_host, void* stream);
+/* Same through HOST buffers (pageable or pinned): copies inputs host->device,
+ * runs, copies the result (and optional correspondences) back. */
+int o3db_icp_point_to_plane_host(const float* source_host, int64_t n, const float* target_host,
+                                 const float* target_normals_host, int64_t m,
+                                 const double init_source_to_target_host[16],
+                                 const o3db_icp_options* options, o3db_icp_result* result_host,
+                                 int64_t* correspondences_host, double* per_iteration_host);
+
+/* ------------------------------------------------------------------------
+ * Multi-GPU: one process per GPU; NCCL is dlopen()ed at run time
+ * (libnccl.so.2 — torch's bundled copy if torch is loaded, else the system one).
+ * The reference has no collective layer.
+ * ---------------------------------------------------------------------- */
+#define O3DB_UNIQUE_ID_BYTES 128
+int o3db_comm_get_unique_id(uint8_t id_out[O3DB_UNIQUE_ID_BYTES]);
+int o3db_comm_create(const uint8_t id[O3DB_UNIQUE_ID_BYTES], int rank, int world_size, o3db_comm** out);
+int o3db_comm_allreduce_f64(o3db_comm* comm, double* buf_dev, int count, void* stream);
+void o3db_comm_destroy(o3db_comm* comm);
+
+/* ------------------------------------------------------------------------
+ * TSDF voxel block grid — replaces, for the slam::Model layout
+ * (t/pipelines/slam/Model.cpp:23-36: tsdf f32[1], weight u16[1], color u16[3],
+ * keys int32x3), core::HashMap (core/hashmap/HashMap.cpp:117-216) with the CUDA
+ * backend (core/hashmap/CUDA/StdGPUHashBackend.h), DepthTouchCUDA
+ * (t/geometry/kernel/VoxelBlockGrid.h:345-356, VoxelBlockGridCUDA.cu:106-227)
+ * and IntegrateCUDA<u16,u8,f32,u16,u16> / <f32,f32,f32,u16,u16>
+ * (VoxelBlockGrid.h:369-381, VoxelBlockGridImpl.h:151-308).
+ * ---------------------------------------------------------------------- */
+typedef struct o3db_vbg o3db_vbg;
+
+typedef enum { O3DB_DEPTH_U16 = 0, O3DB_DEPTH_F32 = 1 } o3db_depth_dtype;
+typedef enum { O3DB_COLOR_NONE = 0, O3DB_COLOR_U8 = 1, O3DB_COLOR_F32 = 2 } o3db_color_dtype;
+
+/* VoxelBlockGrid ctor (t/geometry/VoxelBlockGrid.cpp:34-92): block_count is the
+ * initial capacity (slam::Model est_block_count); with_color allocates u16x3. */
+int o3db_vbg_create(float voxel_size, int block_resolution, int64_t block_count, int with_color,
+                    void* stream, o3db_vbg** out);
+void o3db_vbg_destroy(o3db_vbg* vbg);
+
+/* HashMap::Size / GetCapacity / Reserve (HashMap.cpp:47-77, 210-216). */
+int64_t o3db_vbg_size(o3db_vbg* vbg, void* stream);
+int64_t o3db_vbg_capacity(const o3db_vbg* vbg);
+int o3db_vbg_reserve(o3db_vbg* vbg, int64_t capacity, void* stream);
+
+/* HashMap::Activate (HashMap.cpp:166-181) / Find (:183-197) on int32x3 keys.
+ * buf_indices_dev [n] int32 (slot in the key/value buffers; -1 for Find misses),
+ * masks_dev [n] u8 (Activate: 1 for exactly one inserter of each NEW key;
+ * Find: 1 if present).  Activate grows (rehash) like upstream when
+ * size + n > capacity. */
+int o3db_vbg_activate(o3db_vbg* vbg, const int32_t* keys_dev, int64_t n, int32_t* buf_indices_dev,
+                      uint8_t* masks_dev, void* stream);
+int o3db_vbg_find(o3db_vbg* vbg, const int32_t* keys_dev, int64_t n, int32_t* buf_indices_dev,
+                  uint8_t* masks_dev, void* stream);
+/* HashMap::GetActiveIndices (:199-203): writes Size() buf indices, returns the count. */
+int64_t o3db_vbg_active_indices(o3db_vbg* vbg, int32_t* buf_indices_dev, int64_t max_count, void* stream);
+
+/* Raw buffers (HashMap::GetKeyTensor / GetValueTensor): keys [capacity,3] int32,
+ * tsdf [capacity,res^3] f32, weight [capacity,res^3] u16, color [capacity,res^3,3] u16.
+ * Pointers are invalidated by a growth (Reserve). */
+int32_t* o3db_vbg_key_buffer(o3db_vbg* vbg);
+float* o3db_vbg_tsdf_buffer(o3db_vbg* vbg);
+uint16_t* o3db_vbg_weight_buffer(o3db_vbg* vbg);
+uint16_t* o3db_vbg_color_buffer(o3db_vbg* vbg);
+/* The 64-bit key hash used by the table == utility::MiniVecHash<int,3>
+ * (core/hashmap/Dispatch.h:67-81); exposed for bit-exact parity tests. */
+int o3db_hash_keys(const int32_t* keys_dev, int64_t n, uint64_t* hashes_dev, void* stream);
+
+/* VoxelBlockGrid::GetUniqueBlockCoordinates(depth, ...) (VoxelBlockGrid.cpp:212-245)
+ * -> DepthTouchCUDA.  Writes the unique frustum block keys ([*,3] int32, order
+ * undefined as upstream) to block_coords_dev (capacity max_blocks; upstream's
+ * frustum map capacity is (W/4)(H/4)*4) and their number to *num_blocks_host
+ * (stream synchronise).  intrinsic: 3x3, extrinsic: 4x4 world->camera, host f64. */
+int o3db_vbg_unique_block_coordinates(o3db_vbg* vbg, const void* depth_dev, int depth_dtype,
+                                      int rows, int cols, const double intrinsic_host[9],
+                                      const double extrinsic_host[16], float depth_scale,
+                                      float depth_max, float trunc_voxel_multiplier,
+                                      int32_t* block_coords_dev, int64_t max_blocks,
+                                      int64_t* num_blocks_host, void* stream);
+
+/* VoxelBlockGrid::Integrate(block_coords, depth, color, ...) (VoxelBlockGrid.cpp:292-326):
+ * Activate + Find + IntegrateCUDA.  color_dev may be NULL (depth-only overload). */
+int o3db_vbg_integrate(o3db_vbg* vbg, const int32_t* block_coords_dev, int64_t num_blocks,
+                       const void* depth_dev, int depth_dtype, const void* color_dev, int color_dtype,
+                       int rows, int cols, const double depth_intrinsic_host[9],
+                       const double color_intrinsic_host[9], const double extrinsic_host[16],
+                       float depth_scale, float depth_max, float trunc_voxel_multiplier, void* stream);
+
+/* slam::Model::Integrate (t/pipelines/slam/Model.cpp:91-106) as ONE fused,
+ * host-sync-free pipeline: frustum touch + global activate + integrate.
+ * num_blocks_host (optional) receives the frame's frustum block count of the
+ * PREVIOUS call unless `sync` is non-zero. */
+int o3db_vbg_integrate_frame(o3db_vbg* vbg, const void* depth_dev, int depth_dtype,
+                             const void* color_dev, int color_dtype, int rows, int cols,
+                             const double intrinsic_host[9], const double extrinsic_host[16],
+                             float depth_scale, float depth_max, float trunc_voxel_multiplier,
+                             void* stream);
+/* Same through HOST images (pinned recommended): H2D copies included. */
+int o3db_vbg_integrate_frame_host(o3db_vbg* vbg, const void* depth_host, int depth_dtype,
+                                  const void* color_host, int color_dtype, int rows, int cols,
+                                  const double intrinsic_host[9], const double extrinsic_host[16],
+                                  float depth_scale, float depth_max, float trunc_voxel_multiplier,
+                                  void* stream);
+/* Block keys of the last integrated frame (Model::frustum_block_coords_): copies
+ * up to max_blocks keys, returns the count (stream synchronise). */
+int64_t o3db_vbg_last_frustum_blocks(o3db_vbg* vbg, int32_t* block_coords_dev, int64_t max_blocks,
+                                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OPEN3D_B200_H_ */

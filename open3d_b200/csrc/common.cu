@@ -1,0 +1,24 @@
+// common.cu — last-error storage, version, launch counter.
+#include "common.cuh"
+
+namespace o3db {
+
+static thread_local char g_last_error[1024] = "";
+std::atomic<uint64_t> g_launch_count{0};
+
+void set_last_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+    va_end(ap);
+}
+
+const char* last_error() { return g_last_error; }
+
+}  // namespace o3db
+
+extern "C" {
+const char* o3db_last_error(void) { return o3db::last_error(); }
+int o3db_version(void) { return O3DB_VERSION_MAJOR * 1000 + O3DB_VERSION_MINOR; }
+uint64_t o3db_kernel_launch_count(void) { return o3db::g_launch_count.load(); }
+}

@@ -1,0 +1,1084 @@
+// tsdf.cu — sparse voxel-block TSDF volume for sm_100a: lock-free open-addressing
+// hash of int32x3 block keys, frustum block discovery ("touch") and the fused
+// per-voxel depth-projection / weight-fusion kernel.  See include/open3d_b200.h
+// for the reference interfaces replaced and DESIGN.md for layout + rooflines.
+//
+// Bit-exactness: everything that feeds a floor()/truncation (block keys, pixel
+// selection) is evaluated with explicit round-to-nearest intrinsics in the
+// reference's source order, so that nvcc cannot contract it into FMAs; the CPU
+// oracle is compiled with -ffp-contract=off.  Keys and pixel choices therefore
+// agree bit for bit; TSDF values then agree bit for bit as well.
+//
+// No CPU fallback: every entry point needs a CUDA device.
+#include <climits>
+#include <cmath>
+#include <new>
+
+#include "common.cuh"
+
+namespace o3db {
+
+static constexpr int kT = 256;
+static constexpr int kEmpty = -1;
+static constexpr int kTomb = INT_MIN;
+static constexpr int kStepSize = 3;                 // VoxelBlockGridCUDA.cu:125 step_size
+static constexpr int kSamples = kStepSize + 1;      // est_multipler_factor
+static constexpr int kStride = 4;                   // VoxelBlockGrid.cpp:221 down_factor
+
+// ------------------------------------------------------------------- hash
+
+// utility::MiniVecHash<int,3> (core/hashmap/Dispatch.h:67-81): FNV-1a style over
+// the elements, int32 sign-extended to uint64.
+__host__ __device__ __forceinline__ uint64_t minivec_hash(int x, int y, int z) {
+    uint64_t h = 14695981039346656037ull;
+    h ^= (uint64_t)(int64_t)x;
+    h *= 1099511628211ull;
+    h ^= (uint64_t)(int64_t)y;
+    h *= 1099511628211ull;
+    h ^= (uint64_t)(int64_t)z;
+    h *= 1099511628211ull;
+    return h;
+}
+
+__device__ __forceinline__ unsigned bucket_of(uint64_t h, unsigned mask) {
+    return ((unsigned)h ^ (unsigned)(h >> 32)) & mask;
+}
+
+// Open addressing, linear probing.  table[b] is
+//   kEmpty            free
+//   v >= 0            committed: slot v of the key/value buffers
+//   v <= -2           provisional (inserted by the running call): candidate -(v+2)
+//   kTomb             dead bucket (only after an overflow)
+struct Table {
+    int* table;
+    unsigned mask;          // nbuckets - 1
+    const int* keys;        // committed keys [capacity,3]
+};
+
+enum { kResInserted = -2, kResDuplicate = -3, kResFull = -4, kResMiss = -5 };
+
+// Looks `k` up; if absent and INSERT, claims a bucket with the provisional marker
+// of candidate `cand` (whose key must already be globally visible in cand_keys).
+// Returns slot >= 0 (committed), kResInserted (+ *bucket), kResDuplicate (another
+// candidate of this call holds the key), kResMiss or kResFull.
+template <bool INSERT>
+__device__ __forceinline__ int probe(const Table& t, const int* __restrict__ cand_keys, int cand, int kx, int ky,
+                                     int kz, unsigned* bucket) {
+    unsigned b = bucket_of(minivec_hash(kx, ky, kz), t.mask);
+    for (unsigned n = 0; n <= t.mask; ++n, b = (b + 1) & t.mask) {
+        int v = __ldcg(&t.table[b]);
+        if (v == kEmpty) {
+            if (!INSERT) return kResMiss;
+            const int old = atomicCAS(&t.table[b], kEmpty, -(cand + 2));
+            if (old == kEmpty) {
+                *bucket = b;
+                return kResInserted;
+            }
+            v = old;
+        }
+        if (v == kTomb) continue;
+        const int* kk = v >= 0 ? t.keys + 3 * (size_t)v : cand_keys + 3 * (size_t)(-(v + 2));
+        if (__ldcg(kk) == kx && __ldcg(kk + 1) == ky && __ldcg(kk + 2) == kz) return v >= 0 ? v : kResDuplicate;
+    }
+    return kResFull;
+}
+
+// --------------------------------------------------------- camera geometry
+
+// t/geometry/kernel/GeometryIndexer.h:25-144 TransformIndexer: all f32.
+struct Cam {
+    float e[3][4];
+    float fx, fy, cx, cy;
+    float scale;
+};
+
+__device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float dvd(float a, float b) { return __fdiv_rn(a, b); }
+
+// GeometryIndexer.h:62-78 RigidTransform
+__device__ __forceinline__ void rigid(const Cam& c, float x, float y, float z, float& xo, float& yo, float& zo) {
+    x = mul(x, c.scale);
+    y = mul(y, c.scale);
+    z = mul(z, c.scale);
+    xo = add(add(add(mul(x, c.e[0][0]), mul(y, c.e[0][1])), mul(z, c.e[0][2])), c.e[0][3]);
+    yo = add(add(add(mul(x, c.e[1][0]), mul(y, c.e[1][1])), mul(z, c.e[1][2])), c.e[1][3]);
+    zo = add(add(add(mul(x, c.e[2][0]), mul(y, c.e[2][1])), mul(z, c.e[2][2])), c.e[2][3]);
+}
+// :100-108 Project
+__device__ __forceinline__ void project(const Cam& c, float x, float y, float z, float& u, float& v) {
+    const float inv_z = dvd(1.0f, z);
+    u = add(mul(mul(c.fx, x), inv_z), c.cx);
+    v = add(mul(mul(c.fy, y), inv_z), c.cy);
+}
+// :111-120 Unproject
+__device__ __forceinline__ void unproject(const Cam& c, float u, float v, float d, float& x, float& y, float& z) {
+    x = dvd(mul(sub(u, c.cx), d), c.fx);
+    y = dvd(mul(sub(v, c.cy), d), c.fy);
+    z = d;
+}
+// :294-297 InBoundary(x, y) with shape (rows, cols)
+__device__ __forceinline__ bool in_boundary(float x, float y, int rows, int cols) {
+    return y >= 0 && x >= 0 && y <= rows - 1.0f && x <= cols - 1.0f;
+}
+
+// ------------------------------------------------------------------ touch
+
+struct TouchArgs {
+    const void* depth;
+    int rows, cols;
+    Cam cam;                 // intrinsics + camera->world pose, scale 1 (VoxelBlockGridCUDA.cu:120)
+    float block_size, sdf_trunc, depth_scale, depth_max;
+    Table tab;
+    int* cand_keys;          // [rows/4 * cols/4 * 4, 3] per-call candidate keys
+    // fused mode (stamp != nullptr): touched committed slots + newly claimed buckets
+    int* stamp;              // [capacity] last frame id that touched the slot
+    int frame_id;
+    int* exist_list;         // touched committed slots
+    int2* new_list;          // (bucket, candidate) of keys first seen in this frame
+    int* counters;           // [0] n_exist, [1] n_new, [2] overflow flag
+    int max_list;
+};
+
+// VoxelBlockGridCUDA.cu:145-189 (DepthTouch lambda) fused with the hash insert
+// (:200-204) so that candidate keys never make a round trip through a dense list.
+template <typename depth_t>
+__global__ void __launch_bounds__(kT) touch_kernel(TouchArgs a) {
+    const int cols_s = a.cols / kStride, rows_s = a.rows / kStride;
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= cols_s * rows_s) return;
+    const int y = (w / cols_s) * kStride;
+    const int x = (w % cols_s) * kStride;
+    const float d = dvd((float)((const depth_t*)a.depth)[(size_t)y * a.cols + x], a.depth_scale);
+    if (!(d > 0 && d < a.depth_max)) return;
+    float xc, yc, zc, xg, yg, zg;
+    unproject(a.cam, (float)x, (float)y, 1.0f, xc, yc, zc);
+    rigid(a.cam, xc, yc, zc, xg, yg, zg);
+    const float xo = a.cam.e[0][3], yo = a.cam.e[1][3], zo = a.cam.e[2][3];
+    const float xd = sub(xg, xo), yd = sub(yg, yo), zd = sub(zg, zo);
+    const float t_min = fmaxf(sub(d, a.sdf_trunc), 0.0f);
+    const float t_max = fminf(add(d, a.sdf_trunc), a.depth_max);
+    const float t_step = dvd(sub(t_max, t_min), (float)kStepSize);
+    float t = t_min;
+    int px = 0, py = 0, pz = 0;
+#pragma unroll
+    for (int step = 0; step <= kStepSize; ++step) {
+        const int kx = (int)floorf(dvd(add(xo, mul(t, xd)), a.block_size));
+        const int ky = (int)floorf(dvd(add(yo, mul(t, yd)), a.block_size));
+        const int kz = (int)floorf(dvd(add(zo, mul(t, zd)), a.block_size));
+        t = add(t, t_step);
+        if (step > 0 && kx == px && ky == py && kz == pz) continue;  // consecutive samples in one block
+        px = kx;
+        py = ky;
+        pz = kz;
+        const int cand = w * kSamples + step;
+        int* ck = a.cand_keys + 3 * (size_t)cand;
+        ck[0] = kx;
+        ck[1] = ky;
+        ck[2] = kz;
+        __threadfence();
+        unsigned bucket = 0;
+        const int r = probe<true>(a.tab, a.cand_keys, cand, kx, ky, kz, &bucket);
+        if (r >= 0) {
+            if (a.stamp && atomicExch(&a.stamp[r], a.frame_id) != a.frame_id) {
+                const int p = atomicAdd(&a.counters[0], 1);
+                if (p < a.max_list) a.exist_list[p] = r;
+                else a.counters[2] = 1;
+            }
+        } else if (r == kResInserted) {
+            const int p = atomicAdd(&a.counters[1], 1);
+            if (p < a.max_list) a.new_list[p] = make_int2((int)bucket, cand);
+            else a.counters[2] = 1;
+        } else if (r == kResFull) {
+            a.counters[2] = 1;
+        }
+    }
+}
+
+// Stand-alone GetUniqueBlockCoordinates: the winners' keys are the unique set.
+__global__ void emit_unique_keys_kernel(const int2* __restrict__ new_list, const int* __restrict__ counters,
+                                        const int* __restrict__ cand_keys, int* __restrict__ out, int max_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = min(counters[1], max_out);
+    if (i >= n) return;
+    const int* k = cand_keys + 3 * (size_t)new_list[i].y;
+    out[3 * i] = k[0];
+    out[3 * i + 1] = k[1];
+    out[3 * i + 2] = k[2];
+}
+
+// --------------------------------------------------- stand-alone hash ops
+
+struct MapArgs {
+    Table tab;
+    int* keys_rw;        // committed key buffer (writable view of tab.keys)
+    const int* in_keys;  // [n,3]
+    int n;
+    int* buf_indices;
+    uint8_t* masks;
+    int* bucket_of_input;  // scratch [n]
+    int* size;             // device counter
+    int capacity;
+    int* overflow;
+};
+
+// HashMap::Activate pass 1: claim buckets with provisional markers (candidate id =
+// input index; the candidate key array is the read-only input itself).
+__global__ void activate_claim_kernel(MapArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    unsigned bucket = 0;
+    const int r = probe<true>(a.tab, a.in_keys, i, a.in_keys[3 * i], a.in_keys[3 * i + 1], a.in_keys[3 * i + 2], &bucket);
+    a.bucket_of_input[i] = r == kResInserted ? (int)bucket : -1;
+    if (a.masks) a.masks[i] = r == kResInserted ? 1 : 0;
+    if (r == kResFull) *a.overflow = 1;
+}
+// pass 2: winners pop a slot (CUDAHashBackendBufferAccessor.h:80-83 heap_top), publish key + slot.
+__global__ void activate_commit_kernel(MapArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const int b = a.bucket_of_input[i];
+    if (b < 0) return;
+    const int slot = atomicAdd(a.size, 1);
+    if (slot >= a.capacity) {
+        atomicSub(a.size, 1);
+        a.tab.table[b] = kTomb;
+        if (a.masks) a.masks[i] = 0;
+        *a.overflow = 1;
+        return;
+    }
+    a.keys_rw[3 * (size_t)slot] = a.in_keys[3 * i];
+    a.keys_rw[3 * (size_t)slot + 1] = a.in_keys[3 * i + 1];
+    a.keys_rw[3 * (size_t)slot + 2] = a.in_keys[3 * i + 2];
+    a.tab.table[b] = slot;
+}
+// HashMap::Find (also pass 3 of Activate: every input learns its slot).
+__global__ void find_kernel(MapArgs a, bool write_masks) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    unsigned bucket;
+    const int r = probe<false>(a.tab, a.in_keys, 0, a.in_keys[3 * i], a.in_keys[3 * i + 1], a.in_keys[3 * i + 2], &bucket);
+    if (a.buf_indices) a.buf_indices[i] = r >= 0 ? r : -1;
+    if (write_masks && a.masks) a.masks[i] = r >= 0 ? 1 : 0;
+}
+
+__global__ void rehash_kernel(int* table, unsigned mask, const int* keys, int n) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    unsigned b = bucket_of(minivec_hash(keys[3 * s], keys[3 * s + 1], keys[3 * s + 2]), mask);
+    for (;; b = (b + 1) & mask)
+        if (atomicCAS(&table[b], kEmpty, s) == kEmpty) return;
+}
+
+__global__ void hash_keys_kernel(const int* __restrict__ keys, int64_t n, uint64_t* __restrict__ out) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = minivec_hash(keys[3 * i], keys[3 * i + 1], keys[3 * i + 2]);
+}
+
+__global__ void iota_kernel(int* out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = i;
+}
+
+// --------------------------------------------------------------- integrate
+
+struct IntegrateArgs {
+    const void* depth;
+    const void* color;       // may be null
+    int rows, cols;
+    Cam dcam;                // depth intrinsics + world->camera extrinsics, scale = voxel_size
+    Cam ccam;                // colour intrinsics, identity extrinsics, scale 1
+    float sdf_trunc, depth_scale, depth_max, color_multiplier;
+    int resolution;          // 16 on the fast path
+    const int* block_keys;   // [capacity,3]
+    float* tsdf;
+    uint16_t* weight;
+    uint16_t* color_buf;     // may be null
+    // list mode
+    const int* buf_indices;
+    int n_blocks;
+    // fused mode (counters != nullptr): exist_list ++ new_list, commit on the fly
+    const int* exist_list;
+    const int2* new_list;
+    const int* cand_keys;
+    int* counters;           // [0] n_exist [1] n_new [2] overflow [3] ticket
+    int* size;
+    int* table;
+    int* keys_rw;
+    int* stamp;
+    int* frame_slots;        // [max] slots of this frame's frustum blocks (Model::frustum_block_coords_)
+    int* frame_count;
+    int* max_new;            // running max of blocks first seen in one frame
+    int frame_id;
+    int capacity;
+};
+
+// VoxelBlockGridImpl.h:226-303 for one voxel.  Returns false if the voxel is not updated.
+template <typename depth_t>
+__device__ __forceinline__ bool voxel_sdf(const IntegrateArgs& a, int x, int y, int z, float& sdf, int& ui, int& vi) {
+    float xc, yc, zc, u, v;
+    rigid(a.dcam, (float)x, (float)y, (float)z, xc, yc, zc);
+    project(a.dcam, xc, yc, zc, u, v);
+    if (!in_boundary(u, v, a.rows, a.cols)) return false;
+    ui = (int)u;
+    vi = (int)v;
+    const float depth = dvd((float)__ldg(&((const depth_t*)a.depth)[(size_t)vi * a.cols + ui]), a.depth_scale);
+    sdf = sub(depth, zc);
+    if (depth <= 0 || depth > a.depth_max || zc <= 0 || sdf < -a.sdf_trunc) return false;
+    sdf = sdf < a.sdf_trunc ? sdf : a.sdf_trunc;
+    sdf = dvd(sdf, a.sdf_trunc);
+    return true;
+}
+
+// One 16^3 block per CTA iteration; each thread owns 4 consecutive x voxels per
+// pass (128-bit tsdf, 64-bit weight, 3x64-bit colour accesses, fully coalesced).
+template <typename depth_t, typename color_in_t, bool HAS_COLOR>
+__device__ __forceinline__ void integrate_block16(const IntegrateArgs& a, int slot, int xb, int yb, int zb) {
+    float* tsdf = a.tsdf + (size_t)slot * 4096;
+    uint16_t* wt = a.weight + (size_t)slot * 4096;
+    uint16_t* cb = HAS_COLOR ? a.color_buf + (size_t)slot * 4096 * 3 : nullptr;
+#pragma unroll 1
+    for (int it = 0; it < 4; ++it) {
+        const int quad = it * kT + threadIdx.x;
+        const int xq = (quad & 3) * 4, yv = (quad >> 2) & 15, zv = quad >> 6;
+        const int lin = quad * 4;
+        float sdf[4];
+        int ui[4], vi[4];
+        bool up[4];
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            up[k] = voxel_sdf<depth_t>(a, xb * 16 + xq + k, yb * 16 + yv, zb * 16 + zv, sdf[k], ui[k], vi[k]);
+            any |= up[k];
+        }
+        if (!any) continue;
+        float4 t4 = *reinterpret_cast<float4*>(tsdf + lin);
+        ushort4 w4 = *reinterpret_cast<ushort4*>(wt + lin);
+        float tv[4] = {t4.x, t4.y, t4.z, t4.w};
+        unsigned short wv[4] = {w4.x, w4.y, w4.z, w4.w};
+        unsigned short cv[12];
+        if (HAS_COLOR) {
+            const uint2* cp = reinterpret_cast<const uint2*>(cb + (size_t)lin * 3);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const uint2 c2 = cp[k];
+                cv[4 * k + 0] = (unsigned short)(c2.x & 0xffffu);
+                cv[4 * k + 1] = (unsigned short)(c2.x >> 16);
+                cv[4 * k + 2] = (unsigned short)(c2.y & 0xffffu);
+                cv[4 * k + 3] = (unsigned short)(c2.y >> 16);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (!up[k]) continue;
+            const float inv_wsum = dvd(1.0f, (float)((int)wv[k] + 1));   // :274
+            const float weight = (float)wv[k];
+            tv[k] = mul(add(mul(weight, tv[k]), sdf[k]), inv_wsum);     // :276
+            if (HAS_COLOR) {
+                float px, py, pz, uf, vf;
+                unproject(a.dcam, (float)ui[k], (float)vi[k], 1.0f, px, py, pz);   // :283
+                project(a.ccam, px, py, pz, uf, vf);                                 // :286
+                if (in_boundary(uf, vf, a.rows, a.cols)) {
+                    const int cu = (int)roundf(uf), cw = (int)roundf(vf);
+                    const color_in_t* in = (const color_in_t*)a.color + ((size_t)cw * a.cols + cu) * 3;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const float v = mul(add(mul(weight, (float)cv[3 * k + c]),
+                                                mul((float)__ldg(&in[c]), a.color_multiplier)),
+                                            inv_wsum);                              // :295-298
+                        cv[3 * k + c] = (unsigned short)v;
+                    }
+                }
+            }
+            wv[k] = (unsigned short)add(weight, 1.0f);                  // :302
+        }
+        *reinterpret_cast<float4*>(tsdf + lin) = make_float4(tv[0], tv[1], tv[2], tv[3]);
+        *reinterpret_cast<ushort4*>(wt + lin) = make_ushort4(wv[0], wv[1], wv[2], wv[3]);
+        if (HAS_COLOR) {
+            uint2* cp = reinterpret_cast<uint2*>(cb + (size_t)lin * 3);
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                cp[k] = make_uint2((unsigned)cv[4 * k] | ((unsigned)cv[4 * k + 1] << 16),
+                                   (unsigned)cv[4 * k + 2] | ((unsigned)cv[4 * k + 3] << 16));
+        }
+    }
+}
+
+// Generic resolution (any res, scalar accesses) — parity path for res != 16.
+template <typename depth_t, typename color_in_t, bool HAS_COLOR>
+__device__ __forceinline__ void integrate_block_generic(const IntegrateArgs& a, int slot, int xb, int yb, int zb) {
+    const int res = a.resolution, res3 = res * res * res;
+    for (int vox = threadIdx.x; vox < res3; vox += kT) {
+        const int xv = vox % res, yv = (vox / res) % res, zv = vox / (res * res);
+        float sdf;
+        int ui, vi;
+        if (!voxel_sdf<depth_t>(a, xb * res + xv, yb * res + yv, zb * res + zv, sdf, ui, vi)) continue;
+        const size_t lin = (size_t)slot * res3 + vox;
+        const unsigned short w = a.weight[lin];
+        const float inv_wsum = dvd(1.0f, (float)((int)w + 1));
+        const float weight = (float)w;
+        a.tsdf[lin] = mul(add(mul(weight, a.tsdf[lin]), sdf), inv_wsum);
+        if (HAS_COLOR) {
+            float px, py, pz, uf, vf;
+            unproject(a.dcam, (float)ui, (float)vi, 1.0f, px, py, pz);
+            project(a.ccam, px, py, pz, uf, vf);
+            if (in_boundary(uf, vf, a.rows, a.cols)) {
+                const int cu = (int)roundf(uf), cw = (int)roundf(vf);
+                const color_in_t* in = (const color_in_t*)a.color + ((size_t)cw * a.cols + cu) * 3;
+                for (int c = 0; c < 3; ++c)
+                    a.color_buf[3 * lin + c] = (unsigned short)mul(
+                            add(mul(weight, (float)a.color_buf[3 * lin + c]), mul((float)in[c], a.color_multiplier)),
+                            inv_wsum);
+            }
+        }
+        a.weight[lin] = (unsigned short)add(weight, 1.0f);
+    }
+}
+
+template <typename depth_t, typename color_in_t, bool HAS_COLOR>
+__global__ void __launch_bounds__(kT) integrate_kernel(IntegrateArgs a) {
+    __shared__ int s_slot, s_key[3];
+    const bool fused = a.counters != nullptr;
+    int n_exist = 0, n_total = a.n_blocks, size0 = 0;
+    if (fused) {
+        n_exist = a.counters[0];
+        n_total = n_exist + a.counters[1];
+        size0 = *a.size;
+        if (a.counters[2]) n_total = 0;   // overflow: the host reports it; nothing is integrated
+    }
+    for (int b = blockIdx.x; b < n_total; b += gridDim.x) {
+        if (threadIdx.x == 0) {
+            int slot;
+            if (!fused) {
+                slot = a.buf_indices[b];
+            } else if (b < n_exist) {
+                slot = a.exist_list[b];
+            } else {
+                // commit a block first seen in this frame: slot = old size + rank
+                const int2 nl = a.new_list[b - n_exist];
+                slot = size0 + (b - n_exist);
+                if (slot < a.capacity) {
+                    const int* k = a.cand_keys + 3 * (size_t)nl.y;
+                    a.keys_rw[3 * (size_t)slot] = k[0];
+                    a.keys_rw[3 * (size_t)slot + 1] = k[1];
+                    a.keys_rw[3 * (size_t)slot + 2] = k[2];
+                    a.stamp[slot] = a.frame_id;
+                    a.table[nl.x] = slot;
+                } else {
+                    a.table[nl.x] = kTomb;
+                    a.counters[2] = 1;
+                    slot = -1;
+                }
+            }
+            s_slot = slot;
+            if (slot >= 0) {
+                const int* k = (fused && b >= n_exist) ? a.cand_keys + 3 * (size_t)a.new_list[b - n_exist].y
+                                                       : a.block_keys + 3 * (size_t)slot;
+                s_key[0] = k[0];
+                s_key[1] = k[1];
+                s_key[2] = k[2];
+                if (fused) a.frame_slots[b] = slot;
+            }
+        }
+        __syncthreads();
+        const int slot = s_slot;
+        if (slot >= 0) {
+            if (a.resolution == 16) integrate_block16<depth_t, color_in_t, HAS_COLOR>(a, slot, s_key[0], s_key[1], s_key[2]);
+            else integrate_block_generic<depth_t, color_in_t, HAS_COLOR>(a, slot, s_key[0], s_key[1], s_key[2]);
+        }
+        __syncthreads();
+    }
+    if (fused) {
+        // last CTA publishes the new size and re-arms the per-frame counters
+        __shared__ bool s_last;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) s_last = atomicAdd(&a.counters[3], 1) == (int)gridDim.x - 1;
+        __syncthreads();
+        if (s_last && threadIdx.x == 0) {
+            const int n_new = a.counters[1];
+            const int ns = min(size0 + n_new, a.capacity);
+            *a.frame_count = a.counters[2] ? 0 : n_total;
+            *a.size = ns;
+            if (n_new > *a.max_new) *a.max_new = n_new;
+            a.counters[0] = 0;
+            a.counters[1] = 0;
+            a.counters[3] = 0;
+            // counters[2] (overflow) is sticky until the host reads it
+        }
+    }
+}
+
+__global__ void gather_keys_kernel(const int* __restrict__ keys, const int* __restrict__ slots, int n,
+                                   int* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int s = slots[i];
+    out[3 * i] = keys[3 * (size_t)s];
+    out[3 * i + 1] = keys[3 * (size_t)s + 1];
+    out[3 * i + 2] = keys[3 * (size_t)s + 2];
+}
+
+}  // namespace o3db
+
+using namespace o3db;
+
+struct o3db_vbg {
+    float voxel_size = 0;
+    int resolution = 16;
+    int64_t capacity = 0;
+    bool with_color = false;
+    // hash map
+    int* table = nullptr;
+    unsigned nbuckets = 0;
+    int* keys = nullptr;
+    int* stamp = nullptr;
+    int* size_dev = nullptr;       // [0] size
+    int* counters = nullptr;       // [0] n_exist [1] n_new [2] overflow [3] ticket
+    // values
+    float* tsdf = nullptr;
+    uint16_t* weight = nullptr;
+    uint16_t* color = nullptr;
+    // per-frame scratch (sized for the frustum capacity (W/4)(H/4)*4)
+    int64_t frustum_cap = 0;
+    int* cand_keys = nullptr;
+    int* exist_list = nullptr;
+    int2* new_list = nullptr;
+    int* frame_slots = nullptr;
+    int* frame_count = nullptr;
+    // frustum-only table for the stand-alone GetUniqueBlockCoordinates
+    int* ftable = nullptr;
+    unsigned fbuckets = 0;
+    // staging for host-image entry point
+    void* d_depth = nullptr;
+    void* d_color = nullptr;
+    size_t d_depth_bytes = 0, d_color_bytes = 0;
+    // host mirrors: size_dev[0..15] is copied to pinned memory after every fused frame
+    // (ring of 2) so that capacity can be managed without a per-frame host sync.
+    int* h_pinned = nullptr;       // [0..15] synchronous read-back, [16..47] ring of 2 x 16
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    int frame_id = 0;
+    int64_t frames = 0;            // fused frames launched
+    int64_t known_size = 0;        // size as last read back (a lower bound)
+    int64_t max_new_seen = 0;
+};
+
+namespace o3db {
+
+static unsigned pow2_at_least(int64_t v) {
+    unsigned p = 16;
+    while ((int64_t)p < v) p <<= 1;
+    return p;
+}
+
+static size_t res3(const o3db_vbg* v) { return (size_t)v->resolution * v->resolution * v->resolution; }
+
+static int alloc_map(o3db_vbg* v, int64_t capacity, cudaStream_t st) {
+    v->capacity = capacity;
+    v->nbuckets = pow2_at_least(2 * capacity);
+    const size_t r3 = res3(v);
+    O3DB_CUDA_CHECK(cudaMallocAsync(&v->table, (size_t)v->nbuckets * sizeof(int), st));
+    O3DB_CUDA_CHECK(cudaMallocAsync(&v->keys, (size_t)capacity * 3 * sizeof(int), st));
+    O3DB_CUDA_CHECK(cudaMallocAsync(&v->stamp, (size_t)capacity * sizeof(int), st));
+    O3DB_CUDA_CHECK(cudaMallocAsync(&v->tsdf, (size_t)capacity * r3 * sizeof(float), st));
+    O3DB_CUDA_CHECK(cudaMallocAsync(&v->weight, (size_t)capacity * r3 * sizeof(uint16_t), st));
+    if (v->with_color) O3DB_CUDA_CHECK(cudaMallocAsync(&v->color, (size_t)capacity * r3 * 3 * sizeof(uint16_t), st));
+    O3DB_CUDA_CHECK(cudaMemsetAsync(v->table, 0xff, (size_t)v->nbuckets * sizeof(int), st));
+    O3DB_CUDA_CHECK(cudaMemsetAsync(v->keys, 0, (size_t)capacity * 3 * sizeof(int), st));
+    O3DB_CUDA_CHECK(cudaMemsetAsync(v->stamp, 0xff, (size_t)capacity * sizeof(int), st));
+    // value buffers are zero-initialised at allocation (CUDAHashBackendBufferAccessor.h:56-57)
+    O3DB_CUDA_CHECK(cudaMemsetAsync(v->tsdf, 0, (size_t)capacity * r3 * sizeof(float), st));
+    O3DB_CUDA_CHECK(cudaMemsetAsync(v->weight, 0, (size_t)capacity * r3 * sizeof(uint16_t), st));
+    if (v->with_color) O3DB_CUDA_CHECK(cudaMemsetAsync(v->color, 0, (size_t)capacity * r3 * 3 * sizeof(uint16_t), st));
+    return O3DB_OK;
+}
+
+static int ensure_frame_scratch(o3db_vbg* v, int rows, int cols, cudaStream_t st) {
+    const int64_t need = (int64_t)(rows / kStride) * (cols / kStride) * kSamples;   // VoxelBlockGrid.cpp:225-227
+    if (need <= v->frustum_cap) return O3DB_OK;
+    if (v->cand_keys) {
+        cudaFreeAsync(v->cand_keys, st);
+        cudaFreeAsync(v->exist_list, st);
+        cudaFreeAsync(v->new_list, st);
+        cudaFreeAsync(v->frame_slots, st);
+        cudaFreeAsync(v->ftable, st);
+    }
+    v->frustum_cap = need;
+    v->fbuckets = pow2_at_least(2 * need);
+    O3DB_CUDA_CHECK(cudaMallocAsync(&v->cand_keys, (size_t)need * 3 * sizeof(int), st));
+    O3DB_CUDA_CHECK(cudaMallocAsync(&v->exist_list, (size_t)need * sizeof(int), st));
+    O3DB_CUDA_CHECK(cudaMallocAsync(&v->new_list, (size_t)need * sizeof(int2), st));
+    O3DB_CUDA_CHECK(cudaMallocAsync(&v->frame_slots, (size_t)need * sizeof(int), st));
+    O3DB_CUDA_CHECK(cudaMallocAsync(&v->ftable, (size_t)v->fbuckets * sizeof(int), st));
+    return O3DB_OK;
+}
+
+// t/geometry/Utility.h:77-115 InverseTransformation (f64, same operation order)
+static void inverse_transformation(const double* T, double* Ti) {
+    Ti[0] = T[0]; Ti[1] = T[4]; Ti[2] = T[8];
+    Ti[4] = T[1]; Ti[5] = T[5]; Ti[6] = T[9];
+    Ti[8] = T[2]; Ti[9] = T[6]; Ti[10] = T[10];
+    Ti[3] = -(Ti[0] * T[3] + Ti[1] * T[7] + Ti[2] * T[11]);
+    Ti[7] = -(Ti[4] * T[3] + Ti[5] * T[7] + Ti[6] * T[11]);
+    Ti[11] = -(Ti[8] * T[3] + Ti[9] * T[7] + Ti[10] * T[11]);
+    Ti[12] = 0; Ti[13] = 0; Ti[14] = 0; Ti[15] = 1;
+}
+
+static Cam make_cam(const double* K, const double* E, float scale) {
+    Cam c;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 4; ++j) c.e[i][j] = (float)E[i * 4 + j];
+    c.fx = (float)K[0];
+    c.fy = (float)K[4];
+    c.cx = (float)K[2];
+    c.cy = (float)K[5];
+    c.scale = scale;
+    return c;
+}
+
+static int grow(o3db_vbg* v, int64_t new_capacity, cudaStream_t st) {
+    // HashMap::Reserve (HashMap.cpp:47-77): upstream re-inserts active entries into
+    // new buffers; here slots keep their indices, only the table is rebuilt.
+    O3DB_CUDA_CHECK(cudaStreamSynchronize(st));
+    int size = 0;
+    O3DB_CUDA_CHECK(cudaMemcpy(&size, v->size_dev, sizeof(int), cudaMemcpyDeviceToHost));
+    o3db_vbg old = *v;
+    int rc = alloc_map(v, new_capacity, st);
+    if (rc) return rc;
+    const size_t r3 = res3(v);
+    if (size > 0) {
+        O3DB_CUDA_CHECK(cudaMemcpyAsync(v->keys, old.keys, (size_t)size * 3 * sizeof(int), cudaMemcpyDeviceToDevice, st));
+        O3DB_CUDA_CHECK(cudaMemcpyAsync(v->stamp, old.stamp, (size_t)size * sizeof(int), cudaMemcpyDeviceToDevice, st));
+        O3DB_CUDA_CHECK(cudaMemcpyAsync(v->tsdf, old.tsdf, (size_t)size * r3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        O3DB_CUDA_CHECK(cudaMemcpyAsync(v->weight, old.weight, (size_t)size * r3 * sizeof(uint16_t), cudaMemcpyDeviceToDevice, st));
+        if (v->with_color)
+            O3DB_CUDA_CHECK(cudaMemcpyAsync(v->color, old.color, (size_t)size * r3 * 3 * sizeof(uint16_t), cudaMemcpyDeviceToDevice, st));
+        rehash_kernel<<<(unsigned)ceil_div(size, kT), kT, 0, st>>>(v->table, v->nbuckets - 1, v->keys, size);
+        O3DB_LAUNCH_CHECK();
+    }
+    cudaFreeAsync(old.table, st);
+    cudaFreeAsync(old.keys, st);
+    cudaFreeAsync(old.stamp, st);
+    cudaFreeAsync(old.tsdf, st);
+    cudaFreeAsync(old.weight, st);
+    if (old.color) cudaFreeAsync(old.color, st);
+    return O3DB_OK;
+}
+
+static int absorb_status(o3db_vbg* v, const int* h) {
+    v->known_size = h[0];
+    v->max_new_seen = std::max<int64_t>(v->max_new_seen, h[9]);
+    if (h[6]) {
+        set_last_error("voxel block hash map capacity (%lld blocks) exceeded; call o3db_vbg_reserve with a larger capacity",
+                       (long long)v->capacity);
+        return O3DB_ERR_CAPACITY;
+    }
+    return O3DB_OK;
+}
+
+// size_dev layout: [0] size, [4] n_exist [5] n_new [6] overflow [7] ticket, [8] frame_count, [9] max_new
+static int read_status(o3db_vbg* v, cudaStream_t st) {
+    O3DB_CUDA_CHECK(cudaMemcpyAsync(v->h_pinned, v->size_dev, 16 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    O3DB_CUDA_CHECK(cudaStreamSynchronize(st));
+    return absorb_status(v, v->h_pinned);
+}
+
+template <typename F>
+static int dispatch_integrate(int depth_dtype, int color_dtype, bool has_color, F&& f) {
+    // instantiations of VoxelBlockGridCUDA.cu:238-244 restricted to the slam::Model value layout
+    if (depth_dtype == O3DB_DEPTH_U16) {
+        if (!has_color) return f(integrate_kernel<uint16_t, uint8_t, false>);
+        if (color_dtype == O3DB_COLOR_U8) return f(integrate_kernel<uint16_t, uint8_t, true>);
+        set_last_error("u16 depth requires u8 color (kernel/VoxelBlockGrid.cpp:107-146)");
+        return O3DB_ERR_INVALID;
+    }
+    if (depth_dtype == O3DB_DEPTH_F32) {
+        if (!has_color) return f(integrate_kernel<float, float, false>);
+        if (color_dtype == O3DB_COLOR_F32) return f(integrate_kernel<float, float, true>);
+        set_last_error("f32 depth requires f32 color (kernel/VoxelBlockGrid.cpp:107-146)");
+        return O3DB_ERR_INVALID;
+    }
+    set_last_error("Unsupported depth dtype");
+    return O3DB_ERR_INVALID;
+}
+
+static IntegrateArgs base_integrate_args(o3db_vbg* v, const void* depth, const void* color, int color_dtype, int rows,
+                                         int cols, const double* dK, const double* cK, const double* E,
+                                         float depth_scale, float depth_max, float trunc_mult) {
+    IntegrateArgs a{};
+    a.depth = depth;
+    a.color = color;
+    a.rows = rows;
+    a.cols = cols;
+    a.dcam = make_cam(dK, E, v->voxel_size);                       // VoxelBlockGridImpl.h:184
+    const double eye[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    a.ccam = make_cam(cK ? cK : dK, eye, 1.0f);                     // :185-187
+    a.sdf_trunc = v->voxel_size * trunc_mult;                       // VoxelBlockGrid.cpp:325
+    a.depth_scale = depth_scale;
+    a.depth_max = depth_max;
+    a.color_multiplier = color_dtype == O3DB_COLOR_F32 ? 255.0f : 1.0f;   // VoxelBlockGridImpl.h:216-218
+    a.resolution = v->resolution;
+    a.block_keys = v->keys;
+    a.tsdf = v->tsdf;
+    a.weight = v->weight;
+    a.color_buf = v->color;
+    a.capacity = (int)v->capacity;
+    return a;
+}
+
+static int check_images(const void* depth, int depth_dtype, const void* color, int color_dtype, int rows, int cols) {
+    O3DB_REQUIRE(depth != nullptr && rows > 0 && cols > 0, "depth image is empty");
+    O3DB_REQUIRE(depth_dtype == O3DB_DEPTH_U16 || depth_dtype == O3DB_DEPTH_F32, "Unsupported depth image dtype");
+    O3DB_REQUIRE(color == nullptr || color_dtype == O3DB_COLOR_U8 || color_dtype == O3DB_COLOR_F32,
+                 "Unsupported color image dtype");
+    return O3DB_OK;
+}
+
+static TouchArgs make_touch_args(o3db_vbg* v, const void* depth, int rows, int cols, const double* K, const double* E,
+                                 float depth_scale, float depth_max, float trunc_mult) {
+    TouchArgs t{};
+    double pose[16];
+    inverse_transformation(E, pose);               // VoxelBlockGridCUDA.cu:119
+    t.depth = depth;
+    t.rows = rows;
+    t.cols = cols;
+    t.cam = make_cam(K, pose, 1.0f);               // :120
+    t.block_size = v->voxel_size * v->resolution;  // :143
+    t.sdf_trunc = v->voxel_size * trunc_mult;      // VoxelBlockGrid.cpp:241
+    t.depth_scale = depth_scale;
+    t.depth_max = depth_max;
+    t.cand_keys = v->cand_keys;
+    t.new_list = v->new_list;
+    t.exist_list = v->exist_list;
+    t.counters = v->counters;
+    t.max_list = (int)v->frustum_cap;
+    return t;
+}
+
+}  // namespace o3db
+
+extern "C" {
+
+int o3db_vbg_create(float voxel_size, int block_resolution, int64_t block_count, int with_color, void* stream,
+                    o3db_vbg** out) {
+    O3DB_REQUIRE(out != nullptr, "o3db_vbg_create: out is null");
+    *out = nullptr;
+    O3DB_REQUIRE(voxel_size > 0, "voxel_size must be positive");
+    O3DB_REQUIRE(block_resolution >= 1 && block_resolution <= 32, "block_resolution must be in 1..32");
+    O3DB_REQUIRE(block_count >= 1 && block_count < (int64_t(1) << 29), "block_count out of range");
+    cudaStream_t st = (cudaStream_t)stream;
+    o3db_vbg* v = new (std::nothrow) o3db_vbg();
+    O3DB_REQUIRE(v != nullptr, "out of host memory");
+    v->voxel_size = voxel_size;
+    v->resolution = block_resolution;
+    v->with_color = with_color != 0;
+    int rc = alloc_map(v, block_count, st);
+    cudaError_t e = cudaSuccess;
+    if (rc == O3DB_OK) e = cudaMallocAsync(&v->size_dev, 16 * sizeof(int), st);
+    if (rc == O3DB_OK && e == cudaSuccess) e = cudaMemsetAsync(v->size_dev, 0, 16 * sizeof(int), st);
+    if (rc == O3DB_OK && e == cudaSuccess) e = cudaMallocHost(&v->h_pinned, 48 * sizeof(int));
+    if (rc == O3DB_OK && e == cudaSuccess) e = cudaEventCreateWithFlags(&v->ev[0], cudaEventDisableTiming);
+    if (rc == O3DB_OK && e == cudaSuccess) e = cudaEventCreateWithFlags(&v->ev[1], cudaEventDisableTiming);
+    if (rc != O3DB_OK || e != cudaSuccess) {
+        if (e != cudaSuccess) {
+            set_last_error("o3db_vbg_create: %s", cudaGetErrorString(e));
+            rc = O3DB_ERR_CUDA;
+        }
+        o3db_vbg_destroy(v);
+        return rc;
+    }
+    v->counters = v->size_dev + 4;
+    v->frame_count = v->size_dev + 8;
+    memset(v->h_pinned, 0, 48 * sizeof(int));
+    *out = v;
+    return O3DB_OK;
+}
+
+void o3db_vbg_destroy(o3db_vbg* v) {
+    if (!v) return;
+    cudaDeviceSynchronize();
+    void* ptrs[] = {v->table, v->keys, v->stamp, v->size_dev, v->tsdf, v->weight, v->color, v->cand_keys,
+                    v->exist_list, v->new_list, v->frame_slots, v->ftable, v->d_depth, v->d_color};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    if (v->h_pinned) cudaFreeHost(v->h_pinned);
+    for (auto& e : v->ev)
+        if (e) cudaEventDestroy(e);
+    delete v;
+}
+
+int64_t o3db_vbg_size(o3db_vbg* v, void* stream) {
+    if (!v) return O3DB_ERR_INVALID;
+    int rc = read_status(v, (cudaStream_t)stream);
+    if (rc) return rc;
+    return v->known_size;
+}
+
+int64_t o3db_vbg_capacity(const o3db_vbg* v) { return v ? v->capacity : 0; }
+
+int o3db_vbg_reserve(o3db_vbg* v, int64_t capacity, void* stream) {
+    O3DB_REQUIRE(v != nullptr, "o3db_vbg_reserve: null handle");
+    if (capacity <= v->capacity) return O3DB_OK;
+    return grow(v, capacity, (cudaStream_t)stream);
+}
+
+int32_t* o3db_vbg_key_buffer(o3db_vbg* v) { return v ? v->keys : nullptr; }
+float* o3db_vbg_tsdf_buffer(o3db_vbg* v) { return v ? v->tsdf : nullptr; }
+uint16_t* o3db_vbg_weight_buffer(o3db_vbg* v) { return v ? v->weight : nullptr; }
+uint16_t* o3db_vbg_color_buffer(o3db_vbg* v) { return v ? v->color : nullptr; }
+
+int o3db_hash_keys(const int32_t* keys_dev, int64_t n, uint64_t* hashes_dev, void* stream) {
+    O3DB_REQUIRE(n >= 0 && (n == 0 || (keys_dev && hashes_dev)), "o3db_hash_keys: bad arguments");
+    if (n == 0) return O3DB_OK;
+    hash_keys_kernel<<<(unsigned)ceil_div(n, kT), kT, 0, (cudaStream_t)stream>>>(keys_dev, n, hashes_dev);
+    O3DB_LAUNCH_CHECK();
+    return O3DB_OK;
+}
+
+int o3db_vbg_activate(o3db_vbg* v, const int32_t* keys_dev, int64_t n, int32_t* buf_indices_dev, uint8_t* masks_dev,
+                      void* stream) {
+    O3DB_REQUIRE(v != nullptr && n >= 0 && n < INT_MAX && (n == 0 || keys_dev), "o3db_vbg_activate: bad arguments");
+    if (n == 0) return O3DB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    // HashMap.cpp:166-181: grow when Size() + len(keys) > capacity, to max(new_size, 2*capacity)
+    int rc = read_status(v, st);
+    if (rc) return rc;
+    const int64_t new_size = v->known_size + n;
+    if (new_size > v->capacity) {
+        rc = grow(v, std::max(new_size, 2 * v->capacity), st);
+        if (rc) return rc;
+    }
+    int* scratch = nullptr;
+    O3DB_CUDA_CHECK(cudaMallocAsync(&scratch, (size_t)n * sizeof(int), st));
+    MapArgs a{};
+    a.tab = Table{v->table, v->nbuckets - 1, v->keys};
+    a.keys_rw = v->keys;
+    a.in_keys = keys_dev;
+    a.n = (int)n;
+    a.buf_indices = buf_indices_dev;
+    a.masks = masks_dev;
+    a.bucket_of_input = scratch;
+    a.size = v->size_dev;
+    a.capacity = (int)v->capacity;
+    a.overflow = v->counters + 2;
+    const unsigned nb = (unsigned)ceil_div(n, kT);
+    activate_claim_kernel<<<nb, kT, 0, st>>>(a);
+    O3DB_LAUNCH_CHECK();
+    activate_commit_kernel<<<nb, kT, 0, st>>>(a);
+    O3DB_LAUNCH_CHECK();
+    if (buf_indices_dev) {
+        find_kernel<<<nb, kT, 0, st>>>(a, false);
+        O3DB_LAUNCH_CHECK();
+    }
+    O3DB_CUDA_CHECK(cudaFreeAsync(scratch, st));
+    return O3DB_OK;
+}
+
+int o3db_vbg_find(o3db_vbg* v, const int32_t* keys_dev, int64_t n, int32_t* buf_indices_dev, uint8_t* masks_dev,
+                  void* stream) {
+    O3DB_REQUIRE(v != nullptr && n >= 0 && n < INT_MAX && (n == 0 || keys_dev), "o3db_vbg_find: bad arguments");
+    if (n == 0) return O3DB_OK;
+    MapArgs a{};
+    a.tab = Table{v->table, v->nbuckets - 1, v->keys};
+    a.in_keys = keys_dev;
+    a.n = (int)n;
+    a.buf_indices = buf_indices_dev;
+    a.masks = masks_dev;
+    find_kernel<<<(unsigned)ceil_div(n, kT), kT, 0, (cudaStream_t)stream>>>(a, true);
+    O3DB_LAUNCH_CHECK();
+    return O3DB_OK;
+}
+
+int64_t o3db_vbg_active_indices(o3db_vbg* v, int32_t* buf_indices_dev, int64_t max_count, void* stream) {
+    if (!v) return O3DB_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = read_status(v, st);
+    if (rc) return rc;
+    const int64_t n = std::min<int64_t>(v->known_size, max_count);
+    if (n > 0 && buf_indices_dev) {
+        iota_kernel<<<(unsigned)ceil_div(n, kT), kT, 0, st>>>(buf_indices_dev, (int)n);
+        O3DB_LAUNCH_CHECK();
+    }
+    return v->known_size;
+}
+
+int o3db_vbg_unique_block_coordinates(o3db_vbg* v, const void* depth_dev, int depth_dtype, int rows, int cols,
+                                      const double K[9], const double E[16], float depth_scale, float depth_max,
+                                      float trunc_mult, int32_t* block_coords_dev, int64_t max_blocks,
+                                      int64_t* num_blocks_host, void* stream) {
+    O3DB_REQUIRE(v != nullptr && K && E, "o3db_vbg_unique_block_coordinates: null argument");
+    int rc = check_images(depth_dev, depth_dtype, nullptr, 0, rows, cols);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = ensure_frame_scratch(v, rows, cols, st);
+    if (rc) return rc;
+    // frustum_hashmap_->Clear() (VoxelBlockGrid.cpp:234)
+    O3DB_CUDA_CHECK(cudaMemsetAsync(v->ftable, 0xff, (size_t)v->fbuckets * sizeof(int), st));
+    O3DB_CUDA_CHECK(cudaMemsetAsync(v->counters, 0, 2 * sizeof(int), st));
+    TouchArgs t = make_touch_args(v, depth_dev, rows, cols, K, E, depth_scale, depth_max, trunc_mult);
+    t.tab = Table{v->ftable, v->fbuckets - 1, v->keys};
+    t.stamp = nullptr;
+    const int nthreads = (rows / kStride) * (cols / kStride);
+    const unsigned nb = (unsigned)std::max<int64_t>(1, ceil_div(nthreads, kT));
+    if (depth_dtype == O3DB_DEPTH_U16) touch_kernel<uint16_t><<<nb, kT, 0, st>>>(t);
+    else touch_kernel<float><<<nb, kT, 0, st>>>(t);
+    O3DB_LAUNCH_CHECK();
+    int h[2] = {0, 0};
+    O3DB_CUDA_CHECK(cudaMemcpyAsync(h, v->counters, sizeof(h), cudaMemcpyDeviceToHost, st));
+    O3DB_CUDA_CHECK(cudaStreamSynchronize(st));
+    const int64_t n = h[1];
+    if (num_blocks_host) *num_blocks_host = n;
+    if (n == 0) {  // VoxelBlockGridCUDA.cu:193-198
+        set_last_error("No block is touched in TSDF volume, abort integration. Please check specified parameters, "
+                       "especially depth_scale and voxel_size");
+        return O3DB_ERR_NO_BLOCKS;
+    }
+    if (block_coords_dev) {
+        O3DB_REQUIRE(max_blocks >= n, "block_coords buffer too small: %lld < %lld", (long long)max_blocks, (long long)n);
+        emit_unique_keys_kernel<<<(unsigned)ceil_div(n, kT), kT, 0, st>>>(v->new_list, v->counters, v->cand_keys,
+                                                                          block_coords_dev, (int)max_blocks);
+        O3DB_LAUNCH_CHECK();
+    }
+    O3DB_CUDA_CHECK(cudaMemsetAsync(v->counters, 0, 2 * sizeof(int), st));
+    return O3DB_OK;
+}
+
+int o3db_vbg_integrate(o3db_vbg* v, const int32_t* block_coords_dev, int64_t num_blocks, const void* depth_dev,
+                       int depth_dtype, const void* color_dev, int color_dtype, int rows, int cols,
+                       const double dK[9], const double cK[9], const double E[16], float depth_scale,
+                       float depth_max, float trunc_mult, void* stream) {
+    O3DB_REQUIRE(v != nullptr && dK && E && block_coords_dev && num_blocks > 0 && num_blocks < INT_MAX,
+                 "o3db_vbg_integrate: bad arguments");
+    int rc = check_images(depth_dev, depth_dtype, color_dev, color_dtype, rows, cols);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool has_color = color_dev != nullptr && v->with_color;   // VoxelBlockGridImpl.h:206-207
+    int* buf = nullptr;
+    O3DB_CUDA_CHECK(cudaMallocAsync(&buf, (size_t)num_blocks * sizeof(int), st));
+    // VoxelBlockGrid.cpp:313-315: Activate, then Find
+    rc = o3db_vbg_activate(v, block_coords_dev, num_blocks, buf, nullptr, st);
+    if (rc) {
+        cudaFreeAsync(buf, st);
+        return rc;
+    }
+    IntegrateArgs a = base_integrate_args(v, depth_dev, has_color ? color_dev : nullptr, color_dtype, rows, cols, dK, cK,
+                                          E, depth_scale, depth_max, trunc_mult);
+    a.buf_indices = buf;
+    a.n_blocks = (int)num_blocks;
+    const unsigned grid = (unsigned)std::min<int64_t>(num_blocks, (int64_t)num_sms() * 8);
+    rc = dispatch_integrate(depth_dtype, color_dtype, has_color, [&](auto kern) -> int {
+        kern<<<grid, kT, 0, st>>>(a);
+        O3DB_LAUNCH_CHECK();
+        return (int)O3DB_OK;
+    });
+    cudaFreeAsync(buf, st);
+    return rc;
+}
+
+int o3db_vbg_integrate_frame(o3db_vbg* v, const void* depth_dev, int depth_dtype, const void* color_dev,
+                             int color_dtype, int rows, int cols, const double K[9], const double E[16],
+                             float depth_scale, float depth_max, float trunc_mult, void* stream) {
+    O3DB_REQUIRE(v != nullptr && K && E, "o3db_vbg_integrate_frame: null argument");
+    int rc = check_images(depth_dev, depth_dtype, color_dev, color_dtype, rows, cols);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = ensure_frame_scratch(v, rows, cols, st);
+    if (rc) return rc;
+    // Capacity management without a per-frame host sync: wait for the frame launched two
+    // calls ago (normally long finished), read the size it published, and grow ahead of
+    // need (HashMap.cpp:166-181 grows when size + n > capacity).  Three frames (two in
+    // flight + this one) may add blocks the host has not seen yet.
+    const int slot = (int)(v->frames & 1);
+    if (v->frames >= 2) {
+        O3DB_CUDA_CHECK(cudaEventSynchronize(v->ev[slot]));
+        rc = absorb_status(v, v->h_pinned + 16 + 16 * slot);
+        if (rc) return rc;
+    }
+    const int64_t per_frame = std::max<int64_t>(2 * v->max_new_seen, 2048);
+    if (v->known_size + 3 * per_frame > v->capacity) {
+        rc = read_status(v, st);
+        if (rc) return rc;
+        if (v->known_size + 3 * per_frame > v->capacity) {
+            rc = grow(v, std::max<int64_t>(2 * v->capacity, v->known_size + 6 * per_frame), st);
+            if (rc) return rc;
+        }
+    }
+    const bool has_color = color_dev != nullptr && v->with_color;
+    v->frame_id += 1;
+    TouchArgs t = make_touch_args(v, depth_dev, rows, cols, K, E, depth_scale, depth_max, trunc_mult);
+    t.tab = Table{v->table, v->nbuckets - 1, v->keys};
+    t.stamp = v->stamp;
+    t.frame_id = v->frame_id;
+    const int nthreads = (rows / kStride) * (cols / kStride);
+    const unsigned nb = (unsigned)std::max<int64_t>(1, ceil_div(nthreads, kT));
+    if (depth_dtype == O3DB_DEPTH_U16) touch_kernel<uint16_t><<<nb, kT, 0, st>>>(t);
+    else touch_kernel<float><<<nb, kT, 0, st>>>(t);
+    O3DB_LAUNCH_CHECK();
+    IntegrateArgs a = base_integrate_args(v, depth_dev, has_color ? color_dev : nullptr, color_dtype, rows, cols, K, K, E,
+                                          depth_scale, depth_max, trunc_mult);
+    a.exist_list = v->exist_list;
+    a.new_list = v->new_list;
+    a.cand_keys = v->cand_keys;
+    a.counters = v->counters;
+    a.size = v->size_dev;
+    a.table = v->table;
+    a.keys_rw = v->keys;
+    a.stamp = v->stamp;
+    a.frame_slots = v->frame_slots;
+    a.frame_count = v->frame_count;
+    a.max_new = v->size_dev + 9;
+    a.frame_id = v->frame_id;
+    const unsigned grid = (unsigned)num_sms() * 8;
+    rc = dispatch_integrate(depth_dtype, color_dtype, has_color, [&](auto kern) -> int {
+        kern<<<grid, kT, 0, st>>>(a);
+        O3DB_LAUNCH_CHECK();
+        return (int)O3DB_OK;
+    });
+    if (rc) return rc;
+    O3DB_CUDA_CHECK(cudaMemcpyAsync(v->h_pinned + 16 + 16 * slot, v->size_dev, 16 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    O3DB_CUDA_CHECK(cudaEventRecord(v->ev[slot], st));
+    v->frames += 1;
+    return O3DB_OK;
+}
+
+int o3db_vbg_integrate_frame_host(o3db_vbg* v, const void* depth_host, int depth_dtype, const void* color_host,
+                                  int color_dtype, int rows, int cols, const double K[9], const double E[16],
+                                  float depth_scale, float depth_max, float trunc_mult, void* stream) {
+    O3DB_REQUIRE(v != nullptr, "o3db_vbg_integrate_frame_host: null handle");
+    int rc = check_images(depth_host, depth_dtype, color_host, color_dtype, rows, cols);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t dbytes = (size_t)rows * cols * (depth_dtype == O3DB_DEPTH_U16 ? 2 : 4);
+    const size_t cbytes = color_host ? (size_t)rows * cols * 3 * (color_dtype == O3DB_COLOR_U8 ? 1 : 4) : 0;
+    if (dbytes > v->d_depth_bytes) {
+        if (v->d_depth) cudaFreeAsync(v->d_depth, st);
+        O3DB_CUDA_CHECK(cudaMallocAsync(&v->d_depth, dbytes, st));
+        v->d_depth_bytes = dbytes;
+    }
+    if (cbytes > v->d_color_bytes) {
+        if (v->d_color) cudaFreeAsync(v->d_color, st);
+        O3DB_CUDA_CHECK(cudaMallocAsync(&v->d_color, cbytes, st));
+        v->d_color_bytes = cbytes;
+    }
+    O3DB_CUDA_CHECK(cudaMemcpyAsync(v->d_depth, depth_host, dbytes, cudaMemcpyHostToDevice, st));
+    if (cbytes) O3DB_CUDA_CHECK(cudaMemcpyAsync(v->d_color, color_host, cbytes, cudaMemcpyHostToDevice, st));
+    return o3db_vbg_integrate_frame(v, v->d_depth, depth_dtype, cbytes ? v->d_color : nullptr, color_dtype, rows, cols, K,
+                                    E, depth_scale, depth_max, trunc_mult, st);
+}
+
+int64_t o3db_vbg_last_frustum_blocks(o3db_vbg* v, int32_t* block_coords_dev, int64_t max_blocks, void* stream) {
+    if (!v) return O3DB_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = read_status(v, st);
+    if (rc) return rc;
+    const int64_t n = v->h_pinned[8];
+    const int64_t m = std::min(n, max_blocks);
+    if (m > 0 && block_coords_dev) {
+        gather_keys_kernel<<<(unsigned)ceil_div(m, kT), kT, 0, st>>>(v->keys, v->frame_slots, (int)m, block_coords_dev);
+        O3DB_LAUNCH_CHECK();
+    }
+    return n;
+}
+
+}  // extern "C"

@@ -1,0 +1,297 @@
+"""Host-side mirror of the pieces of ``open3d.t.geometry`` the hot path touches:
+``PointCloud`` (positions / normals / colors + ``transform``), ``Image`` and
+``VoxelBlockGrid`` (``compute_unique_block_coordinates``, ``integrate``,
+``hashmap``/``attribute`` access).  Reference: cpp/open3d/t/geometry/
+{PointCloud,VoxelBlockGrid}.cpp and cpp/pybind/t/geometry/voxel_block_grid.cpp:112-165.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .. import _libshim as _s
+from ..._lib import (COLOR_F32, COLOR_NONE, COLOR_U8, DEPTH_F32, DEPTH_U16, check, dptr, lib)
+from ...core import as_device_f32_points, as_host_f64_4x4, current_stream_ptr
+
+
+class PointCloud:
+    """t::geometry::PointCloud restricted to positions / normals / colors
+    (t/geometry/PointCloud.h).  Attributes live in ``self.point`` like upstream."""
+
+    def __init__(self, positions=None, device=None):
+        self.point = {}
+        if positions is not None:
+            self.point["positions"] = as_device_f32_points(positions, "positions")
+
+    # accessors named as in pybind (t/geometry/pointcloud.cpp)
+    @property
+    def positions(self):
+        return self.point.get("positions")
+
+    def has_point_positions(self):
+        return "positions" in self.point and self.point["positions"].shape[0] > 0
+
+    def has_point_normals(self):
+        return "normals" in self.point and self.point["normals"].shape[0] > 0
+
+    def has_point_colors(self):
+        return "colors" in self.point and self.point["colors"].shape[0] > 0
+
+    def set_point_normals(self, normals):
+        self.point["normals"] = as_device_f32_points(normals, "normals")
+        return self
+
+    def set_point_colors(self, colors):
+        self.point["colors"] = as_device_f32_points(colors, "colors")
+        return self
+
+    def clone(self):
+        out = PointCloud()
+        out.point = {k: v.clone() for k, v in self.point.items()}
+        return out
+
+    def transform(self, transformation):
+        """PointCloud::Transform (t/geometry/PointCloud.cpp:352-371): in place on
+        positions and, if present, normals."""
+        T = as_host_f64_4x4(transformation)
+        p = self.point["positions"]
+        check(lib.o3db_transform_points(dptr(T), p.data_ptr(), p.shape[0], current_stream_ptr()))
+        if self.has_point_normals():
+            n = self.point["normals"]
+            check(lib.o3db_transform_normals(dptr(T), n.data_ptr(), n.shape[0], current_stream_ptr()))
+        return self
+
+
+class Image:
+    """t::geometry::Image as a thin holder of an [H,W,C] tensor."""
+
+    def __init__(self, tensor=None):
+        if tensor is None:
+            tensor = torch.empty((0, 0, 1), dtype=torch.uint8)
+        if isinstance(tensor, np.ndarray):
+            tensor = torch.from_numpy(np.ascontiguousarray(tensor))
+        if tensor.dim() == 2:
+            tensor = tensor.unsqueeze(-1)
+        self._t = tensor
+
+    def as_tensor(self):
+        return self._t
+
+    @property
+    def rows(self):
+        return int(self._t.shape[0])
+
+    @property
+    def columns(self):
+        return int(self._t.shape[1])
+
+
+def _image_tensor(img):
+    if img is None:
+        return None
+    if isinstance(img, Image):
+        img = img.as_tensor()
+    if isinstance(img, np.ndarray):
+        img = torch.from_numpy(np.ascontiguousarray(img))
+    if img.numel() == 0:
+        return None
+    if not img.is_cuda:
+        img = img.cuda()
+    return img.contiguous()
+
+
+def _depth_dtype(t):
+    # CheckDepthTensor (t/geometry/Utility.h:25-44): UInt16 or Float32, one channel
+    if t.dtype == torch.uint16:
+        return DEPTH_U16
+    if t.dtype == torch.float32:
+        return DEPTH_F32
+    raise RuntimeError(f"Unsupported depth image dtype {t.dtype}")
+
+
+def _color_dtype(t):
+    if t is None:
+        return COLOR_NONE
+    if t.dtype == torch.uint8:
+        return COLOR_U8
+    if t.dtype == torch.float32:
+        return COLOR_F32
+    raise RuntimeError(f"Unsupported color image dtype {t.dtype}")
+
+
+def _k9(K):
+    if isinstance(K, torch.Tensor):
+        K = K.detach().cpu().numpy()
+    K = np.ascontiguousarray(np.asarray(K, dtype=np.float64))
+    if K.shape != (3, 3):
+        raise RuntimeError(f"Unsupported intrinsic matrix shape {K.shape}")  # CheckIntrinsicTensor
+    return K
+
+
+class _BlockHashMap:
+    """View of the grid's core::HashMap (int32x3 keys)."""
+
+    def __init__(self, vbg):
+        self._v = vbg
+
+    def size(self):
+        return int(check(lib.o3db_vbg_size(self._v._h, current_stream_ptr())))
+
+    def capacity(self):
+        return int(lib.o3db_vbg_capacity(self._v._h))
+
+    def reserve(self, capacity):
+        check(lib.o3db_vbg_reserve(self._v._h, int(capacity), current_stream_ptr()))
+
+    def _keys_arg(self, keys):
+        if isinstance(keys, np.ndarray):
+            keys = torch.from_numpy(np.ascontiguousarray(keys))
+        if keys.dtype != torch.int32:
+            raise RuntimeError(f"Unsupported block coordinate dtype {keys.dtype}")  # CheckBlockCoordinates
+        return keys.cuda().contiguous().reshape(-1, 3)
+
+    def activate(self, keys):
+        """HashMap::Activate -> (buf_indices int32 [n], masks bool [n])."""
+        keys = self._keys_arg(keys)
+        n = keys.shape[0]
+        buf = torch.empty(n, dtype=torch.int32, device=keys.device)
+        masks = torch.empty(n, dtype=torch.uint8, device=keys.device)
+        check(lib.o3db_vbg_activate(self._v._h, keys.data_ptr(), n, buf.data_ptr(), masks.data_ptr(),
+                                    current_stream_ptr()))
+        return buf, masks.bool()
+
+    def find(self, keys):
+        keys = self._keys_arg(keys)
+        n = keys.shape[0]
+        buf = torch.empty(n, dtype=torch.int32, device=keys.device)
+        masks = torch.empty(n, dtype=torch.uint8, device=keys.device)
+        check(lib.o3db_vbg_find(self._v._h, keys.data_ptr(), n, buf.data_ptr(), masks.data_ptr(),
+                                current_stream_ptr()))
+        return buf, masks.bool()
+
+    def active_buf_indices(self):
+        n = self.size()
+        out = torch.empty(n, dtype=torch.int32, device="cuda")
+        check(lib.o3db_vbg_active_indices(self._v._h, out.data_ptr(), n, current_stream_ptr()))
+        return out
+
+    def key_tensor(self):
+        """HashMap::GetKeyTensor: [capacity, 3] int32 view of the key buffer."""
+        return _s.device_view(lib.o3db_vbg_key_buffer(self._v._h), (self.capacity(), 3), torch.int32)
+
+
+class VoxelBlockGrid:
+    """t::geometry::VoxelBlockGrid for the slam::Model attribute layout
+    (tsdf Float32[1], weight UInt16[1], color UInt16[3]; slam/Model.cpp:28-35)."""
+
+    def __init__(self, attr_names=("tsdf", "weight", "color"),
+                 attr_dtypes=(torch.float32, torch.uint16, torch.uint16),
+                 attr_channels=((1,), (1,), (3,)), voxel_size=0.0058, block_resolution=16,
+                 block_count=10000, device="cuda:0"):
+        names = list(attr_names)
+        if "tsdf" not in names or "weight" not in names:
+            raise RuntimeError("TSDF and/or weight not allocated in blocks, please implement customized integration.")
+        layout = dict(zip(names, attr_dtypes))
+        if layout["tsdf"] != torch.float32 or layout["weight"] != torch.uint16 or \
+                layout.get("color", torch.uint16) != torch.uint16:
+            raise RuntimeError("open3d_b200 implements the slam::Model layout only: tsdf Float32, weight UInt16, "
+                               "color UInt16")
+        self.voxel_size = float(voxel_size)
+        self.block_resolution = int(block_resolution)
+        self._with_color = "color" in names
+        h = C.c_void_p()
+        check(lib.o3db_vbg_create(self.voxel_size, self.block_resolution, int(block_count), int(self._with_color),
+                                  current_stream_ptr(), C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            lib.o3db_vbg_destroy(h)
+            self._h = None
+
+    def hashmap(self):
+        return _BlockHashMap(self)
+
+    def attribute(self, name):
+        """VoxelBlockGrid::GetAttribute: [capacity, res, res, res, C] view of a value buffer."""
+        cap = int(lib.o3db_vbg_capacity(self._h))
+        r = self.block_resolution
+        if name == "tsdf":
+            return _s.device_view(lib.o3db_vbg_tsdf_buffer(self._h), (cap, r, r, r, 1), torch.float32)
+        if name == "weight":
+            return _s.device_view(lib.o3db_vbg_weight_buffer(self._h), (cap, r, r, r, 1), torch.uint16)
+        if name == "color" and self._with_color:
+            return _s.device_view(lib.o3db_vbg_color_buffer(self._h), (cap, r, r, r, 3), torch.uint16)
+        raise RuntimeError(f"Attribute {name} not found")
+
+    def compute_unique_block_coordinates(self, depth, intrinsic, extrinsic, depth_scale=1000.0, depth_max=3.0,
+                                         trunc_voxel_multiplier=8.0):
+        """VoxelBlockGrid::GetUniqueBlockCoordinates(depth, ...) (VoxelBlockGrid.cpp:212-245)."""
+        d = _image_tensor(depth)
+        if d is None:
+            raise RuntimeError("depth image is empty")
+        rows, cols = int(d.shape[0]), int(d.shape[1])
+        K, E = _k9(intrinsic), as_host_f64_4x4(extrinsic, "extrinsic")
+        cap = (rows // 4) * (cols // 4) * 4
+        out = torch.empty((cap, 3), dtype=torch.int32, device=d.device)
+        n = C.c_int64(0)
+        check(lib.o3db_vbg_unique_block_coordinates(self._h, d.data_ptr(), _depth_dtype(d), rows, cols, dptr(K),
+                                                    dptr(E), float(depth_scale), float(depth_max),
+                                                    float(trunc_voxel_multiplier), out.data_ptr(), cap,
+                                                    C.byref(n), current_stream_ptr()))
+        return out[: n.value]
+
+    def integrate(self, block_coords, depth, color=None, depth_intrinsic=None, color_intrinsic=None, extrinsic=None,
+                  depth_scale=1000.0, depth_max=3.0, trunc_voxel_multiplier=8.0):
+        """VoxelBlockGrid::Integrate (VoxelBlockGrid.cpp:292-326)."""
+        d = _image_tensor(depth)
+        c = _image_tensor(color)
+        if d is None:
+            raise RuntimeError("depth image is empty")
+        rows, cols = int(d.shape[0]), int(d.shape[1])
+        if c is not None and (int(c.shape[0]) != rows or int(c.shape[1]) != cols or c.shape[-1] != 3):
+            raise RuntimeError("Unsupported color image shape")
+        bc = self.hashmap()._keys_arg(block_coords)
+        dK = _k9(depth_intrinsic)
+        cK = _k9(color_intrinsic if color_intrinsic is not None else depth_intrinsic)
+        E = as_host_f64_4x4(extrinsic, "extrinsic")
+        check(lib.o3db_vbg_integrate(self._h, bc.data_ptr(), bc.shape[0], d.data_ptr(), _depth_dtype(d),
+                                     None if c is None else c.data_ptr(), _color_dtype(c), rows, cols, dptr(dK),
+                                     dptr(cK), dptr(E), float(depth_scale), float(depth_max),
+                                     float(trunc_voxel_multiplier), current_stream_ptr()))
+
+    # fused path used by slam.Model.integrate
+    def integrate_frame(self, depth, color, intrinsic, extrinsic, depth_scale=1000.0, depth_max=3.0,
+                        trunc_voxel_multiplier=8.0):
+        K, E = _k9(intrinsic), as_host_f64_4x4(extrinsic, "extrinsic")
+        host = (isinstance(depth, torch.Tensor) and not depth.is_cuda) or isinstance(depth, np.ndarray)
+        if host:
+            d = torch.from_numpy(np.ascontiguousarray(depth)) if isinstance(depth, np.ndarray) else depth.contiguous()
+            c = None
+            if color is not None and (not isinstance(color, torch.Tensor) or color.numel() > 0):
+                c = torch.from_numpy(np.ascontiguousarray(color)) if isinstance(color, np.ndarray) else color.contiguous()
+            rows, cols = int(d.shape[0]), int(d.shape[1])
+            check(lib.o3db_vbg_integrate_frame_host(self._h, d.data_ptr(), _depth_dtype(d),
+                                                    None if c is None else c.data_ptr(), _color_dtype(c), rows, cols,
+                                                    dptr(K), dptr(E), float(depth_scale), float(depth_max),
+                                                    float(trunc_voxel_multiplier), current_stream_ptr()))
+            return
+        d = _image_tensor(depth)
+        c = _image_tensor(color)
+        rows, cols = int(d.shape[0]), int(d.shape[1])
+        check(lib.o3db_vbg_integrate_frame(self._h, d.data_ptr(), _depth_dtype(d),
+                                           None if c is None else c.data_ptr(), _color_dtype(c), rows, cols, dptr(K),
+                                           dptr(E), float(depth_scale), float(depth_max),
+                                           float(trunc_voxel_multiplier), current_stream_ptr()))
+
+    def last_frustum_block_coordinates(self):
+        cap = 76800
+        out = torch.empty((cap, 3), dtype=torch.int32, device="cuda")
+        n = int(check(lib.o3db_vbg_last_frustum_blocks(self._h, out.data_ptr(), cap, current_stream_ptr())))
+        if n > cap:
+            out = torch.empty((n, 3), dtype=torch.int32, device="cuda")
+            check(lib.o3db_vbg_last_frustum_blocks(self._h, out.data_ptr(), n, current_stream_ptr()))
+        return out[:n]

@@ -1,0 +1,103 @@
+"""Mirror of ``open3d.t.pipelines.slam`` for the integration path
+(cpp/open3d/t/pipelines/slam/{Model.cpp,Model.h,Frame.h};
+cpp/pybind/t/pipelines/slam/slam.cpp:58-160).
+
+``Model.integrate`` is the fused, host-sync-free pipeline
+``o3db_vbg_integrate_frame`` (frustum touch + hash activate + TSDF fusion).
+``track_frame_to_model`` / ``synthesize_model_frame`` (RGB-D odometry, ray
+casting) are SURVEY.md §8f "next" rows and raise until built.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from ...geometry import Image, VoxelBlockGrid
+from ....core import as_host_f64_4x4
+
+
+class Frame:
+    """slam::Frame (slam/Frame.h): a named bag of image tensors + intrinsics."""
+
+    def __init__(self, height, width, intrinsics, device="cuda:0"):
+        self._h, self._w = int(height), int(width)
+        K = intrinsics.detach().cpu().numpy() if isinstance(intrinsics, torch.Tensor) else np.asarray(intrinsics)
+        self._K = np.ascontiguousarray(K, dtype=np.float64)
+        self._data = {}
+
+    def height(self):
+        return self._h
+
+    def width(self):
+        return self._w
+
+    def get_intrinsics(self):
+        return self._K
+
+    def set_data(self, name, data):
+        self._data[name] = data
+
+    def get_data(self, name):
+        return self._data.get(name, torch.empty(0))
+
+    def set_data_from_image(self, name, image):
+        self._data[name] = image.as_tensor() if isinstance(image, Image) else image
+
+    def get_data_as_image(self, name):
+        return Image(self.get_data(name))
+
+
+class Model:
+    """slam::Model (slam/Model.cpp:23-36): owns a VoxelBlockGrid{tsdf f32, weight u16,
+    color u16x3} and the current frame pose."""
+
+    def __init__(self, voxel_size=0.0058, block_resolution=16, block_count=10000, transformation=None,
+                 device="cuda:0"):
+        self.voxel_grid = VoxelBlockGrid(("tsdf", "weight", "color"),
+                                         (torch.float32, torch.uint16, torch.uint16), ((1,), (1,), (3,)),
+                                         voxel_size, block_resolution, block_count, device)
+        self.transformation_frame_to_world = as_host_f64_4x4(np.eye(4) if transformation is None else transformation)
+        self.frame_id = -1
+        self._frustum_dirty = False
+
+    def get_current_frame_pose(self):
+        return self.transformation_frame_to_world
+
+    def update_frame_pose(self, frame_id, T_frame_to_world):
+        """Model::UpdateFramePose (slam/Model.h:99-108)."""
+        if frame_id != self.frame_id + 1:
+            print(f"[Warning] Skipped {frame_id - self.frame_id - 1} frames in update T!")
+        self.frame_id = frame_id
+        self.transformation_frame_to_world = as_host_f64_4x4(T_frame_to_world)
+
+    def integrate(self, input_frame, depth_scale=1000.0, depth_max=3.0, trunc_voxel_multiplier=8.0):
+        """Model::Integrate (slam/Model.cpp:91-106)."""
+        depth = input_frame.get_data("depth")
+        color = input_frame.get_data("color")
+        T = self.transformation_frame_to_world
+        # t::geometry::InverseTransformation (t/geometry/Utility.h:77-115), f64 on the host
+        E = np.eye(4)
+        R, t = T[:3, :3], T[:3, 3]
+        E[:3, :3] = R.T
+        E[0, 3] = -(E[0, 0] * t[0] + E[0, 1] * t[1] + E[0, 2] * t[2])
+        E[1, 3] = -(E[1, 0] * t[0] + E[1, 1] * t[1] + E[1, 2] * t[2])
+        E[2, 3] = -(E[2, 0] * t[0] + E[2, 1] * t[1] + E[2, 2] * t[2])
+        if isinstance(color, torch.Tensor) and color.numel() == 0:
+            color = None
+        self.voxel_grid.integrate_frame(depth, color, input_frame.get_intrinsics(), E, depth_scale, depth_max,
+                                        trunc_voxel_multiplier)
+        self._frustum_dirty = True
+
+    @property
+    def frustum_block_coords(self):
+        """Model::frustum_block_coords_ — the block keys touched by the last integrated frame."""
+        return self.voxel_grid.last_frustum_block_coordinates()
+
+    def get_hashmap(self):
+        return self.voxel_grid.hashmap()
+
+    def track_frame_to_model(self, *args, **kwargs):
+        raise RuntimeError("Model.track_frame_to_model (RGB-D odometry) is not built yet: SURVEY.md §8f next #2")
+
+    def synthesize_model_frame(self, *args, **kwargs):
+        raise RuntimeError("Model.synthesize_model_frame (ray casting) is not built yet: SURVEY.md §8f next #4")

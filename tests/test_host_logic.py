@@ -1,0 +1,74 @@
+"""Host-side logic of the reference-facing Python surface, without a GPU:
+argument validation mirrors AssertInputMultiScaleICP (Registration.cpp:119-219)
+and the product fails loudly when no CUDA device exists (no CPU fallback)."""
+import numpy as np
+import pytest
+import torch
+
+import open3d_b200 as o3d
+from open3d_b200.t.pipelines import registration as reg
+
+needs_no_gpu = pytest.mark.skipif(torch.cuda.is_available(), reason="exercises the no-GPU failure path")
+
+
+def _clouds(n=64):
+    rng = np.random.default_rng(0)
+    p = rng.uniform(0, 1, (n, 3)).astype(np.float32)
+    src = o3d.t.geometry.PointCloud(p)
+    tgt = o3d.t.geometry.PointCloud(p.copy())
+    tgt.set_point_normals(np.tile(np.array([[0, 0, 1]], np.float32), (n, 1)))
+    return src, tgt
+
+
+def test_defaults_match_reference():
+    c = reg.ICPConvergenceCriteria()
+    assert (c.relative_fitness, c.relative_rmse, c.max_iteration) == (1e-6, 1e-6, 30)   # Registration.h:43-48
+    k = reg.robust_kernel.RobustKernel()
+    assert (int(k.type), k.scaling_parameter, k.shape_parameter) == (0, 1.0, 1.0)
+    assert [m.name for m in reg.RobustKernelMethod] == ["L2Loss", "L1Loss", "HuberLoss", "CauchyLoss", "GMLoss",
+                                                        "TukeyLoss", "GeneralizedLoss"]
+    assert reg.TransformationEstimationForColoredICP(lambda_geometric=7).lambda_geometric == 0.968
+
+
+def test_input_validation_errors():
+    src, tgt = _clouds()
+    est = reg.TransformationEstimationPointToPlane()
+    with pytest.raises(RuntimeError, match="Max correspondence distance"):
+        reg.icp(src, tgt, 0.0, np.eye(4), est)
+    with pytest.raises(RuntimeError, match="normal"):
+        reg.icp(src, o3d.t.geometry.PointCloud(src.point["positions"]), 0.1, np.eye(4), est)
+    with pytest.raises(RuntimeError, match="empty"):
+        reg.icp(o3d.t.geometry.PointCloud(), tgt, 0.1, np.eye(4), est)
+    with pytest.raises(RuntimeError, match="must be same"):
+        reg.multi_scale_icp(src, tgt, [-1, -1], [reg.ICPConvergenceCriteria()], [0.1, 0.1], np.eye(4), est)
+    with pytest.raises(RuntimeError, match="decreasing"):
+        reg.multi_scale_icp(src, tgt, [0.01, 0.02], [reg.ICPConvergenceCriteria()] * 2, [0.1, 0.1], np.eye(4), est)
+    with pytest.raises(RuntimeError, match=r"\[4, 4\]"):
+        reg.icp(src, tgt, 0.1, np.eye(3), est)
+    with pytest.raises(RuntimeError, match="Float32"):
+        o3d.t.geometry.PointCloud(np.zeros((4, 3), np.float64))
+    with pytest.raises(RuntimeError, match=r"\[N, 3\]"):
+        o3d.t.geometry.PointCloud(np.zeros((4, 2), np.float32))
+
+
+@needs_no_gpu
+def test_no_cpu_fallback_icp():
+    src, tgt = _clouds()
+    with pytest.raises(RuntimeError, match="(?i)cuda"):
+        reg.icp(src, tgt, 0.1, np.eye(4), reg.TransformationEstimationPointToPlane())
+
+
+@needs_no_gpu
+def test_no_cpu_fallback_tsdf():
+    with pytest.raises(RuntimeError, match="(?i)cuda"):
+        o3d.t.pipelines.slam.Model(0.008, 16, 100)
+
+
+def test_shard_range_partitions():
+    from open3d_b200.distributed import shard_range
+    for n, w in [(10, 3), (2_000_000, 8), (5, 8), (0, 2)]:
+        spans = [shard_range(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [e - b for b, e in spans]
+        assert max(sizes) - min(sizes) <= 1

@@ -1,0 +1,254 @@
+"""GPU parity tests of the TSDF path: CUDA (through the C ABI / the reference-facing
+python surface) vs the CPU oracle.  Block keys, hash values and voxel-block sets
+must be bit-exact; TSDF / weight / colour values are compared exactly as well
+(the kernels evaluate the reference's f32 expressions without FMA contraction),
+with the north_star tolerance (1e-5 relative) as the documented bound.
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from tests.synth import PRIMESENSE_K, camera_pose, render_depth
+
+pytestmark = pytest.mark.gpu
+
+VOXEL, RES, TRUNC_MULT = 0.008, 16, 8.0   # BASELINE config 3; slam::Model defaults (Model.h)
+SCALE, DMAX = 1000.0, 3.0
+
+
+@pytest.fixture(scope="module")
+def o3d():
+    import open3d_b200
+    assert torch.cuda.is_available()
+    return open3d_b200
+
+
+def _frame(i, color=False, f32=False):
+    T = camera_pose(i)
+    out = render_depth(T, with_color=color)
+    depth, col = (out if color else (out, None))
+    depth = depth.numpy()
+    if f32:
+        depth = depth.astype(np.float32)
+        col = None if col is None else (col.numpy().astype(np.float32) / 255.0)
+    elif col is not None:
+        col = col.numpy()
+    return T, oracle.inverse_transformation(T), depth, col
+
+
+def _sorted_keys(k):
+    k = np.asarray(k, np.int32).reshape(-1, 3)
+    return k[np.lexsort((k[:, 2], k[:, 1], k[:, 0]))]
+
+
+def test_key_hash_is_minivec_hash_bit_exact():
+    from open3d_b200 import _lib as L
+    rng = np.random.default_rng(0)
+    keys = rng.integers(-2**31, 2**31 - 1, (4096, 3), dtype=np.int64).astype(np.int32)
+    keys[:4] = [[0, 0, 0], [-1, 3, 2], [1, 2, 3], [2**31 - 1, -2**31, -7]]
+    k = torch.from_numpy(keys).cuda()
+    out = torch.empty(len(keys), dtype=torch.int64, device="cuda")
+    L.check(L.lib.o3db_hash_keys(k.data_ptr(), len(keys), out.data_ptr(), 0))
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy().view(np.uint64), oracle.minivec_hash(keys))
+
+
+def test_hashmap_reference_kat_and_semantics(kats, o3d):
+    k = kats["vbg_indexing"]   # cpp/tests/t/geometry/VoxelBlockGrid.cpp:199-219
+    vbg = o3d.t.geometry.VoxelBlockGrid(voxel_size=3.0 / 512, block_resolution=2, block_count=10)
+    hm = vbg.hashmap()
+    keys = np.array(k["keys"], np.int32)
+    buf, masks = hm.activate(keys)
+    assert int(masks.sum()) == k["expected_unique"] == hm.size()
+    buf = buf.cpu().numpy()
+    table = hm.key_tensor().cpu().numpy()
+    assert (table[buf] == keys).all()                      # every input learned the slot of its key
+    assert len(set(buf.tolist())) == 3 and set(buf.tolist()) == {0, 1, 2}
+    m = masks.cpu().numpy()
+    for key in {tuple(r) for r in keys.tolist()}:          # exactly one inserter per unique key
+        assert m[[tuple(r) == key for r in keys.tolist()]].sum() == 1
+    buf2, masks2 = hm.activate(keys)                       # re-activation inserts nothing
+    assert not masks2.any() and np.array_equal(buf2.cpu().numpy(), buf) and hm.size() == 3
+    fb, fm = hm.find(np.array([[1, 2, 3], [9, 9, 9]], np.int32))
+    assert fm.tolist() == [True, False] and fb[1].item() == -1 and (table[fb[0].item()] == [1, 2, 3]).all()
+    assert sorted(hm.active_buf_indices().tolist()) == [0, 1, 2]
+    assert vbg.attribute("tsdf").shape == (10, 2, 2, 2, 1) and vbg.attribute("color").shape == (10, 2, 2, 2, 3)
+
+
+def test_hashmap_growth_from_tiny_capacity(o3d):
+    """cpp/tests/core/HashMap.cpp:262-305: capacity 2 -> 20000 distinct keys, with values kept."""
+    vbg = o3d.t.geometry.VoxelBlockGrid(voxel_size=0.01, block_resolution=2, block_count=2)
+    hm = vbg.hashmap()
+    rng = np.random.default_rng(1)
+    keys = np.unique(rng.integers(-500, 500, (30000, 3)).astype(np.int32), axis=0)[:20000]
+    first = keys[:2]
+    buf0, _ = hm.activate(first)
+    vbg.attribute("tsdf")[buf0.long(), 0, 0, 0, 0] = torch.tensor([1.5, -2.5], device="cuda")
+    dup = np.concatenate([keys, keys[::7]])                 # duplicates inside one call
+    buf, masks = hm.activate(dup)
+    assert hm.size() == 20000 and hm.capacity() >= 20000
+    assert int(masks.sum()) == 20000 - 2
+    table = hm.key_tensor().cpu().numpy()
+    assert (table[buf.cpu().numpy()] == dup).all()
+    assert np.array_equal(_sorted_keys(table[:20000]), _sorted_keys(keys))
+    fb, fm = hm.find(first)
+    assert fm.all() and np.array_equal(fb.cpu().numpy(), buf0.cpu().numpy())   # slots survive growth
+    assert vbg.attribute("tsdf")[fb.long(), 0, 0, 0, 0].tolist() == [1.5, -2.5]
+
+
+@pytest.mark.parametrize("frame_id,f32", [(0, False), (137, False), (500, True)])
+def test_depth_touch_block_set_bit_exact(o3d, frame_id, f32):
+    T, E, depth, _ = _frame(frame_id, f32=f32)
+    vbg = o3d.t.geometry.VoxelBlockGrid(voxel_size=VOXEL, block_resolution=RES, block_count=1000)
+    got = vbg.compute_unique_block_coordinates(torch.from_numpy(depth), PRIMESENSE_K, E, SCALE, DMAX, TRUNC_MULT)
+    want = oracle.depth_touch(depth, PRIMESENSE_K, E, RES, VOXEL, VOXEL * TRUNC_MULT, SCALE, DMAX, 4)
+    got = got.cpu().numpy()
+    assert len(got) == len(want) > 100
+    assert len(np.unique(got, axis=0)) == len(got)          # unique
+    assert np.array_equal(_sorted_keys(got), want)          # identical set, bit for bit
+
+
+def test_depth_touch_no_block_is_an_error(o3d):
+    vbg = o3d.t.geometry.VoxelBlockGrid(voxel_size=VOXEL, block_resolution=RES, block_count=100)
+    with pytest.raises(RuntimeError, match="No block is touched"):
+        vbg.compute_unique_block_coordinates(torch.zeros((480, 640), dtype=torch.uint16), PRIMESENSE_K, np.eye(4))
+
+
+def _oracle_volume(cap, color):
+    return (np.zeros((cap, 3), np.int32), np.zeros((cap, RES ** 3), np.float32),
+            np.zeros((cap, RES ** 3), np.uint16), np.zeros((cap, RES ** 3, 3), np.uint16) if color else None)
+
+
+def _compare_volumes(vbg, okeys, otsdf, owt, ocol, osize):
+    hm = vbg.hashmap()
+    assert hm.size() == osize
+    gkeys = hm.key_tensor().cpu().numpy()[:osize]
+    assert np.array_equal(_sorted_keys(gkeys), _sorted_keys(okeys[:osize]))   # same block set
+    # slot order is implementation-defined on both sides: align by key
+    lut = {tuple(k): i for i, k in enumerate(okeys[:osize].tolist())}
+    perm = np.array([lut[tuple(k)] for k in gkeys.tolist()])
+    gt = vbg.attribute("tsdf").cpu().numpy().reshape(-1, RES ** 3)[:osize]
+    gw = vbg.attribute("weight").cpu().numpy().reshape(-1, RES ** 3)[:osize]
+    assert np.array_equal(gw, owt[perm])
+    np.testing.assert_allclose(gt, otsdf[perm], rtol=1e-5, atol=1e-7)           # north_star bound
+    assert np.array_equal(gt.view(np.uint32), otsdf[perm].view(np.uint32))      # and in fact bit-exact
+    if ocol is not None:
+        gc = vbg.attribute("color").cpu().numpy().reshape(-1, RES ** 3, 3)[:osize]
+        assert np.array_equal(gc, ocol[perm])
+    return int((gw > 0).sum())
+
+
+@pytest.mark.parametrize("color,f32", [(False, False), (True, False), (True, True)])
+def test_integrate_unfused_api_vs_oracle(o3d, color, f32):
+    """GetUniqueBlockCoordinates + Integrate (VoxelBlockGrid.cpp:212-326) over 3 frames."""
+    cap = 6000
+    vbg = o3d.t.geometry.VoxelBlockGrid(voxel_size=VOXEL, block_resolution=RES, block_count=cap)
+    okeys, otsdf, owt, ocol = _oracle_volume(cap, color)
+    osize = 0
+    for fid in (0, 40, 80):
+        T, E, depth, col = _frame(fid, color=color, f32=f32)
+        bc = vbg.compute_unique_block_coordinates(torch.from_numpy(depth), PRIMESENSE_K, E, SCALE, DMAX, TRUNC_MULT)
+        vbg.integrate(bc, torch.from_numpy(depth), None if col is None else torch.from_numpy(col), PRIMESENSE_K,
+                      PRIMESENSE_K, E, SCALE, DMAX, TRUNC_MULT)
+        want = oracle.depth_touch(depth, PRIMESENSE_K, E, RES, VOXEL, VOXEL * TRUNC_MULT, SCALE, DMAX, 4)
+        bi, _, osize, rc = oracle.hashmap_activate(okeys, osize, want)
+        assert rc == 0
+        oracle.tsdf_integrate(depth, col, bi, okeys, otsdf, owt, ocol, PRIMESENSE_K, PRIMESENSE_K, E, RES, VOXEL,
+                              VOXEL * TRUNC_MULT, SCALE, DMAX)
+    updated = _compare_volumes(vbg, okeys, otsdf, owt, ocol, osize)
+    assert updated > 100000
+
+
+@pytest.mark.parametrize("color,host", [(False, False), (True, False), (True, True)])
+def test_model_integrate_fused_vs_oracle(o3d, color, host):
+    """slam::Model::Integrate (Model.cpp:91-106), fused pipeline, 6 frames incl. revisits."""
+    slam = o3d.t.pipelines.slam
+    cap = 8000
+    model = slam.Model(VOXEL, RES, cap)
+    okeys, otsdf, owt, ocol = _oracle_volume(cap, True)
+    osize = 0
+    for n, fid in enumerate((0, 3, 6, 200, 203, 0)):
+        T, E, depth, col = _frame(fid, color=color)
+        frame = slam.Frame(480, 640, PRIMESENSE_K)
+        d = torch.from_numpy(depth)
+        c = None if col is None else torch.from_numpy(col)
+        frame.set_data("depth", d if host else d.cuda())
+        if c is not None:
+            frame.set_data("color", c if host else c.cuda())
+        model.update_frame_pose(n, T)
+        model.integrate(frame, SCALE, DMAX, TRUNC_MULT)
+        want = oracle.depth_touch(depth, PRIMESENSE_K, E, RES, VOXEL, VOXEL * TRUNC_MULT, SCALE, DMAX, 4)
+        got = model.frustum_block_coords.cpu().numpy()
+        assert np.array_equal(_sorted_keys(got), want)      # Model::frustum_block_coords_
+        bi, _, osize, rc = oracle.hashmap_activate(okeys, osize, want)
+        assert rc == 0
+        oracle.tsdf_integrate(depth, col, bi, okeys, otsdf, owt, ocol if color else None, PRIMESENSE_K, PRIMESENSE_K,
+                              E, RES, VOXEL, VOXEL * TRUNC_MULT, SCALE, DMAX)
+    _compare_volumes(model.voxel_grid, okeys, otsdf, owt, ocol if color else None, osize)
+    if not color:   # colour buffer untouched by depth-only integration
+        assert int(model.voxel_grid.attribute("color").view(torch.int16).count_nonzero()) == 0
+
+
+def test_fused_path_grows_transparently(o3d):
+    slam = o3d.t.pipelines.slam
+    model = slam.Model(VOXEL, RES, 64)       # far too small: must grow, never drop blocks
+    total = set()
+    for n, fid in enumerate(range(0, 400, 50)):
+        T, E, depth, _ = _frame(fid)
+        frame = slam.Frame(480, 640, PRIMESENSE_K)
+        frame.set_data("depth", torch.from_numpy(depth).cuda())
+        model.update_frame_pose(n, T)
+        model.integrate(frame, SCALE, DMAX, TRUNC_MULT)
+        total |= {tuple(k) for k in oracle.depth_touch(depth, PRIMESENSE_K, E, RES, VOXEL, VOXEL * TRUNC_MULT,
+                                                      SCALE, DMAX, 4).tolist()}
+    hm = model.get_hashmap()
+    assert hm.size() == len(total) and hm.capacity() >= len(total)
+    keys = hm.key_tensor().cpu().numpy()[: hm.size()]
+    assert {tuple(k) for k in keys.tolist()} == total
+
+
+def test_generic_block_resolution_vs_oracle(o3d):
+    """res = 8 goes through the generic (non-vectorised) integrate path."""
+    res, cap = 8, 20000
+    vbg = o3d.t.geometry.VoxelBlockGrid(voxel_size=VOXEL, block_resolution=res, block_count=cap)
+    T, E, depth, _ = _frame(10)
+    bc = vbg.compute_unique_block_coordinates(torch.from_numpy(depth), PRIMESENSE_K, E, SCALE, DMAX, TRUNC_MULT)
+    vbg.integrate(bc, torch.from_numpy(depth), None, PRIMESENSE_K, PRIMESENSE_K, E, SCALE, DMAX, TRUNC_MULT)
+    want = oracle.depth_touch(depth, PRIMESENSE_K, E, res, VOXEL, VOXEL * TRUNC_MULT, SCALE, DMAX, 4)
+    okeys = np.zeros((cap, 3), np.int32)
+    otsdf = np.zeros((cap, res ** 3), np.float32)
+    owt = np.zeros((cap, res ** 3), np.uint16)
+    bi, _, osize, _ = oracle.hashmap_activate(okeys, 0, want)
+    oracle.tsdf_integrate(depth, None, bi, okeys, otsdf, owt, None, PRIMESENSE_K, PRIMESENSE_K, E, res, VOXEL,
+                          VOXEL * TRUNC_MULT, SCALE, DMAX)
+    hm = vbg.hashmap()
+    assert hm.size() == osize
+    gkeys = hm.key_tensor().cpu().numpy()[:osize]
+    lut = {tuple(k): i for i, k in enumerate(okeys[:osize].tolist())}
+    perm = np.array([lut[tuple(k)] for k in gkeys.tolist()])
+    gt = vbg.attribute("tsdf").cpu().numpy().reshape(-1, res ** 3)[:osize]
+    gw = vbg.attribute("weight").cpu().numpy().reshape(-1, res ** 3)[:osize]
+    assert np.array_equal(gw, owt[perm]) and np.array_equal(gt.view(np.uint32), otsdf[perm].view(np.uint32))
+
+
+def test_idempotent_weight_property_full_sequence(o3d):
+    """Size-independent property at BASELINE scale (50 frames of the config-3 trajectory):
+    integrating the same frame k times gives weight == k on every observed voxel and leaves
+    tsdf unchanged (running mean of identical samples), up to f32 rounding."""
+    slam = o3d.t.pipelines.slam
+    model = slam.Model(VOXEL, RES, 40000)
+    T, E, depth, _ = _frame(25)
+    frame = slam.Frame(480, 640, PRIMESENSE_K)
+    frame.set_data("depth", torch.from_numpy(depth).cuda())
+    model.update_frame_pose(0, T)
+    model.integrate(frame)
+    n = model.get_hashmap().size()
+    t1 = model.voxel_grid.attribute("tsdf")[:n].clone()
+    w1 = model.voxel_grid.attribute("weight")[:n].clone()
+    for _ in range(4):
+        model.integrate(frame)
+    assert model.get_hashmap().size() == n
+    w5 = model.voxel_grid.attribute("weight")[:n]
+    assert torch.equal(w5.int(), w1.int() * 5) and set(w1.int().unique().tolist()) == {0, 1}
+    torch.testing.assert_close(model.voxel_grid.attribute("tsdf")[:n], t1, rtol=0, atol=2e-6)
