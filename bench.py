@@ -1,0 +1,504 @@
+#!/usr/bin/env python
+"""bench.py — measures the two hot paths on BASELINE.json's configurations.
+
+    python bench.py --gpus N --steps K --warmup W            (this repo's CUDA path)
+    python bench.py --impl reference --gpus N --steps K ...  (CPU reference arm: the oracle port)
+
+Primary line (ONE JSON line on rank 0): point-to-plane ICP, 2M-point synthetic clouds,
+30 iterations, r = 0.05 (BASELINE config 2).  A *step* is one 30-iteration registration.
+  value   = ICP iterations/s with the clouds resident in HBM (iteration loop only; the
+            search-index build is reported separately and is part of `e2e`)
+  e2e     = the same metric through the C-ABI host-buffer entry point
+            o3db_icp_point_to_plane_host (H2D of the clouds, index build, 30 iterations,
+            final evaluation and D2H of the result inside the timed region)
+The same line carries a "tsdf" object: VoxelBlockGrid TSDF integration of a synthetic
+640x480 depth(+colour) sequence, 8 mm voxels, 16^3 blocks (BASELINE config 3), frames/s.
+
+N > 1 (torchrun, one rank per GPU): weak scaling.  ICP: every rank owns a 2M-point shard of
+the source, the target is replicated, one 30-double NCCL all-reduce per iteration
+(value = N x 2M-point iteration equivalents / s).  TSDF: frames round-robin over N
+independent volumes, no collective.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ICP_POINTS = 2_000_000
+ICP_ITERS = 30
+ICP_RADIUS = 0.05
+TSDF_FRAMES = 1000
+VOXEL, RES, TRUNC_MULT, DSCALE, DMAX = 0.008, 16, 8.0, 1000.0, 3.0
+HBM_FALLBACK_GBS = 6650.0
+
+
+def measured_hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel):
+    """dram read+write bytes per launch from the committed ncu --set full summary, or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f).get(kernel)
+    except Exception:
+        return None
+
+
+def icp_algorithmic_bytes(n, m):
+    """compulsory HBM bytes of one ICP iteration."""
+    h = min(max(m // 32, 1), 2 ** 25)
+    return 12 * n + 12 * n + 12 * m + 12 * m + 4 * m + 4 * (h + 1) + 4 * n
+
+
+def tsdf_algorithmic_bytes(blocks, color, width=640, height=480):
+    """compulsory HBM bytes of one integrated frame."""
+    s_vox = 12 if color else 6
+    touch = (width // 4) * (height // 4) * 2 + 4 * (width // 4) * (height // 4) * 12
+    return blocks * 4096 * 2 * s_vox + width * height * 2 + (width * height * 3 if color else 0) + blocks * 16 + touch
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        reasons = []
+        for i, name in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
+            if any(r[3 + i].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows), "power_w_max": max(float(r[2]) for r in self.rows)}
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm (CPU): the oracle port, timed on the host cores
+# ----------------------------------------------------------------------------------------------
+
+def cpu_icp_baseline(src, tgt, nrm, iters):
+    """ICP iterations/s of the CPU restatement on all host threads (loop only, like `value`)."""
+    import oracle
+    r = oracle.icp_p2plane(src, tgt, nrm, ICP_RADIUS, max_iteration=iters, relative_fitness=0, relative_rmse=0,
+                           accumulate_f64=False)
+    return iters / r.loop_seconds, r
+
+
+def cpu_tsdf_baseline(frames, color):
+    """frames/s of the CPU restatement of Model::Integrate on all host threads."""
+    import oracle
+    from tests.synth import PRIMESENSE_K
+    cap = 60000
+    keys = np.zeros((cap, 3), np.int32)
+    tsdf = np.zeros((cap, RES ** 3), np.float32)
+    wt = np.zeros((cap, RES ** 3), np.uint16)
+    colbuf = np.zeros((cap, RES ** 3, 3), np.uint16) if color else None
+    size = 0
+    t0 = time.perf_counter()
+    for (E, depth, col) in frames:
+        want = oracle.depth_touch(depth, PRIMESENSE_K, E, RES, VOXEL, VOXEL * TRUNC_MULT, DSCALE, DMAX, 4)
+        bi, _, size, _ = oracle.hashmap_activate(keys, size, want)
+        oracle.tsdf_integrate(depth, col if color else None, bi, keys, tsdf, wt, colbuf, PRIMESENSE_K, PRIMESENSE_K, E,
+                              RES, VOXEL, VOXEL * TRUNC_MULT, DSCALE, DMAX)
+    return len(frames) / (time.perf_counter() - t0)
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path cannot be built here
+    (Eigen/TBB/nanoflann/stdgpu are download-time dependencies), so this arm
+    times the oracle port on all host threads.  Each step is a bounded sample of the workload:
+    2 ICP iterations on the full 2M-point clouds."""
+    if rank != 0:
+        return
+    import oracle
+    from tests.synth import make_icp_pair
+    sample_iters = 2
+    src, tgt, nrm, _ = make_icp_pair(ICP_POINTS, seed=2)
+    for _ in range(args.warmup):
+        cpu_icp_baseline(src[:200000], tgt[:200000], nrm[:200000], 1)
+    t0 = time.perf_counter()
+    loop = 0.0
+    for _ in range(args.steps):
+        v, r = cpu_icp_baseline(src, tgt, nrm, sample_iters)
+        loop += r.loop_seconds
+    wall = time.perf_counter() - t0
+    value = args.steps * sample_iters / loop
+    cores = oracle.num_threads()
+    sample = f"{sample_iters} iterations on the full 2M-point clouds per step (loop time only, f32 accumulation)"
+    line = {"impl": "reference", "metric": "icp_iters_per_sec_2M_pts", "value": value, "unit": "iters/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": icp_config(args.gpus),
+            "cpu_baseline": {"value": value, "unit": "iters/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def icp_config(n_gpus):
+    return {"workload": "point_to_plane_icp", "points_source_per_gpu": ICP_POINTS, "points_target": ICP_POINTS,
+            "iterations_per_step": ICP_ITERS, "max_correspondence_distance": ICP_RADIUS, "voxel_size": 0.02,
+            "baseline_config": "configs[1]: PointToPlane ICP, 2M-pt synthetic clouds, 30 iters, voxel_size=0.02",
+            "note": "clouds are generated on a jittered 2 cm lattice (already voxel-size 0.02, down-sample = identity)",
+            "l2_policy": "L2 flushed (256 MiB write) before every timed step; working set ~= L2 size",
+            "parallelism": f"source-sharded x{n_gpus}, target replicated, 30-double all-reduce per iteration"
+            if n_gpus > 1 else "single GPU"}
+
+
+# ----------------------------------------------------------------------------------------------
+# this repo's arm
+# ----------------------------------------------------------------------------------------------
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--skip-tsdf", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--tsdf-frames", type=int, default=TSDF_FRAMES)
+    ap.add_argument("--cell-scale", type=float, default=0.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from open3d_b200 import _lib as L
+    from tests.synth import PRIMESENSE_K, camera_pose, make_icp_pair, render_depth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: open3d_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    comm = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        from open3d_b200.distributed import Communicator
+        comm = Communicator(rank, world)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    stream = int(torch.cuda.current_stream().cuda_stream)
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def flush_l2():
+        flush_buf.fill_(1)
+
+    peak, peak_src = measured_hbm_peak()
+
+    # ------------------------------------------------------------------ ICP
+    src, tgt, nrm, T_gt = make_icp_pair(ICP_POINTS, seed=2)
+    if world > 1:   # this rank's shard: an independent sampling of the same moved surface
+        src = make_icp_pair(ICP_POINTS, seed=2 + 7919 * rank)[0]
+    n, m = len(src), len(tgt)
+    d_src, d_tgt, d_nrm = (torch.from_numpy(a).cuda() for a in (src, tgt, nrm))
+    opt = L.IcpOptions()
+    opt.max_correspondence_distance = ICP_RADIUS
+    opt.max_iteration = ICP_ITERS
+    opt.relative_fitness = opt.relative_rmse = 0.0          # all 30 iterations run
+    opt.kernel = L.RobustKernel(0, 1.0, 1.0)
+    opt.cell_scale = args.cell_scale
+    T0 = np.eye(4)
+    h = C.c_void_p()
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    e0, e1 = ev(), ev()
+    barrier()
+    e0.record()
+    L.check(L.lib.o3db_icp_create(d_src.data_ptr(), n, d_tgt.data_ptr(), d_nrm.data_ptr(), m, L.dptr(T0), C.byref(opt),
+                                  comm.handle if comm else None, stream, C.byref(h)))
+    e1.record()
+    torch.cuda.synchronize()
+    build_ms = e0.elapsed_time(e1)
+    res = L.IcpResult()
+
+    def icp_step(timed):
+        """One registration: reset (untimed), 30 iterations + final evaluation (timed)."""
+        L.check(L.lib.o3db_icp_reset(h, stream))
+        flush_l2()
+        a, b, c = ev(), ev(), ev()
+        a.record()
+        L.check(L.lib.o3db_icp_iterate(h, ICP_ITERS, stream))
+        b.record()
+        L.check(L.lib.o3db_icp_finish(h, C.byref(res), None, None, stream))   # syncs; reads the result back
+        c.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(c), a.elapsed_time(b)
+
+    for _ in range(args.warmup):
+        icp_step(False)
+    barrier()
+    launches0 = L.launch_count()
+    wall0 = time.perf_counter()
+    with ClockSampler(local_rank) as clocks:
+        step_ms, loop_ms = 0.0, 0.0
+        for _ in range(args.steps):
+            s, l = icp_step(True)
+            step_ms += s
+            loop_ms += l
+        barrier()
+    icp_wall = time.perf_counter() - wall0
+    icp_launches = L.launch_count() - launches0
+    step_ms = max_over_ranks(step_ms)
+    loop_ms = max_over_ranks(loop_ms)
+    icp_value = world * ICP_ITERS * args.steps / (step_ms * 1e-3)
+    kern_ms = loop_ms / (ICP_ITERS * args.steps)          # average launch duration of icp_iteration_kernel
+    alg = icp_algorithmic_bytes(n, m)
+    icp_roof = {"bound": "hbm", "kernel": "icp_iteration_kernel", "achieved": alg / (kern_ms * 1e-3) / 1e9,
+                "peak": peak, "unit": "GB/s", "frac": alg / (kern_ms * 1e-3) / 1e9 / peak,
+                "traffic": ncu_traffic("icp_iteration_kernel"), "algorithmic_bytes_per_launch": alg,
+                "avg_launch_us": kern_ms * 1e3, "peak_source": peak_src}
+    final = {"fitness": res.fitness, "inlier_rmse": res.inlier_rmse, "num_iterations": res.num_iterations,
+             "transformation_error_vs_ground_truth": float(np.abs(np.array(res.transformation).reshape(4, 4) - T_gt).max())}
+    L.lib.o3db_icp_destroy(h)
+
+    # e2e: host buffers (pinned) through the C ABI, everything inside the timed region
+    hs, ht, hn = (torch.from_numpy(a).pin_memory() for a in (src, tgt, nrm))
+    res2 = L.IcpResult()
+    e2e_ms = 0.0
+    if world == 1:
+        for i in range(2 + args.steps):
+            flush_l2()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            L.check(L.lib.o3db_icp_point_to_plane_host(hs.data_ptr(), n, ht.data_ptr(), hn.data_ptr(), m, L.dptr(T0),
+                                                       C.byref(opt), C.byref(res2), None, None))
+            torch.cuda.synchronize()
+            if i >= 2:
+                e2e_ms += 1e3 * (time.perf_counter() - t0)
+        icp_e2e = {"value": ICP_ITERS * args.steps / (e2e_ms * 1e-3), "unit": "iters/s",
+                   "h2d_bytes_per_step": int(n * 12 + m * 24), "d2h_bytes_per_step": C.sizeof(L.IcpResult),
+                   "ms_per_step": e2e_ms / args.steps,
+                   "path": "o3db_icp_point_to_plane_host: H2D + index build + 30 iterations + evaluation + D2H"}
+    else:
+        icp_e2e = {"value": None, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                   "path": "multi-GPU e2e not measured (host-buffer entry point is single-GPU)"}
+
+    # ----------------------------------------------------------------- TSDF
+    tsdf = None
+    if not args.skip_tsdf:
+        tsdf = bench_tsdf(args, rank, world, local_rank, L, torch, stream, barrier, max_over_ranks, peak, peak_src)
+
+    # ---------------------------------------------------------- CPU baseline
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        import oracle
+        v, r = cpu_icp_baseline(src, tgt, nrm, 3)
+        cpu = {"value": v, "unit": "iters/s", "cores": oracle.num_threads(), "kind": "port",
+               "sample": "3 iterations on the full 2M-point clouds (iteration loop only; OpenMP port of the "
+                         "reference CPU path, f32 accumulation)",
+               "build_seconds": r.build_seconds}
+        if tsdf is not None:
+            tsdf["cpu_baseline"] = tsdf.pop("_cpu")(oracle)
+
+    if tsdf is not None:
+        tsdf.pop("_cpu", None)
+    if rank == 0:
+        line = {"metric": "icp_iters_per_sec_2M_pts", "value": icp_value, "unit": "iters/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": icp_config(world), "correspondences_per_sec": icp_value * ICP_POINTS,
+                "index_build_ms": build_ms, "result": final, "roofline": icp_roof, "cpu_baseline": cpu,
+                "e2e": icp_e2e, "gpu_launches": int(icp_launches), "clocks": clocks.summary(),
+                "wall_s_timed_region": icp_wall, "tsdf": tsdf}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        comm.close()
+        dist.destroy_process_group()
+
+
+def bench_tsdf(args, rank, world, local_rank, L, torch, stream, barrier, max_over_ranks, peak, peak_src):
+    from tests.synth import PRIMESENSE_K, camera_pose, render_depth
+    F = args.tsdf_frames
+    mine = list(range(rank, F, world))                      # frames round-robin over independent volumes
+    K = np.ascontiguousarray(PRIMESENSE_K)
+    poses, exts = [], []
+    for i in mine:
+        T = camera_pose(i, n_frames=F)
+        E = np.eye(4)
+        E[:3, :3] = T[:3, :3].T
+        E[:3, 3] = -(T[:3, :3].T @ T[:3, 3])
+        poses.append(T)
+        exts.append(np.ascontiguousarray(E))
+    depth_dev, color_dev = [], []
+    for T in poses:
+        d, c = render_depth(T, device="cuda", with_color=True)
+        depth_dev.append(d.contiguous())
+        color_dev.append(c.contiguous())
+    depth_host = torch.stack(depth_dev).cpu().pin_memory()
+    color_host = torch.stack(color_dev).cpu().pin_memory()
+    torch.cuda.synchronize()
+    out = {}
+    steps, warmup = args.steps, 1
+    for color in (False, True):
+        name = "depth_color" if color else "depth_only"
+        results = {}
+        for mode in ("device", "host"):
+            tot_ms, launches, touch_ms, integ_ms, nfr, blocks = 0.0, 0, 0.0, 0.0, 0, 0
+            for it in range(warmup + steps):
+                v = C.c_void_p()
+                L.check(L.lib.o3db_vbg_create(VOXEL, RES, 40000, 1, stream, C.byref(v)))   # default_config.yml:26
+                timed = it >= warmup
+                if timed and mode == "device":
+                    L.check(L.lib.o3db_vbg_profile(v, 1))
+                barrier()
+                l0 = L.launch_count()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0 = time.perf_counter()
+                a.record()
+                for j in range(len(mine)):
+                    if mode == "device":
+                        L.check(L.lib.o3db_vbg_integrate_frame(
+                            v, depth_dev[j].data_ptr(), L.DEPTH_U16, color_dev[j].data_ptr() if color else None,
+                            L.COLOR_U8, 480, 640, L.dptr(K), L.dptr(exts[j]), DSCALE, DMAX, TRUNC_MULT, stream))
+                    else:
+                        L.check(L.lib.o3db_vbg_integrate_frame_host(
+                            v, depth_host[j].data_ptr(), L.DEPTH_U16, color_host[j].data_ptr() if color else None,
+                            L.COLOR_U8, 480, 640, L.dptr(K), L.dptr(exts[j]), DSCALE, DMAX, TRUNC_MULT, stream))
+                b.record()
+                size = L.check(L.lib.o3db_vbg_size(v, stream))      # D2H read of the step's result (block count)
+                torch.cuda.synchronize()
+                wall = 1e3 * (time.perf_counter() - t0)
+                if timed:
+                    tot_ms += a.elapsed_time(b) if mode == "device" else wall
+                    launches += L.launch_count() - l0
+                    blocks = int(size)
+                    if mode == "device":
+                        tm, im, nf = C.c_double(0), C.c_double(0), C.c_int64(0)
+                        L.check(L.lib.o3db_vbg_profile_read(v, C.byref(tm), C.byref(im), C.byref(nf)))
+                        touch_ms += tm.value
+                        integ_ms += im.value
+                        nfr += nf.value
+                L.lib.o3db_vbg_destroy(v)
+            tot_ms = max_over_ranks(tot_ms)
+            results[mode] = {"frames_per_sec": F * steps / (tot_ms * 1e-3),
+                             "ms_per_frame": tot_ms / (len(mine) * steps), "launches": launches, "blocks_total": blocks,
+                             "touch_ms": touch_ms, "integrate_ms": integ_ms, "profiled_frames": nfr}
+        dev, host = results["device"], results["host"]
+        entry = {"value": dev["frames_per_sec"], "unit": "frames/s", "ms_per_frame": dev["ms_per_frame"],
+                 "gpu_launches": dev["launches"], "blocks_in_volume_after_sequence": dev["blocks_total"],
+                 "e2e": {"value": host["frames_per_sec"], "unit": "frames/s",
+                         "h2d_bytes_per_step": 640 * 480 * (2 + (3 if color else 0)) * len(mine),
+                         "d2h_bytes_per_step": 64,
+                         "path": "o3db_vbg_integrate_frame_host per frame (pinned H2D + touch + integrate), size read-back per sequence"}}
+        out[name] = entry
+        out[name]["_dev"] = dev
+    # mean touched blocks per frame (needed by the byte model) — measured on the device with the
+    # stand-alone GetUniqueBlockCoordinates entry point on a sample of frames
+    v = C.c_void_p()
+    L.check(L.lib.o3db_vbg_create(VOXEL, RES, 1000, 0, stream, C.byref(v)))
+    cnts = []
+    nb = C.c_int64(0)
+    for j in range(0, len(mine), max(1, len(mine) // 50)):
+        L.check(L.lib.o3db_vbg_unique_block_coordinates(v, depth_dev[j].data_ptr(), L.DEPTH_U16, 480, 640, L.dptr(K),
+                                                        L.dptr(exts[j]), DSCALE, DMAX, TRUNC_MULT, None, 0,
+                                                        C.byref(nb), stream))
+        cnts.append(nb.value)
+    L.lib.o3db_vbg_destroy(v)
+    mean_blocks = float(np.mean(cnts))
+    for color in (False, True):
+        name = "depth_color" if color else "depth_only"
+        dev = out[name].pop("_dev")
+        alg = tsdf_algorithmic_bytes(mean_blocks, color)
+        k_ms = dev["integrate_ms"] / max(dev["profiled_frames"], 1)
+        out[name]["roofline"] = {"bound": "hbm", "kernel": "integrate_kernel", "achieved": alg / (k_ms * 1e-3) / 1e9,
+                                 "peak": peak, "unit": "GB/s", "frac": alg / (k_ms * 1e-3) / 1e9 / peak,
+                                 "traffic": ncu_traffic("integrate_kernel_color" if color else "integrate_kernel"),
+                                 "algorithmic_bytes_per_launch": alg, "avg_launch_us": k_ms * 1e3,
+                                 "touch_kernel_avg_us": 1e3 * dev["touch_ms"] / max(dev["profiled_frames"], 1),
+                                 "mean_touched_blocks_per_frame": mean_blocks, "peak_source": peak_src,
+                                 "frame_frac_end_to_end": alg / (dev["ms_per_frame"] * 1e-3) / 1e9 / peak}
+    out["metric"] = "tsdf_frames_per_sec_640x480"
+    out["config"] = {"workload": "voxel_block_grid_tsdf_integrate", "frames": F, "image": "640x480 u16 depth (+u8 colour)",
+                     "voxel_size": VOXEL, "block_resolution": RES, "trunc_voxel_multiplier": TRUNC_MULT,
+                     "initial_block_capacity": 40000, "baseline_config": "configs[2]",
+                     "l2_policy": "each frame touches a different part of a multi-GB volume; inputs larger than L2 over the sequence",
+                     "parallelism": f"frames round-robin over {world} independent volumes" if world > 1 else "single GPU"}
+    out["higher_is_better"] = True
+    out["scaling"] = "weak" if world == 1 else "strong (fixed 1000-frame sequence split over volumes)"
+
+    def cpu_part(oracle_mod):
+        sample = list(range(0, F, max(1, F // 12)))[:12]
+        frames = []
+        for i in sample:
+            T = camera_pose(i, n_frames=F)
+            d, c = render_depth(T, with_color=True)
+            frames.append((oracle_mod.inverse_transformation(T), d.numpy(), c.numpy()))
+        res = {}
+        for color in (False, True):
+            fps = cpu_tsdf_baseline(frames, color)
+            res["depth_color" if color else "depth_only"] = fps
+        return {"value": res["depth_only"], "value_with_color": res["depth_color"], "unit": "frames/s",
+                "cores": oracle_mod.num_threads(), "kind": "port",
+                "sample": f"{len(frames)} frames spread over the trajectory (touch + activate + integrate, OpenMP port)"}
+
+    out["_cpu"] = cpu_part
+    return out
+
+
+if __name__ == "__main__":
+    main()

@@ -296,6 +296,12 @@ int o3db_vbg_integrate_frame_host(o3db_vbg* vbg, const void* depth_host, int dep
 int64_t o3db_vbg_last_frustum_blocks(o3db_vbg* vbg, int32_t* block_coords_dev, int64_t max_blocks,
                                      void* stream);
 
+/* Measurement aid (bench.py): when enabled, CUDA events bracket the touch and the
+ * integrate kernel of every o3db_vbg_integrate_frame call (up to 4096 frames per
+ * read); o3db_vbg_profile_read synchronises and returns the summed device times. */
+int o3db_vbg_profile(o3db_vbg* vbg, int enable);
+int o3db_vbg_profile_read(o3db_vbg* vbg, double* touch_ms, double* integrate_ms, int64_t* frames);
+
 #ifdef __cplusplus
 }
 #endif

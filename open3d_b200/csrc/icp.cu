@@ -422,8 +422,9 @@ __device__ __forceinline__ float robust_weight(const Robust& k, float r) {
         }
         default: {  // generalized
             const float s2 = k.scale * k.scale;
-            if (fabs(k.shape - 2.0) < 1e-3) return (float)(1.0 / (double)s2);
-            if (fabs(k.shape) < 1e-3) return (float)(2.0 / (r * r + 2 * s2));
+            // open3d::IsClose (GeometryMacros.h:58-63) is relative: the shape ~ 0 branch of
+            // RobustKernelImpl.h:85-91 can never be taken; only shape ~ 2 is special-cased.
+            if (k.shape > (1.0 - 1e-3) * 2.0 && k.shape < (1.0 + 1e-3) * 2.0) return (float)(1.0 / (double)s2);
             const float q = r / k.scale;
             if (k.shape < -1e7) return (float)(exp((double)(q * q) / (-2.0)) / (double)s2);
             return (float)(pow((double)(q * q) / fabs(k.shape - 2.0) + 1, (k.shape / 2.0) - 1.0) / (double)s2);
@@ -450,11 +451,15 @@ template <bool L2LOSS>
 __device__ __forceinline__ void accumulate_p2plane(float (&acc)[kNumSums], const Robust& rk, float sx, float sy,
                                                    float sz, float tx, float ty, float tz, float nx, float ny,
                                                    float nz) {
-    const float r = (sx - tx) * nx + (sy - ty) * ny + (sz - tz) * nz;
+    // r and J are evaluated without FMA contraction, in the reference's operation order, so
+    // that residual-dependent robust weights (e.g. L1: 1/|r|) see the same r as the CPU path
+    // even when (s - t).n cancels to ~0; the accumulation below may fuse.
+    const float r = __fadd_rn(__fadd_rn(__fmul_rn(__fsub_rn(sx, tx), nx), __fmul_rn(__fsub_rn(sy, ty), ny)),
+                              __fmul_rn(__fsub_rn(sz, tz), nz));
     float J[6];
-    J[0] = nz * sy - ny * sz;
-    J[1] = nx * sz - nz * sx;
-    J[2] = ny * sx - nx * sy;
+    J[0] = __fsub_rn(__fmul_rn(nz, sy), __fmul_rn(ny, sz));
+    J[1] = __fsub_rn(__fmul_rn(nx, sz), __fmul_rn(nz, sx));
+    J[2] = __fsub_rn(__fmul_rn(ny, sx), __fmul_rn(nx, sy));
     J[3] = nx;
     J[4] = ny;
     J[5] = nz;

@@ -13,6 +13,7 @@
 #include <climits>
 #include <cmath>
 #include <new>
+#include <vector>
 
 #include "common.cuh"
 
@@ -562,6 +563,10 @@ struct o3db_vbg {
     int64_t frames = 0;            // fused frames launched
     int64_t known_size = 0;        // size as last read back (a lower bound)
     int64_t max_new_seen = 0;
+    // optional per-kernel timing (o3db_vbg_profile)
+    std::vector<cudaEvent_t> prof_ev;
+    int64_t prof_frames = 0;
+    bool prof_on = false;
 };
 
 namespace o3db {
@@ -805,6 +810,8 @@ void o3db_vbg_destroy(o3db_vbg* v) {
     if (v->h_pinned) cudaFreeHost(v->h_pinned);
     for (auto& e : v->ev)
         if (e) cudaEventDestroy(e);
+    for (auto& e : v->prof_ev)
+        if (e) cudaEventDestroy(e);
     delete v;
 }
 
@@ -1012,9 +1019,12 @@ int o3db_vbg_integrate_frame(o3db_vbg* v, const void* depth_dev, int depth_dtype
     t.frame_id = v->frame_id;
     const int nthreads = (rows / kStride) * (cols / kStride);
     const unsigned nb = (unsigned)std::max<int64_t>(1, ceil_div(nthreads, kT));
+    const bool prof = v->prof_on && (size_t)(3 * v->prof_frames + 2) < v->prof_ev.size();
+    if (prof) cudaEventRecord(v->prof_ev[3 * v->prof_frames], st);
     if (depth_dtype == O3DB_DEPTH_U16) touch_kernel<uint16_t><<<nb, kT, 0, st>>>(t);
     else touch_kernel<float><<<nb, kT, 0, st>>>(t);
     O3DB_LAUNCH_CHECK();
+    if (prof) cudaEventRecord(v->prof_ev[3 * v->prof_frames + 1], st);
     IntegrateArgs a = base_integrate_args(v, depth_dev, has_color ? color_dev : nullptr, color_dtype, rows, cols, K, K, E,
                                           depth_scale, depth_max, trunc_mult);
     a.exist_list = v->exist_list;
@@ -1036,6 +1046,10 @@ int o3db_vbg_integrate_frame(o3db_vbg* v, const void* depth_dev, int depth_dtype
         return (int)O3DB_OK;
     });
     if (rc) return rc;
+    if (prof) {
+        cudaEventRecord(v->prof_ev[3 * v->prof_frames + 2], st);
+        v->prof_frames += 1;
+    }
     O3DB_CUDA_CHECK(cudaMemcpyAsync(v->h_pinned + 16 + 16 * slot, v->size_dev, 16 * sizeof(int), cudaMemcpyDeviceToHost, st));
     O3DB_CUDA_CHECK(cudaEventRecord(v->ev[slot], st));
     v->frames += 1;
@@ -1065,6 +1079,35 @@ int o3db_vbg_integrate_frame_host(o3db_vbg* v, const void* depth_host, int depth
     if (cbytes) O3DB_CUDA_CHECK(cudaMemcpyAsync(v->d_color, color_host, cbytes, cudaMemcpyHostToDevice, st));
     return o3db_vbg_integrate_frame(v, v->d_depth, depth_dtype, cbytes ? v->d_color : nullptr, color_dtype, rows, cols, K,
                                     E, depth_scale, depth_max, trunc_mult, st);
+}
+
+int o3db_vbg_profile(o3db_vbg* v, int enable) {
+    O3DB_REQUIRE(v != nullptr, "o3db_vbg_profile: null handle");
+    if (enable && v->prof_ev.empty()) {
+        v->prof_ev.resize(3 * 4096);
+        for (auto& e : v->prof_ev) O3DB_CUDA_CHECK(cudaEventCreate(&e));
+    }
+    v->prof_on = enable != 0;
+    v->prof_frames = 0;
+    return O3DB_OK;
+}
+
+int o3db_vbg_profile_read(o3db_vbg* v, double* touch_ms, double* integrate_ms, int64_t* frames) {
+    O3DB_REQUIRE(v != nullptr, "o3db_vbg_profile_read: null handle");
+    double t = 0, g = 0;
+    for (int64_t f = 0; f < v->prof_frames; ++f) {
+        float a = 0, b = 0;
+        O3DB_CUDA_CHECK(cudaEventSynchronize(v->prof_ev[3 * f + 2]));
+        O3DB_CUDA_CHECK(cudaEventElapsedTime(&a, v->prof_ev[3 * f], v->prof_ev[3 * f + 1]));
+        O3DB_CUDA_CHECK(cudaEventElapsedTime(&b, v->prof_ev[3 * f + 1], v->prof_ev[3 * f + 2]));
+        t += a;
+        g += b;
+    }
+    if (touch_ms) *touch_ms = t;
+    if (integrate_ms) *integrate_ms = g;
+    if (frames) *frames = v->prof_frames;
+    v->prof_frames = 0;
+    return O3DB_OK;
 }
 
 int64_t o3db_vbg_last_frustum_blocks(o3db_vbg* v, int32_t* block_coords_dev, int64_t max_blocks, void* stream) {

@@ -54,7 +54,8 @@ _u16p = C.POINTER(C.c_uint16)
 class _IcpResult(C.Structure):
     _fields_ = [("num_iterations", C.c_int), ("converged", C.c_int),
                 ("fitness", C.c_double), ("inlier_rmse", C.c_double),
-                ("transformation", C.c_double * 16)]
+                ("transformation", C.c_double * 16), ("loop_seconds", C.c_double),
+                ("build_seconds", C.c_double)]
 
 
 def _declare(L):
@@ -267,6 +268,8 @@ class IcpResult:
     per_iteration: np.ndarray  # [num_iterations_executed, 2] (fitness, rmse)
     correspondences: np.ndarray  # [N] int64
     status: int  # 0 ok, 1 singular system (the reference raises)
+    loop_seconds: float = 0.0
+    build_seconds: float = 0.0
 
 
 def icp_p2plane(source, target, target_normals, max_corr_dist, init=None, max_iteration=30,
@@ -288,7 +291,7 @@ def icp_p2plane(source, target, target_normals, max_corr_dist, init=None, max_it
     executed = int(np.sum(~np.isnan(per[:, 0])))
     return IcpResult(np.array(res.transformation, np.float64).reshape(4, 4), res.fitness,
                      res.inlier_rmse, bool(res.converged), res.num_iterations,
-                     per[:executed].copy(), corr, rc)
+                     per[:executed].copy(), corr, rc, res.loop_seconds, res.build_seconds)
 
 
 def inverse_transformation(T) -> np.ndarray:

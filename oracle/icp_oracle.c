@@ -12,6 +12,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -82,10 +83,12 @@ double orc_robust_weight_f64(int method, double scale, double shape,
             double v = 1.0 - q * q;
             return v * v;
         }
-        case 6: /* GeneralizedLoss :78-112 */
-            if (fabs(shape - 2.0) < 1e-3) {
+        case 6: /* GeneralizedLoss :78-112.  open3d::IsClose (GeometryMacros.h:58-63) is a
+                 * RELATIVE test: x > (1-rtol) y && x < (1+rtol) y, which can never hold for
+                 * y == 0, so the "shape ~ 0" branch of the reference is dead code. */
+            if (shape > (1.0 - 1e-3) * 2.0 && shape < (1.0 + 1e-3) * 2.0) {
                 return 1.0 / (scale * scale);
-            } else if (fabs(shape - 0.0) < 1e-3) {
+            } else if (shape > (1.0 - 1e-3) * 0.0 && shape < (1.0 + 1e-3) * 0.0) {
                 return 2.0 / (r * r + 2 * scale * scale);
             } else if (shape < -1e7) {
                 return exp(((r / scale) * (r / scale)) / (-2.0)) /
@@ -124,10 +127,10 @@ float orc_robust_weight_f32(int method, double scale_d, double shape,
             return (float)(v * v);
         }
         case 6:
-            if (fabs(shape - 2.0) < 1e-3) {
+            if (shape > (1.0 - 1e-3) * 2.0 && shape < (1.0 + 1e-3) * 2.0) {
                 double const_val = 1.0 / (double)(scale * scale);
                 return (float)const_val;
-            } else if (fabs(shape - 0.0) < 1e-3) {
+            } else if (shape > (1.0 - 1e-3) * 0.0 && shape < (1.0 + 1e-3) * 0.0) {
                 return (float)(2.0 / (r * r + 2 * (scale * scale)));
             } else if (shape < -1e7) {
                 float q = r / scale;
@@ -677,6 +680,12 @@ double orc_rmse_p2plane_f32(const float* src, const float* tgt,
 
 /* ---------------------------------------------------------------- ICP loop */
 
+static double now_s(void) {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
 static void matmul4(const double A[16], const double B[16], double C[16]) {
     double R[16];
     for (int i = 0; i < 4; ++i)
@@ -740,7 +749,9 @@ int orc_icp_p2plane_f32(const float* source, int64_t n, const float* target,
     orc_transform_points_f32(T, src, n);
 
     orc_grid g;
+    const double t_build0 = now_s();
     if (grid_build(&g, target, m, max_corr_dist) != 0) return -1;
+    const double t_loop0 = now_s();
 
     double fitness = 0, rmse = 0, prev_fitness = 0, prev_rmse = 0;
     int64_t cnt = 0;
@@ -788,6 +799,8 @@ int orc_icp_p2plane_f32(const float* source, int64_t n, const float* target,
      * `break` has not been incremented. */
     int iterations = it;
     (void)early;
+    res->loop_seconds = now_s() - t_loop0;
+    res->build_seconds = t_loop0 - t_build0;
     /* :424-431 final evaluation on the last scale */
     compute_registration_result(&g, src, n, max_corr_dist, corr, &fitness, &rmse,
                                 &cnt);

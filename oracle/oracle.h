@@ -139,6 +139,8 @@ typedef struct {
     double fitness;        /* final fitness_ */
     double inlier_rmse;    /* final inlier_rmse_ */
     double transformation[16]; /* row-major 4x4 f64 */
+    double loop_seconds;   /* wall time of the iteration loop only (no index build / final evaluation) */
+    double build_seconds;  /* wall time of the search-index build */
 } orc_icp_result;
 
 /* t/pipelines/registration/Registration.cpp:24-62, 275-360, 362-444 for one

@@ -1,0 +1,92 @@
+// ref_shim stub: the few members of core::Tensor / Dtype / Device / SizeVector the
+// reference's *Impl.h headers touch, over caller-owned host memory.
+#pragma once
+#include <cstdint>
+#include <initializer_list>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "open3d/utility/Logging.h"
+
+namespace open3d {
+namespace core {
+
+class SizeVector : public std::vector<int64_t> {
+public:
+    using std::vector<int64_t>::vector;
+};
+
+class Dtype {
+public:
+    Dtype() : size_(0), code_(0) {}
+    Dtype(int64_t size, int code) : size_(size), code_(code) {}
+    int64_t ByteSize() const { return size_; }
+    bool operator==(const Dtype& o) const { return size_ == o.size_ && code_ == o.code_; }
+    bool operator!=(const Dtype& o) const { return !(*this == o); }
+    std::string ToString() const { return "Dtype"; }
+    static const Dtype Float32, Float64, UInt8, UInt16, Int32, Int64, Bool;
+private:
+    int64_t size_;
+    int code_;
+};
+inline const Dtype Dtype::Float32(4, 1);
+inline const Dtype Dtype::Float64(8, 2);
+inline const Dtype Dtype::UInt8(1, 3);
+inline const Dtype Dtype::UInt16(2, 4);
+inline const Dtype Dtype::Int32(4, 5);
+inline const Dtype Dtype::Int64(8, 6);
+inline const Dtype Dtype::Bool(1, 7);
+static const Dtype Float32 = Dtype::Float32;
+static const Dtype Float64 = Dtype::Float64;
+static const Dtype UInt8 = Dtype::UInt8;
+static const Dtype UInt16 = Dtype::UInt16;
+static const Dtype Int32 = Dtype::Int32;
+static const Dtype Int64 = Dtype::Int64;
+
+class Device {
+public:
+    Device() {}
+    explicit Device(const std::string&) {}
+    bool operator==(const Device&) const { return true; }
+    bool IsCPU() const { return true; }
+    bool IsCUDA() const { return false; }
+    bool IsSYCL() const { return false; }
+    std::string ToString() const { return "CPU:0"; }
+};
+
+class Tensor {
+public:
+    Tensor() : ptr_(nullptr) {}
+    Tensor(void* ptr, SizeVector shape, Dtype dtype) : ptr_(ptr), shape_(shape), dtype_(dtype) {}
+    bool IsContiguous() const { return true; }
+    SizeVector GetShape() const { return shape_; }
+    int64_t GetShape(int i) const { return shape_[i]; }
+    int64_t NumDims() const { return (int64_t)shape_.size(); }
+    int64_t GetLength() const { return shape_.empty() ? 0 : shape_[0]; }
+    int64_t NumElements() const {
+        if (ptr_ == nullptr) return 0;
+        int64_t n = 1;
+        for (auto s : shape_) n *= s;
+        return n;
+    }
+    Dtype GetDtype() const { return dtype_; }
+    Device GetDevice() const { return Device(); }
+    void* GetDataPtr() { return ptr_; }
+    const void* GetDataPtr() const { return ptr_; }
+    template <typename T>
+    T* GetDataPtr() { return static_cast<T*>(ptr_); }
+    template <typename T>
+    const T* GetDataPtr() const { return static_cast<const T*>(ptr_); }
+    static Tensor Eye(int64_t n, Dtype, const Device&) {
+        static double eye[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+        return Tensor(eye, {n, n}, Dtype::Float64);
+    }
+private:
+    void* ptr_;
+    SizeVector shape_;
+    Dtype dtype_;
+};
+
+}  // namespace core
+}  // namespace open3d

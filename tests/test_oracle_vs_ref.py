@@ -1,0 +1,192 @@
+"""Validate the CPU oracle against the REAL reference code: oracle/_ref/libo3dref.so holds
+functions compiled straight from Open3D's own headers (oracle/ref_shim/ref_shim.cpp lists
+them with file:line).  Every comparison here is bit-exact.  CPU only."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "oracle", "_ref", "libo3dref.so")
+
+pytestmark = pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref not built (needs /root/reference)")
+
+f32p, f64p, i64p, i32p = (C.POINTER(t) for t in (C.c_float, C.c_double, C.c_int64, C.c_int))
+
+
+@pytest.fixture(scope="module")
+def ref():
+    L = C.CDLL(REF)
+    L.ref_spatial_hash.restype = C.c_uint64
+    L.ref_spatial_hash.argtypes = [C.c_int] * 3
+    L.ref_minivec_hash_i32x3.restype = C.c_uint64
+    L.ref_minivec_hash_i32x3.argtypes = [C.c_int] * 3
+    L.ref_robust_weight_f64.restype = C.c_double
+    L.ref_robust_weight_f64.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double]
+    L.ref_robust_weight_f32.restype = C.c_float
+    L.ref_robust_weight_f32.argtypes = [C.c_int, C.c_double, C.c_double, C.c_float]
+    L.ref_jacobian_p2plane_f32.argtypes = [C.c_int64, f32p, f32p, f32p, i64p, f32p, f32p]
+    L.ref_jacobian_colored_f32.argtypes = [C.c_int64] + [f32p] * 6 + [i64p, C.c_float, C.c_float, f32p, f32p, f32p, f32p]
+    L.ref_pose_to_transformation.argtypes = [f64p, f64p]
+    L.ref_transform_points_f32.argtypes = [f32p, f32p, C.c_int64]
+    L.ref_transform_normals_f32.argtypes = [f32p, f32p, C.c_int64]
+    L.ref_compute_voxel_index_f32.argtypes = [f32p, C.c_float, i32p]
+    L.ref_transform_indexer.argtypes = [f64p, f64p, C.c_float, C.c_int, f32p, f32p]
+    L.ref_workload_to_coord3.argtypes = [C.c_int, C.c_int, i32p]
+    L.ref_in_boundary2.argtypes = [C.c_int, C.c_int, C.c_float, C.c_float]
+    return L
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t)
+
+
+def test_hashes(ref):
+    rng = np.random.default_rng(0)
+    keys = rng.integers(-2**31, 2**31 - 1, (500, 3), dtype=np.int64).astype(np.int32)
+    keys[:3] = [[0, 0, 0], [-1, 3, 2], [2**31 - 1, -2**31, 5]]
+    want = [ref.ref_minivec_hash_i32x3(*map(int, k)) for k in keys]
+    assert oracle.minivec_hash(keys).tolist() == want
+    cells = rng.integers(-100000, 100000, (500, 3)).astype(np.int32)
+    assert oracle.spatial_hash(cells).tolist() == [ref.ref_spatial_hash(*map(int, c)) for c in cells]
+    for p, inv in [((-0.05, 0.149, 0.1), 10.0), ((3.7, -2.2, 0.0), 7.5), ((1e-8, -1e-8, 5.0), 10.0)]:
+        a = np.array(p, np.float32)
+        out = np.zeros(3, np.int32)
+        ref.ref_compute_voxel_index_f32(_p(a, f32p), inv, _p(out, i32p))
+        assert oracle.compute_voxel_index(a, inv).tolist() == out.tolist()
+
+
+def test_robust_kernel_weights_bit_exact(ref):
+    rs = [0.98, -0.37, 1e-4, 2.5, -7.0, 0.0311]
+    for method in range(7):
+        for scale in (1.0, 0.05, 3.0):
+            for shape in (1.0, 2.0, 2.0015, 1.9975, 0.0, 0.0005, -2.0, -1e8, 0.5):
+                for r in rs:
+                    assert oracle.robust_weight(method, scale, shape, r) == ref.ref_robust_weight_f64(method, scale, shape, r)
+                    a = oracle.robust_weight(method, scale, shape, r, f32=True)
+                    b = ref.ref_robust_weight_f32(method, scale, shape, r)
+                    assert np.float32(a).tobytes() == np.float32(b).tobytes(), (method, scale, shape, r, a, b)
+
+
+def test_jacobian_and_sums_bit_exact(ref):
+    from tests.synth import make_icp_pair
+    src, tgt, nrm, _ = make_icp_pair(3000, seed=21)
+    idx, _, _ = oracle.hybrid_search(tgt, src, 0.05, 1)
+    corr = np.ascontiguousarray(idx[:, 0].astype(np.int64))
+    # re-accumulate the 29 sums in f32, in index order, from the REFERENCE's Jacobian function
+    acc = np.zeros(29, np.float32)
+    J = np.zeros(6, np.float32)
+    r = C.c_float(0)
+    for i in range(len(src)):
+        if not ref.ref_jacobian_p2plane_f32(i, _p(src, f32p), _p(tgt, f32p), _p(nrm, f32p), _p(corr, i64p), _p(J, f32p), C.byref(r)):
+            continue
+        rr = np.float32(r.value)
+        s = 0
+        for j in range(6):
+            for k in range(j + 1):
+                acc[s] += J[j] * np.float32(1.0) * J[k]
+                s += 1
+            acc[21 + j] += J[j] * np.float32(1.0) * rr
+        acc[27] += rr
+        acc[28] += np.float32(1)
+    got = oracle.pose_p2plane_sums(src, tgt, nrm, corr)["sums32"]
+    assert got.tobytes() == acc.tobytes()
+
+
+def test_colored_jacobian_bit_exact(ref):
+    from tests.synth import make_colors, make_icp_pair
+    src, tgt, nrm, _ = make_icp_pair(400, seed=22)
+    sc, tc = make_colors(src), make_colors(tgt)
+    grad = np.random.default_rng(1).normal(0, 0.5, tgt.shape).astype(np.float32)
+    idx, _, _ = oracle.hybrid_search(tgt, src, 0.05, 1)
+    corr = np.ascontiguousarray(idx[:, 0].astype(np.int64))
+    lam = 0.968
+    slg, slp = np.float32(np.sqrt(lam)), np.float32(np.sqrt(1.0 - lam))
+    acc = np.zeros(29, np.float64)
+    JG, JI = np.zeros(6, np.float32), np.zeros(6, np.float32)
+    rG, rI = C.c_float(0), C.c_float(0)
+    one = np.float32(1)
+    for i in range(len(src)):
+        ok = ref.ref_jacobian_colored_f32(i, _p(src, f32p), _p(sc, f32p), _p(tgt, f32p), _p(nrm, f32p), _p(tc, f32p),
+                                          _p(grad, f32p), _p(corr, i64p), float(slg), float(slp), _p(JG, f32p),
+                                          _p(JI, f32p), C.byref(rG), C.byref(rI))
+        if not ok:
+            continue
+        g, q = np.float32(rG.value), np.float32(rI.value)
+        s = 0
+        for j in range(6):
+            for k in range(j + 1):
+                acc[s] += np.float32(JG[j] * one * JG[k] + JI[j] * one * JI[k])
+                s += 1
+            acc[21 + j] += np.float32(JG[j] * one * g + JI[j] * one * q)
+        acc[27] += np.float32(g * g + q * q)
+        acc[28] += 1
+    got = oracle.pose_colored_sums(src, sc, tgt, nrm, tc, grad, corr, lam)["sums64"]
+    assert np.array_equal(got, acc)
+
+
+def test_pose_transform_and_indexers_bit_exact(ref):
+    rng = np.random.default_rng(3)
+    for _ in range(20):
+        pose = rng.normal(0, 0.3, 6)
+        T = np.zeros(16)
+        ref.ref_pose_to_transformation(_p(pose, f64p), _p(T, f64p))
+        assert np.array_equal(oracle.pose_to_transformation(pose).ravel(), T)
+    T = oracle.pose_to_transformation(np.array([0.2, -0.1, 0.4, 1.0, -2.0, 0.5]))
+    pts = rng.uniform(-4, 4, (999, 3)).astype(np.float32)
+    Tf = np.ascontiguousarray(T.astype(np.float32))
+    a, b = pts.copy(), pts.copy()
+    ref.ref_transform_points_f32(_p(Tf, f32p), _p(a, f32p), len(a))
+    ref.ref_transform_normals_f32(_p(Tf, f32p), _p(b, f32p), len(b))
+    assert oracle.transform_points(T, pts).tobytes() == a.tobytes()
+    assert oracle.transform_normals(T, pts).tobytes() == b.tobytes()
+    # ArrayIndexer conventions the TSDF oracle relies on
+    out = np.zeros(3, np.int32)
+    for res in (2, 8, 16):
+        for w in range(0, res ** 3, 7):
+            ref.ref_workload_to_coord3(res, w, _p(out, i32p))
+            assert out.tolist() == [w % res, (w // res) % res, w // (res * res)]
+    for x, y in [(0, 0), (639, 479), (639.0001, 10), (-0.0, 5), (-1e-7, 5), (10, 479.5), (np.nan, 1)]:
+        want = bool(y >= 0 and x >= 0 and y <= 480 - 1.0 and x <= 640 - 1.0)
+        assert bool(ref.ref_in_boundary2(480, 640, x, y)) == want
+
+
+def test_tsdf_geometry_against_transform_indexer(ref):
+    """One voxel of oracle.tsdf_integrate re-derived with the reference's TransformIndexer."""
+    from tests.synth import PRIMESENSE_K, camera_pose, render_depth
+    T = camera_pose(17)
+    E = oracle.inverse_transformation(T)
+    depth = render_depth(T).numpy()
+    keys = oracle.depth_touch(depth, PRIMESENSE_K, E)
+    cap = len(keys)
+    tsdf = np.zeros((cap, 4096), np.float32)
+    wt = np.zeros((cap, 4096), np.uint16)
+    oracle.tsdf_integrate(depth, None, np.arange(cap, dtype=np.int32), keys, tsdf, wt, None, PRIMESENSE_K, PRIMESENSE_K, E)
+    K = np.ascontiguousarray(PRIMESENSE_K)
+    Ec = np.ascontiguousarray(E)
+    rng = np.random.default_rng(5)
+    checked = 0
+    trunc = np.float32(0.008) * np.float32(8.0)
+    for b in rng.integers(0, cap, 300):
+        v = int(rng.integers(0, 4096))
+        xv, yv, zv = v % 16, (v // 16) % 16, v // 256
+        vin = np.array([keys[b][0] * 16 + xv, keys[b][1] * 16 + yv, keys[b][2] * 16 + zv], np.float32)
+        cam, uv = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        ref.ref_transform_indexer(_p(K, f64p), _p(Ec, f64p), 0.008, 0, _p(vin, f32p), _p(cam, f32p))
+        ref.ref_transform_indexer(_p(K, f64p), _p(Ec, f64p), 0.008, 1, _p(cam, f32p), _p(uv, f32p))
+        u, vv = uv[0], uv[1]
+        if not ref.ref_in_boundary2(480, 640, float(u), float(vv)):
+            assert wt[b, v] == 0
+            continue
+        d = np.float32(depth[int(vv), int(u)]) / np.float32(1000.0)
+        sdf = np.float32(d - cam[2])
+        if d <= 0 or d > 3.0 or cam[2] <= 0 or sdf < -trunc:
+            assert wt[b, v] == 0
+            continue
+        sdf = np.float32(min(sdf, trunc)) / trunc
+        assert wt[b, v] == 1 and np.float32(tsdf[b, v]).tobytes() == np.float32((np.float32(0) * np.float32(0) + sdf) * np.float32(1.0)).tobytes()
+        checked += 1
+    assert checked > 50
