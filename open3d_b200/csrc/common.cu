@@ -15,6 +15,19 @@ void set_last_error(const char* fmt, ...) {
 
 const char* last_error() { return g_last_error; }
 
+void configure_memory_pool() {
+    static thread_local int configured_device = -1;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev == configured_device) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+    configured_device = dev;
+}
+
 }  // namespace o3db
 
 extern "C" {

@@ -62,6 +62,11 @@ inline int num_sms() {
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// Keep freed stream-ordered allocations cached in the device's default memory pool (the
+// default release threshold of 0 hands everything back to the driver at every synchronise,
+// which makes each create/destroy cycle re-map hundreds of MB).
+void configure_memory_pool();
+
 #ifdef __CUDACC__
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

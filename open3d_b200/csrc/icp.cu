@@ -22,6 +22,26 @@ static constexpr int kMaxCellsPerAxis = 4096;
 static constexpr int kNumSums = 30;   // 29 reference slots + sum of dist^2
 static constexpr int kSumStride = 32;
 static constexpr int kFlushEvery = 16;
+#ifndef ICP_CELL_SCALE
+#define ICP_CELL_SCALE 0.5
+#endif
+static constexpr double kDefaultCellScale = ICP_CELL_SCALE;
+#ifndef ICP_GROUP
+#define ICP_GROUP 0   // 0: two-pass per-lane search (default), 1: pruned per-lane search, 2..32: group search
+#endif
+#ifndef ICP_MIN_BLOCKS
+#define ICP_MIN_BLOCKS 3
+#endif
+#ifndef ICP_ACC_SMEM
+#define ICP_ACC_SMEM 0
+#endif
+#ifndef ICP_FLAT
+#define ICP_FLAT 0   // 1: flattened pass-1 scan (measured slower on B200: one load in flight per lane)
+#endif
+#ifndef ICP_DEFAULT_VARIANT
+#define ICP_DEFAULT_VARIANT 1
+#endif
+static constexpr int kGroup = ICP_GROUP;   // lanes sharing one candidate list in the fused ICP search (0 = per-lane search)
 
 // --------------------------------------------------------------------- bbox
 
@@ -65,12 +85,35 @@ __device__ __forceinline__ void apply_transform(const float* __restrict__ T, flo
     const float oy = T[4] * px + T[5] * py + T[6] * pz + T[7];
     const float oz = T[8] * px + T[9] * py + T[10] * pz + T[11];
     const float ow = T[12] * px + T[13] * py + T[14] * pz + T[15];
-    x = ox / ow;
-    y = oy / ow;
-    z = oz / ow;
+    if (ow == 1.0f) {   // rigid transforms: x / 1 == x exactly, skip three IEEE divisions
+        x = ox;
+        y = oy;
+        z = oz;
+    } else {
+        x = ox / ow;
+        y = oy / ow;
+        z = oz / ow;
+    }
+}
+
+// Sort key of the working source: tile-major (16 x 16 x 4 cells per tile, cells row-major
+// inside), so that 256 consecutive sorted queries occupy a compact 3-D box whose candidate
+// rows can be staged in shared memory.  Only locality depends on it, never correctness.
+static constexpr int kTileX = 16, kTileY = 16, kTileZ = 4;
+__host__ __device__ inline int64_t tiled_key_space(int nx, int ny, int nz) {
+    return (int64_t)((nx + kTileX - 1) / kTileX) * ((ny + kTileY - 1) / kTileY) * ((nz + kTileZ - 1) / kTileZ) *
+           (kTileX * kTileY * kTileZ);
+}
+__device__ __forceinline__ unsigned cell_key_tiled(const Grid& g, float x, float y, float z) {
+    const int ix = cell1(x, g.ox, g.inv_c, g.nx), iy = cell1(y, g.oy, g.inv_c, g.ny), iz = cell1(z, g.oz, g.inv_c, g.nz);
+    const int ntx = (g.nx + kTileX - 1) / kTileX, nty = (g.ny + kTileY - 1) / kTileY;
+    const int tile = ((iz / kTileZ) * nty + iy / kTileY) * ntx + ix / kTileX;
+    const int local = ((iz % kTileZ) * kTileY + iy % kTileY) * kTileX + ix % kTileX;
+    return (unsigned)tile * (unsigned)(kTileX * kTileY * kTileZ) + (unsigned)local;
 }
 
 // key[i] = cell of (optionally transformed) point i, rank[i] = arrival order in the cell.
+// TRANSFORM = true is the source path (tile-major key); false the target (row-major key).
 template <bool TRANSFORM>
 __global__ void count_kernel(const float* __restrict__ pts, int64_t n, Grid g, Affine T,
                              unsigned* __restrict__ count, unsigned* __restrict__ key,
@@ -79,7 +122,7 @@ __global__ void count_kernel(const float* __restrict__ pts, int64_t n, Grid g, A
     if (i >= n) return;
     float x = pts[3 * i], y = pts[3 * i + 1], z = pts[3 * i + 2];
     if (TRANSFORM) apply_transform(T.m, x, y, z);
-    const unsigned k = cell_key(g, x, y, z);
+    const unsigned k = TRANSFORM ? cell_key_tiled(g, x, y, z) : cell_key(g, x, y, z);
     key[i] = k;
     rank[i] = atomicAdd(&count[k], 1u);
 }
@@ -275,6 +318,7 @@ static int grid_from_bbox(const float mn[3], const float mx[3], double radius, d
 // (the grid dimensions depend on the bounding box).
 static int nns_build(o3db_nns* s, const float* pts, const float* nrm, int64_t m, double radius,
                      double cell_scale, cudaStream_t st) {
+    configure_memory_pool();
     s->m = m;
     s->radius = radius;
     unsigned* d_bbox = nullptr;
@@ -443,6 +487,16 @@ __device__ __forceinline__ void flush_acc(float (&acc)[kNumSums], double (*s_war
         const double v = warp_sum((double)acc[k]);
         if (lane == 0) s_warp[w][k] += v;
         acc[k] = 0.f;
+    }
+}
+
+__device__ __forceinline__ void flush_acc_smem(float (*s_acc)[kThreads], double (*s_warp)[kSumStride]) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < kNumSums; ++k) {
+        const double v = warp_sum((double)s_acc[k][threadIdx.x]);
+        if (lane == 0) s_warp[w][k] += v;
+        s_acc[k][threadIdx.x] = 0.f;
     }
 }
 
@@ -739,6 +793,7 @@ struct IcpArgs {
     int64_t n;            // local source points
     double n_total;       // source points over all ranks (fitness denominator)
     float rr, thr;
+    float r1, r1_accept2;   // pass-1 radius of the two-pass search (= cell size) and its acceptance bound
     Robust rk;
     double* partials;
     IcpState* st;
@@ -831,7 +886,7 @@ __device__ void icp_finalize_evaluate(const IcpArgs& a, const double* sums) {
 // 30-scalar reduction, and (last block) solve + pose update + convergence test.
 // MODE 0 = iterate, MODE 1 = evaluate (no Jacobian; writes correspondences).
 template <bool L2LOSS, int MODE>
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, ICP_MIN_BLOCKS)
 icp_iteration_kernel(IcpArgs a) {
     __shared__ double s_warp[kThreads / 32][kSumStride];
     __shared__ double s_final[kSumStride];
@@ -843,18 +898,296 @@ icp_iteration_kernel(IcpArgs a) {
     __syncthreads();
     if (MODE == 0 && s_done) return;
 
+#if ICP_FLAT
+    __shared__ unsigned s_rng[18][kThreads];   // per-thread row ranges of the flattened pass-1 scan
+#endif
+#if ICP_ACC_SMEM
+    // per-thread accumulators live in shared memory (column tid of s_acc): the 30 values are
+    // only in registers while one correspondence is being expanded, which leaves the search
+    // the whole register budget and lets one more block fit per SM
+    __shared__ float s_acc[kNumSums][kThreads];
+#pragma unroll
+    for (int k = 0; k < kNumSums; ++k) s_acc[k][threadIdx.x] = 0.f;
+#else
+    float acc[kNumSums];
+#pragma unroll
+    for (int k = 0; k < kNumSums; ++k) acc[k] = 0.f;
+#endif
+    int since = 0;
+    for (int64_t base = (int64_t)blockIdx.x * kThreads; base < a.n; base += (int64_t)gridDim.x * kThreads) {
+        const int64_t i = base + threadIdx.x;
+        const bool live = i < a.n;
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live) {
+            p = a.src[i];
+            apply_transform(s_U, p.x, p.y, p.z);   // Registration.cpp:322 (PointCloud::Transform), fused
+            a.src[i] = p;
+        }
+        Best b;
+        if (kGroup > 1) {
+            nn_search_group<(kGroup > 1 ? kGroup : 2)>(a.g, a.tgt, a.cs, live, p.x, p.y, p.z, a.rr, a.thr, b);
+        } else if (kGroup == 1) {
+            b.j = -1;
+            if (live) nn_search<true>(a.g, a.tgt, a.cs, p.x, p.y, p.z, a.rr, a.thr, b);
+        } else {
+            b.j = -1;
+#if ICP_FLAT
+            if (live) nn_search_two_pass_flat<kThreads>(a.g, a.tgt, a.cs, p.x, p.y, p.z, a.r1, a.r1_accept2, a.rr, a.thr, s_rng, b);
+#else
+            if (live) nn_search_two_pass(a.g, a.tgt, a.cs, p.x, p.y, p.z, a.r1, a.r1_accept2, a.rr, a.thr, b);
+#endif
+        }
+        if (live) {
+            if (b.j >= 0) {
+#if ICP_ACC_SMEM
+                if (MODE == 0) {
+                    float term[kNumSums];
+#pragma unroll
+                    for (int k = 0; k < kNumSums; ++k) term[k] = 0.f;
+                    const float4 nn = __ldg(&a.nrm[b.j]);
+                    accumulate_p2plane<L2LOSS>(term, a.rk, p.x, p.y, p.z, b.x, b.y, b.z, nn.x, nn.y, nn.z);
+                    term[29] = b.d;
+#pragma unroll
+                    for (int k = 0; k < kNumSums; ++k) s_acc[k][threadIdx.x] += term[k];
+                } else {
+                    s_acc[28][threadIdx.x] += 1.0f;
+                    s_acc[29][threadIdx.x] += b.d;
+                }
+#else
+                if (MODE == 0) {
+                    const float4 nn = __ldg(&a.nrm[b.j]);
+                    accumulate_p2plane<L2LOSS>(acc, a.rk, p.x, p.y, p.z, b.x, b.y, b.z, nn.x, nn.y, nn.z);
+                } else {
+                    acc[28] += 1.0f;
+                }
+                acc[29] += b.d;
+#endif
+            }
+            if (MODE == 1 && a.corr_out) a.corr_out[__float_as_int(p.w)] = b.j >= 0 ? (int64_t)b.idx : (int64_t)-1;
+        }
+        if (++since == kFlushEvery) {
+#if ICP_ACC_SMEM
+            flush_acc_smem(s_acc, s_warp);
+#else
+            flush_acc(acc, s_warp);
+#endif
+            since = 0;
+        }
+    }
+#if ICP_ACC_SMEM
+    flush_acc_smem(s_acc, s_warp);
+#else
+    flush_acc(acc, s_warp);
+#endif
+    if (!block_reduce_to_global(s_warp, a.partials, &a.st->ticket, s_final)) return;
+    if (a.fuse_finalize) {
+        if (threadIdx.x == 0) {
+            if (MODE == 0) icp_finalize_iteration(a, s_final);
+            else icp_finalize_evaluate(a, s_final);
+        }
+    } else if (threadIdx.x < kNumSums) {
+        a.st->sums[threadIdx.x] = s_final[threadIdx.x];
+    }
+}
+
+
+// ------------------------------------------------ TMA-staged tile variant
+
+// Shared-memory tile of one 256-query chunk: the candidate rows of the chunk's cell box are
+// brought in with cp.async.bulk (TMA, one bulk copy per non-empty (y,z) row — a row of cells
+// is one contiguous run of float4 points) and the matching cell_start segments with coalesced
+// loads; the per-query scan then touches shared memory only.
+static constexpr int kTilePts = 2560;   // float4 candidates  (40 KB)
+static constexpr int kTileCs = 4096;    // staged cell_start entries (16 KB)
+static constexpr int kTileRows = 256;   // (y,z) rows of the box (one per thread)
+
+struct __align__(16) TileSmem {
+    float4 pts[kTilePts];
+    unsigned cs[kTileCs];
+    int row_delta[kTileRows];            // smem index minus global index of the row's points
+    unsigned long long mbar;
+    int bbox[6];
+    int ok;
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(b))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
+    unsigned done;
+    do {
+        asm volatile(
+                "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(smem_u32(b)), "r"(parity)
+                : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ float4 lds128(unsigned addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
+// scan_range() over candidates staged in shared memory; `base` is the shared address that
+// global index 0 of this row would have (may wrap below the window; only [s, e) is touched).
+__device__ __forceinline__ void scan_range_smem(unsigned base, unsigned s, unsigned e, float qx, float qy, float qz,
+                                                Best& b) {
+    for (unsigned j = s; j < e; j += 4) {
+        float4 t[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) t[k] = lds128(base + min(j + k, e - 1) * 16u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float dx = t[k].x - qx, dy = t[k].y - qy, dz = t[k].z - qz;
+            const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            const int idx = __float_as_int(t[k].w);
+            if (d < b.d || (d == b.d && idx < b.idx)) {
+                b.d = d;
+                b.j = (int)min(j + k, e - 1);
+                b.idx = idx;
+                b.x = t[k].x;
+                b.y = t[k].y;
+                b.z = t[k].z;
+            }
+        }
+    }
+}
+
+template <bool L2LOSS, int MODE>
+__global__ void __launch_bounds__(kThreads, ICP_MIN_BLOCKS)
+icp_iteration_tile_kernel(IcpArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TileSmem& sm = *reinterpret_cast<TileSmem*>(smem_raw);
+    __shared__ double s_warp[kThreads / 32][kSumStride];
+    __shared__ double s_final[kSumStride];
+    __shared__ float s_U[16];
+    __shared__ int s_done;
+    if (threadIdx.x == 0) {
+        s_done = *(volatile int*)&a.st->done;
+        mbar_init(&sm.mbar, 1);
+    }
+    if (threadIdx.x < 16) s_U[threadIdx.x] = a.st->Uf[threadIdx.x];
+    for (int k = threadIdx.x; k < (kThreads / 32) * kSumStride; k += kThreads) (&s_warp[0][0])[k] = 0.0;
+    __syncthreads();
+    if (MODE == 0 && s_done) return;
+
+    const Grid& g = a.g;
+    const int kBig = 0x3fffffff;
+    unsigned phase = 0;
     float acc[kNumSums];
 #pragma unroll
     for (int k = 0; k < kNumSums; ++k) acc[k] = 0.f;
     int since = 0;
     for (int64_t base = (int64_t)blockIdx.x * kThreads; base < a.n; base += (int64_t)gridDim.x * kThreads) {
         const int64_t i = base + threadIdx.x;
-        if (i < a.n) {
-            float4 p = a.src[i];
+        const bool live = i < a.n;
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live) {
+            p = a.src[i];
             apply_transform(s_U, p.x, p.y, p.z);   // Registration.cpp:322 (PointCloud::Transform), fused
             a.src[i] = p;
-            Best b;
-            nn_search<true>(a.g, a.tgt, a.cs, p.x, p.y, p.z, a.rr, a.thr, b);
+        }
+        // ---- this query's pass-1 cell box and the block's union of them
+        const bool inside = live && !(hi_bound(p.x, a.rr) < g.bmin[0] || lo_bound(p.x, a.rr) > g.bmax[0] ||
+                                      hi_bound(p.y, a.rr) < g.bmin[1] || lo_bound(p.y, a.rr) > g.bmax[1] ||
+                                      hi_bound(p.z, a.rr) < g.bmin[2] || lo_bound(p.z, a.rr) > g.bmax[2] ||
+                                      !(p.x == p.x) || !(p.y == p.y) || !(p.z == p.z));
+        int x0 = kBig, x1 = -kBig, y0 = kBig, y1 = -kBig, z0 = kBig, z1 = -kBig;
+        if (inside) {
+            x0 = cell1(lo_bound(p.x, a.r1), g.ox, g.inv_c, g.nx);
+            x1 = cell1(hi_bound(p.x, a.r1), g.ox, g.inv_c, g.nx);
+            y0 = cell1(lo_bound(p.y, a.r1), g.oy, g.inv_c, g.ny);
+            y1 = cell1(hi_bound(p.y, a.r1), g.oy, g.inv_c, g.ny);
+            z0 = cell1(lo_bound(p.z, a.r1), g.oz, g.inv_c, g.nz);
+            z1 = cell1(hi_bound(p.z, a.r1), g.oz, g.inv_c, g.nz);
+        }
+        if (threadIdx.x < 6) sm.bbox[threadIdx.x] = (threadIdx.x & 1) ? -kBig : kBig;
+        __syncthreads();
+        {
+            int mn[3] = {x0, y0, z0}, mx[3] = {x1, y1, z1};
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    mn[k] = min(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
+                    mx[k] = max(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
+                }
+            }
+            if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    atomicMin(&sm.bbox[2 * k], mn[k]);
+                    atomicMax(&sm.bbox[2 * k + 1], mx[k]);
+                }
+            }
+        }
+        __syncthreads();
+        const int BX0 = sm.bbox[0], BX1 = sm.bbox[1], BY0 = sm.bbox[2], BY1 = sm.bbox[3], BZ0 = sm.bbox[4],
+                  BZ1 = sm.bbox[5];
+        const int ty = BY1 - BY0 + 1, tz = BZ1 - BZ0 + 1, W = BX1 - BX0 + 2;   // W entries per row
+        const int rows = ty * tz;
+        bool tile_ok = BX0 <= BX1 && rows <= kTileRows && (int64_t)rows * W <= kTileCs;
+        // ---- stage the cell_start segments of every row of the box (coalesced)
+        if (tile_ok) {
+            for (int e = threadIdx.x; e < rows * W; e += kThreads) {
+                const int r = e / W, k = e - r * W;
+                const int iy = BY0 + r % ty, iz = BZ0 + r / ty;
+                sm.cs[e] = __ldg(&a.cs[(iz * g.ny + iy) * g.nx + BX0 + k]);
+            }
+        }
+        __syncthreads();
+        // ---- per-row candidate runs -> shared offsets; one bulk copy per non-empty row
+        unsigned cnt = 0, gstart = 0;
+        if (tile_ok && threadIdx.x < rows) {
+            gstart = sm.cs[threadIdx.x * W];
+            cnt = sm.cs[threadIdx.x * W + W - 1] - gstart;
+        }
+        unsigned total;
+        const unsigned off = block_exclusive_scan(cnt, total);
+        tile_ok = tile_ok && total <= (unsigned)kTilePts;
+        if (tile_ok) {
+            if (threadIdx.x < rows) sm.row_delta[threadIdx.x] = (int)off - (int)gstart;
+            if (threadIdx.x == 0) mbar_expect_tx(&sm.mbar, total * 16u);
+        }
+        __syncthreads();
+        if (tile_ok) {
+            if (cnt > 0) bulk_g2s(&sm.pts[off], a.tgt + gstart, cnt * 16u, &sm.mbar);
+            mbar_wait(&sm.mbar, phase);
+            phase ^= 1u;
+        }
+        // ---- search
+        Best b;
+        b.d = a.thr;
+        b.j = -1;
+        b.idx = 0x7fffffff;
+        b.x = b.y = b.z = 0.f;
+        if (inside) {
+            bool need_global = !tile_ok;
+            if (tile_ok) {
+                const unsigned pts_base = smem_u32(sm.pts);
+                for (int iz = z0; iz <= z1; ++iz)
+                    for (int iy = y0; iy <= y1; ++iy) {
+                        const int r = (iz - BZ0) * ty + (iy - BY0);
+                        const unsigned s = sm.cs[r * W + (x0 - BX0)], e = sm.cs[r * W + (x1 - BX0) + 1];
+                        scan_range_smem(pts_base + (unsigned)sm.row_delta[r] * 16u, s, e, p.x, p.y, p.z, b);
+                    }
+                need_global = !(b.j >= 0 && b.d <= a.r1_accept2) && a.r1 < a.rr;
+            }
+            if (need_global) nn_search_two_pass(g, a.tgt, a.cs, p.x, p.y, p.z, a.r1, a.r1_accept2, a.rr, a.thr, b);
+        }
+        if (live) {
             if (b.j >= 0) {
                 if (MODE == 0) {
                     const float4 nn = __ldg(&a.nrm[b.j]);
@@ -870,6 +1203,8 @@ icp_iteration_kernel(IcpArgs a) {
             flush_acc(acc, s_warp);
             since = 0;
         }
+        __syncthreads();   // everyone is done with the tile before the next chunk overwrites it
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     flush_acc(acc, s_warp);
     if (!block_reduce_to_global(s_warp, a.partials, &a.st->ticket, s_final)) return;
@@ -917,6 +1252,8 @@ struct o3db_icp {
     IcpState* h_st = nullptr;        // pinned
     o3db_comm* comm = nullptr;
     int grid_blocks = 0;
+    int variant = 2;                 // 1 = direct global search, 2 = TMA-staged tiles
+    int64_t src_keys = 0;            // size of the source sort key space
     int launched = 0;
     bool l2loss = true;
 };
@@ -935,6 +1272,8 @@ static IcpArgs make_args(o3db_icp* c) {
     const float r = (float)c->opt.max_correspondence_distance;
     a.thr = r * r;                       // FixedRadiusSearchImpl.cuh:692: T(radius) * T(radius)
     a.rr = r * (1.0f + 1e-6f);
+    a.r1 = fminf(c->nns.g.c, a.rr);
+    a.r1_accept2 = (a.r1 * (1.0f - 1e-4f)) * (a.r1 * (1.0f - 1e-4f));
     a.rk.method = c->opt.kernel.method;
     a.rk.scale = (float)c->opt.kernel.scale;
     a.rk.shape = c->opt.kernel.shape;
@@ -1217,8 +1556,10 @@ int o3db_icp_create(const float* source_dev, int64_t n, const float* target_dev,
     c->comm = comm;
     c->l2loss = options->kernel.method == O3DB_ROBUST_L2;
     memcpy(c->init_T, init_T, sizeof(c->init_T));
+    // fine cells (half the radius) by default: pass 1 of the two-pass search then covers the
+    // +-1 cell box, which holds the nearest neighbour of every already roughly aligned point
     int rc = nns_build(&c->nns, target_dev, target_normals_dev, m, options->max_correspondence_distance,
-                       options->cell_scale, st);
+                       options->cell_scale > 0 ? options->cell_scale : kDefaultCellScale, st);
     if (rc) {
         o3db_icp_destroy(c);
         return rc;
@@ -1242,13 +1583,27 @@ int o3db_icp_create(const float* source_dev, int64_t n, const float* target_dev,
     } while (0)
     // fitness denominator over all ranks
     c->n_total = (double)n;
+    // 1 = direct (two-pass search straight from global/L1), 2 = TMA-staged shared-memory tiles.
+    // Default: whichever measured faster on B200 — currently the direct kernel.
+    c->variant = options->search_variant == 2 ? 2 : (options->search_variant == 1 ? 1 : ICP_DEFAULT_VARIANT);
     int occ = 1;
-    if (c->l2loss)
+    if (c->variant == 2) {
+        const int smem = (int)sizeof(TileSmem);
+        ICP_CUDA(cudaFuncSetAttribute(icp_iteration_tile_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        ICP_CUDA(cudaFuncSetAttribute(icp_iteration_tile_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        ICP_CUDA(cudaFuncSetAttribute(icp_iteration_tile_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        if (c->l2loss)
+            ICP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, icp_iteration_tile_kernel<true, 0>, kThreads, smem));
+        else
+            ICP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, icp_iteration_tile_kernel<false, 0>, kThreads, smem));
+    } else if (c->l2loss) {
         ICP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, icp_iteration_kernel<true, 0>, kThreads, 0));
-    else
+    } else {
         ICP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, icp_iteration_kernel<false, 0>, kThreads, 0));
+    }
     c->grid_blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, kThreads), (int64_t)num_sms() * std::max(occ, 1)));
-    const int64_t ncell = c->nns.ncell;
+    const int64_t ncell = tiled_key_space(c->nns.g.nx, c->nns.g.ny, c->nns.g.nz);   // tile-major source keys
+    c->src_keys = ncell;
     ICP_CUDA(cudaMallocAsync(&c->src4, n * sizeof(float4), st));
     ICP_CUDA(cudaMallocAsync(&c->src_key, n * sizeof(unsigned), st));
     ICP_CUDA(cudaMallocAsync(&c->src_rank, n * sizeof(unsigned), st));
@@ -1300,8 +1655,13 @@ int o3db_icp_iterate(o3db_icp* c, int iterations, void* stream) {
     const int todo = std::min(iterations, c->opt.max_iteration - c->launched);
     IcpArgs a = make_args(c);
     for (int k = 0; k < todo; ++k) {
-        if (c->l2loss) icp_iteration_kernel<true, 0><<<c->grid_blocks, kThreads, 0, st>>>(a);
-        else icp_iteration_kernel<false, 0><<<c->grid_blocks, kThreads, 0, st>>>(a);
+        if (c->variant == 2) {
+            if (c->l2loss) icp_iteration_tile_kernel<true, 0><<<c->grid_blocks, kThreads, sizeof(TileSmem), st>>>(a);
+            else icp_iteration_tile_kernel<false, 0><<<c->grid_blocks, kThreads, sizeof(TileSmem), st>>>(a);
+        } else {
+            if (c->l2loss) icp_iteration_kernel<true, 0><<<c->grid_blocks, kThreads, 0, st>>>(a);
+            else icp_iteration_kernel<false, 0><<<c->grid_blocks, kThreads, 0, st>>>(a);
+        }
         O3DB_LAUNCH_CHECK();
         if (c->comm) {
             int rc = o3db_comm_allreduce_f64(c->comm, (double*)((char*)c->st + offsetof(IcpState, sums)), kNumSums, st);
@@ -1320,7 +1680,8 @@ int o3db_icp_finish(o3db_icp* c, o3db_icp_result* result, int64_t* correspondenc
     cudaStream_t st = (cudaStream_t)stream;
     IcpArgs a = make_args(c);
     a.corr_out = correspondences_dev;
-    icp_iteration_kernel<true, 1><<<c->grid_blocks, kThreads, 0, st>>>(a);
+    if (c->variant == 2) icp_iteration_tile_kernel<true, 1><<<c->grid_blocks, kThreads, sizeof(TileSmem), st>>>(a);
+    else icp_iteration_kernel<true, 1><<<c->grid_blocks, kThreads, 0, st>>>(a);
     O3DB_LAUNCH_CHECK();
     if (c->comm) {
         int rc = o3db_comm_allreduce_f64(c->comm, (double*)((char*)c->st + offsetof(IcpState, sums)), kNumSums, st);
@@ -1370,6 +1731,7 @@ int o3db_icp_point_to_plane_host(const float* source_host, int64_t n, const floa
                                  int64_t* correspondences_host, double* per_iteration_host) {
     O3DB_REQUIRE(source_host && target_host && n > 0 && m > 0, "Source and/or Target pointcloud is empty.");
     O3DB_REQUIRE(target_normals_host != nullptr, "Target pointcloud missing normals attribute.");
+    configure_memory_pool();
     cudaStream_t st = 0;
     float *d_src = nullptr, *d_tgt = nullptr, *d_nrm = nullptr;
     int64_t* d_corr = nullptr;

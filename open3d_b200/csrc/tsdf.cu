@@ -146,13 +146,22 @@ struct TouchArgs {
 // (:200-204) so that candidate keys never make a round trip through a dense list.
 template <typename depth_t>
 __global__ void __launch_bounds__(kT) touch_kernel(TouchArgs a) {
+    // One thread per (strided pixel, ray sample): 4x the threads of the reference's launch
+    // (VoxelBlockGridCUDA.cu:145) and a 4x shorter dependent chain per thread — the kernel is
+    // pure latency (a few table round trips), so parallelism is what buys time.
     const int cols_s = a.cols / kStride, rows_s = a.rows / kStride;
-    const int w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= cols_s * rows_s) return;
-    const int y = (w / cols_s) * kStride;
-    const int x = (w % cols_s) * kStride;
-    const float d = dvd((float)((const depth_t*)a.depth)[(size_t)y * a.cols + x], a.depth_scale);
-    if (!(d > 0 && d < a.depth_max)) return;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int w = tid / kSamples, step = tid % kSamples;
+    const int lane = threadIdx.x & 31;
+    bool valid = w < cols_s * rows_s;
+    float d = 0.f;
+    int x = 0, y = 0;
+    if (valid) {
+        y = (w / cols_s) * kStride;
+        x = (w % cols_s) * kStride;
+        d = dvd((float)__ldg(&((const depth_t*)a.depth)[(size_t)y * a.cols + x]), a.depth_scale);
+        valid = d > 0 && d < a.depth_max;
+    }
     float xc, yc, zc, xg, yg, zg;
     unproject(a.cam, (float)x, (float)y, 1.0f, xc, yc, zc);
     rigid(a.cam, xc, yc, zc, xg, yg, zg);
@@ -161,39 +170,43 @@ __global__ void __launch_bounds__(kT) touch_kernel(TouchArgs a) {
     const float t_min = fmaxf(sub(d, a.sdf_trunc), 0.0f);
     const float t_max = fminf(add(d, a.sdf_trunc), a.depth_max);
     const float t_step = dvd(sub(t_max, t_min), (float)kStepSize);
-    float t = t_min;
-    int px = 0, py = 0, pz = 0;
-#pragma unroll
-    for (int step = 0; step <= kStepSize; ++step) {
-        const int kx = (int)floorf(dvd(add(xo, mul(t, xd)), a.block_size));
-        const int ky = (int)floorf(dvd(add(yo, mul(t, yd)), a.block_size));
-        const int kz = (int)floorf(dvd(add(zo, mul(t, zd)), a.block_size));
-        t = add(t, t_step);
-        if (step > 0 && kx == px && ky == py && kz == pz) continue;  // consecutive samples in one block
-        px = kx;
-        py = ky;
-        pz = kz;
-        const int cand = w * kSamples + step;
+    float t = t_min;                       // t += t_step, `step` times, exactly as the reference's loop
+    for (int s = 0; s < step; ++s) t = add(t, t_step);
+    const int kx = (int)floorf(dvd(add(xo, mul(t, xd)), a.block_size));
+    const int ky = (int)floorf(dvd(add(yo, mul(t, yd)), a.block_size));
+    const int kz = (int)floorf(dvd(add(zo, mul(t, zd)), a.block_size));
+    // neighbouring rays / samples of a warp mostly hit the same few blocks: one lane per distinct
+    // key does the table work (hash match first, then an exact key comparison with the leader)
+    const uint64_t h = minivec_hash(kx, ky, kz);
+    const unsigned tag = valid ? ((unsigned)h ^ (unsigned)(h >> 32)) | 1u : (unsigned)(lane << 1);
+    const unsigned peers = __match_any_sync(0xffffffffu, tag);
+    const int leader = __ffs(peers) - 1;
+    const int lx = __shfl_sync(0xffffffffu, kx, leader), ly = __shfl_sync(0xffffffffu, ky, leader),
+              lz = __shfl_sync(0xffffffffu, kz, leader);
+    if (!valid || (lane != leader && lx == kx && ly == ky && lz == kz)) return;
+    unsigned bucket = 0;
+    const int cand = tid;                  // == w * kSamples + step
+    int r = probe<false>(a.tab, a.cand_keys, 0, kx, ky, kz, &bucket);   // read-only fast path
+    if (r == kResMiss) {
         int* ck = a.cand_keys + 3 * (size_t)cand;
         ck[0] = kx;
         ck[1] = ky;
         ck[2] = kz;
-        __threadfence();
-        unsigned bucket = 0;
-        const int r = probe<true>(a.tab, a.cand_keys, cand, kx, ky, kz, &bucket);
-        if (r >= 0) {
-            if (a.stamp && atomicExch(&a.stamp[r], a.frame_id) != a.frame_id) {
-                const int p = atomicAdd(&a.counters[0], 1);
-                if (p < a.max_list) a.exist_list[p] = r;
-                else a.counters[2] = 1;
-            }
-        } else if (r == kResInserted) {
-            const int p = atomicAdd(&a.counters[1], 1);
-            if (p < a.max_list) a.new_list[p] = make_int2((int)bucket, cand);
+        __threadfence();   // the candidate key must be visible before its marker is
+        r = probe<true>(a.tab, a.cand_keys, cand, kx, ky, kz, &bucket);
+    }
+    if (r >= 0) {
+        if (a.stamp && __ldcg(&a.stamp[r]) != a.frame_id && atomicExch(&a.stamp[r], a.frame_id) != a.frame_id) {
+            const int p = atomicAdd(&a.counters[0], 1);
+            if (p < a.max_list) a.exist_list[p] = r;
             else a.counters[2] = 1;
-        } else if (r == kResFull) {
-            a.counters[2] = 1;
         }
+    } else if (r == kResInserted) {
+        const int p = atomicAdd(&a.counters[1], 1);
+        if (p < a.max_list) a.new_list[p] = make_int2((int)bucket, cand);
+        else a.counters[2] = 1;
+    } else if (r == kResFull) {
+        a.counters[2] = 1;
     }
 }
 
@@ -334,14 +347,15 @@ __device__ __forceinline__ bool voxel_sdf(const IntegrateArgs& a, int x, int y, 
 
 // One 16^3 block per CTA iteration; each thread owns 4 consecutive x voxels per
 // pass (128-bit tsdf, 64-bit weight, 3x64-bit colour accesses, fully coalesced).
+// One quarter (4 z-slices = 1024 voxels) of a 16^3 block per CTA pass; each thread owns 4
+// consecutive x voxels (128-bit tsdf, 64-bit weight, 3x64-bit colour accesses, fully coalesced).
 template <typename depth_t, typename color_in_t, bool HAS_COLOR>
-__device__ __forceinline__ void integrate_block16(const IntegrateArgs& a, int slot, int xb, int yb, int zb) {
+__device__ __forceinline__ void integrate_block16(const IntegrateArgs& a, int slot, int unit, int xb, int yb, int zb) {
     float* tsdf = a.tsdf + (size_t)slot * 4096;
     uint16_t* wt = a.weight + (size_t)slot * 4096;
     uint16_t* cb = HAS_COLOR ? a.color_buf + (size_t)slot * 4096 * 3 : nullptr;
-#pragma unroll 1
-    for (int it = 0; it < 4; ++it) {
-        const int quad = it * kT + threadIdx.x;
+    {
+        const int quad = unit * kT + threadIdx.x;
         const int xq = (quad & 3) * 4, yv = (quad >> 2) & 15, zv = quad >> 6;
         const int lin = quad * 4;
         float sdf[4];
@@ -353,7 +367,7 @@ __device__ __forceinline__ void integrate_block16(const IntegrateArgs& a, int sl
             up[k] = voxel_sdf<depth_t>(a, xb * 16 + xq + k, yb * 16 + yv, zb * 16 + zv, sdf[k], ui[k], vi[k]);
             any |= up[k];
         }
-        if (!any) continue;
+        if (!any) return;
         float4 t4 = *reinterpret_cast<float4*>(tsdf + lin);
         ushort4 w4 = *reinterpret_cast<ushort4*>(wt + lin);
         float tv[4] = {t4.x, t4.y, t4.z, t4.w};
@@ -448,44 +462,50 @@ __global__ void __launch_bounds__(kT) integrate_kernel(IntegrateArgs a) {
         size0 = *a.size;
         if (a.counters[2]) n_total = 0;   // overflow: the host reports it; nothing is integrated
     }
-    for (int b = blockIdx.x; b < n_total; b += gridDim.x) {
+    // work unit = one quarter of a 16^3 block (whole block for other resolutions)
+    const int upb = a.resolution == 16 ? 4 : 1;
+    for (int wu = blockIdx.x; wu < n_total * upb; wu += gridDim.x) {
+        const int b = wu / upb, unit = wu % upb;
         if (threadIdx.x == 0) {
             int slot;
+            const int* k;
             if (!fused) {
                 slot = a.buf_indices[b];
+                k = a.block_keys + 3 * (size_t)slot;
             } else if (b < n_exist) {
                 slot = a.exist_list[b];
+                k = a.block_keys + 3 * (size_t)slot;
             } else {
-                // commit a block first seen in this frame: slot = old size + rank
+                // a block first seen in this frame: slot = old size + rank; unit 0 commits it
                 const int2 nl = a.new_list[b - n_exist];
                 slot = size0 + (b - n_exist);
-                if (slot < a.capacity) {
-                    const int* k = a.cand_keys + 3 * (size_t)nl.y;
+                k = a.cand_keys + 3 * (size_t)nl.y;
+                if (slot >= a.capacity) {
+                    slot = -1;
+                    if (unit == 0) {
+                        a.table[nl.x] = kTomb;
+                        a.counters[2] = 1;
+                    }
+                } else if (unit == 0) {
                     a.keys_rw[3 * (size_t)slot] = k[0];
                     a.keys_rw[3 * (size_t)slot + 1] = k[1];
                     a.keys_rw[3 * (size_t)slot + 2] = k[2];
                     a.stamp[slot] = a.frame_id;
                     a.table[nl.x] = slot;
-                } else {
-                    a.table[nl.x] = kTomb;
-                    a.counters[2] = 1;
-                    slot = -1;
                 }
             }
             s_slot = slot;
             if (slot >= 0) {
-                const int* k = (fused && b >= n_exist) ? a.cand_keys + 3 * (size_t)a.new_list[b - n_exist].y
-                                                       : a.block_keys + 3 * (size_t)slot;
                 s_key[0] = k[0];
                 s_key[1] = k[1];
                 s_key[2] = k[2];
-                if (fused) a.frame_slots[b] = slot;
+                if (fused && unit == 0) a.frame_slots[b] = slot;
             }
         }
         __syncthreads();
         const int slot = s_slot;
         if (slot >= 0) {
-            if (a.resolution == 16) integrate_block16<depth_t, color_in_t, HAS_COLOR>(a, slot, s_key[0], s_key[1], s_key[2]);
+            if (a.resolution == 16) integrate_block16<depth_t, color_in_t, HAS_COLOR>(a, slot, unit, s_key[0], s_key[1], s_key[2]);
             else integrate_block_generic<depth_t, color_in_t, HAS_COLOR>(a, slot, s_key[0], s_key[1], s_key[2]);
         }
         __syncthreads();
@@ -772,6 +792,7 @@ int o3db_vbg_create(float voxel_size, int block_resolution, int64_t block_count,
     O3DB_REQUIRE(voxel_size > 0, "voxel_size must be positive");
     O3DB_REQUIRE(block_resolution >= 1 && block_resolution <= 32, "block_resolution must be in 1..32");
     O3DB_REQUIRE(block_count >= 1 && block_count < (int64_t(1) << 29), "block_count out of range");
+    configure_memory_pool();
     cudaStream_t st = (cudaStream_t)stream;
     o3db_vbg* v = new (std::nothrow) o3db_vbg();
     O3DB_REQUIRE(v != nullptr, "out of host memory");
@@ -926,7 +947,7 @@ int o3db_vbg_unique_block_coordinates(o3db_vbg* v, const void* depth_dev, int de
     TouchArgs t = make_touch_args(v, depth_dev, rows, cols, K, E, depth_scale, depth_max, trunc_mult);
     t.tab = Table{v->ftable, v->fbuckets - 1, v->keys};
     t.stamp = nullptr;
-    const int nthreads = (rows / kStride) * (cols / kStride);
+    const int nthreads = (rows / kStride) * (cols / kStride) * kSamples;
     const unsigned nb = (unsigned)std::max<int64_t>(1, ceil_div(nthreads, kT));
     if (depth_dtype == O3DB_DEPTH_U16) touch_kernel<uint16_t><<<nb, kT, 0, st>>>(t);
     else touch_kernel<float><<<nb, kT, 0, st>>>(t);
@@ -973,7 +994,7 @@ int o3db_vbg_integrate(o3db_vbg* v, const int32_t* block_coords_dev, int64_t num
                                           E, depth_scale, depth_max, trunc_mult);
     a.buf_indices = buf;
     a.n_blocks = (int)num_blocks;
-    const unsigned grid = (unsigned)std::min<int64_t>(num_blocks, (int64_t)num_sms() * 8);
+    const unsigned grid = (unsigned)std::min<int64_t>(num_blocks * 4, (int64_t)num_sms() * 8);
     rc = dispatch_integrate(depth_dtype, color_dtype, has_color, [&](auto kern) -> int {
         kern<<<grid, kT, 0, st>>>(a);
         O3DB_LAUNCH_CHECK();
@@ -1017,7 +1038,7 @@ int o3db_vbg_integrate_frame(o3db_vbg* v, const void* depth_dev, int depth_dtype
     t.tab = Table{v->table, v->nbuckets - 1, v->keys};
     t.stamp = v->stamp;
     t.frame_id = v->frame_id;
-    const int nthreads = (rows / kStride) * (cols / kStride);
+    const int nthreads = (rows / kStride) * (cols / kStride) * kSamples;
     const unsigned nb = (unsigned)std::max<int64_t>(1, ceil_div(nthreads, kT));
     const bool prof = v->prof_on && (size_t)(3 * v->prof_frames + 2) < v->prof_ev.size();
     if (prof) cudaEventRecord(v->prof_ev[3 * v->prof_frames], st);
