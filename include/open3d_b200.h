@@ -291,6 +291,18 @@ int o3db_vbg_integrate_frame_host(o3db_vbg* vbg, const void* depth_host, int dep
                                   const double intrinsic_host[9], const double extrinsic_host[16],
                                   float depth_scale, float depth_max, float trunc_voxel_multiplier,
                                   void* stream);
+/* Throughput form of the same call for a pre-recorded sequence: n_frames images of
+ * identical size/dtype, frame f at depth_ptrs[f] / color_ptrs[f] (device pointers if
+ * `host_images` is 0, host pointers — pinned recommended — otherwise), extrinsics_host is
+ * n_frames x 16 doubles.  Semantically identical to calling o3db_vbg_integrate_frame[_host]
+ * n_frames times in order (same kernels, same order, bit-identical volume); it only removes
+ * the per-call host overhead of the caller's language binding. */
+int o3db_vbg_integrate_sequence(o3db_vbg* vbg, int64_t n_frames, const void* const* depth_ptrs,
+                                int depth_dtype, const void* const* color_ptrs, int color_dtype,
+                                int rows, int cols, const double intrinsic_host[9],
+                                const double* extrinsics_host, float depth_scale, float depth_max,
+                                float trunc_voxel_multiplier, int host_images, void* stream);
+
 /* Block keys of the last integrated frame (Model::frustum_block_coords_): copies
  * up to max_blocks keys, returns the count (stream synchronise). */
 int64_t o3db_vbg_last_frustum_blocks(o3db_vbg* vbg, int32_t* block_coords_dev, int64_t max_blocks,

@@ -93,6 +93,7 @@ _SIGS = {
     "o3db_vbg_integrate": (_i, [_vp, _vp, _i64, _vp, _i, _vp, _i, _i, _i, _dp, _dp, _dp, _f, _f, _f, _vp]),
     "o3db_vbg_integrate_frame": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _dp, _dp, _f, _f, _f, _vp]),
     "o3db_vbg_integrate_frame_host": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _dp, _dp, _f, _f, _f, _vp]),
+    "o3db_vbg_integrate_sequence": (_i, [_vp, _i64, _vp, _i, _vp, _i, _i, _i, _dp, _dp, _f, _f, _f, _i, _vp]),
     "o3db_vbg_last_frustum_blocks": (_i64, [_vp, _vp, _i64, _vp]),
     "o3db_vbg_profile": (_i, [_vp, _i]),
     "o3db_vbg_profile_read": (_i, [_vp, _dp, _dp, C.POINTER(_i64)]),

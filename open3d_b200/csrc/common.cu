@@ -1,6 +1,9 @@
 // common.cu — last-error storage, version, launch counter.
 #include "common.cuh"
 
+#include <mutex>
+#include <vector>
+
 namespace o3db {
 
 static thread_local char g_last_error[1024] = "";
@@ -26,6 +29,30 @@ void configure_memory_pool() {
     }
     cudaGetLastError();
     configured_device = dev;
+}
+
+static std::mutex g_pinned_mu;
+static std::vector<void*> g_pinned_free;
+
+void* pinned_acquire(size_t bytes) {
+    if (bytes > 4096) return nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_pinned_mu);
+        if (!g_pinned_free.empty()) {
+            void* p = g_pinned_free.back();
+            g_pinned_free.pop_back();
+            return p;
+        }
+    }
+    void* p = nullptr;
+    if (cudaMallocHost(&p, 4096) != cudaSuccess) return nullptr;
+    return p;
+}
+
+void pinned_release(void* p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_pinned_mu);
+    g_pinned_free.push_back(p);
 }
 
 }  // namespace o3db

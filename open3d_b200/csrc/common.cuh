@@ -67,6 +67,11 @@ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 // which makes each create/destroy cycle re-map hundreds of MB).
 void configure_memory_pool();
 
+// Small pinned host blocks (result read-back) recycled through a process-wide free list:
+// cudaMallocHost / cudaFreeHost cost ~1 ms each and would otherwise dominate short calls.
+void* pinned_acquire(size_t bytes);     // bytes <= 4096
+void pinned_release(void* p);
+
 #ifdef __CUDACC__
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

@@ -17,13 +17,26 @@
 
 namespace o3db {
 
+// All fields are in GRID axis order: grid-x is the fastest-varying axis of the CSR table.
+// ax[k] names the real coordinate (0 = x, 1 = y, 2 = z) that grid axis k follows; the host
+// makes the axis with the smallest extent the fastest one, so that for surface-like clouds a
+// whole "column" of cells along the thin direction is one short contiguous run.
 struct Grid {
     float ox, oy, oz;   // origin = bbox min
-    float inv_c, c;     // cell size (>= search radius) and reciprocal
+    float inv_c, c;     // cell size and reciprocal
     float tol;          // pruning slack covering binning round-off
     int nx, ny, nz;
     float bmin[3], bmax[3];
+    int ax[3];
 };
+
+__device__ __forceinline__ float pick_axis(int a, float x, float y, float z) { return a == 0 ? x : (a == 1 ? y : z); }
+// real (x,y,z) -> grid-ordered (gx,gy,gz)
+__device__ __forceinline__ void to_grid(const Grid& g, float x, float y, float z, float& gx, float& gy, float& gz) {
+    gx = pick_axis(g.ax[0], x, y, z);
+    gy = pick_axis(g.ax[1], x, y, z);
+    gz = pick_axis(g.ax[2], x, y, z);
+}
 
 // Monotone binning: x <= y  =>  cell1(x) <= cell1(y)  (sub, mul by a positive
 // constant, floor and clamp are all monotone under round-to-nearest).  Coverage
@@ -33,7 +46,9 @@ __device__ __forceinline__ int cell1(float x, float o, float inv_c, int n) {
     return min(max(i, 0), n - 1);
 }
 
-__device__ __forceinline__ unsigned cell_key(const Grid& g, float x, float y, float z) {
+__device__ __forceinline__ unsigned cell_key(const Grid& g, float rx, float ry, float rz) {
+    float x, y, z;
+    to_grid(g, rx, ry, rz, x, y, z);
     const int ix = cell1(x, g.ox, g.inv_c, g.nx);
     const int iy = cell1(y, g.oy, g.inv_c, g.ny);
     const int iz = cell1(z, g.oz, g.inv_c, g.nz);
@@ -44,6 +59,8 @@ __device__ __forceinline__ unsigned cell_key(const Grid& g, float x, float y, fl
 // given that dist^2 was accepted in f32: r' = r (1 + 1e-6) plus 2 ulp of |q|.
 __device__ __forceinline__ float lo_bound(float q, float rr) { return (q - rr) - fabsf(q) * 2.4e-7f; }
 __device__ __forceinline__ float hi_bound(float q, float rr) { return (q + rr) + fabsf(q) * 2.4e-7f; }
+
+static constexpr unsigned kSlabMax = 32;   // longest slab scanned whole (see nn_search_two_pass)
 
 struct Best {
     float d;    // best dist^2 so far (starts at the threshold: accepts d <= thr)
@@ -83,11 +100,11 @@ __device__ __forceinline__ void scan_range(const float4* __restrict__ pts, unsig
 // skip_cx >= 0: that cell was scanned already.
 __device__ __forceinline__ void scan_row(const Grid& g, const float4* __restrict__ pts,
                                          const unsigned* __restrict__ cs, int row, int x0, int x1, int skip_cx,
-                                         float gap2, float qx, float qy, float qz, Best& b) {
+                                         float gap2, float gqx, float qx, float qy, float qz, Best& b) {
     // admissible |dx|: dx^2 <= best - gap2 (1e-6 best covers the rounding of the subtraction)
     const float ex = sqrtf(fmaf(b.d, 1e-6f, b.d - gap2)) * 1.00001f;
-    const int xa = max(x0, cell1(lo_bound(qx, ex), g.ox, g.inv_c, g.nx));
-    const int xb = min(x1, cell1(hi_bound(qx, ex), g.ox, g.inv_c, g.nx));
+    const int xa = max(x0, cell1(lo_bound(gqx, ex), g.ox, g.inv_c, g.nx));
+    const int xb = min(x1, cell1(hi_bound(gqx, ex), g.ox, g.inv_c, g.nx));
     if (skip_cx < xa || skip_cx > xb) {
         if (xa <= xb) scan_range(pts, cs[row + xa], cs[row + xb + 1], qx, qy, qz, b);
     } else {
@@ -109,9 +126,11 @@ __device__ __forceinline__ void nn_search(const Grid& g, const float4* __restric
     b.j = -1;
     b.idx = 0x7fffffff;
     b.x = b.y = b.z = 0.f;
-    const float lx = lo_bound(qx, rr), hx = hi_bound(qx, rr);
-    const float ly = lo_bound(qy, rr), hy = hi_bound(qy, rr);
-    const float lz = lo_bound(qz, rr), hz = hi_bound(qz, rr);
+    float gx, gy, gz;                       // the query in grid axis order (cells / gaps only)
+    to_grid(g, qx, qy, qz, gx, gy, gz);
+    const float lx = lo_bound(gx, rr), hx = hi_bound(gx, rr);
+    const float ly = lo_bound(gy, rr), hy = hi_bound(gy, rr);
+    const float lz = lo_bound(gz, rr), hz = hi_bound(gz, rr);
     // entirely outside the bounding box (or NaN): no candidate can pass
     if (hx < g.bmin[0] || lx > g.bmax[0] || hy < g.bmin[1] || ly > g.bmax[1] || hz < g.bmin[2] ||
         lz > g.bmax[2] || !(qx == qx) || !(qy == qy) || !(qz == qz))
@@ -119,8 +138,8 @@ __device__ __forceinline__ void nn_search(const Grid& g, const float4* __restric
     const int x0 = cell1(lx, g.ox, g.inv_c, g.nx), x1 = cell1(hx, g.ox, g.inv_c, g.nx);
     const int y0 = cell1(ly, g.oy, g.inv_c, g.ny), y1 = cell1(hy, g.oy, g.inv_c, g.ny);
     const int z0 = cell1(lz, g.oz, g.inv_c, g.nz), z1 = cell1(hz, g.oz, g.inv_c, g.nz);
-    const int cx = cell1(qx, g.ox, g.inv_c, g.nx);
-    const int cy = cell1(qy, g.oy, g.inv_c, g.ny), cz = cell1(qz, g.oz, g.inv_c, g.nz);
+    const int cx = cell1(gx, g.ox, g.inv_c, g.nx);
+    const int cy = cell1(gy, g.oy, g.inv_c, g.ny), cz = cell1(gz, g.oz, g.inv_c, g.nz);
     if (!PRUNE) {
         for (int iz = z0; iz <= z1; ++iz)
             for (int iy = y0; iy <= y1; ++iy) {
@@ -132,24 +151,24 @@ __device__ __forceinline__ void nn_search(const Grid& g, const float4* __restric
     {
         const int row = (cz * g.ny + cy) * g.nx;
         scan_range(pts, cs[row + cx], cs[row + cx + 1], qx, qy, qz, b);   // own cell
-        scan_row(g, pts, cs, row, x0, x1, cx, 0.f, qx, qy, qz, b);         // rest of the own row
+        scan_row(g, pts, cs, row, x0, x1, cx, 0.f, gx, qx, qy, qz, b);     // rest of the own row
     }
     for (int iz = z0; iz <= z1; ++iz) {
-        float gz = 0.f;
-        if (iz > cz) gz = (g.oz + (float)iz * g.c) - qz - g.tol;
-        else if (iz < cz) gz = qz - (g.oz + (float)(iz + 1) * g.c) - g.tol;
-        gz = fmaxf(gz, 0.f);
-        gz *= gz;
-        if (gz > b.d) continue;
+        float dz = 0.f;
+        if (iz > cz) dz = (g.oz + (float)iz * g.c) - gz - g.tol;
+        else if (iz < cz) dz = gz - (g.oz + (float)(iz + 1) * g.c) - g.tol;
+        dz = fmaxf(dz, 0.f);
+        dz *= dz;
+        if (dz > b.d) continue;
         for (int iy = y0; iy <= y1; ++iy) {
             if (iy == cy && iz == cz) continue;
-            float gy = 0.f;
-            if (iy > cy) gy = (g.oy + (float)iy * g.c) - qy - g.tol;
-            else if (iy < cy) gy = qy - (g.oy + (float)(iy + 1) * g.c) - g.tol;
-            gy = fmaxf(gy, 0.f);
-            const float gap2 = fmaf(gy, gy, gz);
+            float dy = 0.f;
+            if (iy > cy) dy = (g.oy + (float)iy * g.c) - gy - g.tol;
+            else if (iy < cy) dy = gy - (g.oy + (float)(iy + 1) * g.c) - g.tol;
+            dy = fmaxf(dy, 0.f);
+            const float gap2 = fmaf(dy, dy, dz);
             if (gap2 > b.d) continue;  // strict: keeps exact ties reachable
-            scan_row(g, pts, cs, (iz * g.ny + iy) * g.nx, x0, x1, -1, gap2, qx, qy, qz, b);
+            scan_row(g, pts, cs, (iz * g.ny + iy) * g.nx, x0, x1, -1, gap2, gx, qx, qy, qz, b);
         }
     }
 }
@@ -168,211 +187,51 @@ __device__ __forceinline__ void nn_search_two_pass(const Grid& g, const float4* 
     b.j = -1;
     b.idx = 0x7fffffff;
     b.x = b.y = b.z = 0.f;
-    if (hi_bound(qx, rr) < g.bmin[0] || lo_bound(qx, rr) > g.bmax[0] || hi_bound(qy, rr) < g.bmin[1] ||
-        lo_bound(qy, rr) > g.bmax[1] || hi_bound(qz, rr) < g.bmin[2] || lo_bound(qz, rr) > g.bmax[2] ||
+    float gx, gy, gz;
+    to_grid(g, qx, qy, qz, gx, gy, gz);
+    if (hi_bound(gx, rr) < g.bmin[0] || lo_bound(gx, rr) > g.bmax[0] || hi_bound(gy, rr) < g.bmin[1] ||
+        lo_bound(gy, rr) > g.bmax[1] || hi_bound(gz, rr) < g.bmin[2] || lo_bound(gz, rr) > g.bmax[2] ||
         !(qx == qx) || !(qy == qy) || !(qz == qz))
         return;
-    const int x0 = cell1(lo_bound(qx, r1), g.ox, g.inv_c, g.nx), x1 = cell1(hi_bound(qx, r1), g.ox, g.inv_c, g.nx);
-    const int y0 = cell1(lo_bound(qy, r1), g.oy, g.inv_c, g.ny), y1 = cell1(hi_bound(qy, r1), g.oy, g.inv_c, g.ny);
-    const int z0 = cell1(lo_bound(qz, r1), g.oz, g.inv_c, g.nz), z1 = cell1(hi_bound(qz, r1), g.oz, g.inv_c, g.nz);
-    if (y1 - y0 <= 2 && z1 - z0 <= 2) {
-        // the usual case (r1 == cell size): at most 3 x 3 rows.  All 18 CSR offsets are
-        // requested before the first candidate is touched (memory-level parallelism instead
-        // of nine serialised L2 round trips); rows outside the box get an empty range.
-        unsigned rs[9], re[9];
+    const int x0 = cell1(lo_bound(gx, r1), g.ox, g.inv_c, g.nx), x1 = cell1(hi_bound(gx, r1), g.ox, g.inv_c, g.nx);
+    const int y0 = cell1(lo_bound(gy, r1), g.oy, g.inv_c, g.ny), y1 = cell1(hi_bound(gy, r1), g.oy, g.inv_c, g.ny);
+    const int z0 = cell1(lo_bound(gz, r1), g.oz, g.inv_c, g.nz), z1 = cell1(hi_bound(gz, r1), g.oz, g.inv_c, g.nz);
+    if (z1 - z0 <= 2) {
+        // SLABS.  For every grid-z of the box, the cells [all grid-x] x [y0..y1] are ONE contiguous
+        // run of the table (x fastest, then y).  Grid-x is the cloud's thin direction, so for
+        // surface-like data the run holds just the handful of points of 3 cell columns — the same
+        // candidates as nine per-row runs, in a third of the loops and a third of the CSR loads.
+        // A slab that turns out long (volumetric data) is scanned row by row over [x0..x1] instead.
+        unsigned ss[3], se[3];
 #pragma unroll
-        for (int dz = 0; dz < 3; ++dz)
-#pragma unroll
-            for (int dy = 0; dy < 3; ++dy) {
-                const bool on = (z0 + dz <= z1) && (y0 + dy <= y1);
-                const int row = (min(z0 + dz, z1) * g.ny + min(y0 + dy, y1)) * g.nx;
-                const unsigned s = __ldg(&cs[row + x0]), e = __ldg(&cs[row + x1 + 1]);
-                rs[dz * 3 + dy] = s;
-                re[dz * 3 + dy] = on ? e : s;
-            }
-#pragma unroll
-        for (int k = 0; k < 9; ++k) scan_range(pts, rs[k], re[k], qx, qy, qz, b);
-    } else {
-        for (int iz = z0; iz <= z1; ++iz)
-            for (int iy = y0; iy <= y1; ++iy) {
-                const int row = (iz * g.ny + iy) * g.nx;
-                scan_range(pts, cs[row + x0], cs[row + x1 + 1], qx, qy, qz, b);
-            }
-    }
-    if (b.j >= 0 && b.d <= r1_accept2) return;
-    nn_search<true>(g, pts, cs, qx, qy, qz, rr, thr, b);
-}
-
-// Same two-pass search, with pass 1 FLATTENED: the (up to) nine row ranges of the box are
-// parked in shared memory (column threadIdx.x of s_rng[18][blockDim]) and walked by ONE loop
-// per lane.  A warp then runs max_lane(total candidates) iterations instead of
-// sum_rows(max_lane(row candidates)) — the lanes of a warp look at different rows, so the
-// row-by-row version leaves most lanes idle most of the time (ncu: 14 of 32 lanes active).
-template <int BLOCK>
-__device__ __forceinline__ void nn_search_two_pass_flat(const Grid& g, const float4* __restrict__ pts,
-                                                        const unsigned* __restrict__ cs, float qx, float qy,
-                                                        float qz, float r1, float r1_accept2, float rr, float thr,
-                                                        unsigned (*s_rng)[BLOCK], Best& b) {
-    b.d = thr;
-    b.j = -1;
-    b.idx = 0x7fffffff;
-    b.x = b.y = b.z = 0.f;
-    if (hi_bound(qx, rr) < g.bmin[0] || lo_bound(qx, rr) > g.bmax[0] || hi_bound(qy, rr) < g.bmin[1] ||
-        lo_bound(qy, rr) > g.bmax[1] || hi_bound(qz, rr) < g.bmin[2] || lo_bound(qz, rr) > g.bmax[2] ||
-        !(qx == qx) || !(qy == qy) || !(qz == qz))
-        return;
-    const int x0 = cell1(lo_bound(qx, r1), g.ox, g.inv_c, g.nx), x1 = cell1(hi_bound(qx, r1), g.ox, g.inv_c, g.nx);
-    const int y0 = cell1(lo_bound(qy, r1), g.oy, g.inv_c, g.ny), y1 = cell1(hi_bound(qy, r1), g.oy, g.inv_c, g.ny);
-    const int z0 = cell1(lo_bound(qz, r1), g.oz, g.inv_c, g.nz), z1 = cell1(hi_bound(qz, r1), g.oz, g.inv_c, g.nz);
-    if (y1 - y0 <= 2 && z1 - z0 <= 2) {
-        const int t = threadIdx.x;
-        unsigned rs[9], re[9];
-#pragma unroll
-        for (int dz = 0; dz < 3; ++dz)
-#pragma unroll
-            for (int dy = 0; dy < 3; ++dy) {
-                const bool on = (z0 + dz <= z1) && (y0 + dy <= y1);
-                const int row = (min(z0 + dz, z1) * g.ny + min(y0 + dy, y1)) * g.nx;
-                const unsigned s = __ldg(&cs[row + x0]), e = __ldg(&cs[row + x1 + 1]);
-                rs[dz * 3 + dy] = s;
-                re[dz * 3 + dy] = on ? e : s;
-            }
-#pragma unroll
-        for (int k = 1; k < 9; ++k) {   // row 0 stays in registers
-            s_rng[2 * k][t] = rs[k];
-            s_rng[2 * k + 1][t] = re[k];
+        for (int dz = 0; dz < 3; ++dz) {
+            const bool on = z0 + dz <= z1;
+            const int plane = min(z0 + dz, z1) * g.ny;
+            const unsigned s = __ldg(&cs[(plane + y0) * g.nx]), e = __ldg(&cs[(plane + y1 + 1) * g.nx]);
+            ss[dz] = s;
+            se[dz] = on ? e : s;
         }
-        unsigned j = rs[0], e = re[0];
-        int row = 0;
-        for (;;) {
-            while (j >= e) {
-                if (++row >= 9) goto pass1_done;
-                j = s_rng[2 * row][t];
-                e = s_rng[2 * row + 1][t];
-            }
-            const float4 c = __ldg(&pts[j]);
-            const float dx = c.x - qx, dy = c.y - qy, dz = c.z - qz;
-            const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-            const int idx = __float_as_int(c.w);
-            if (d < b.d || (d == b.d && idx < b.idx)) {
-                b.d = d;
-                b.j = (int)j;
-                b.idx = idx;
-                b.x = c.x;
-                b.y = c.y;
-                b.z = c.z;
-            }
-            ++j;
-        }
-    pass1_done:;
-    } else {
-        for (int iz = z0; iz <= z1; ++iz)
-            for (int iy = y0; iy <= y1; ++iy) {
-                const int row = (iz * g.ny + iy) * g.nx;
-                scan_range(pts, cs[row + x0], cs[row + x1 + 1], qx, qy, qz, b);
-            }
-    }
-    if (b.j >= 0 && b.d <= r1_accept2) return;
-    nn_search<true>(g, pts, cs, qx, qy, qz, rr, thr, b);
-}
-
-// ---------------------------------------------------------------------------
-// Group search: G consecutive lanes (spatially neighbouring queries of the cell-sorted
-// source) share ONE candidate list, so every lane of the group runs the same loops with the
-// same addresses (no intra-group divergence, broadcast loads):
-//   stage A  all points of the cells that contain the group's queries ("core box")
-//   stage B  whatever else lies within sqrt(best) of any lane (union of the lanes' boxes
-//            for their current best distance), minus the core box
-// Every point within a lane's best distance is visited, so the result is the exact nearest
-// neighbour (ties -> lower index), identical to nn_search().  If the group is not compact
-// (its union box is much larger than a single lane's), each lane falls back to nn_search().
-// Must be called by all 32 lanes (inactive lanes pass valid = false).
-// Out-of-line copy of the per-lane search for the rare non-compact group (keeps the hot
-// path's register budget).
-__device__ __noinline__ void nn_search_slow(const Grid& g, const float4* __restrict__ pts,
-                                            const unsigned* __restrict__ cs, float qx, float qy, float qz,
-                                            float rr, float thr, Best& b) {
-    nn_search<true>(g, pts, cs, qx, qy, qz, rr, thr, b);
-}
-
-// Shuffles name only the G lanes of the group in their mask: groups of one warp take
-// different paths (early return of non-compact groups, different trip counts), so a
-// full-warp mask would dead-lock.
-template <int G>
-__device__ __forceinline__ unsigned group_mask() {
-    return G >= 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
-}
-
-template <int G>
-__device__ __forceinline__ void group_minmax(int& lo, int& hi) {
-    const unsigned m = group_mask<G>();
 #pragma unroll
-    for (int o = 1; o < G; o <<= 1) {
-        lo = min(lo, __shfl_xor_sync(m, lo, o));
-        hi = max(hi, __shfl_xor_sync(m, hi, o));
-    }
-}
-
-template <int G>
-__device__ __forceinline__ void nn_search_group(const Grid& g, const float4* __restrict__ pts,
-                                                const unsigned* __restrict__ cs, bool valid, float qx, float qy,
-                                                float qz, float rr, float thr, Best& b) {
-    b.d = thr;
-    b.j = -1;
-    b.idx = 0x7fffffff;
-    b.x = b.y = b.z = 0.f;
-    const float lx = lo_bound(qx, rr), hx = hi_bound(qx, rr);
-    const float ly = lo_bound(qy, rr), hy = hi_bound(qy, rr);
-    const float lz = lo_bound(qz, rr), hz = hi_bound(qz, rr);
-    const bool inside = valid && !(hx < g.bmin[0] || lx > g.bmax[0] || hy < g.bmin[1] || ly > g.bmax[1] ||
-                                   hz < g.bmin[2] || lz > g.bmax[2] || !(qx == qx) || !(qy == qy) || !(qz == qz));
-    const int kBig = 0x3fffffff;
-    // ---- stage A: the cells holding the group's queries
-    const int cx = cell1(qx, g.ox, g.inv_c, g.nx), cy = cell1(qy, g.oy, g.inv_c, g.ny),
-              cz = cell1(qz, g.oz, g.inv_c, g.nz);
-    int CX0 = inside ? cx : kBig, CX1 = inside ? cx : -kBig;
-    int CY0 = inside ? cy : kBig, CY1 = inside ? cy : -kBig;
-    int CZ0 = inside ? cz : kBig, CZ1 = inside ? cz : -kBig;
-    group_minmax<G>(CX0, CX1);
-    group_minmax<G>(CY0, CY1);
-    group_minmax<G>(CZ0, CZ1);
-    // compactness guard (group-uniform): a group straddling the end of a cell row would drag
-    // in a huge box; such groups use the per-lane search instead
-    const bool compact = CX0 <= CX1 && (CX1 - CX0) <= 6 && (CY1 - CY0) <= 3 && (CZ1 - CZ0) <= 3;
-    if (!compact) {
-        if (inside) nn_search<true>(g, pts, cs, qx, qy, qz, rr, thr, b);
-        return;
-    }
-    for (int iz = CZ0; iz <= CZ1; ++iz)
-        for (int iy = CY0; iy <= CY1; ++iy) {
-            const int row = (iz * g.ny + iy) * g.nx;
-            scan_range(pts, cs[row + CX0], cs[row + CX1 + 1], qx, qy, qz, b);
-        }
-    // ---- stage B: union of the lanes' boxes for their current best distance
-    const float e = sqrtf(b.d) * 1.00001f;   // b.d <= thr; the slack covers sqrt/rounding
-    int UX0 = kBig, UX1 = -kBig, UY0 = kBig, UY1 = -kBig, UZ0 = kBig, UZ1 = -kBig;
-    if (inside) {
-        UX0 = cell1(lo_bound(qx, e), g.ox, g.inv_c, g.nx);
-        UX1 = cell1(hi_bound(qx, e), g.ox, g.inv_c, g.nx);
-        UY0 = cell1(lo_bound(qy, e), g.oy, g.inv_c, g.ny);
-        UY1 = cell1(hi_bound(qy, e), g.oy, g.inv_c, g.ny);
-        UZ0 = cell1(lo_bound(qz, e), g.oz, g.inv_c, g.nz);
-        UZ1 = cell1(hi_bound(qz, e), g.oz, g.inv_c, g.nz);
-    }
-    group_minmax<G>(UX0, UX1);
-    group_minmax<G>(UY0, UY1);
-    group_minmax<G>(UZ0, UZ1);
-    for (int iz = UZ0; iz <= UZ1; ++iz)
-        for (int iy = UY0; iy <= UY1; ++iy) {
-            const int row = (iz * g.ny + iy) * g.nx;
-            const bool core_row = iz >= CZ0 && iz <= CZ1 && iy >= CY0 && iy <= CY1;
-            if (!core_row) {
-                scan_range(pts, cs[row + UX0], cs[row + UX1 + 1], qx, qy, qz, b);
+        for (int dz = 0; dz < 3; ++dz) {
+            if (se[dz] - ss[dz] <= kSlabMax) {
+                scan_range(pts, ss[dz], se[dz], qx, qy, qz, b);
             } else {
-                if (UX0 < CX0) scan_range(pts, cs[row + UX0], cs[row + CX0], qx, qy, qz, b);
-                if (UX1 > CX1) scan_range(pts, cs[row + CX1 + 1], cs[row + UX1 + 1], qx, qy, qz, b);
+                const int plane = (z0 + dz) * g.ny;
+                for (int iy = y0; iy <= y1; ++iy) {
+                    const int row = (plane + iy) * g.nx;
+                    scan_range(pts, cs[row + x0], cs[row + x1 + 1], qx, qy, qz, b);
+                }
             }
         }
+    } else {
+        for (int iz = z0; iz <= z1; ++iz)
+            for (int iy = y0; iy <= y1; ++iy) {
+                const int row = (iz * g.ny + iy) * g.nx;
+                scan_range(pts, cs[row + x0], cs[row + x1 + 1], qx, qy, qz, b);
+            }
+    }
+    if (b.j >= 0 && b.d <= r1_accept2) return;
+    nn_search<true>(g, pts, cs, qx, qy, qz, rr, thr, b);
 }
 
 }  // namespace o3db

@@ -5,6 +5,7 @@
 // No CPU fallback: every entry point needs a CUDA device.
 #include <cfloat>
 #include <cstddef>
+#include <algorithm>
 #include <climits>
 #include <cmath>
 #include <new>
@@ -26,22 +27,19 @@ static constexpr int kFlushEvery = 16;
 #define ICP_CELL_SCALE 0.5
 #endif
 static constexpr double kDefaultCellScale = ICP_CELL_SCALE;
-#ifndef ICP_GROUP
-#define ICP_GROUP 0   // 0: two-pass per-lane search (default), 1: pruned per-lane search, 2..32: group search
+#ifndef ICP_TWO_PASS
+#define ICP_TWO_PASS 1   // 1: slab/two-pass search on the fine grid (default), 0: pruned single-pass search
 #endif
+static constexpr bool kTwoPass = ICP_TWO_PASS != 0;
 #ifndef ICP_MIN_BLOCKS
 #define ICP_MIN_BLOCKS 3
 #endif
 #ifndef ICP_ACC_SMEM
 #define ICP_ACC_SMEM 0
 #endif
-#ifndef ICP_FLAT
-#define ICP_FLAT 0   // 1: flattened pass-1 scan (measured slower on B200: one load in flight per lane)
-#endif
 #ifndef ICP_DEFAULT_VARIANT
 #define ICP_DEFAULT_VARIANT 1
 #endif
-static constexpr int kGroup = ICP_GROUP;   // lanes sharing one candidate list in the fused ICP search (0 = per-lane search)
 
 // --------------------------------------------------------------------- bbox
 
@@ -104,7 +102,9 @@ __host__ __device__ inline int64_t tiled_key_space(int nx, int ny, int nz) {
     return (int64_t)((nx + kTileX - 1) / kTileX) * ((ny + kTileY - 1) / kTileY) * ((nz + kTileZ - 1) / kTileZ) *
            (kTileX * kTileY * kTileZ);
 }
-__device__ __forceinline__ unsigned cell_key_tiled(const Grid& g, float x, float y, float z) {
+__device__ __forceinline__ unsigned cell_key_tiled(const Grid& g, float rx, float ry, float rz) {
+    float x, y, z;
+    to_grid(g, rx, ry, rz, x, y, z);
     const int ix = cell1(x, g.ox, g.inv_c, g.nx), iy = cell1(y, g.oy, g.inv_c, g.ny), iz = cell1(z, g.oz, g.inv_c, g.nz);
     const int ntx = (g.nx + kTileX - 1) / kTileX, nty = (g.ny + kTileY - 1) / kTileY;
     const int tile = ((iz / kTileZ) * nty + iy / kTileY) * ntx + ix / kTileX;
@@ -289,26 +289,37 @@ static int grid_from_bbox(const float mn[3], const float mx[3], double radius, d
         ext[a] = std::max(0.0, (double)mx[a] - (double)mn[a]);
         maxabs = std::max(maxabs, std::max(std::fabs((double)mn[a]), std::fabs((double)mx[a])));
     }
+    // grid axis order: fastest = the real axis with the smallest extent (ties: z, then y),
+    // slowest = the one with the largest
+    int order[3] = {2, 1, 0};
+    std::stable_sort(order, order + 3, [&](int a, int b) { return ext[a] < ext[b]; });
+    for (int k = 0; k < 3; ++k) g->ax[k] = order[k];
     for (;;) {
-        double nx = std::floor(ext[0] / c) + 1, ny = std::floor(ext[1] / c) + 1, nz = std::floor(ext[2] / c) + 1;
-        if (nx <= kMaxCellsPerAxis && ny <= kMaxCellsPerAxis && nz <= kMaxCellsPerAxis &&
-            nx * ny * nz <= (double)kMaxCells) {
-            g->nx = (int)nx;
-            g->ny = (int)ny;
-            g->nz = (int)nz;
+        double n[3];
+        bool ok = true;
+        double prod = 1;
+        for (int k = 0; k < 3; ++k) {
+            n[k] = std::floor(ext[order[k]] / c) + 1;
+            ok = ok && n[k] <= kMaxCellsPerAxis;
+            prod *= n[k];
+        }
+        if (ok && prod <= (double)kMaxCells) {
+            g->nx = (int)n[0];
+            g->ny = (int)n[1];
+            g->nz = (int)n[2];
             break;
         }
         c *= 1.25;
     }
     g->c = (float)c;
     g->inv_c = 1.0f / g->c;
-    g->ox = mn[0];
-    g->oy = mn[1];
-    g->oz = mn[2];
+    g->ox = mn[order[0]];
+    g->oy = mn[order[1]];
+    g->oz = mn[order[2]];
     g->tol = (float)(c * 2e-3 + maxabs * 1e-6);
-    for (int a = 0; a < 3; ++a) {
-        g->bmin[a] = mn[a];
-        g->bmax[a] = mx[a];
+    for (int k = 0; k < 3; ++k) {
+        g->bmin[k] = mn[order[k]];
+        g->bmax[k] = mx[order[k]];
     }
     *ncell = (int64_t)g->nx * g->ny * g->nz;
     return O3DB_OK;
@@ -394,9 +405,11 @@ hybrid_search_knn_kernel(Grid g, const float4* __restrict__ pts, const unsigned*
     int bi[kMaxKnn];
     float bd[kMaxKnn];
     int c = 0;
-    const float lx = lo_bound(qx, rr), hx = hi_bound(qx, rr);
-    const float ly = lo_bound(qy, rr), hy = hi_bound(qy, rr);
-    const float lz = lo_bound(qz, rr), hz = hi_bound(qz, rr);
+    float gx, gy, gz;
+    to_grid(g, qx, qy, qz, gx, gy, gz);
+    const float lx = lo_bound(gx, rr), hx = hi_bound(gx, rr);
+    const float ly = lo_bound(gy, rr), hy = hi_bound(gy, rr);
+    const float lz = lo_bound(gz, rr), hz = hi_bound(gz, rr);
     const bool outside = hx < g.bmin[0] || lx > g.bmax[0] || hy < g.bmin[1] || ly > g.bmax[1] ||
                          hz < g.bmin[2] || lz > g.bmax[2] || !(qx == qx) || !(qy == qy) || !(qz == qz);
     if (!outside) {
@@ -898,9 +911,6 @@ icp_iteration_kernel(IcpArgs a) {
     __syncthreads();
     if (MODE == 0 && s_done) return;
 
-#if ICP_FLAT
-    __shared__ unsigned s_rng[18][kThreads];   // per-thread row ranges of the flattened pass-1 scan
-#endif
 #if ICP_ACC_SMEM
     // per-thread accumulators live in shared memory (column tid of s_acc): the 30 values are
     // only in registers while one correspondence is being expanded, which leaves the search
@@ -924,18 +934,10 @@ icp_iteration_kernel(IcpArgs a) {
             a.src[i] = p;
         }
         Best b;
-        if (kGroup > 1) {
-            nn_search_group<(kGroup > 1 ? kGroup : 2)>(a.g, a.tgt, a.cs, live, p.x, p.y, p.z, a.rr, a.thr, b);
-        } else if (kGroup == 1) {
-            b.j = -1;
-            if (live) nn_search<true>(a.g, a.tgt, a.cs, p.x, p.y, p.z, a.rr, a.thr, b);
-        } else {
-            b.j = -1;
-#if ICP_FLAT
-            if (live) nn_search_two_pass_flat<kThreads>(a.g, a.tgt, a.cs, p.x, p.y, p.z, a.r1, a.r1_accept2, a.rr, a.thr, s_rng, b);
-#else
-            if (live) nn_search_two_pass(a.g, a.tgt, a.cs, p.x, p.y, p.z, a.r1, a.r1_accept2, a.rr, a.thr, b);
-#endif
+        b.j = -1;
+        if (live) {
+            if (kTwoPass) nn_search_two_pass(a.g, a.tgt, a.cs, p.x, p.y, p.z, a.r1, a.r1_accept2, a.rr, a.thr, b);
+            else nn_search<true>(a.g, a.tgt, a.cs, p.x, p.y, p.z, a.rr, a.thr, b);
         }
         if (live) {
             if (b.j >= 0) {
@@ -1100,18 +1102,20 @@ icp_iteration_tile_kernel(IcpArgs a) {
             a.src[i] = p;
         }
         // ---- this query's pass-1 cell box and the block's union of them
-        const bool inside = live && !(hi_bound(p.x, a.rr) < g.bmin[0] || lo_bound(p.x, a.rr) > g.bmax[0] ||
-                                      hi_bound(p.y, a.rr) < g.bmin[1] || lo_bound(p.y, a.rr) > g.bmax[1] ||
-                                      hi_bound(p.z, a.rr) < g.bmin[2] || lo_bound(p.z, a.rr) > g.bmax[2] ||
+        float gx, gy, gz;   // the query in grid axis order
+        to_grid(g, p.x, p.y, p.z, gx, gy, gz);
+        const bool inside = live && !(hi_bound(gx, a.rr) < g.bmin[0] || lo_bound(gx, a.rr) > g.bmax[0] ||
+                                      hi_bound(gy, a.rr) < g.bmin[1] || lo_bound(gy, a.rr) > g.bmax[1] ||
+                                      hi_bound(gz, a.rr) < g.bmin[2] || lo_bound(gz, a.rr) > g.bmax[2] ||
                                       !(p.x == p.x) || !(p.y == p.y) || !(p.z == p.z));
         int x0 = kBig, x1 = -kBig, y0 = kBig, y1 = -kBig, z0 = kBig, z1 = -kBig;
         if (inside) {
-            x0 = cell1(lo_bound(p.x, a.r1), g.ox, g.inv_c, g.nx);
-            x1 = cell1(hi_bound(p.x, a.r1), g.ox, g.inv_c, g.nx);
-            y0 = cell1(lo_bound(p.y, a.r1), g.oy, g.inv_c, g.ny);
-            y1 = cell1(hi_bound(p.y, a.r1), g.oy, g.inv_c, g.ny);
-            z0 = cell1(lo_bound(p.z, a.r1), g.oz, g.inv_c, g.nz);
-            z1 = cell1(hi_bound(p.z, a.r1), g.oz, g.inv_c, g.nz);
+            x0 = cell1(lo_bound(gx, a.r1), g.ox, g.inv_c, g.nx);
+            x1 = cell1(hi_bound(gx, a.r1), g.ox, g.inv_c, g.nx);
+            y0 = cell1(lo_bound(gy, a.r1), g.oy, g.inv_c, g.ny);
+            y1 = cell1(hi_bound(gy, a.r1), g.oy, g.inv_c, g.ny);
+            z0 = cell1(lo_bound(gz, a.r1), g.oz, g.inv_c, g.nz);
+            z1 = cell1(hi_bound(gz, a.r1), g.oz, g.inv_c, g.nz);
         }
         if (threadIdx.x < 6) sm.bbox[threadIdx.x] = (threadIdx.x & 1) ? -kBig : kBig;
         __syncthreads();
@@ -1531,7 +1535,7 @@ void o3db_icp_destroy(o3db_icp* c) {
     if (c->partials) cudaFreeAsync(c->partials, 0);
     if (c->per_iter) cudaFreeAsync(c->per_iter, 0);
     if (c->st) cudaFreeAsync(c->st, 0);
-    if (c->h_st) cudaFreeHost(c->h_st);
+    if (c->h_st) pinned_release(c->h_st);
     delete c;
 }
 
@@ -1611,7 +1615,13 @@ int o3db_icp_create(const float* source_dev, int64_t n, const float* target_dev,
     ICP_CUDA(cudaMallocAsync(&c->partials, (size_t)c->grid_blocks * kSumStride * sizeof(double), st));
     ICP_CUDA(cudaMallocAsync(&c->per_iter, (size_t)std::max(1, options->max_iteration) * 2 * sizeof(double), st));
     ICP_CUDA(cudaMallocAsync(&c->st, sizeof(IcpState), st));
-    ICP_CUDA(cudaMallocHost(&c->h_st, sizeof(IcpState)));
+    static_assert(sizeof(IcpState) <= 4096, "IcpState must fit a pinned block");
+    c->h_st = (IcpState*)pinned_acquire(sizeof(IcpState));
+    if (!c->h_st) {
+        set_last_error("pinned host allocation failed");
+        o3db_icp_destroy(c);
+        return O3DB_ERR_CUDA;
+    }
     ICP_CUDA(cudaMemsetAsync(c->partials, 0, (size_t)c->grid_blocks * kSumStride * sizeof(double), st));
     ICP_CUDA(cudaMemsetAsync(c->per_iter, 0, (size_t)std::max(1, options->max_iteration) * 2 * sizeof(double), st));
     // sort order of the source: target-grid cell of the initially transformed point

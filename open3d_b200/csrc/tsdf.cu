@@ -571,10 +571,14 @@ struct o3db_vbg {
     // frustum-only table for the stand-alone GetUniqueBlockCoordinates
     int* ftable = nullptr;
     unsigned fbuckets = 0;
-    // staging for host-image entry point
-    void* d_depth = nullptr;
-    void* d_color = nullptr;
-    size_t d_depth_bytes = 0, d_color_bytes = 0;
+    // staging for the host-image entry point: two slots, uploads on a private copy stream so
+    // that frame f+1's H2D overlaps frame f's kernels
+    void* d_depth[2] = {nullptr, nullptr};
+    void* d_color[2] = {nullptr, nullptr};
+    size_t d_depth_bytes[2] = {0, 0}, d_color_bytes[2] = {0, 0};
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
+    int64_t host_frames = 0;
     // host mirrors: size_dev[0..15] is copied to pinned memory after every fused frame
     // (ring of 2) so that capacity can be managed without a per-frame host sync.
     int* h_pinned = nullptr;       // [0..15] synchronous read-back, [16..47] ring of 2 x 16
@@ -803,7 +807,10 @@ int o3db_vbg_create(float voxel_size, int block_resolution, int64_t block_count,
     cudaError_t e = cudaSuccess;
     if (rc == O3DB_OK) e = cudaMallocAsync(&v->size_dev, 16 * sizeof(int), st);
     if (rc == O3DB_OK && e == cudaSuccess) e = cudaMemsetAsync(v->size_dev, 0, 16 * sizeof(int), st);
-    if (rc == O3DB_OK && e == cudaSuccess) e = cudaMallocHost(&v->h_pinned, 48 * sizeof(int));
+    if (rc == O3DB_OK && e == cudaSuccess) {
+        v->h_pinned = (int*)pinned_acquire(48 * sizeof(int));
+        if (!v->h_pinned) e = cudaErrorMemoryAllocation;
+    }
     if (rc == O3DB_OK && e == cudaSuccess) e = cudaEventCreateWithFlags(&v->ev[0], cudaEventDisableTiming);
     if (rc == O3DB_OK && e == cudaSuccess) e = cudaEventCreateWithFlags(&v->ev[1], cudaEventDisableTiming);
     if (rc != O3DB_OK || e != cudaSuccess) {
@@ -825,14 +832,20 @@ void o3db_vbg_destroy(o3db_vbg* v) {
     if (!v) return;
     cudaDeviceSynchronize();
     void* ptrs[] = {v->table, v->keys, v->stamp, v->size_dev, v->tsdf, v->weight, v->color, v->cand_keys,
-                    v->exist_list, v->new_list, v->frame_slots, v->ftable, v->d_depth, v->d_color};
+                    v->exist_list, v->new_list, v->frame_slots, v->ftable, v->d_depth[0], v->d_depth[1],
+                    v->d_color[0], v->d_color[1]};
     for (void* p : ptrs)
         if (p) cudaFree(p);
-    if (v->h_pinned) cudaFreeHost(v->h_pinned);
+    if (v->h_pinned) pinned_release(v->h_pinned);
     for (auto& e : v->ev)
         if (e) cudaEventDestroy(e);
     for (auto& e : v->prof_ev)
         if (e) cudaEventDestroy(e);
+    for (int i = 0; i < 2; ++i) {
+        if (v->copied[i]) cudaEventDestroy(v->copied[i]);
+        if (v->consumed[i]) cudaEventDestroy(v->consumed[i]);
+    }
+    if (v->copy_stream) cudaStreamDestroy(v->copy_stream);
     delete v;
 }
 
@@ -1086,20 +1099,56 @@ int o3db_vbg_integrate_frame_host(o3db_vbg* v, const void* depth_host, int depth
     cudaStream_t st = (cudaStream_t)stream;
     const size_t dbytes = (size_t)rows * cols * (depth_dtype == O3DB_DEPTH_U16 ? 2 : 4);
     const size_t cbytes = color_host ? (size_t)rows * cols * 3 * (color_dtype == O3DB_COLOR_U8 ? 1 : 4) : 0;
-    if (dbytes > v->d_depth_bytes) {
-        if (v->d_depth) cudaFreeAsync(v->d_depth, st);
-        O3DB_CUDA_CHECK(cudaMallocAsync(&v->d_depth, dbytes, st));
-        v->d_depth_bytes = dbytes;
+    if (!v->copy_stream) {
+        O3DB_CUDA_CHECK(cudaStreamCreateWithFlags(&v->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            O3DB_CUDA_CHECK(cudaEventCreateWithFlags(&v->copied[i], cudaEventDisableTiming));
+            O3DB_CUDA_CHECK(cudaEventCreateWithFlags(&v->consumed[i], cudaEventDisableTiming));
+        }
     }
-    if (cbytes > v->d_color_bytes) {
-        if (v->d_color) cudaFreeAsync(v->d_color, st);
-        O3DB_CUDA_CHECK(cudaMallocAsync(&v->d_color, cbytes, st));
-        v->d_color_bytes = cbytes;
+    const int slot = (int)(v->host_frames & 1);
+    // the slot is free once the kernels of the frame that used it two calls ago are done
+    O3DB_CUDA_CHECK(cudaStreamWaitEvent(v->copy_stream, v->consumed[slot], 0));
+    if (dbytes > v->d_depth_bytes[slot]) {
+        O3DB_CUDA_CHECK(cudaStreamSynchronize(v->copy_stream));
+        if (v->d_depth[slot]) O3DB_CUDA_CHECK(cudaFree(v->d_depth[slot]));
+        O3DB_CUDA_CHECK(cudaMalloc(&v->d_depth[slot], dbytes));
+        v->d_depth_bytes[slot] = dbytes;
     }
-    O3DB_CUDA_CHECK(cudaMemcpyAsync(v->d_depth, depth_host, dbytes, cudaMemcpyHostToDevice, st));
-    if (cbytes) O3DB_CUDA_CHECK(cudaMemcpyAsync(v->d_color, color_host, cbytes, cudaMemcpyHostToDevice, st));
-    return o3db_vbg_integrate_frame(v, v->d_depth, depth_dtype, cbytes ? v->d_color : nullptr, color_dtype, rows, cols, K,
-                                    E, depth_scale, depth_max, trunc_mult, st);
+    if (cbytes > v->d_color_bytes[slot]) {
+        O3DB_CUDA_CHECK(cudaStreamSynchronize(v->copy_stream));
+        if (v->d_color[slot]) O3DB_CUDA_CHECK(cudaFree(v->d_color[slot]));
+        O3DB_CUDA_CHECK(cudaMalloc(&v->d_color[slot], cbytes));
+        v->d_color_bytes[slot] = cbytes;
+    }
+    O3DB_CUDA_CHECK(cudaMemcpyAsync(v->d_depth[slot], depth_host, dbytes, cudaMemcpyHostToDevice, v->copy_stream));
+    if (cbytes) O3DB_CUDA_CHECK(cudaMemcpyAsync(v->d_color[slot], color_host, cbytes, cudaMemcpyHostToDevice, v->copy_stream));
+    O3DB_CUDA_CHECK(cudaEventRecord(v->copied[slot], v->copy_stream));
+    O3DB_CUDA_CHECK(cudaStreamWaitEvent(st, v->copied[slot], 0));
+    const int rc2 = o3db_vbg_integrate_frame(v, v->d_depth[slot], depth_dtype, cbytes ? v->d_color[slot] : nullptr, color_dtype,
+                                             rows, cols, K, E, depth_scale, depth_max, trunc_mult, st);
+    O3DB_CUDA_CHECK(cudaEventRecord(v->consumed[slot], st));
+    v->host_frames += 1;
+    return rc2;
+}
+
+int o3db_vbg_integrate_sequence(o3db_vbg* v, int64_t n_frames, const void* const* depth_ptrs, int depth_dtype,
+                                const void* const* color_ptrs, int color_dtype, int rows, int cols,
+                                const double K[9], const double* extrinsics, float depth_scale, float depth_max,
+                                float trunc_mult, int host_images, void* stream) {
+    O3DB_REQUIRE(v != nullptr && n_frames >= 0 && (n_frames == 0 || (depth_ptrs && extrinsics && K)),
+                 "o3db_vbg_integrate_sequence: bad arguments");
+    for (int64_t f = 0; f < n_frames; ++f) {
+        const void* c = color_ptrs ? color_ptrs[f] : nullptr;
+        const int rc = host_images ? o3db_vbg_integrate_frame_host(v, depth_ptrs[f], depth_dtype, c, color_dtype, rows,
+                                                                   cols, K, extrinsics + 16 * f, depth_scale,
+                                                                   depth_max, trunc_mult, stream)
+                                   : o3db_vbg_integrate_frame(v, depth_ptrs[f], depth_dtype, c, color_dtype, rows, cols, K,
+                                                              extrinsics + 16 * f, depth_scale, depth_max, trunc_mult,
+                                                              stream);
+        if (rc != O3DB_OK) return rc;
+    }
+    return O3DB_OK;
 }
 
 int o3db_vbg_profile(o3db_vbg* v, int enable) {

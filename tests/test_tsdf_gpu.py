@@ -252,3 +252,47 @@ def test_idempotent_weight_property_full_sequence(o3d):
     w5 = model.voxel_grid.attribute("weight")[:n]
     assert torch.equal(w5.int(), w1.int() * 5) and set(w1.int().unique().tolist()) == {0, 1}
     torch.testing.assert_close(model.voxel_grid.attribute("tsdf")[:n], t1, rtol=0, atol=2e-6)
+
+
+def test_integrate_sequence_equals_per_frame_calls(o3d):
+    """o3db_vbg_integrate_sequence is the same kernels in the same order: bit-identical volume."""
+    import ctypes as C
+    from open3d_b200 import _lib as L
+    frames = [_frame(f, color=True) for f in (0, 5, 10, 15)]
+    K = np.ascontiguousarray(PRIMESENSE_K)
+
+    def volume(use_sequence, host):
+        v = C.c_void_p()
+        L.check(L.lib.o3db_vbg_create(VOXEL, RES, 6000, 1, 0, C.byref(v)))
+        deps = [torch.from_numpy(f[2]) for f in frames]
+        cols = [torch.from_numpy(f[3]) for f in frames]
+        if host:
+            deps, cols = [d.pin_memory() for d in deps], [c.pin_memory() for c in cols]
+        else:
+            deps, cols = [d.cuda() for d in deps], [c.cuda() for c in cols]
+        exts = np.ascontiguousarray(np.stack([f[1] for f in frames]).reshape(-1, 16))
+        if use_sequence:
+            P = C.c_void_p * len(frames)
+            L.check(L.lib.o3db_vbg_integrate_sequence(v, len(frames), P(*[d.data_ptr() for d in deps]), L.DEPTH_U16,
+                                                      P(*[c.data_ptr() for c in cols]), L.COLOR_U8, 480, 640, L.dptr(K),
+                                                      L.dptr(exts), SCALE, DMAX, TRUNC_MULT, int(host), 0))
+        else:
+            fn = L.lib.o3db_vbg_integrate_frame_host if host else L.lib.o3db_vbg_integrate_frame
+            for i in range(len(frames)):
+                L.check(fn(v, deps[i].data_ptr(), L.DEPTH_U16, cols[i].data_ptr(), L.COLOR_U8, 480, 640, L.dptr(K),
+                           L.dptr(np.ascontiguousarray(exts[i])), SCALE, DMAX, TRUNC_MULT, 0))
+        n = int(L.check(L.lib.o3db_vbg_size(v, 0)))
+        from open3d_b200.t._libshim import device_view
+        keys = device_view(L.lib.o3db_vbg_key_buffer(v), (n, 3), torch.int32).cpu().numpy().copy()
+        tsdf = device_view(L.lib.o3db_vbg_tsdf_buffer(v), (n, 4096), torch.float32).cpu().numpy().copy()
+        wt = device_view(L.lib.o3db_vbg_weight_buffer(v), (n, 4096), torch.uint16).cpu().numpy().copy()
+        col = device_view(L.lib.o3db_vbg_color_buffer(v), (n, 4096 * 3), torch.uint16).cpu().numpy().copy()
+        L.lib.o3db_vbg_destroy(v)
+        order = np.lexsort((keys[:, 2], keys[:, 1], keys[:, 0]))
+        return keys[order], tsdf[order], wt[order], col[order]
+
+    ref = volume(False, False)
+    for use_seq, host in ((True, False), (True, True), (False, True)):
+        got = volume(use_seq, host)
+        for a, b in zip(ref, got):
+            assert np.array_equal(a, b)
