@@ -76,28 +76,55 @@ def tsdf_algorithmic_bytes(blocks, color, width=640, height=480):
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
-
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clocks / throttle reasons during the timed region (B200_PROFILING.md): NVML in-process
+    every 5 ms (the timed region is tens of milliseconds), nvidia-smi as a fallback."""
 
     def __init__(self, index=0):
         self.index = index
-        self.rows = []
+        self.rows = []   # (sm_mhz, sm_max_mhz, power_w, reasons_bitmask)
         self._stop = threading.Event()
         self._t = threading.Thread(target=self._run, daemon=True)
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self):
+        n = self._nvml
+        sm = n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self._h, n.NVML_CLOCK_SM)
+        pw = n.nvmlDeviceGetPowerUsage(self._h) / 1000.0
+        rs = n.nvmlDeviceGetCurrentClocksEventReasons(self._h) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else n.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+        self.rows.append((float(sm), float(mx), pw, int(rs)))
+
+    def _sample_smi(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout
+        p = [x.strip() for x in out.strip().split(",")]
+        if len(p) >= 7:
+            bits = 0
+            for i, b in enumerate((0x8, 0x40, 0x20, 0x4)):   # hw_slowdown, hw_thermal, sw_thermal, sw_power_cap
+                if p[3 + i].lower().startswith("active"):
+                    bits |= b
+            self.rows.append((float(p[0]), float(p[1]), float(p[2]), bits))
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
-                if len(parts) >= 7:
-                    self.rows.append(parts)
+                if self._nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.005 if self._nvml is not None else 0.2)
 
     def __enter__(self):
         self._t.start()
@@ -110,13 +137,14 @@ class ClockSampler:
     def summary(self):
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        sm = sorted(float(r[0]) for r in self.rows)
-        reasons = []
-        for i, name in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
-            if any(r[3 + i].lower().startswith("active") for r in self.rows):
-                reasons.append(name)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "samples": len(self.rows), "power_w_max": max(float(r[2]) for r in self.rows)}
+        sm = sorted(r[0] for r in self.rows)
+        bits = 0
+        for r in self.rows:
+            bits |= r[3]
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        reasons = [n for b, n in names.items() if bits & b]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.rows[0][1], "reasons": reasons, "samples": len(self.rows),
+                "power_w_max": max(r[2] for r in self.rows), "source": "nvml" if self._nvml is not None else "nvidia-smi"}
 
 
 # ----------------------------------------------------------------------------------------------

@@ -134,6 +134,19 @@ int o3db_transform_points(const double transformation_host[16], float* points_de
 int o3db_transform_normals(const double transformation_host[16], float* normals_dev, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------
+ * t::geometry::PointCloud::VoxelDownSample(voxel_size, "mean") (t/geometry/PointCloud.cpp:496-560),
+ * the pyramid build in front of the ICP loop (registration/Registration.cpp:237-240, 266-269).
+ * One output point per occupied voxel floor(p / voxel_size): the mean of the positions and of
+ * the optional normals / colors (not re-normalised, as upstream).  Output buffers need room for
+ * n points; *num_out_host receives the voxel count (stream synchronise).  Output order is
+ * undefined (upstream: hash-map slot order).
+ * ---------------------------------------------------------------------- */
+int o3db_voxel_down_sample(const float* positions_dev, const float* normals_dev /* may be NULL */,
+                           const float* colors_dev /* may be NULL */, int64_t n, double voxel_size,
+                           float* positions_out_dev, float* normals_out_dev, float* colors_out_dev,
+                           int64_t* num_out_host, void* stream);
+
+/* ------------------------------------------------------------------------
  * Fused, device-resident ICP loop — replaces
  * t::pipelines::registration::ICP / MultiScaleICP / DoSingleScaleICPIterations /
  * ComputeRegistrationResult (registration/Registration.cpp:24-62, 93-106, 275-444)

@@ -62,6 +62,7 @@ _SIGS = {
     "o3db_pose_to_transformation": (None, [_dp, _dp]),
     "o3db_transform_points": (_i, [_dp, _vp, _i64, _vp]),
     "o3db_transform_normals": (_i, [_dp, _vp, _i64, _vp]),
+    "o3db_voxel_down_sample": (_i, [_vp, _vp, _vp, _i64, _dbl, _vp, _vp, _vp, C.POINTER(_i64), _vp]),
     "o3db_icp_create": (_i, [_vp, _i64, _vp, _vp, _i64, _dp, C.POINTER(IcpOptions), _vp, _vp, C.POINTER(_vp)]),
     "o3db_icp_reset": (_i, [_vp, _vp]),
     "o3db_icp_iterate": (_i, [_vp, _i, _vp]),

@@ -52,6 +52,33 @@ class PointCloud:
         out.point = {k: v.clone() for k, v in self.point.items()}
         return out
 
+    def voxel_down_sample(self, voxel_size, reduction="mean"):
+        """PointCloud::VoxelDownSample (t/geometry/PointCloud.cpp:496-560)."""
+        if voxel_size <= 0:
+            raise RuntimeError("voxel_size must be positive.")
+        if reduction != "mean":
+            raise RuntimeError("Reduction can only be 'mean' for VoxelDownSample.")
+        import ctypes as C
+        p = self.point["positions"]
+        n = int(p.shape[0])
+        nrm = self.point.get("normals")
+        col = self.point.get("colors")
+        po = torch.empty_like(p)
+        no = torch.empty_like(nrm) if nrm is not None else None
+        co = torch.empty_like(col) if col is not None else None
+        m = C.c_int64(0)
+        check(lib.o3db_voxel_down_sample(p.data_ptr(), None if nrm is None else nrm.data_ptr(),
+                                         None if col is None else col.data_ptr(), n, float(voxel_size), po.data_ptr(),
+                                         None if no is None else no.data_ptr(), None if co is None else co.data_ptr(),
+                                         C.byref(m), current_stream_ptr()))
+        out = PointCloud()
+        out.point["positions"] = po[: m.value].contiguous()
+        if no is not None:
+            out.point["normals"] = no[: m.value].contiguous()
+        if co is not None:
+            out.point["colors"] = co[: m.value].contiguous()
+        return out
+
     def transform(self, transformation):
         """PointCloud::Transform (t/geometry/PointCloud.cpp:352-371): in place on
         positions and, if present, normals."""

@@ -270,13 +270,19 @@ def multi_scale_icp(source, target, voxel_sizes, criteria_list, max_corresponden
     for i in range(n_scales - 1):   # Registration.cpp:190-200
         if voxel_sizes[i] < voxel_sizes[i + 1]:
             raise RuntimeError(" [MultiScaleICP]: Voxel sizes must be in strictly decreasing order.")
-    if any(v > 0 for v in voxel_sizes):
-        raise RuntimeError("voxel_size > 0 needs PointCloud::VoxelDownSample, which is the next component to be "
-                           "built (SURVEY.md §8f #1); pass voxel_size = -1 with pre-downsampled clouds.")
+    # InitializePointCloudPyramidForMultiScaleICP (Registration.cpp:221-273)
+    src_pyr, tgt_pyr = [None] * n_scales, [None] * n_scales
+    if voxel_sizes[-1] <= 0:
+        src_pyr[-1], tgt_pyr[-1] = source, target          # (the loop clones the source itself)
+    else:
+        src_pyr[-1], tgt_pyr[-1] = source.voxel_down_sample(voxel_sizes[-1]), target.voxel_down_sample(voxel_sizes[-1])
+    for k in range(n_scales - 2, -1, -1):
+        src_pyr[k] = src_pyr[k + 1].voxel_down_sample(voxel_sizes[k])
+        tgt_pyr[k] = tgt_pyr[k + 1].voxel_down_sample(voxel_sizes[k])
     result = RegistrationResult(T)
     total = 0
     for s_idx in range(n_scales):
-        result, executed, _ = _run_single_scale(source, target, max_correspondence_distances[s_idx],
+        result, executed, _ = _run_single_scale(src_pyr[s_idx], tgt_pyr[s_idx], max_correspondence_distances[s_idx],
                                                 result.transformation, estimation_method, criteria_list[s_idx],
                                                 callback_after_iteration, total, s_idx)
         total += result.num_iterations

@@ -114,6 +114,8 @@ def _declare(L):
     L.orc_hashmap_activate.restype = C.c_int
     L.orc_hashmap_activate.argtypes = [_i32p, C.c_int64, _i64p, _i32p, C.c_int64,
                                        _i32p, _u8p]
+    L.orc_voxel_down_sample_f32.restype = C.c_int64
+    L.orc_voxel_down_sample_f32.argtypes = [_f32p, _f32p, _f32p, C.c_int64, C.c_double, _f32p, _f32p, _f32p, _i32p]
     L.orc_num_threads.restype = C.c_int
     L.orc_num_threads.argtypes = []
 
@@ -361,3 +363,23 @@ def hashmap_activate(table_keys, size, keys):
     rc = lib().orc_hashmap_activate(_p(table_keys, _i32p), table_keys.shape[0], C.byref(sz),
                                     _p(keys, _i32p), n, _p(bi, _i32p), _p(mk, _u8p))
     return bi, mk.astype(bool), sz.value, rc
+
+
+def voxel_down_sample(positions, voxel_size, normals=None, colors=None):
+    """-> dict(positions, normals, colors, keys): one mean point per occupied voxel, voxels sorted."""
+    pos = _arr(positions, np.float32).reshape(-1, 3)
+    n = pos.shape[0]
+    nrm = None if normals is None else _arr(normals, np.float32).reshape(-1, 3)
+    col = None if colors is None else _arr(colors, np.float32).reshape(-1, 3)
+    po = np.empty((n, 3), np.float32)
+    no = np.empty((n, 3), np.float32) if nrm is not None else None
+    co = np.empty((n, 3), np.float32) if col is not None else None
+    keys = np.empty((n, 3), np.int32)
+    null = C.POINTER(C.c_float)()
+    m = lib().orc_voxel_down_sample_f32(_p(pos, _f32p), null if nrm is None else _p(nrm, _f32p),
+                                        null if col is None else _p(col, _f32p), n, float(voxel_size),
+                                        _p(po, _f32p), null if no is None else _p(no, _f32p),
+                                        null if co is None else _p(co, _f32p), _p(keys, _i32p))
+    assert m >= 0
+    return {"positions": po[:m].copy(), "normals": None if no is None else no[:m].copy(),
+            "colors": None if co is None else co[:m].copy(), "keys": keys[:m].copy()}

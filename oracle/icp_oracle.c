@@ -819,3 +819,60 @@ int orc_icp_p2plane_f32(const float* source, int64_t n, const float* target,
     free(corr);
     return 0;
 }
+
+/* ------------------------------------------------------- VoxelDownSample */
+
+typedef struct {
+    int32_t k[3];
+    int64_t i;
+} vds_entry;
+
+static int vds_cmp(const void* a, const void* b) {
+    const vds_entry* x = (const vds_entry*)a;
+    const vds_entry* y = (const vds_entry*)b;
+    for (int c = 0; c < 3; ++c) {
+        if (x->k[c] < y->k[c]) return -1;
+        if (x->k[c] > y->k[c]) return 1;
+    }
+    return x->i < y->i ? -1 : (x->i > y->i ? 1 : 0);
+}
+
+/* t/geometry/PointCloud.cpp:496-560 */
+int64_t orc_voxel_down_sample_f32(const float* pos, const float* nrm, const float* col, int64_t n,
+                                  double voxel_size, float* pos_out, float* nrm_out, float* col_out,
+                                  int32_t* keys_out) {
+    if (n <= 0) return 0;
+    vds_entry* e = (vds_entry*)malloc((size_t)n * sizeof(vds_entry));
+    if (!e) return -1;
+    const float vs = (float)voxel_size; /* scalar -> tensor dtype (Float32) */
+    for (int64_t i = 0; i < n; ++i) {
+        for (int c = 0; c < 3; ++c) e[i].k[c] = (int32_t)floorf(pos[3 * i + c] / vs); /* :506-507 */
+        e[i].i = i;
+    }
+    qsort(e, (size_t)n, sizeof(vds_entry), vds_cmp);
+    int64_t m = 0;
+    for (int64_t s = 0; s < n;) {
+        int64_t t = s;
+        double ap[3] = {0, 0, 0}, an[3] = {0, 0, 0}, ac[3] = {0, 0, 0};
+        while (t < n && e[t].k[0] == e[s].k[0] && e[t].k[1] == e[s].k[1] && e[t].k[2] == e[s].k[2]) {
+            const int64_t i = e[t].i;
+            for (int c = 0; c < 3; ++c) {
+                ap[c] += pos[3 * i + c];
+                if (nrm) an[c] += nrm[3 * i + c];
+                if (col) ac[c] += col[3 * i + c];
+            }
+            ++t;
+        }
+        const double cnt = (double)(t - s);
+        for (int c = 0; c < 3; ++c) {
+            pos_out[3 * m + c] = (float)(ap[c] / cnt);
+            if (nrm && nrm_out) nrm_out[3 * m + c] = (float)(an[c] / cnt);
+            if (col && col_out) col_out[3 * m + c] = (float)(ac[c] / cnt);
+            if (keys_out) keys_out[3 * m + c] = e[s].k[c];
+        }
+        ++m;
+        s = t;
+    }
+    free(e);
+    return m;
+}

@@ -159,6 +159,21 @@ int orc_icp_p2plane_f32(const float* source, int64_t n, const float* target,
                         orc_icp_result* result, double* per_iter,
                         int64_t* corr_out);
 
+/* ------------------------------------------------------- VoxelDownSample */
+
+/* t/geometry/PointCloud.cpp:496-560 PointCloud::VoxelDownSample(voxel_size, "mean"):
+ * voxel = floor(p / voxel_size) evaluated in f32 (the division is a Float32 tensor op),
+ * one output point per occupied voxel = mean of every attribute (positions, and normals /
+ * colors when given; normals are NOT re-normalised upstream).  The reference accumulates
+ * in f32 with IndexAdd_ (order undefined); this restatement accumulates in f64 and rounds
+ * once.  Output order upstream is the hash map's slot order (undefined); here voxels are
+ * sorted lexicographically by (vx, vy, vz) and voxel_keys_out (may be NULL) receives them.
+ * Returns the number of voxels.  SURVEY.md 8f #1; parity unpinned offline (the reference's
+ * tests compare against a downloaded cloud), set-of-voxels exact by construction. */
+int64_t orc_voxel_down_sample_f32(const float* positions, const float* normals, const float* colors,
+                                  int64_t n, double voxel_size, float* positions_out,
+                                  float* normals_out, float* colors_out, int32_t* voxel_keys_out);
+
 /* ------------------------------------------------------------------- TSDF */
 
 /* t/geometry/kernel/GeometryIndexer.h:136-143 stores intrinsics/extrinsics as

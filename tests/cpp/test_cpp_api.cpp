@@ -1,0 +1,145 @@
+// C++ surface test (include/open3d_b200.hpp): reads like the reference's own
+// cpp/tests/t/pipelines/registration tests.  Exit code 0 = pass.
+//   mode "host": argument validation + no-device behaviour (runs anywhere)
+//   mode "gpu" : ICP + Model::Integrate on the device, checked against the CPU oracle
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "open3d_b200.hpp"
+extern "C" {
+#include "oracle.h"
+}
+
+namespace reg = open3d_b200::t::pipelines::registration;
+namespace geo = open3d_b200::t::geometry;
+namespace slam = open3d_b200::t::pipelines::slam;
+
+#define EXPECT(c)                                                      \
+    do {                                                               \
+        if (!(c)) {                                                    \
+            std::printf("FAILED %s:%d: %s\n", __FILE__, __LINE__, #c); \
+            return 1;                                                  \
+        }                                                              \
+    } while (0)
+
+template <class F>
+static bool throws_with(F&& f, const char* needle) {
+    try {
+        f();
+    } catch (const std::runtime_error& e) {
+        return std::strstr(e.what(), needle) != nullptr;
+    }
+    return false;
+}
+
+static int host_mode() {
+    float dummy[3] = {0, 0, 0};
+    geo::PointCloud empty, src{dummy, nullptr, 1}, tgt_no_normals{dummy, nullptr, 1}, tgt{dummy, dummy, 1};
+    EXPECT(throws_with([&] { reg::ICP(empty, tgt, 0.1); }, "empty"));
+    EXPECT(throws_with([&] { reg::ICP(src, tgt_no_normals, 0.1); }, "normal"));
+    EXPECT(throws_with([&] { reg::ICP(src, tgt, 0.0); }, "Max correspondence distance"));
+    EXPECT(throws_with([&] { reg::ICP(src, tgt, 0.1, {{1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}}, {}, {}, 0.02); },
+                       "VoxelDownSample"));
+    reg::ICPConvergenceCriteria c;
+    EXPECT(c.relative_fitness_ == 1e-6 && c.relative_rmse_ == 1e-6 && c.max_iteration_ == 30);
+    reg::RobustKernel k;
+    EXPECT(k.type_ == reg::RobustKernelMethod::L2Loss && k.scaling_parameter_ == 1.0 && k.shape_parameter_ == 1.0);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        // no CPU fallback: the call must fail loudly
+        EXPECT(throws_with([&] { reg::ICP(src, tgt, 0.1); }, "CUDA") || throws_with([&] { reg::ICP(src, tgt, 0.1); }, "cuda"));
+        EXPECT(throws_with([&] { slam::Model m(0.008f); }, "CUDA") || throws_with([&] { slam::Model m(0.008f); }, "cuda"));
+    }
+    std::printf("cpp host-mode ok\n");
+    return 0;
+}
+
+static int gpu_mode() {
+    // a tilted plane with noise, moved by a small rigid motion
+    const int side = 200, n = side * side;
+    std::vector<float> tgt(3 * n), nrm(3 * n), src(3 * n);
+    std::mt19937 rng(7);
+    std::uniform_real_distribution<float> jit(-0.4f, 0.4f);
+    for (int i = 0; i < side; ++i)
+        for (int j = 0; j < side; ++j) {
+            const int k = i * side + j;
+            const float x = (i + 0.5f + jit(rng)) * 0.02f, y = (j + 0.5f + jit(rng)) * 0.02f;
+            const float z = 0.3f * std::sin(1.1f * x) * std::cos(0.9f * y) + 0.05f * std::sin(5 * x + 1);
+            const float dzdx = 0.33f * std::cos(1.1f * x) * std::cos(0.9f * y) + 0.25f * std::cos(5 * x + 1);
+            const float dzdy = -0.27f * std::sin(1.1f * x) * std::sin(0.9f * y);
+            const float inv = 1.0f / std::sqrt(dzdx * dzdx + dzdy * dzdy + 1);
+            tgt[3 * k] = x; tgt[3 * k + 1] = y; tgt[3 * k + 2] = z;
+            nrm[3 * k] = -dzdx * inv; nrm[3 * k + 1] = -dzdy * inv; nrm[3 * k + 2] = inv;
+            src[3 * k] = x + 0.012f; src[3 * k + 1] = y - 0.008f; src[3 * k + 2] = z + 0.01f;
+        }
+    float *d_src, *d_tgt, *d_nrm;
+    int64_t* d_corr;
+    EXPECT(cudaMalloc(&d_src, sizeof(float) * 3 * n) == cudaSuccess);
+    EXPECT(cudaMalloc(&d_tgt, sizeof(float) * 3 * n) == cudaSuccess);
+    EXPECT(cudaMalloc(&d_nrm, sizeof(float) * 3 * n) == cudaSuccess);
+    EXPECT(cudaMalloc(&d_corr, sizeof(int64_t) * n) == cudaSuccess);
+    cudaMemcpy(d_src, src.data(), sizeof(float) * 3 * n, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_tgt, tgt.data(), sizeof(float) * 3 * n, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_nrm, nrm.data(), sizeof(float) * 3 * n, cudaMemcpyHostToDevice);
+    geo::PointCloud S{d_src, nullptr, n}, T{d_tgt, d_nrm, n};
+    int calls = 0;
+    auto res = reg::ICP(S, T, 0.05, {{1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}}, reg::TransformationEstimationPointToPlane(),
+                        reg::ICPConvergenceCriteria(0, 0, 8), -1.0, [&](int, double, double) { ++calls; }, d_corr);
+    EXPECT(calls == 8 && res.num_iterations_ == 8 && !res.converged_);
+    const double I[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    orc_icp_result ref;
+    std::vector<double> per(16);
+    EXPECT(orc_icp_p2plane_f32(src.data(), n, tgt.data(), nrm.data(), n, 0.05, I, 8, 0, 0, 0, 1.0, 1.0, 1, &ref, per.data(),
+                               nullptr) == 0);
+    for (int i = 0; i < 16; ++i) EXPECT(std::fabs(res.transformation_[i] - ref.transformation[i]) < 2e-5);
+    EXPECT(std::fabs(res.fitness_ - ref.fitness) < 2e-4 && std::fabs(res.inlier_rmse_ - ref.inlier_rmse) < 2e-6);
+    EXPECT(res.per_iteration_.size() == 8 && res.per_iteration_[0][0] == per[0]);
+    // robust kernel + singular system error text
+    EXPECT(throws_with(
+            [&] {
+                std::vector<float> z(3 * 64, 0.f), up(3 * 64, 0.f);
+                for (int i = 0; i < 64; ++i) up[3 * i + 2] = 1.f;
+                cudaMemcpy(d_src, z.data(), sizeof(float) * 3 * 64, cudaMemcpyHostToDevice);
+                cudaMemcpy(d_tgt, z.data(), sizeof(float) * 3 * 64, cudaMemcpyHostToDevice);
+                cudaMemcpy(d_nrm, up.data(), sizeof(float) * 3 * 64, cudaMemcpyHostToDevice);
+                geo::PointCloud s2{d_src, nullptr, 64}, t2{d_tgt, d_nrm, 64};
+                reg::ICP(s2, t2, 0.05);
+            },
+            "Singular 6x6"));
+    // slam::Model on a constant-depth frame (a wall 1.5 m away)
+    std::vector<uint16_t> depth(480 * 640, 1500);
+    uint16_t* d_depth;
+    EXPECT(cudaMalloc(&d_depth, depth.size() * 2) == cudaSuccess);
+    cudaMemcpy(d_depth, depth.data(), depth.size() * 2, cudaMemcpyHostToDevice);
+    slam::Model model(0.008f, 16, 4000);
+    slam::Frame f;
+    f.height = 480; f.width = 640; f.depth = d_depth;
+    model.UpdateFramePose(0, {{1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}});
+    model.Integrate(f);
+    std::vector<int32_t> keys(3 * 76800);
+    const double K[9] = {525.0, 0, 319.5, 0, 525.0, 239.5, 0, 0, 1};
+    const int64_t want = orc_depth_touch(depth.data(), 0, 480, 640, K, I, 16, 0.008f, 0.064f, 1000.0f, 3.0f, 4, keys.data(), 76800);
+    EXPECT(want > 100 && model.NumBlocks() == want);
+    f.depth = depth.data();
+    f.images_on_host = true;
+    model.Integrate(f);   // same frame again through the host-image path: no new blocks
+    EXPECT(model.NumBlocks() == want);
+    std::printf("cpp gpu-mode ok: fitness %.4f rmse %.5f blocks %lld\n", res.fitness_, res.inlier_rmse_, (long long)want);
+    return 0;
+}
+
+int main(int argc, char** argv) {
+    const std::string mode = argc > 1 ? argv[1] : "host";
+    try {
+        return mode == "gpu" ? gpu_mode() : host_mode();
+    } catch (const std::exception& e) {
+        std::printf("unexpected exception: %s\n", e.what());
+        return 2;
+    }
+}

@@ -367,3 +367,55 @@ def test_icp_reproducibility_and_properties_at_scale(o3d):
     d = (moved[m] - t[corr[m]]).norm(dim=1)
     assert float(d.max()) <= 0.05 * (1 + 1e-4)
     assert abs(float((d ** 2).mean().sqrt()) - a.inlier_rmse) < 1e-5
+
+
+# ------------------------------------------------- VoxelDownSample
+
+def _by_voxel(pos, vs, *attrs):
+    k = np.floor(pos / np.float32(vs)).astype(np.int64)
+    order = np.lexsort((k[:, 2], k[:, 1], k[:, 0]))
+    return (k[order], pos[order]) + tuple(a[order] for a in attrs)
+
+
+@pytest.mark.parametrize("n,vs", [(50000, 0.05), (200000, 0.031), (1000, 10.0)])
+def test_voxel_down_sample_vs_oracle(o3d, n, vs):
+    src, tgt, nrm, _ = make_icp_pair(n, seed=15)
+    tgt = tgt - 2.5                                   # negative coordinates too
+    col = make_colors(tgt, 2)
+    pc = o3d.t.geometry.PointCloud(tgt).set_point_normals(nrm).set_point_colors(col)
+    down = pc.voxel_down_sample(vs)
+    ref = oracle.voxel_down_sample(tgt, vs, normals=nrm, colors=col)
+    gp, gn, gc = (down.point[k].cpu().numpy() for k in ("positions", "normals", "colors"))
+    assert len(gp) == len(ref["positions"])           # same set of occupied voxels ...
+    kg, gp, gn, gc = _by_voxel(gp, vs, gn, gc)
+    assert np.array_equal(kg, ref["keys"].astype(np.int64))   # ... bit-exact voxel keys
+    # means: f32 atomics (as the reference's IndexAdd_) vs the oracle's f64 accumulation
+    np.testing.assert_allclose(gp, ref["positions"], rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(gn, ref["normals"], rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(gc, ref["colors"], rtol=1e-5, atol=2e-6)
+    with pytest.raises(RuntimeError, match="voxel_size must be positive"):
+        pc.voxel_down_sample(0.0)
+
+
+def test_multi_scale_icp_with_voxel_pyramid_vs_oracle(o3d):
+    """MultiScaleICP with down-sampling (Registration.cpp:221-273, 362-444), BASELINE config-2 style
+    (voxel_size 0.02 on the last scale) against the same pipeline assembled from oracle pieces."""
+    reg = o3d.t.pipelines.registration
+    src, tgt, nrm, T_gt = make_icp_pair(90000, seed=16)
+    voxels, radii, iters = [0.06, 0.02], [0.12, 0.05], [6, 8]
+    s = o3d.t.geometry.PointCloud(src)
+    t = o3d.t.geometry.PointCloud(tgt).set_point_normals(nrm)
+    res = reg.multi_scale_icp(s, t, voxels, [reg.ICPConvergenceCriteria(0, 0, k) for k in iters], radii, np.eye(4),
+                              reg.TransformationEstimationPointToPlane())
+    # oracle pyramid: finest first, coarser levels from the finer ones
+    s1, t1 = oracle.voxel_down_sample(src, voxels[1]), oracle.voxel_down_sample(tgt, voxels[1], normals=nrm)
+    s0, t0 = oracle.voxel_down_sample(s1["positions"], voxels[0]), oracle.voxel_down_sample(t1["positions"], voxels[0], normals=t1["normals"])
+    T = np.eye(4)
+    for (ss, tt), r, k in zip(((s0, t0), (s1, t1)), radii, iters):
+        ref = oracle.icp_p2plane(ss["positions"], tt["positions"], tt["normals"], r, init=T, max_iteration=k,
+                                 relative_fitness=0, relative_rmse=0)
+        T = ref.transformation
+    assert res.num_iterations == sum(iters)
+    np.testing.assert_allclose(res.transformation, T, atol=5e-5)
+    assert abs(res.fitness - ref.fitness) < 1e-3 and abs(res.inlier_rmse - ref.inlier_rmse) < 1e-5
+    np.testing.assert_allclose(res.transformation, T_gt, atol=3e-3)
