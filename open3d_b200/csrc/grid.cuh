@@ -23,7 +23,9 @@ namespace o3db {
 // whole "column" of cells along the thin direction is one short contiguous run.
 struct Grid {
     float ox, oy, oz;   // origin = bbox min
-    float inv_c, c;     // cell size and reciprocal
+    float inv_c, c;     // cell size and reciprocal (grid-y, grid-z)
+    float inv_cx, cx;   // cell size along grid-x, the thin axis: kThinFactor x coarser — slab scans cross
+                        // all grid-x cells anyway, and the CSR table shrinks by that factor (L2 residency)
     float tol;          // pruning slack covering binning round-off
     int nx, ny, nz;
     float bmin[3], bmax[3];
@@ -49,7 +51,7 @@ __device__ __forceinline__ int cell1(float x, float o, float inv_c, int n) {
 __device__ __forceinline__ unsigned cell_key(const Grid& g, float rx, float ry, float rz) {
     float x, y, z;
     to_grid(g, rx, ry, rz, x, y, z);
-    const int ix = cell1(x, g.ox, g.inv_c, g.nx);
+    const int ix = cell1(x, g.ox, g.inv_cx, g.nx);
     const int iy = cell1(y, g.oy, g.inv_c, g.ny);
     const int iz = cell1(z, g.oz, g.inv_c, g.nz);
     return (unsigned)((iz * g.ny + iy) * g.nx + ix);
@@ -103,8 +105,8 @@ __device__ __forceinline__ void scan_row(const Grid& g, const float4* __restrict
                                          float gap2, float gqx, float qx, float qy, float qz, Best& b) {
     // admissible |dx|: dx^2 <= best - gap2 (1e-6 best covers the rounding of the subtraction)
     const float ex = sqrtf(fmaf(b.d, 1e-6f, b.d - gap2)) * 1.00001f;
-    const int xa = max(x0, cell1(lo_bound(gqx, ex), g.ox, g.inv_c, g.nx));
-    const int xb = min(x1, cell1(hi_bound(gqx, ex), g.ox, g.inv_c, g.nx));
+    const int xa = max(x0, cell1(lo_bound(gqx, ex), g.ox, g.inv_cx, g.nx));
+    const int xb = min(x1, cell1(hi_bound(gqx, ex), g.ox, g.inv_cx, g.nx));
     if (skip_cx < xa || skip_cx > xb) {
         if (xa <= xb) scan_range(pts, cs[row + xa], cs[row + xb + 1], qx, qy, qz, b);
     } else {
@@ -135,10 +137,10 @@ __device__ __forceinline__ void nn_search(const Grid& g, const float4* __restric
     if (hx < g.bmin[0] || lx > g.bmax[0] || hy < g.bmin[1] || ly > g.bmax[1] || hz < g.bmin[2] ||
         lz > g.bmax[2] || !(qx == qx) || !(qy == qy) || !(qz == qz))
         return;
-    const int x0 = cell1(lx, g.ox, g.inv_c, g.nx), x1 = cell1(hx, g.ox, g.inv_c, g.nx);
+    const int x0 = cell1(lx, g.ox, g.inv_cx, g.nx), x1 = cell1(hx, g.ox, g.inv_cx, g.nx);
     const int y0 = cell1(ly, g.oy, g.inv_c, g.ny), y1 = cell1(hy, g.oy, g.inv_c, g.ny);
     const int z0 = cell1(lz, g.oz, g.inv_c, g.nz), z1 = cell1(hz, g.oz, g.inv_c, g.nz);
-    const int cx = cell1(gx, g.ox, g.inv_c, g.nx);
+    const int cx = cell1(gx, g.ox, g.inv_cx, g.nx);
     const int cy = cell1(gy, g.oy, g.inv_c, g.ny), cz = cell1(gz, g.oz, g.inv_c, g.nz);
     if (!PRUNE) {
         for (int iz = z0; iz <= z1; ++iz)
@@ -193,7 +195,7 @@ __device__ __forceinline__ void nn_search_two_pass(const Grid& g, const float4* 
         lo_bound(gy, rr) > g.bmax[1] || hi_bound(gz, rr) < g.bmin[2] || lo_bound(gz, rr) > g.bmax[2] ||
         !(qx == qx) || !(qy == qy) || !(qz == qz))
         return;
-    const int x0 = cell1(lo_bound(gx, r1), g.ox, g.inv_c, g.nx), x1 = cell1(hi_bound(gx, r1), g.ox, g.inv_c, g.nx);
+    const int x0 = cell1(lo_bound(gx, r1), g.ox, g.inv_cx, g.nx), x1 = cell1(hi_bound(gx, r1), g.ox, g.inv_cx, g.nx);
     const int y0 = cell1(lo_bound(gy, r1), g.oy, g.inv_c, g.ny), y1 = cell1(hi_bound(gy, r1), g.oy, g.inv_c, g.ny);
     const int z0 = cell1(lo_bound(gz, r1), g.oz, g.inv_c, g.nz), z1 = cell1(hi_bound(gz, r1), g.oz, g.inv_c, g.nz);
     if (z1 - z0 <= 2) {
@@ -211,15 +213,59 @@ __device__ __forceinline__ void nn_search_two_pass(const Grid& g, const float4* 
             ss[dz] = s;
             se[dz] = on ? e : s;
         }
+        const unsigned n0 = se[0] - ss[0], n1 = se[1] - ss[1], n2 = se[2] - ss[2];
+        if (n0 <= kSlabMax && n1 <= kSlabMax && n2 <= kSlabMax) {
+            // ONE loop over the concatenation of the three slabs: a warp then runs
+            // max_lane(n0+n1+n2)/4 trips instead of sum_slabs(max_lane(n_slab)/4) — the lanes'
+            // slabs fill differently, and padding every slab separately to the warp's worst lane
+            // left two thirds of the candidate slots idle (ncu).  The running best
+            // is one 64-bit key (dist^2 bits : index) so that "closer, ties to the lower index"
+            // is a single unsigned comparison; non-negative floats order like their bit patterns.
+            const unsigned total = n0 + n1 + n2;
+            const unsigned o1 = ss[1] - n0, o2 = ss[2] - n0 - n1;   // virtual index -> global index offsets
+            unsigned long long best = ((unsigned long long)__float_as_uint(thr) << 32) | 0x7fffffffull;
+            unsigned bj = 0xffffffffu;
+            for (unsigned v = 0; v < total; v += 4) {
+                unsigned jj[4];
+                float4 t[4];
 #pragma unroll
-        for (int dz = 0; dz < 3; ++dz) {
-            if (se[dz] - ss[dz] <= kSlabMax) {
-                scan_range(pts, ss[dz], se[dz], qx, qy, qz, b);
-            } else {
-                const int plane = (z0 + dz) * g.ny;
-                for (int iy = y0; iy <= y1; ++iy) {
-                    const int row = (plane + iy) * g.nx;
-                    scan_range(pts, cs[row + x0], cs[row + x1 + 1], qx, qy, qz, b);
+                for (int k = 0; k < 4; ++k) {
+                    const unsigned w = min(v + k, total - 1);
+                    jj[k] = w < n0 ? ss[0] + w : (w < n0 + n1 ? o1 + w : o2 + w);
+                    t[k] = __ldg(&pts[jj[k]]);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float dx = t[k].x - qx, dy = t[k].y - qy, dz = t[k].z - qz;
+                    const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));   // canonical (see scan_range)
+                    const unsigned long long key =
+                            ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_int(t[k].w);
+                    if (key <= best) {   // d >= 0, so the bit patterns order like the values; NaN sorts last
+                        best = key;
+                        bj = jj[k];
+                    }
+                }
+            }
+            if (bj != 0xffffffffu) {
+                const float4 w = __ldg(&pts[bj]);
+                b.d = __uint_as_float((unsigned)(best >> 32));
+                b.idx = (int)(unsigned)(best & 0xffffffffull);
+                b.j = (int)bj;
+                b.x = w.x;
+                b.y = w.y;
+                b.z = w.z;
+            }
+        } else {
+#pragma unroll
+            for (int dz = 0; dz < 3; ++dz) {
+                if (se[dz] - ss[dz] <= kSlabMax) {
+                    scan_range(pts, ss[dz], se[dz], qx, qy, qz, b);
+                } else {
+                    const int plane = (z0 + dz) * g.ny;
+                    for (int iy = y0; iy <= y1; ++iy) {
+                        const int row = (plane + iy) * g.nx;
+                        scan_range(pts, cs[row + x0], cs[row + x1 + 1], qx, qy, qz, b);
+                    }
                 }
             }
         }

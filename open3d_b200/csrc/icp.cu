@@ -20,9 +20,16 @@ namespace o3db {
 static constexpr int kThreads = 256;
 static constexpr int64_t kMaxCells = int64_t(1) << 26;  // 256 MB of u32 CSR offsets at most
 static constexpr int kMaxCellsPerAxis = 4096;
+#ifndef ICP_THIN_FACTOR
+#define ICP_THIN_FACTOR 8
+#endif
+static constexpr double kThinFactor = ICP_THIN_FACTOR;   // grid-x (thin axis) cells are this much coarser
 static constexpr int kNumSums = 30;   // 29 reference slots + sum of dist^2
 static constexpr int kSumStride = 32;
-static constexpr int kFlushEvery = 16;
+#ifndef ICP_FLUSH_EVERY
+#define ICP_FLUSH_EVERY 32
+#endif
+static constexpr int kFlushEvery = ICP_FLUSH_EVERY;   // f32 terms per thread before the f64 tree (error <= kFlushEvery * 2^-24 of sum|term|)
 #ifndef ICP_CELL_SCALE
 #define ICP_CELL_SCALE 0.5
 #endif
@@ -105,7 +112,7 @@ __host__ __device__ inline int64_t tiled_key_space(int nx, int ny, int nz) {
 __device__ __forceinline__ unsigned cell_key_tiled(const Grid& g, float rx, float ry, float rz) {
     float x, y, z;
     to_grid(g, rx, ry, rz, x, y, z);
-    const int ix = cell1(x, g.ox, g.inv_c, g.nx), iy = cell1(y, g.oy, g.inv_c, g.ny), iz = cell1(z, g.oz, g.inv_c, g.nz);
+    const int ix = cell1(x, g.ox, g.inv_cx, g.nx), iy = cell1(y, g.oy, g.inv_c, g.ny), iz = cell1(z, g.oz, g.inv_c, g.nz);
     const int ntx = (g.nx + kTileX - 1) / kTileX, nty = (g.ny + kTileY - 1) / kTileY;
     const int tile = ((iz / kTileZ) * nty + iy / kTileY) * ntx + ix / kTileX;
     const int local = ((iz % kTileZ) * kTileY + iy % kTileY) * kTileX + ix % kTileX;
@@ -299,7 +306,7 @@ static int grid_from_bbox(const float mn[3], const float mx[3], double radius, d
         bool ok = true;
         double prod = 1;
         for (int k = 0; k < 3; ++k) {
-            n[k] = std::floor(ext[order[k]] / c) + 1;
+            n[k] = std::floor(ext[order[k]] / (k == 0 ? c * kThinFactor : c)) + 1;
             ok = ok && n[k] <= kMaxCellsPerAxis;
             prod *= n[k];
         }
@@ -313,6 +320,8 @@ static int grid_from_bbox(const float mn[3], const float mx[3], double radius, d
     }
     g->c = (float)c;
     g->inv_c = 1.0f / g->c;
+    g->cx = (float)(c * kThinFactor);
+    g->inv_cx = 1.0f / g->cx;
     g->ox = mn[order[0]];
     g->oy = mn[order[1]];
     g->oz = mn[order[2]];
@@ -413,7 +422,7 @@ hybrid_search_knn_kernel(Grid g, const float4* __restrict__ pts, const unsigned*
     const bool outside = hx < g.bmin[0] || lx > g.bmax[0] || hy < g.bmin[1] || ly > g.bmax[1] ||
                          hz < g.bmin[2] || lz > g.bmax[2] || !(qx == qx) || !(qy == qy) || !(qz == qz);
     if (!outside) {
-        const int x0 = cell1(lx, g.ox, g.inv_c, g.nx), x1 = cell1(hx, g.ox, g.inv_c, g.nx);
+        const int x0 = cell1(lx, g.ox, g.inv_cx, g.nx), x1 = cell1(hx, g.ox, g.inv_cx, g.nx);
         const int y0 = cell1(ly, g.oy, g.inv_c, g.ny), y1 = cell1(hy, g.oy, g.inv_c, g.ny);
         const int z0 = cell1(lz, g.oz, g.inv_c, g.nz), z1 = cell1(hz, g.oz, g.inv_c, g.nz);
         for (int iz = z0; iz <= z1; ++iz)
@@ -1110,8 +1119,8 @@ icp_iteration_tile_kernel(IcpArgs a) {
                                       !(p.x == p.x) || !(p.y == p.y) || !(p.z == p.z));
         int x0 = kBig, x1 = -kBig, y0 = kBig, y1 = -kBig, z0 = kBig, z1 = -kBig;
         if (inside) {
-            x0 = cell1(lo_bound(gx, a.r1), g.ox, g.inv_c, g.nx);
-            x1 = cell1(hi_bound(gx, a.r1), g.ox, g.inv_c, g.nx);
+            x0 = cell1(lo_bound(gx, a.r1), g.ox, g.inv_cx, g.nx);
+            x1 = cell1(hi_bound(gx, a.r1), g.ox, g.inv_cx, g.nx);
             y0 = cell1(lo_bound(gy, a.r1), g.oy, g.inv_c, g.ny);
             y1 = cell1(hi_bound(gy, a.r1), g.oy, g.inv_c, g.ny);
             z0 = cell1(lo_bound(gz, a.r1), g.oz, g.inv_c, g.nz);
