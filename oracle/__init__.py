@@ -114,6 +114,14 @@ def _declare(L):
     L.orc_hashmap_activate.restype = C.c_int
     L.orc_hashmap_activate.argtypes = [_i32p, C.c_int64, _i64p, _i32p, C.c_int64,
                                        _i32p, _u8p]
+    L.orc_estimate_color_gradients_f32.restype = None
+    L.orc_estimate_color_gradients_f32.argtypes = [_f32p, _f32p, _f32p, C.c_int64, C.c_double, C.c_int, _f32p]
+    L.orc_solve_sym3x3_pinv.restype = None
+    L.orc_solve_sym3x3_pinv.argtypes = [_f64p, _f64p, _f64p]
+    L.orc_icp_colored_f32.restype = C.c_int
+    L.orc_icp_colored_f32.argtypes = [_f32p, _f32p, C.c_int64, _f32p, _f32p, _f32p, _f32p, C.c_int64, C.c_double, _f64p,
+                                      C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double,
+                                      C.POINTER(_IcpResult), _f64p, _i64p]
     L.orc_voxel_down_sample_f32.restype = C.c_int64
     L.orc_voxel_down_sample_f32.argtypes = [_f32p, _f32p, _f32p, C.c_int64, C.c_double, _f32p, _f32p, _f32p, _i32p]
     L.orc_num_threads.restype = C.c_int
@@ -383,3 +391,42 @@ def voxel_down_sample(positions, voxel_size, normals=None, colors=None):
     assert m >= 0
     return {"positions": po[:m].copy(), "normals": None if no is None else no[:m].copy(),
             "colors": None if co is None else co[:m].copy(), "keys": keys[:m].copy()}
+
+
+def estimate_color_gradients(points, normals, colors, radius, max_nn=30) -> np.ndarray:
+    p = _arr(points, np.float32).reshape(-1, 3)
+    nr = _arr(normals, np.float32).reshape(-1, 3)
+    c = _arr(colors, np.float32).reshape(-1, 3)
+    out = np.zeros_like(p)
+    lib().orc_estimate_color_gradients_f32(_p(p, _f32p), _p(nr, _f32p), _p(c, _f32p), p.shape[0], float(radius),
+                                           int(max_nn), _p(out, _f32p))
+    return out
+
+
+def solve_sym3x3_pinv(A, b) -> np.ndarray:
+    A = _arr(A, np.float64).reshape(9)
+    b = _arr(b, np.float64).reshape(3)
+    x = np.zeros(3)
+    lib().orc_solve_sym3x3_pinv(_p(A, _f64p), _p(b, _f64p), _p(x, _f64p))
+    return x
+
+
+def icp_colored(source, source_colors, target, target_normals, target_colors, target_color_gradients,
+                max_corr_dist, init=None, max_iteration=30, relative_fitness=1e-6, relative_rmse=1e-6,
+                lambda_geometric=0.968, robust=("L2Loss", 1.0, 1.0)) -> IcpResult:
+    src, sc = (_arr(a, np.float32).reshape(-1, 3) for a in (source, source_colors))
+    tgt, nrm, tc, tg = (_arr(a, np.float32).reshape(-1, 3) for a in (target, target_normals, target_colors,
+                                                                       target_color_gradients))
+    T0 = _arr(np.eye(4) if init is None else init, np.float64).reshape(16)
+    res = _IcpResult()
+    per = np.full((max(max_iteration, 1), 2), np.nan, np.float64)
+    corr = np.empty(src.shape[0], np.int64)
+    rc = lib().orc_icp_colored_f32(_p(src, _f32p), _p(sc, _f32p), src.shape[0], _p(tgt, _f32p), _p(nrm, _f32p),
+                                   _p(tc, _f32p), _p(tg, _f32p), tgt.shape[0], float(max_corr_dist), _p(T0, _f64p),
+                                   int(max_iteration), float(relative_fitness), float(relative_rmse),
+                                   float(lambda_geometric), ROBUST[robust[0]], float(robust[1]), float(robust[2]),
+                                   C.byref(res), _p(per, _f64p), _p(corr, _i64p))
+    executed = int(np.sum(~np.isnan(per[:, 0])))
+    return IcpResult(np.array(res.transformation, np.float64).reshape(4, 4), res.fitness, res.inlier_rmse,
+                     bool(res.converged), res.num_iterations, per[:executed].copy(), corr, rc, res.loop_seconds,
+                     res.build_seconds)

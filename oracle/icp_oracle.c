@@ -876,3 +876,181 @@ int64_t orc_voxel_down_sample_f32(const float* pos, const float* nrm, const floa
     free(e);
     return m;
 }
+
+/* ------------------------------------------------------------ ColoredICP */
+
+void orc_solve_sym3x3_pinv(const double Ain[9], const double b[3], double x[3]) {
+    double A[3][3], V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) A[i][j] = 0.5 * (Ain[3 * i + j] + Ain[3 * j + i]);
+    for (int sweep = 0; sweep < 64; ++sweep) {
+        double off = fabs(A[0][1]) + fabs(A[0][2]) + fabs(A[1][2]);
+        if (off < 1e-300) break;
+        for (int p = 0; p < 2; ++p)
+            for (int q = p + 1; q < 3; ++q) {
+                if (fabs(A[p][q]) < 1e-300) continue;
+                const double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+                for (int k = 0; k < 3; ++k) {
+                    const double akp = A[k][p], akq = A[k][q];
+                    A[k][p] = c * akp - sn * akq;
+                    A[k][q] = sn * akp + c * akq;
+                }
+                for (int k = 0; k < 3; ++k) {
+                    const double apk = A[p][k], aqk = A[q][k];
+                    A[p][k] = c * apk - sn * aqk;
+                    A[q][k] = sn * apk + c * aqk;
+                }
+                for (int k = 0; k < 3; ++k) {
+                    const double vkp = V[k][p], vkq = V[k][q];
+                    V[k][p] = c * vkp - sn * vkq;
+                    V[k][q] = sn * vkp + c * vkq;
+                }
+            }
+    }
+    x[0] = x[1] = x[2] = 0.0;
+    for (int i = 0; i < 3; ++i) {
+        const double lam = A[i][i];
+        if (fabs(lam) < 1e-10) continue; /* SVD3x3.h:2184-2187 */
+        const double proj = (V[0][i] * b[0] + V[1][i] * b[1] + V[2][i] * b[2]) / lam;
+        for (int k = 0; k < 3; ++k) x[k] += V[k][i] * proj;
+    }
+}
+
+/* PointCloudImpl.h:1066-1165 for one point; idx: its neighbour list (count valid entries). */
+static void color_gradient_point(const float* pts, const float* nrm, const float* col, int64_t i,
+                                 const int32_t* idx, int count, float* out) {
+    const int64_t o = 3 * i;
+    if (count < 4) {
+        out[o] = out[o + 1] = out[o + 2] = 0;
+        return;
+    }
+    const float vt[3] = {pts[o], pts[o + 1], pts[o + 2]};
+    const float nt[3] = {nrm[o], nrm[o + 1], nrm[o + 2]};
+    const float it = (float)((col[o] + col[o + 1] + col[o + 2]) / 3.0);
+    float AtA[9] = {0}, Atb[3] = {0};
+    const float s = vt[0] * nt[0] + vt[1] * nt[1] + vt[2] * nt[2];
+    int k = 1;
+    for (; k < count; ++k) {
+        const int64_t a = 3 * (int64_t)idx[k];
+        if (a == -1) break; /* as written upstream (:1106-1108) */
+        const float va[3] = {pts[a], pts[a + 1], pts[a + 2]};
+        const float d = va[0] * nt[0] + va[1] * nt[1] + va[2] * nt[2] - s;
+        const float vp[3] = {va[0] - d * nt[0], va[1] - d * nt[1], va[2] - d * nt[2]};
+        const float ia = (float)((col[a] + col[a + 1] + col[a + 2]) / 3.0);
+        const float A[3] = {vp[0] - vt[0], vp[1] - vt[1], vp[2] - vt[2]};
+        AtA[0] += A[0] * A[0];
+        AtA[1] += A[1] * A[0];
+        AtA[2] += A[2] * A[0];
+        AtA[4] += A[1] * A[1];
+        AtA[5] += A[2] * A[1];
+        AtA[8] += A[2] * A[2];
+        const float b = ia - it;
+        Atb[0] += A[0] * b;
+        Atb[1] += A[1] * b;
+        Atb[2] += A[2] * b;
+    }
+    const float A[3] = {(k - 1) * nt[0], (k - 1) * nt[1], (k - 1) * nt[2]};
+    AtA[0] += A[0] * A[0];
+    AtA[1] += A[0] * A[1];
+    AtA[2] += A[0] * A[2];
+    AtA[4] += A[1] * A[1];
+    AtA[5] += A[1] * A[2];
+    AtA[8] += A[2] * A[2];
+    AtA[3] = AtA[1];
+    AtA[6] = AtA[2];
+    AtA[7] = AtA[5];
+    double Ad[9], bd[3], xd[3];
+    for (int q = 0; q < 9; ++q) Ad[q] = AtA[q];
+    for (int q = 0; q < 3; ++q) bd[q] = Atb[q];
+    orc_solve_sym3x3_pinv(Ad, bd, xd);
+    out[o] = (float)xd[0];
+    out[o + 1] = (float)xd[1];
+    out[o + 2] = (float)xd[2];
+}
+
+void orc_estimate_color_gradients_f32(const float* pts, const float* nrm, const float* col, int64_t n,
+                                      double radius, int max_nn, float* out) {
+    if (max_nn > ORC_MAX_KNN) max_nn = ORC_MAX_KNN;
+    int32_t* idx = (int32_t*)malloc((size_t)n * max_nn * sizeof(int32_t));
+    float* d2 = (float*)malloc((size_t)n * max_nn * sizeof(float));
+    int32_t* cnt = (int32_t*)malloc((size_t)n * sizeof(int32_t));
+    if (!idx || !d2 || !cnt) abort();
+    orc_hybrid_search_f32(pts, n, pts, n, radius, max_nn, idx, d2, cnt);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) color_gradient_point(pts, nrm, col, i, idx + i * max_nn, cnt[i], out);
+    free(idx);
+    free(d2);
+    free(cnt);
+}
+
+int orc_icp_colored_f32(const float* source, const float* source_colors, int64_t n, const float* target,
+                        const float* nrm, const float* tcol, const float* tgrad, int64_t m,
+                        double max_corr_dist, const double init_T[16], int max_iteration,
+                        double rel_fitness, double rel_rmse, double lambda_geometric, int method,
+                        double scale, double shape, orc_icp_result* res, double* per_iter,
+                        int64_t* corr_out) {
+    float* src = (float*)malloc((size_t)(n > 0 ? n : 1) * 3 * sizeof(float));
+    int64_t* corr = (int64_t*)malloc((size_t)(n > 0 ? n : 1) * sizeof(int64_t));
+    if (!src || !corr) return -1;
+    memcpy(src, source, (size_t)n * 3 * sizeof(float));
+    double T[16];
+    memcpy(T, init_T, sizeof(T));
+    orc_transform_points_f32(T, src, n);
+    orc_grid g;
+    const double t_build0 = now_s();
+    if (grid_build(&g, target, m, max_corr_dist) != 0) return -1;
+    const double t_loop0 = now_s();
+    double fitness = 0, rmse = 0, prev_fitness = 0, prev_rmse = 0;
+    int64_t cnt = 0;
+    int converged = 0, it = 0;
+    for (it = 0; it < max_iteration; ++it) {
+        compute_registration_result(&g, src, n, max_corr_dist, corr, &fitness, &rmse, &cnt);
+        if (cnt == 0) eye4(T);
+        if (fitness <= 2.2250738585072014e-308) {
+            converged = 0;
+            break;
+        }
+        double s64[29], pose[6], U[16];
+        orc_pose_colored_sums_f32(src, source_colors, target, nrm, tcol, tgrad, corr, n, lambda_geometric,
+                                  method, scale, shape, s64, NULL);
+        if (orc_decode_and_solve_6x6(s64, pose, NULL, NULL) != 0) {
+            grid_free(&g);
+            free(src);
+            free(corr);
+            return 1;
+        }
+        orc_pose_to_transformation(pose, U);
+        matmul4(U, T, T);
+        orc_transform_points_f32(U, src, n);
+        if (per_iter) {
+            per_iter[2 * it + 0] = fitness;
+            per_iter[2 * it + 1] = rmse;
+        }
+        if (it != 0 && fabs(prev_fitness - fitness) < rel_fitness && fabs(prev_rmse - rmse) < rel_rmse) {
+            converged = 1;
+            break;
+        }
+        prev_fitness = fitness;
+        prev_rmse = rmse;
+    }
+    res->loop_seconds = now_s() - t_loop0;
+    res->build_seconds = t_loop0 - t_build0;
+    const int iterations = it;
+    compute_registration_result(&g, src, n, max_corr_dist, corr, &fitness, &rmse, &cnt);
+    if (cnt == 0) {
+        eye4(T);
+        converged = 0;
+    }
+    res->num_iterations = iterations;
+    res->converged = converged;
+    res->fitness = fitness;
+    res->inlier_rmse = rmse;
+    memcpy(res->transformation, T, sizeof(T));
+    if (corr_out) memcpy(corr_out, corr, (size_t)n * sizeof(int64_t));
+    grid_free(&g);
+    free(src);
+    free(corr);
+    return 0;
+}

@@ -159,6 +159,31 @@ int orc_icp_p2plane_f32(const float* source, int64_t n, const float* target,
                         orc_icp_result* result, double* per_iter,
                         int64_t* corr_out);
 
+/* ------------------------------------------------------------ ColoredICP */
+
+/* t/geometry/kernel/PointCloudImpl.h:1066-1165 EstimatePointWiseColorGradientKernel driven by
+ * EstimateColorGradientsUsingHybridSearch (:1167-1222): hybrid search of the cloud on itself
+ * (radius, max_nn), skip neighbour 0, project neighbours on the tangent plane, 3x3 normal
+ * equations + the orthogonality row, x = pinv(AtA) Atb.  The per-neighbour arithmetic is f32 as
+ * upstream; the final 3x3 pseudo-inverse is evaluated in f64 by Jacobi eigen-decomposition
+ * (upstream: core/linalg/kernel/SVD3x3.h fast f32 SVD, singular values < 1e-10 dropped) —
+ * agreement with the real solve_svd3x3 is checked in tests/test_oracle_vs_ref.py.
+ * SURVEY.md 8f #3; parity unpinned offline beyond that check. */
+void orc_estimate_color_gradients_f32(const float* points, const float* normals, const float* colors,
+                                      int64_t n, double radius, int max_nn, float* gradients_out);
+
+/* pinv(A) b for a symmetric 3x3 A (row-major), f64 Jacobi; singular values < 1e-10 dropped. */
+void orc_solve_sym3x3_pinv(const double A[9], const double b[3], double x[3]);
+
+/* Registration.cpp:275-444 with TransformationEstimationForColoredICP
+ * (TransformationEstimation.cpp:382-432 -> ComputePoseColoredICP, kernel/Registration.cpp:137-191). */
+int orc_icp_colored_f32(const float* source, const float* source_colors, int64_t n, const float* target,
+                        const float* target_normals, const float* target_colors,
+                        const float* target_color_gradients, int64_t m, double max_corr_dist,
+                        const double init_T[16], int max_iteration, double rel_fitness, double rel_rmse,
+                        double lambda_geometric, int robust_method, double robust_scale,
+                        double robust_shape, orc_icp_result* result, double* per_iter, int64_t* corr_out);
+
 /* ------------------------------------------------------- VoxelDownSample */
 
 /* t/geometry/PointCloud.cpp:496-560 PointCloud::VoxelDownSample(voxel_size, "mean"):

@@ -13,6 +13,7 @@
 //   utility::MiniVecHash<int,3>                                    core/hashmap/Dispatch.h:67-81
 //   DISPATCH_ROBUST_KERNEL_FUNCTION                                t/pipelines/registration/RobustKernelImpl.h:35-115
 //   TransformIndexer, ArrayIndexer                                 t/geometry/kernel/GeometryIndexer.h:25-144, 160-420
+//   solve_svd3x3<float> / <double>                                 core/linalg/kernel/SVD3x3.h:2170-2215
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -24,6 +25,7 @@ using std::min;
 using std::pow;
 
 #include "open3d/core/hashmap/Dispatch.h"
+#include "open3d/core/linalg/kernel/SVD3x3.h"
 #include "open3d/core/nns/NeighborSearchCommon.h"
 #include "open3d/t/geometry/kernel/GeometryIndexer.h"
 #define OPEN3D_SKIP_TRANSFORM_MAIN   // TransformImpl.h:90: keep only the per-point kernels
@@ -127,6 +129,14 @@ void ref_workload_to_coord3(int res, int workload, int out[3]) {
 int ref_in_boundary2(int rows, int cols, float x, float y) {
     o3g::TArrayIndexer<int> idx(open3d::core::SizeVector{rows, cols});
     return idx.InBoundary(x, y) ? 1 : 0;
+}
+
+// x = pinv(A) b through the reference's own fast 3x3 SVD (used by EstimateColorGradients)
+void ref_solve_svd3x3_f32(const float A[9], const float b[3], float x[3]) {
+    open3d::core::linalg::kernel::solve_svd3x3<float>(A, b, x);
+}
+void ref_solve_svd3x3_f64(const double A[9], const double b[3], double x[3]) {
+    open3d::core::linalg::kernel::solve_svd3x3<double>(A, b, x);
 }
 
 }  // extern "C"

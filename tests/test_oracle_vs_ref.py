@@ -190,3 +190,42 @@ def test_tsdf_geometry_against_transform_indexer(ref):
         assert wt[b, v] == 1 and np.float32(tsdf[b, v]).tobytes() == np.float32((np.float32(0) * np.float32(0) + sdf) * np.float32(1.0)).tobytes()
         checked += 1
     assert checked > 50
+
+
+def test_sym3x3_pinv_vs_reference_svd_solver(ref):
+    """oracle.solve_sym3x3_pinv (f64 Jacobi, exact pseudo-inverse) vs the reference's solve_svd3x3
+    (core/linalg/kernel/SVD3x3.h:2170-2215) on the kind of matrices EstimateColorGradients produces
+    (tangent-plane covariance ~1e-2 plus the (i-1)^2 n n^T orthogonality row ~6e2: condition ~1e5).
+
+    The reference's Float32 instantiation runs a 4-sweep approximate Jacobi (rsqrt-based Givens), which on
+    these systems is NOT an accurate solver: measured here median ~12 %, max ~66 % away from the exact
+    solution, while the exact solve of the SAME f32-rounded inputs moves by ~1e-4.  The product therefore
+    computes the exact pseudo-inverse (what the reference's algorithm specifies) and colour-gradient parity is
+    stated against the oracle, not against the reference's solver noise.  This test pins both facts so the
+    gap stays visible: the oracle solves the system (residual ~0), the reference's solver does not."""
+    ref.ref_solve_svd3x3_f32.argtypes = [f32p, f32p, f32p]
+    rng = np.random.default_rng(9)
+    dev_ref, dev_round, res_orc, res_ref = [], [], [], []
+    for _ in range(200):
+        n = rng.normal(size=3)
+        n /= np.linalg.norm(n)
+        P = rng.normal(0, 0.03, (25, 3))
+        P -= np.outer(P @ n, n)                       # tangent-plane offsets
+        A = P.T @ P + 25 * 25 * np.outer(n, n)        # + the orthogonality row (i-1)^2 n n^T
+        b = P.T @ rng.normal(0, 0.1, 25)
+        x = oracle.solve_sym3x3_pinv(A, b)
+        np.testing.assert_allclose(x, np.linalg.solve(A, b), rtol=1e-9, atol=1e-12)
+        A32, b32, x32 = A.ravel().astype(np.float32), b.astype(np.float32), np.zeros(3, np.float32)
+        ref.ref_solve_svd3x3_f32(_p(A32, f32p), _p(b32, f32p), _p(x32, f32p))
+        scale = np.abs(x).max() + 1e-12
+        dev_ref.append(float(np.abs(x32 - x).max() / scale))
+        xr = oracle.solve_sym3x3_pinv(A32.astype(np.float64).reshape(3, 3), b32.astype(np.float64))
+        dev_round.append(float(np.abs(xr - x).max() / scale))
+        res_orc.append(float(np.linalg.norm(A @ x - b) / np.linalg.norm(b)))
+        res_ref.append(float(np.linalg.norm(A @ x32.astype(np.float64) - b) / np.linalg.norm(b)))
+    assert max(res_orc) < 1e-10                       # the oracle solves the system
+    assert max(dev_round) < 5e-3                      # f32 input rounding alone is harmless
+    assert np.all(np.isfinite(dev_ref))
+    # the reference's f32 solver: finite, same order of magnitude, but far from exact (documented gap)
+    assert 1e-3 < float(np.median(dev_ref)) < 0.5, np.median(dev_ref)
+    assert float(np.median(res_ref)) > 100 * max(res_orc)
