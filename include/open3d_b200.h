@@ -146,6 +146,23 @@ int o3db_voxel_down_sample(const float* positions_dev, const float* normals_dev 
                            float* positions_out_dev, float* normals_out_dev, float* colors_out_dev,
                            int64_t* num_out_host, void* stream);
 
+/* Same with up to 4 arbitrary [n,3] f32 point attributes (upstream averages every attribute of the
+ * cloud, PointCloud.cpp:536-552 — e.g. "color_gradients" through the ColoredICP pyramid).
+ * attrs_dev / attrs_out_dev are HOST arrays of num_attrs device pointers. */
+int o3db_voxel_down_sample_attrs(const float* positions_dev, const float* const* attrs_dev, int num_attrs,
+                                 int64_t n, double voxel_size, float* positions_out_dev,
+                                 float* const* attrs_out_dev, int64_t* num_out_host, void* stream);
+
+/* t::geometry::PointCloud::EstimateColorGradients with the hybrid search (t/geometry/PointCloud.cpp:
+ * 723-767, kernel/PointCloudImpl.h:1066-1165 EstimateColorGradientsUsingHybridSearchCUDA): the
+ * "color_gradients" attribute ColoredICP reads on the target.  Normal equations accumulated in f32 in
+ * the reference's order; solved with the exact pseudo-inverse (singular values < 1e-10 dropped as
+ * core/linalg/kernel/SVD3x3.h:2184-2187) — the reference's approximate f32 SVD is not reproduced
+ * (DESIGN.md).  max_nn in 1..32 (reference default 30).  Points with < 4 neighbours get a zero gradient. */
+int o3db_estimate_color_gradients(const float* positions_dev, const float* normals_dev, const float* colors_dev,
+                                  int64_t n, double radius, int max_nn, float* color_gradients_dev /* [n,3] */,
+                                  void* stream);
+
 /* ------------------------------------------------------------------------
  * Fused, device-resident ICP loop — replaces
  * t::pipelines::registration::ICP / MultiScaleICP / DoSingleScaleICPIterations /
@@ -185,6 +202,17 @@ int o3db_icp_create(const float* source_dev, int64_t n, const float* target_dev,
                     const float* target_normals_dev, int64_t m,
                     const double init_source_to_target_host[16], const o3db_icp_options* options,
                     o3db_comm* comm, void* stream, o3db_icp** out);
+/* Same loop for TransformationEstimationForColoredICP (TransformationEstimation.cpp:229-296,
+ * kernel/RegistrationImpl.h:337-425): colours are [.,3] f32 in the reference's value range, the
+ * target's color_gradients come from o3db_estimate_color_gradients (or upstream's
+ * EstimateColorGradients); lambda_geometric as upstream (default 0.968).  Everything else
+ * (search, convergence rule, result) is identical to the point-to-plane handle and the same
+ * iterate / finish / reset / destroy calls apply. */
+int o3db_icp_create_colored(const float* source_dev, const float* source_colors_dev, int64_t n,
+                            const float* target_dev, const float* target_normals_dev,
+                            const float* target_colors_dev, const float* target_color_gradients_dev, int64_t m,
+                            const double init_source_to_target_host[16], const o3db_icp_options* options,
+                            double lambda_geometric, o3db_comm* comm, void* stream, o3db_icp** out);
 /* Restore the state right after o3db_icp_create (source re-gathered, T = init). */
 int o3db_icp_reset(o3db_icp* icp, void* stream);
 /* Enqueue up to `iterations` ICP iterations (asynchronous, no host sync). */
@@ -202,6 +230,12 @@ int o3db_icp_point_to_plane(const float* source_dev, int64_t n, const float* tar
                             const double init_source_to_target_host[16],
                             const o3db_icp_options* options, o3db_icp_result* result_host,
                             int64_t* correspondences_dev, double* per_iteration_host, void* stream);
+int o3db_icp_colored(const float* source_dev, const float* source_colors_dev, int64_t n, const float* target_dev,
+                     const float* target_normals_dev, const float* target_colors_dev,
+                     const float* target_color_gradients_dev, int64_t m,
+                     const double init_source_to_target_host[16], const o3db_icp_options* options,
+                     double lambda_geometric, o3db_icp_result* result_host, int64_t* correspondences_dev,
+                     double* per_iteration_host, void* stream);
 /* Same through HOST buffers (pageable or pinned): copies inputs host->device,
  * runs, copies the result (and optional correspondences) back. */
 int o3db_icp_point_to_plane_host(const float* source_host, int64_t n, const float* target_host,

@@ -63,6 +63,13 @@ _SIGS = {
     "o3db_transform_points": (_i, [_dp, _vp, _i64, _vp]),
     "o3db_transform_normals": (_i, [_dp, _vp, _i64, _vp]),
     "o3db_voxel_down_sample": (_i, [_vp, _vp, _vp, _i64, _dbl, _vp, _vp, _vp, C.POINTER(_i64), _vp]),
+    "o3db_voxel_down_sample_attrs": (_i, [_vp, C.POINTER(_vp), _i, _i64, _dbl, _vp, C.POINTER(_vp), C.POINTER(_i64),
+                                          _vp]),
+    "o3db_estimate_color_gradients": (_i, [_vp, _vp, _vp, _i64, _dbl, _i, _vp, _vp]),
+    "o3db_icp_create_colored": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _dp, C.POINTER(IcpOptions), _dbl, _vp,
+                                     _vp, C.POINTER(_vp)]),
+    "o3db_icp_colored": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _dp, C.POINTER(IcpOptions), _dbl,
+                              C.POINTER(IcpResult), _vp, _dp, _vp]),
     "o3db_icp_create": (_i, [_vp, _i64, _vp, _vp, _i64, _dp, C.POINTER(IcpOptions), _vp, _vp, C.POINTER(_vp)]),
     "o3db_icp_reset": (_i, [_vp, _vp]),
     "o3db_icp_iterate": (_i, [_vp, _i, _vp]),

@@ -552,6 +552,48 @@ __device__ __forceinline__ void accumulate_p2plane(float (&acc)[kNumSums], const
     acc[28] += 1.0f;
 }
 
+// ComputePoseColoredICP per-correspondence body (RegistrationImpl.h:337-425 / RegistrationCUDA.cu:119-183):
+// geometric + photometric Jacobian rows, two robust weights, same 29-slot layout.
+template <bool L2LOSS>
+__device__ __forceinline__ void accumulate_colored(float (&acc)[kNumSums], const Robust& rk, const float (&vs)[3],
+                                                   const float (&vt)[3], const float (&nt)[3], float is, float it,
+                                                   const float (&dit)[3], float sqrt_lg, float sqrt_lp) {
+    const float d = (vs[0] - vt[0]) * nt[0] + (vs[1] - vt[1]) * nt[1] + (vs[2] - vt[2]) * nt[2];
+    float JG[6], JI[6];
+    JG[0] = sqrt_lg * (-vs[2] * nt[1] + vs[1] * nt[2]);
+    JG[1] = sqrt_lg * (vs[2] * nt[0] - vs[0] * nt[2]);
+    JG[2] = sqrt_lg * (-vs[1] * nt[0] + vs[0] * nt[1]);
+    JG[3] = sqrt_lg * nt[0];
+    JG[4] = sqrt_lg * nt[1];
+    JG[5] = sqrt_lg * nt[2];
+    const float rG = sqrt_lg * d;
+    const float vp[3] = {vs[0] - d * nt[0], vs[1] - d * nt[1], vs[2] - d * nt[2]};
+    const float is_proj = dit[0] * (vp[0] - vt[0]) + dit[1] * (vp[1] - vt[1]) + dit[2] * (vp[2] - vt[2]) + it;
+    const float sd = dit[0] * nt[0] + dit[1] * nt[1] + dit[2] * nt[2];
+    const float dM[3] = {sd * nt[0] - dit[0], sd * nt[1] - dit[1], sd * nt[2] - dit[2]};
+    JI[0] = sqrt_lp * (-vs[2] * dM[1] + vs[1] * dM[2]);
+    JI[1] = sqrt_lp * (vs[2] * dM[0] - vs[0] * dM[2]);
+    JI[2] = sqrt_lp * (-vs[1] * dM[0] + vs[0] * dM[1]);
+    JI[3] = sqrt_lp * dM[0];
+    JI[4] = sqrt_lp * dM[1];
+    JI[5] = sqrt_lp * dM[2];
+    const float rI = sqrt_lp * (is - is_proj);
+    const float wG = L2LOSS ? 1.0f : robust_weight(rk, rG);
+    const float wI = L2LOSS ? 1.0f : robust_weight(rk, rI);
+    int p = 0;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+#pragma unroll
+        for (int k = 0; k <= j; ++k) acc[p++] += JG[j] * wG * JG[k] + JI[j] * wI * JI[k];
+        acc[21 + j] += JG[j] * wG * rG + JI[j] * wI * rI;
+    }
+    acc[27] += rG * rG + rI * rI;
+    acc[28] += 1.0f;
+}
+
+// intensity of an RGB triple exactly as upstream: float sum, divided by the double literal 3.0
+__device__ __forceinline__ float color_intensity(float r, float g, float b) { return (float)((r + g + b) / 3.0); }
+
 // Block epilogue: per-warp slots -> block partial -> (last block) grand total in
 // block-index order.  Returns true in the last block, with s_final[] filled.
 __device__ __forceinline__ bool block_reduce_to_global(double (*s_warp)[kSumStride], double* __restrict__ partials,
@@ -714,41 +756,10 @@ pose_colored_kernel(const float* __restrict__ src, const float* __restrict__ src
             const float vs[3] = {src[s], src[s + 1], src[s + 2]};
             const float vt[3] = {tgt[t], tgt[t + 1], tgt[t + 2]};
             const float nt[3] = {nrm[t], nrm[t + 1], nrm[t + 2]};
-            const float d = (vs[0] - vt[0]) * nt[0] + (vs[1] - vt[1]) * nt[1] + (vs[2] - vt[2]) * nt[2];
-            float JG[6], JI[6];
-            JG[0] = sqrt_lg * (-vs[2] * nt[1] + vs[1] * nt[2]);
-            JG[1] = sqrt_lg * (vs[2] * nt[0] - vs[0] * nt[2]);
-            JG[2] = sqrt_lg * (-vs[1] * nt[0] + vs[0] * nt[1]);
-            JG[3] = sqrt_lg * nt[0];
-            JG[4] = sqrt_lg * nt[1];
-            JG[5] = sqrt_lg * nt[2];
-            const float rG = sqrt_lg * d;
-            const float vp[3] = {vs[0] - d * nt[0], vs[1] - d * nt[1], vs[2] - d * nt[2]};
-            const float is = (float)((src_c[s] + src_c[s + 1] + src_c[s + 2]) / 3.0);
-            const float it = (float)((tgt_c[t] + tgt_c[t + 1] + tgt_c[t + 2]) / 3.0);
+            const float is = color_intensity(src_c[s], src_c[s + 1], src_c[s + 2]);
+            const float it = color_intensity(tgt_c[t], tgt_c[t + 1], tgt_c[t + 2]);
             const float dit[3] = {tgt_g[t], tgt_g[t + 1], tgt_g[t + 2]};
-            const float is_proj =
-                    dit[0] * (vp[0] - vt[0]) + dit[1] * (vp[1] - vt[1]) + dit[2] * (vp[2] - vt[2]) + it;
-            const float sd = dit[0] * nt[0] + dit[1] * nt[1] + dit[2] * nt[2];
-            const float dM[3] = {sd * nt[0] - dit[0], sd * nt[1] - dit[1], sd * nt[2] - dit[2]};
-            JI[0] = sqrt_lp * (-vs[2] * dM[1] + vs[1] * dM[2]);
-            JI[1] = sqrt_lp * (vs[2] * dM[0] - vs[0] * dM[2]);
-            JI[2] = sqrt_lp * (-vs[1] * dM[0] + vs[0] * dM[1]);
-            JI[3] = sqrt_lp * dM[0];
-            JI[4] = sqrt_lp * dM[1];
-            JI[5] = sqrt_lp * dM[2];
-            const float rI = sqrt_lp * (is - is_proj);
-            const float wG = L2LOSS ? 1.0f : robust_weight(rk, rG);
-            const float wI = L2LOSS ? 1.0f : robust_weight(rk, rI);
-            int p = 0;
-#pragma unroll
-            for (int j = 0; j < 6; ++j) {
-#pragma unroll
-                for (int k = 0; k <= j; ++k) acc[p++] += JG[j] * wG * JG[k] + JI[j] * wI * JI[k];
-                acc[21 + j] += JG[j] * wG * rG + JI[j] * wI * rI;
-            }
-            acc[27] += rG * rG + rI * rI;
-            acc[28] += 1.0f;
+            accumulate_colored<L2LOSS>(acc, rk, vs, vt, nt, is, it, dit, sqrt_lg, sqrt_lp);
         }
         if (++since == kFlushEvery) {
             flush_acc(acc, s_warp);
@@ -790,6 +801,23 @@ __global__ void transform_normals_kernel(float* __restrict__ p, int64_t n, Affin
     p[3 * i + 2] = T.m[8] * x + T.m[9] * y + T.m[10] * z;
 }
 
+// ColoredICP side arrays, in the sort order of the working clouds (orig index = .w of the float4)
+__global__ void pack_target_color_kernel(const float4* __restrict__ pts4, const float* __restrict__ col,
+                                         const float* __restrict__ grad, int64_t m, float4* __restrict__ tcg) {
+    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    const int64_t o = 3 * (int64_t)__float_as_int(pts4[j].w);
+    tcg[j] = make_float4(grad[o], grad[o + 1], grad[o + 2], color_intensity(col[o], col[o + 1], col[o + 2]));
+}
+
+__global__ void pack_source_intensity_kernel(const float4* __restrict__ src4, const float* __restrict__ col,
+                                             int64_t n, float* __restrict__ sint) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t o = 3 * (int64_t)__float_as_int(src4[i].w);
+    sint[i] = color_intensity(col[o], col[o + 1], col[o + 2]);
+}
+
 // ------------------------------------------------------------ fused ICP loop
 
 struct IcpState {        // lives in device memory; read back once at the end
@@ -824,6 +852,10 @@ struct IcpArgs {
     double rel_fitness, rel_rmse;
     int max_iteration;
     int fuse_finalize;    // 0: leave the totals in st->sums (multi-GPU all-reduce follows)
+    // ColoredICP only (null otherwise)
+    const float4* tcg;    // per sorted target point: colour gradient xyz, .w = intensity
+    const float* sint;    // per sorted source point: intensity
+    float sqrt_lg, sqrt_lp;
 };
 
 __device__ void set_identity(double* T, float* Uf) {
@@ -907,7 +939,7 @@ __device__ void icp_finalize_evaluate(const IcpArgs& a, const double* sums) {
 // source in place, exact 1-NN within the radius through the grid, Jacobian,
 // 30-scalar reduction, and (last block) solve + pose update + convergence test.
 // MODE 0 = iterate, MODE 1 = evaluate (no Jacobian; writes correspondences).
-template <bool L2LOSS, int MODE>
+template <bool L2LOSS, int MODE, bool COLORED = false>
 __global__ void __launch_bounds__(kThreads, ICP_MIN_BLOCKS)
 icp_iteration_kernel(IcpArgs a) {
     __shared__ double s_warp[kThreads / 32][kSumStride];
@@ -967,7 +999,15 @@ icp_iteration_kernel(IcpArgs a) {
 #else
                 if (MODE == 0) {
                     const float4 nn = __ldg(&a.nrm[b.j]);
-                    accumulate_p2plane<L2LOSS>(acc, a.rk, p.x, p.y, p.z, b.x, b.y, b.z, nn.x, nn.y, nn.z);
+                    if (COLORED) {
+                        const float4 cg = __ldg(&a.tcg[b.j]);
+                        const float vs[3] = {p.x, p.y, p.z}, vt[3] = {b.x, b.y, b.z}, nt[3] = {nn.x, nn.y, nn.z};
+                        const float dit[3] = {cg.x, cg.y, cg.z};
+                        accumulate_colored<L2LOSS>(acc, a.rk, vs, vt, nt, __ldg(&a.sint[i]), cg.w, dit, a.sqrt_lg,
+                                                   a.sqrt_lp);
+                    } else {
+                        accumulate_p2plane<L2LOSS>(acc, a.rk, p.x, p.y, p.z, b.x, b.y, b.z, nn.x, nn.y, nn.z);
+                    }
                 } else {
                     acc[28] += 1.0f;
                 }
@@ -1269,6 +1309,12 @@ struct o3db_icp {
     int64_t src_keys = 0;            // size of the source sort key space
     int launched = 0;
     bool l2loss = true;
+    // ColoredICP (TransformationEstimationForColoredICP); null / unused for point-to-plane
+    bool colored = false;
+    const float* src_colors_user = nullptr;
+    float4* tcg4 = nullptr;          // sorted target: colour gradient xyz + intensity
+    float* sint = nullptr;           // sorted source: intensity
+    double lambda_geometric = 0.968;
 };
 
 namespace o3db {
@@ -1298,6 +1344,10 @@ static IcpArgs make_args(o3db_icp* c) {
     a.rel_rmse = c->opt.relative_rmse;
     a.max_iteration = c->opt.max_iteration;
     a.fuse_finalize = c->comm ? 0 : 1;
+    a.tcg = c->tcg4;
+    a.sint = c->sint;
+    a.sqrt_lg = (float)sqrt(c->lambda_geometric);          // RegistrationCUDA.cu:205-208
+    a.sqrt_lp = (float)sqrt(1.0 - c->lambda_geometric);
     return a;
 }
 
@@ -1544,13 +1594,26 @@ void o3db_icp_destroy(o3db_icp* c) {
     if (c->partials) cudaFreeAsync(c->partials, 0);
     if (c->per_iter) cudaFreeAsync(c->per_iter, 0);
     if (c->st) cudaFreeAsync(c->st, 0);
+    if (c->tcg4) cudaFreeAsync(c->tcg4, 0);
+    if (c->sint) cudaFreeAsync(c->sint, 0);
     if (c->h_st) pinned_release(c->h_st);
     delete c;
 }
 
-int o3db_icp_create(const float* source_dev, int64_t n, const float* target_dev, const float* target_normals_dev,
-                    int64_t m, const double init_T[16], const o3db_icp_options* options, o3db_comm* comm,
-                    void* stream, o3db_icp** out) {
+}  // extern "C"
+
+namespace o3db {
+struct ColoredInputs {   // all device pointers; null source_colors = plain point-to-plane
+    const float* source_colors = nullptr;
+    const float* target_colors = nullptr;
+    const float* target_color_gradients = nullptr;
+    double lambda_geometric = 0.968;
+};
+}  // namespace o3db
+
+static int icp_create_impl(const float* source_dev, int64_t n, const float* target_dev, const float* target_normals_dev,
+                           int64_t m, const double init_T[16], const o3db_icp_options* options, o3db_comm* comm,
+                           const o3db::ColoredInputs& col, void* stream, o3db_icp** out) {
     O3DB_REQUIRE(out != nullptr, "o3db_icp_create: out is null");
     *out = nullptr;
     O3DB_REQUIRE(options != nullptr && init_T != nullptr, "o3db_icp_create: null options / init");
@@ -1568,6 +1631,9 @@ int o3db_icp_create(const float* source_dev, int64_t n, const float* target_dev,
     c->n = n;
     c->comm = comm;
     c->l2loss = options->kernel.method == O3DB_ROBUST_L2;
+    c->colored = col.source_colors != nullptr;
+    c->src_colors_user = col.source_colors;
+    c->lambda_geometric = col.lambda_geometric;
     memcpy(c->init_T, init_T, sizeof(c->init_T));
     // fine cells (half the radius) by default: pass 1 of the two-pass search then covers the
     // +-1 cell box, which holds the nearest neighbour of every already roughly aligned point
@@ -1599,8 +1665,14 @@ int o3db_icp_create(const float* source_dev, int64_t n, const float* target_dev,
     // 1 = direct (two-pass search straight from global/L1), 2 = TMA-staged shared-memory tiles.
     // Default: whichever measured faster on B200 — currently the direct kernel.
     c->variant = options->search_variant == 2 ? 2 : (options->search_variant == 1 ? 1 : ICP_DEFAULT_VARIANT);
+    if (c->colored) c->variant = 1;   // the tile-staged kernel has no coloured instantiation
     int occ = 1;
-    if (c->variant == 2) {
+    if (c->colored) {
+        if (c->l2loss)
+            ICP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, icp_iteration_kernel<true, 0, true>, kThreads, 0));
+        else
+            ICP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, icp_iteration_kernel<false, 0, true>, kThreads, 0));
+    } else if (c->variant == 2) {
         const int smem = (int)sizeof(TileSmem);
         ICP_CUDA(cudaFuncSetAttribute(icp_iteration_tile_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         ICP_CUDA(cudaFuncSetAttribute(icp_iteration_tile_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -1646,6 +1718,19 @@ int o3db_icp_create(const float* source_dev, int64_t n, const float* target_dev,
     ICP_TRY(exclusive_scan_u32(c->src_start, ncell, scratch, st));
     ICP_CUDA(cudaFreeAsync(scratch, st));
     ICP_TRY(icp_gather_source(c, st));
+    if (c->colored) {
+        ICP_CUDA(cudaMallocAsync(&c->tcg4, m * sizeof(float4), st));
+        ICP_CUDA(cudaMallocAsync(&c->sint, n * sizeof(float), st));
+        pack_target_color_kernel<<<(unsigned)ceil_div(m, kThreads), kThreads, 0, st>>>(
+                c->nns.pts4, col.target_colors, col.target_color_gradients, m, c->tcg4);
+        count_launch();
+        ICP_CUDA(cudaGetLastError());
+        // the source sort order is fixed at creation (o3db_icp_reset re-gathers into the same slots)
+        pack_source_intensity_kernel<<<(unsigned)ceil_div(n, kThreads), kThreads, 0, st>>>(c->src4, col.source_colors, n,
+                                                                                          c->sint);
+        count_launch();
+        ICP_CUDA(cudaGetLastError());
+    }
     ICP_TRY(icp_init_state(c, st));
     if (comm) {
         double* d = nullptr;
@@ -1658,6 +1743,36 @@ int o3db_icp_create(const float* source_dev, int64_t n, const float* target_dev,
     }
     *out = c;
     return O3DB_OK;
+}
+
+extern "C" {
+
+int o3db_icp_create(const float* source_dev, int64_t n, const float* target_dev, const float* target_normals_dev,
+                    int64_t m, const double init_T[16], const o3db_icp_options* options, o3db_comm* comm,
+                    void* stream, o3db_icp** out) {
+    return icp_create_impl(source_dev, n, target_dev, target_normals_dev, m, init_T, options, comm,
+                           o3db::ColoredInputs{}, stream, out);
+}
+
+int o3db_icp_create_colored(const float* source_dev, const float* source_colors_dev, int64_t n,
+                            const float* target_dev, const float* target_normals_dev, const float* target_colors_dev,
+                            const float* target_color_gradients_dev, int64_t m, const double init_T[16],
+                            const o3db_icp_options* options, double lambda_geometric, o3db_comm* comm, void* stream,
+                            o3db_icp** out) {
+    O3DB_REQUIRE(out != nullptr, "o3db_icp_create_colored: out is null");
+    *out = nullptr;
+    // ColoredICP.. TransformationEstimationForColoredICP::ComputeTransformation (TransformationEstimation.cpp:226-262)
+    O3DB_REQUIRE(source_colors_dev != nullptr, "Source pointcloud missing colors attribute.");
+    O3DB_REQUIRE(target_colors_dev != nullptr, "Target pointcloud missing colors attribute.");
+    O3DB_REQUIRE(target_color_gradients_dev != nullptr,
+                 "Target pointcloud missing color_gradients attribute (o3db_estimate_color_gradients).");
+    O3DB_REQUIRE(lambda_geometric >= 0.0 && lambda_geometric <= 1.0, "lambda_geometric must be in [0, 1]");
+    o3db::ColoredInputs col;
+    col.source_colors = source_colors_dev;
+    col.target_colors = target_colors_dev;
+    col.target_color_gradients = target_color_gradients_dev;
+    col.lambda_geometric = lambda_geometric;
+    return icp_create_impl(source_dev, n, target_dev, target_normals_dev, m, init_T, options, comm, col, stream, out);
 }
 
 int o3db_icp_reset(o3db_icp* c, void* stream) {
@@ -1677,6 +1792,9 @@ int o3db_icp_iterate(o3db_icp* c, int iterations, void* stream) {
         if (c->variant == 2) {
             if (c->l2loss) icp_iteration_tile_kernel<true, 0><<<c->grid_blocks, kThreads, sizeof(TileSmem), st>>>(a);
             else icp_iteration_tile_kernel<false, 0><<<c->grid_blocks, kThreads, sizeof(TileSmem), st>>>(a);
+        } else if (c->colored) {
+            if (c->l2loss) icp_iteration_kernel<true, 0, true><<<c->grid_blocks, kThreads, 0, st>>>(a);
+            else icp_iteration_kernel<false, 0, true><<<c->grid_blocks, kThreads, 0, st>>>(a);
         } else {
             if (c->l2loss) icp_iteration_kernel<true, 0><<<c->grid_blocks, kThreads, 0, st>>>(a);
             else icp_iteration_kernel<false, 0><<<c->grid_blocks, kThreads, 0, st>>>(a);
@@ -1736,6 +1854,23 @@ int o3db_icp_point_to_plane(const float* source_dev, int64_t n, const float* tar
                             double* per_iteration_host, void* stream) {
     o3db_icp* c = nullptr;
     int rc = o3db_icp_create(source_dev, n, target_dev, target_normals_dev, m, init_T, options, nullptr, stream, &c);
+    if (rc) return rc;
+    rc = o3db_icp_iterate(c, options->max_iteration, stream);
+    if (rc == O3DB_OK) rc = o3db_icp_finish(c, result, correspondences_dev, per_iteration_host, stream);
+    cudaStreamSynchronize((cudaStream_t)stream);
+    o3db_icp_destroy(c);
+    return rc;
+}
+
+int o3db_icp_colored(const float* source_dev, const float* source_colors_dev, int64_t n, const float* target_dev,
+                     const float* target_normals_dev, const float* target_colors_dev,
+                     const float* target_color_gradients_dev, int64_t m, const double init_T[16],
+                     const o3db_icp_options* options, double lambda_geometric, o3db_icp_result* result,
+                     int64_t* correspondences_dev, double* per_iteration_host, void* stream) {
+    o3db_icp* c = nullptr;
+    int rc = o3db_icp_create_colored(source_dev, source_colors_dev, n, target_dev, target_normals_dev,
+                                     target_colors_dev, target_color_gradients_dev, m, init_T, options,
+                                     lambda_geometric, nullptr, stream, &c);
     if (rc) return rc;
     rc = o3db_icp_iterate(c, options->max_iteration, stream);
     if (rc == O3DB_OK) rc = o3db_icp_finish(c, result, correspondences_dev, per_iteration_host, stream);

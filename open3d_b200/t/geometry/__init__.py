@@ -61,23 +61,44 @@ class PointCloud:
         import ctypes as C
         p = self.point["positions"]
         n = int(p.shape[0])
-        nrm = self.point.get("normals")
-        col = self.point.get("colors")
+        # every [n,3] Float32 attribute is averaged per voxel (PointCloud.cpp:536-552)
+        names = [k for k, v in self.point.items() if k != "positions"]
+        for k in names:
+            v = self.point[k]
+            if v.dtype != torch.float32 or v.dim() != 2 or v.shape[1] != 3 or v.shape[0] != n:
+                raise RuntimeError(f"voxel_down_sample: attribute '{k}' must be [N,3] Float32")
+        if len(names) > 4:
+            raise RuntimeError("voxel_down_sample: at most 4 attributes besides positions")
+        ins = [self.point[k].contiguous() for k in names]
+        outs = [torch.empty_like(v) for v in ins]
         po = torch.empty_like(p)
-        no = torch.empty_like(nrm) if nrm is not None else None
-        co = torch.empty_like(col) if col is not None else None
         m = C.c_int64(0)
-        check(lib.o3db_voxel_down_sample(p.data_ptr(), None if nrm is None else nrm.data_ptr(),
-                                         None if col is None else col.data_ptr(), n, float(voxel_size), po.data_ptr(),
-                                         None if no is None else no.data_ptr(), None if co is None else co.data_ptr(),
-                                         C.byref(m), current_stream_ptr()))
+        in_ptrs = (C.c_void_p * max(len(ins), 1))(*[v.data_ptr() for v in ins])
+        out_ptrs = (C.c_void_p * max(len(outs), 1))(*[v.data_ptr() for v in outs])
+        check(lib.o3db_voxel_down_sample_attrs(p.data_ptr(), in_ptrs, len(ins), n, float(voxel_size), po.data_ptr(),
+                                               out_ptrs, C.byref(m), current_stream_ptr()))
         out = PointCloud()
         out.point["positions"] = po[: m.value].contiguous()
-        if no is not None:
-            out.point["normals"] = no[: m.value].contiguous()
-        if co is not None:
-            out.point["colors"] = co[: m.value].contiguous()
+        for k, v in zip(names, outs):
+            out.point[k] = v[: m.value].contiguous()
         return out
+
+    def estimate_color_gradients(self, max_nn=30, radius=None):
+        """PointCloud::EstimateColorGradients (t/geometry/PointCloud.cpp:723-767), hybrid search: sets
+        the "color_gradients" attribute ColoredICP reads on the target."""
+        if not self.has_point_colors():
+            raise RuntimeError("PointCloud must have colors attribute to estimate color gradients.")
+        if not self.has_point_normals():
+            raise RuntimeError("PointCloud must have normals attribute to estimate color gradients.")
+        if radius is None:
+            raise RuntimeError("open3d_b200 builds the hybrid-search variant: pass radius (upstream's KNN-only and "
+                               "radius-only variants are outside this build's scope).")
+        p, nrm, col = self.point["positions"], self.point["normals"], self.point["colors"]
+        g = torch.empty_like(p)
+        check(lib.o3db_estimate_color_gradients(p.data_ptr(), nrm.data_ptr(), col.data_ptr(), int(p.shape[0]),
+                                                float(radius), int(max_nn), g.data_ptr(), current_stream_ptr()))
+        self.point["color_gradients"] = g
+        return self
 
     def transform(self, transformation):
         """PointCloud::Transform (t/geometry/PointCloud.cpp:352-371): in place on

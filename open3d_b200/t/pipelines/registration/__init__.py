@@ -1,4 +1,4 @@
-"""Mirror of ``open3d.t.pipelines.registration`` for the point-to-plane ICP path
+"""Mirror of ``open3d.t.pipelines.registration`` for the point-to-plane and coloured ICP paths
 (cpp/pybind/t/pipelines/registration/registration.cpp:96-140, 469-530;
 cpp/open3d/t/pipelines/registration/{Registration,TransformationEstimation}.cpp).
 
@@ -144,8 +144,9 @@ class TransformationEstimationPointToPlane(TransformationEstimation):
 
 
 class TransformationEstimationForColoredICP(TransformationEstimation):
-    """TransformationEstimation.h:318-395; only the pose kernel seam is built so far
-    (o3db_compute_pose_colored_icp); the driver / colour-gradient precompute are SURVEY §8f items."""
+    """TransformationEstimation.h:318-395 / TransformationEstimation.cpp:294-432.  The target needs the
+    "color_gradients" attribute (``PointCloud.estimate_color_gradients``; ``icp`` / ``multi_scale_icp``
+    compute it on the finest pyramid level when it is missing, Registration.cpp:243-263)."""
 
     def __init__(self, lambda_geometric: float = 0.968, kernel: RobustKernel | None = None):
         if lambda_geometric < 0 or lambda_geometric > 1.0:
@@ -153,10 +154,43 @@ class TransformationEstimationForColoredICP(TransformationEstimation):
         self.lambda_geometric = lambda_geometric
         self.kernel = kernel if kernel is not None else RobustKernel()
 
-    def compute_pose(self, source, target, correspondences, target_color_gradients):
+    @staticmethod
+    def _check(source, target, need_gradients=True):
+        if not target.has_point_positions() or not source.has_point_positions():
+            raise RuntimeError("Source and/or Target pointcloud is empty.")
+        if not target.has_point_colors() or not source.has_point_colors():
+            raise RuntimeError("Source and/or Target pointcloud missing colors attribute.")
+        if not target.has_point_normals():
+            raise RuntimeError("Target pointcloud missing normals attribute.")
+        if need_gradients and "color_gradients" not in target.point:
+            raise RuntimeError("Target pointcloud missing color_gradients attribute.")
+
+    def compute_rmse(self, source, target, correspondences):
+        """TransformationEstimation.cpp:294-380 — returns, as upstream, the summed squared joint
+        residual (not a root mean), evaluated with torch ops on the device (host-side glue upstream)."""
+        self._check(source, target)
+        corr = _corr_arg(correspondences, source.point["positions"].shape[0])
+        valid = corr != -1
+        idx = corr[valid]
+        vs, cs = source.point["positions"][valid], source.point["colors"][valid]
+        vt, nt = target.point["positions"][idx], target.point["normals"][idx]
+        ct, dit = target.point["colors"][idx], target.point["color_gradients"][idx]
+        d = ((vs - vt) * nt).sum(1, keepdim=True)
+        vs_proj = vs - d * nt
+        i_s, i_t = cs.mean(1, keepdim=True), ct.mean(1, keepdim=True)
+        is_proj = (dit * (vs_proj - vt)).sum(1, keepdim=True) + i_t
+        rg = d * float(np.sqrt(self.lambda_geometric))
+        rp = (i_s - is_proj) * float(np.sqrt(1.0 - self.lambda_geometric))
+        return float((rg * rg + rp * rp).sum().to(torch.float64))
+
+    def compute_pose(self, source, target, correspondences, target_color_gradients=None):
+        """kernel::ComputePoseColoredICP (kernel/Registration.cpp:80-131) through the C ABI seam
+        o3db_compute_pose_colored_icp."""
+        self._check(source, target, need_gradients=target_color_gradients is None)
         s, sc = source.point["positions"], source.point["colors"]
         t, n, tc = target.point["positions"], target.point["normals"], target.point["colors"]
-        g = as_device_f32_points(target_color_gradients, "color_gradients")
+        g = as_device_f32_points(target.point["color_gradients"] if target_color_gradients is None
+                                 else target_color_gradients, "color_gradients")
         corr = _corr_arg(correspondences, s.shape[0])
         pose = torch.zeros(6, dtype=torch.float64, device=s.device)
         sums = torch.zeros(29, dtype=torch.float64, device=s.device)
@@ -168,6 +202,14 @@ class TransformationEstimationForColoredICP(TransformationEstimation):
                                                 pose.data_ptr(), C.byref(residual), C.byref(count),
                                                 current_stream_ptr()))
         return pose, float(residual.value), int(count.value), sums
+
+    def compute_transformation(self, source, target, correspondences, current_transform=None, iteration=0):
+        """TransformationEstimation.cpp:382-432 -> 4x4 Float64 on CPU."""
+        pose, _, _, _ = self.compute_pose(source, target, correspondences)
+        p = np.ascontiguousarray(pose.cpu().numpy())
+        T = np.zeros((4, 4), np.float64)
+        lib.o3db_pose_to_transformation(dptr(p), dptr(T))
+        return T
 
 
 def _options(max_correspondence_distance, criteria, kernel):
@@ -184,12 +226,21 @@ def _options(max_correspondence_distance, criteria, kernel):
 
 def _assert_inputs(source, target, estimation_method, max_correspondence_distance):
     # Registration.cpp:119-219 AssertInputMultiScaleICP
-    if not isinstance(estimation_method, TransformationEstimationPointToPlane):
-        raise RuntimeError("open3d_b200 implements TransformationEstimationPointToPlane; other estimators are "
-                           "outside this build's scope (SURVEY.md §8f).")
+    colored = isinstance(estimation_method, TransformationEstimationForColoredICP)
+    if not colored and not isinstance(estimation_method, TransformationEstimationPointToPlane):
+        raise RuntimeError("open3d_b200 implements TransformationEstimationPointToPlane and "
+                           "TransformationEstimationForColoredICP; other estimators are outside this build's "
+                           "scope (SURVEY.md §8f).")
     if not target.has_point_positions() or not source.has_point_positions():
         raise RuntimeError("Source and/or Target pointcloud is empty.")
-    if not target.has_point_normals():
+    if colored:
+        if not target.has_point_normals():
+            raise RuntimeError("ColoredICP requires target pointcloud to have normals.")
+        if not target.has_point_colors():
+            raise RuntimeError("ColoredICP requires target pointcloud to have colors.")
+        if not source.has_point_colors():
+            raise RuntimeError("ColoredICP requires source pointcloud to have colors.")
+    elif not target.has_point_normals():
         raise RuntimeError("TransformationEstimationPointToPlane require pre-computed normal vectors for target "
                            "PointCloud.")
     if max_correspondence_distance <= 0.0:
@@ -205,8 +256,15 @@ def _run_single_scale(source, target, max_dist, init, estimation, criteria, call
     stream = current_stream_ptr()
     handle = C.c_void_p()
     T0 = np.ascontiguousarray(init, dtype=np.float64)
-    check(lib.o3db_icp_create(s.data_ptr(), s.shape[0], t.data_ptr(), n.data_ptr(), t.shape[0], dptr(T0),
-                              C.byref(opt), None, stream, C.byref(handle)))
+    if isinstance(estimation, TransformationEstimationForColoredICP):
+        estimation._check(source, target)
+        sc, tc, tg = source.point["colors"], target.point["colors"], target.point["color_gradients"]
+        check(lib.o3db_icp_create_colored(s.data_ptr(), sc.data_ptr(), s.shape[0], t.data_ptr(), n.data_ptr(),
+                                          tc.data_ptr(), tg.data_ptr(), t.shape[0], dptr(T0), C.byref(opt),
+                                          float(estimation.lambda_geometric), None, stream, C.byref(handle)))
+    else:
+        check(lib.o3db_icp_create(s.data_ptr(), s.shape[0], t.data_ptr(), n.data_ptr(), t.shape[0], dptr(T0),
+                                  C.byref(opt), None, stream, C.byref(handle)))
     try:
         check(lib.o3db_icp_iterate(handle, opt.max_iteration, stream))
         res = IcpResult()
@@ -257,8 +315,8 @@ def multi_scale_icp(source, target, voxel_sizes, criteria_list, max_corresponden
                     init_source_to_target=None, estimation_method=None, callback_after_iteration=None):
     """MultiScaleICP (Registration.cpp:362-444)."""
     if estimation_method is None:
-        raise RuntimeError("open3d_b200 implements TransformationEstimationPointToPlane; pass it explicitly "
-                           "(the reference default is PointToPoint, which is outside this build's scope).")
+        raise RuntimeError("open3d_b200 implements TransformationEstimationPointToPlane and ...ForColoredICP; pass "
+                           "one explicitly (the reference default is PointToPoint, outside this build's scope).")
     n_scales = len(criteria_list)
     if len(voxel_sizes) != n_scales or len(max_correspondence_distances) != n_scales:
         raise RuntimeError(" [MultiScaleICP]: Size of criterias, voxel_size, max_correspondence_distances vectors "
@@ -276,6 +334,13 @@ def multi_scale_icp(source, target, voxel_sizes, criteria_list, max_corresponden
         src_pyr[-1], tgt_pyr[-1] = source, target          # (the loop clones the source itself)
     else:
         src_pyr[-1], tgt_pyr[-1] = source.voxel_down_sample(voxel_sizes[-1]), target.voxel_down_sample(voxel_sizes[-1])
+    if isinstance(estimation_method, TransformationEstimationForColoredICP) and \
+            "color_gradients" not in target.point:          # Registration.cpp:243-263
+        if voxel_sizes[-1] <= 0:
+            tgt_pyr[-1] = tgt_pyr[-1].clone()               # the caller's target is left untouched
+            tgt_pyr[-1].estimate_color_gradients(30, max_correspondence_distances[-1] * 2.0)
+        else:
+            tgt_pyr[-1].estimate_color_gradients(30, voxel_sizes[-1] * 4.0)
     for k in range(n_scales - 2, -1, -1):
         src_pyr[k] = src_pyr[k + 1].voxel_down_sample(voxel_sizes[k])
         tgt_pyr[k] = tgt_pyr[k + 1].voxel_down_sample(voxel_sizes[k])

@@ -419,3 +419,143 @@ def test_multi_scale_icp_with_voxel_pyramid_vs_oracle(o3d):
     np.testing.assert_allclose(res.transformation, T, atol=5e-5)
     assert abs(res.fitness - ref.fitness) < 1e-3 and abs(res.inlier_rmse - ref.inlier_rmse) < 1e-5
     np.testing.assert_allclose(res.transformation, T_gt, atol=3e-3)
+
+
+# ------------------------------------------------- ColoredICP
+
+def _colored_pair(n, seed):
+    src, tgt, nrm, T_gt = make_icp_pair(n, seed=seed)
+    # the texture lives in the target frame: a source point carries the colour of where it belongs
+    sc = make_colors(oracle.transform_points(T_gt, src), 1)
+    return src, sc, tgt, nrm, make_colors(tgt, 1), T_gt
+
+
+@pytest.mark.parametrize("n,radius,max_nn", [(20000, 0.08, 30), (20000, 0.03, 30), (5000, 0.025, 8)])
+def test_color_gradients_vs_oracle(o3d, n, radius, max_nn):
+    """EstimateColorGradients, hybrid search (PointCloudImpl.h:1066-1165): the f32 normal equations are
+    accumulated in the reference's order, so the solve sees bit-identical systems."""
+    _, _, tgt, nrm, tc, _ = _colored_pair(n, 21)
+    pc = o3d.t.geometry.PointCloud(tgt).set_point_normals(nrm).set_point_colors(tc)
+    pc.estimate_color_gradients(max_nn, radius)
+    g = pc.point["color_gradients"].cpu().numpy()
+    ref = oracle.estimate_color_gradients(tgt, nrm, tc, radius, max_nn)
+    assert g.shape == ref.shape and np.isfinite(g).all()
+    zero = ~ref.any(axis=1)
+    assert np.array_equal(zero, ~g.any(axis=1))           # < 4 neighbours -> exactly zero, same points
+    if radius < 0.03:
+        assert zero.any() and not zero.all()
+    np.testing.assert_allclose(g, ref, rtol=1e-5, atol=1e-5 * np.abs(ref).max())
+    # the gradient is tangential: the orthogonality row drives g . n to ~0
+    assert np.abs((g * nrm).sum(1)).max() < 1e-3 * max(np.abs(g).max(), 1.0)
+    with pytest.raises(RuntimeError, match="colors"):
+        o3d.t.geometry.PointCloud(tgt).set_point_normals(nrm).estimate_color_gradients(30, radius)
+    with pytest.raises(RuntimeError, match="normals"):
+        o3d.t.geometry.PointCloud(tgt).set_point_colors(tc).estimate_color_gradients(30, radius)
+
+
+def _colored_clouds(o3d, src, sc, tgt, nrm, tc, grad=None):
+    s = o3d.t.geometry.PointCloud(src).set_point_colors(sc)
+    t = o3d.t.geometry.PointCloud(tgt).set_point_normals(nrm).set_point_colors(tc)
+    if grad is not None:
+        t.point["color_gradients"] = torch.from_numpy(np.ascontiguousarray(grad, np.float32)).cuda()
+    return s, t
+
+
+@pytest.mark.parametrize("n,iters,robust", [(40000, 1, None), (40000, 12, None), (30000, 8, ("TukeyLoss", 0.05, 1.0))])
+def test_colored_icp_loop_vs_oracle(o3d, n, iters, robust):
+    """Fused ColoredICP loop vs the oracle's loop on identical inputs (gradients given to both)."""
+    reg = o3d.t.pipelines.registration
+    src, sc, tgt, nrm, tc, T_gt = _colored_pair(n, 22)
+    grad = oracle.estimate_color_gradients(tgt, nrm, tc, 0.08, 30)
+    s, t = _colored_clouds(o3d, src, sc, tgt, nrm, tc, grad)
+    kernel = None
+    if robust:
+        kernel = reg.RobustKernel(reg.RobustKernelMethod[robust[0]], robust[1], robust[2])
+    est = reg.TransformationEstimationForColoredICP(0.968, kernel)
+    log = []
+    res = reg.icp(s, t, 0.05, np.eye(4), est, reg.ICPConvergenceCriteria(0, 0, iters), -1.0, log.append)
+    ref = oracle.icp_colored(src, sc, tgt, nrm, tc, grad, 0.05, max_iteration=iters, relative_fitness=0,
+                             relative_rmse=0, lambda_geometric=0.968, robust=robust or ("L2Loss", 1.0, 1.0))
+    assert ref.status == 0 and res.num_iterations == ref.num_iterations == iters
+    per = np.array([[c["fitness"], c["inlier_rmse"]] for c in log])
+    assert per[0, 0] == ref.per_iteration[0, 0] and abs(per[0, 1] - ref.per_iteration[0, 1]) < 1e-12
+    np.testing.assert_allclose(per[:, 0], ref.per_iteration[:, 0], atol=2e-4)
+    np.testing.assert_allclose(per[:, 1], ref.per_iteration[:, 1], atol=2e-6)
+    np.testing.assert_allclose(res.transformation, ref.transformation, atol=1e-7 if iters == 1 else 2e-5)
+    agree = (res.correspondence_set.cpu().numpy() == ref.correspondences).mean()
+    assert agree > 0.999, agree
+    if iters >= 12:
+        np.testing.assert_allclose(res.transformation, T_gt, atol=2e-3)
+    assert "color_gradients" in t.point and "color_gradients" not in s.point
+
+
+def test_colored_icp_differs_from_point_to_plane_and_uses_colour(o3d):
+    """On a PLANE the geometric term cannot see an in-plane shift; only the photometric term can."""
+    reg = o3d.t.pipelines.registration
+    rng = np.random.default_rng(5)
+    tgt = np.zeros((40000, 3), np.float32)
+    tgt[:, :2] = rng.uniform(0, 4, (40000, 2))
+    nrm = np.tile(np.float32([0, 0, 1]), (len(tgt), 1))
+    shift = np.array([0.012, -0.008, 0.0])
+    base = np.zeros((30000, 3))
+    base[:, :2] = rng.uniform(0.2, 3.8, (30000, 2))
+    src = (base - shift).astype(np.float32)                 # T_gt = translation by +shift
+    sc, tc = make_colors(base, 1), make_colors(tgt, 1)
+    s, t = _colored_clouds(o3d, src, sc, tgt, nrm, tc)
+    crit = reg.ICPConvergenceCriteria(0, 0, 25)
+    res_c = reg.icp(s, t, 0.05, np.eye(4), reg.TransformationEstimationForColoredICP(0.5), crit)
+    assert "color_gradients" not in t.point                 # computed on a clone (Registration.cpp:235, 257)
+    np.testing.assert_allclose(res_c.transformation[:3, 3], shift, atol=1.5e-3)
+    grad = oracle.estimate_color_gradients(tgt, nrm, tc, 0.1, 30)   # radius = 2 * max_correspondence_distance
+    ref = oracle.icp_colored(src, sc, tgt, nrm, tc, grad, 0.05, max_iteration=25, relative_fitness=0,
+                             relative_rmse=0, lambda_geometric=0.5)
+    np.testing.assert_allclose(res_c.transformation, ref.transformation, atol=5e-5)
+
+
+def test_colored_multi_scale_icp_with_pyramid_vs_oracle(o3d):
+    """MultiScaleICP + ColoredICP: gradients are estimated on the finest level (radius 4 * voxel) and
+    averaged down the pyramid like any other attribute (Registration.cpp:243-270)."""
+    reg = o3d.t.pipelines.registration
+    src, sc, tgt, nrm, tc, T_gt = _colored_pair(90000, 23)
+    voxels, radii, iters = [0.06, 0.03], [0.12, 0.06], [5, 8]
+    s, t = _colored_clouds(o3d, src, sc, tgt, nrm, tc)
+    res = reg.multi_scale_icp(s, t, voxels, [reg.ICPConvergenceCriteria(0, 0, k) for k in iters], radii, np.eye(4),
+                              reg.TransformationEstimationForColoredICP())
+    s1 = oracle.voxel_down_sample(src, voxels[1], colors=sc)
+    t1 = oracle.voxel_down_sample(tgt, voxels[1], normals=nrm, colors=tc)
+    g1 = oracle.estimate_color_gradients(t1["positions"], t1["normals"], t1["colors"], 4.0 * voxels[1], 30)
+    s0 = oracle.voxel_down_sample(s1["positions"], voxels[0], colors=s1["colors"])
+    t0 = oracle.voxel_down_sample(t1["positions"], voxels[0], normals=t1["normals"], colors=t1["colors"])
+    g0 = oracle.voxel_down_sample(t1["positions"], voxels[0], colors=g1)["colors"]
+    T = np.eye(4)
+    for (ss, tt, gg), r, k in zip(((s0, t0, g0), (s1, t1, g1)), radii, iters):
+        ref = oracle.icp_colored(ss["positions"], ss["colors"], tt["positions"], tt["normals"], tt["colors"], gg, r,
+                                 init=T, max_iteration=k, relative_fitness=0, relative_rmse=0)
+        T = ref.transformation
+    assert res.num_iterations == sum(iters)
+    # the down-sampled clouds agree to f32 rounding only (atomics vs f64 means), which the ill-conditioned
+    # gradient solve amplifies: trajectory-level tolerance
+    np.testing.assert_allclose(res.transformation, T, atol=3e-4)
+    assert abs(res.fitness - ref.fitness) < 2e-3 and abs(res.inlier_rmse - ref.inlier_rmse) < 2e-5
+    np.testing.assert_allclose(res.transformation, T_gt, atol=4e-3)
+
+
+def test_colored_icp_argument_errors(o3d):
+    reg = o3d.t.pipelines.registration
+    src, sc, tgt, nrm, tc, _ = _colored_pair(2000, 24)
+    est = reg.TransformationEstimationForColoredICP()
+    G = o3d.t.geometry.PointCloud
+    with pytest.raises(RuntimeError, match="source pointcloud to have colors"):
+        reg.icp(G(src), G(tgt).set_point_normals(nrm).set_point_colors(tc), 0.05, np.eye(4), est)
+    with pytest.raises(RuntimeError, match="target pointcloud to have colors"):
+        reg.icp(G(src).set_point_colors(sc), G(tgt).set_point_normals(nrm), 0.05, np.eye(4), est)
+    with pytest.raises(RuntimeError, match="target pointcloud to have normals"):
+        reg.icp(G(src).set_point_colors(sc), G(tgt).set_point_colors(tc), 0.05, np.eye(4), est)
+    assert reg.TransformationEstimationForColoredICP(1.5).lambda_geometric == 0.968
+    # estimator-level seam: compute_transformation == one loop iteration's update
+    s, t = _colored_clouds(o3d, src, sc, tgt, nrm, tc, oracle.estimate_color_gradients(tgt, nrm, tc, 0.1, 30))
+    one = reg.icp(s, t, 0.05, np.eye(4), est, reg.ICPConvergenceCriteria(0, 0, 1))
+    idx, _, _ = oracle.hybrid_search(tgt, src, 0.05, 1)
+    T = est.compute_transformation(s, t, torch.from_numpy(idx[:, 0].astype(np.int64)))
+    np.testing.assert_allclose(T, one.transformation, atol=1e-9)
+    assert est.compute_rmse(s, t, torch.from_numpy(idx[:, 0].astype(np.int64))) > 0
