@@ -114,6 +114,13 @@ def _declare(L):
     L.orc_hashmap_activate.restype = C.c_int
     L.orc_hashmap_activate.argtypes = [_i32p, C.c_int64, _i64p, _i32p, C.c_int64,
                                        _i32p, _u8p]
+    L.orc_estimate_range.restype = None
+    L.orc_estimate_range.argtypes = [_i32p, C.c_int64, _f64p, _f64p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.c_float, C.c_float, C.c_float, _f32p]
+    L.orc_ray_cast.restype = None
+    L.orc_ray_cast.argtypes = [_i32p, C.c_int64, _f32p, _u16p, C.c_void_p, _f32p, _f64p, _f64p, C.c_int, C.c_int,
+                               C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                               C.c_int] + [C.c_void_p] * 10
     L.orc_estimate_color_gradients_f32.restype = None
     L.orc_estimate_color_gradients_f32.argtypes = [_f32p, _f32p, _f32p, C.c_int64, C.c_double, C.c_int, _f32p]
     L.orc_solve_sym3x3_pinv.restype = None
@@ -358,6 +365,54 @@ def tsdf_integrate(depth, color, buf_indices, block_keys, tsdf, weight, color_bu
                              _p(dK, _f64p), _p(cK, _f64p), _p(E, _f64p), int(resolution),
                              float(voxel_size), float(sdf_trunc), float(depth_scale),
                              float(depth_max))
+
+
+def estimate_range(block_keys, intrinsic, extrinsic, height, width, down_factor=8, resolution=16,
+                   voxel_size=0.008, depth_min=0.1, depth_max=3.0) -> np.ndarray:
+    """-> [height // down, width // down, 2] f32 (min, max) range map."""
+    keys = _arr(block_keys, np.int32).reshape(-1, 3)
+    K = _arr(intrinsic, np.float64).reshape(9)
+    E = _arr(extrinsic, np.float64).reshape(16)
+    out = np.empty((height // down_factor, width // down_factor, 2), np.float32)
+    lib().orc_estimate_range(_p(keys, _i32p), keys.shape[0], _p(K, _f64p), _p(E, _f64p), int(height), int(width),
+                             int(down_factor), int(resolution), float(voxel_size), float(depth_min),
+                             float(depth_max), _p(out, _f32p))
+    return out
+
+
+RAYCAST_ATTRS = {"depth": (1, np.float32), "vertex": (3, np.float32), "color": (3, np.float32),
+                 "normal": (3, np.float32), "index": (8, np.int64), "mask": (8, np.uint8),
+                 "interp_ratio": (8, np.float32), "interp_ratio_dx": (8, np.float32),
+                 "interp_ratio_dy": (8, np.float32), "interp_ratio_dz": (8, np.float32)}
+
+
+def ray_cast(table_keys, size, tsdf, weight, color_buf, range_map, intrinsic, extrinsic, height, width,
+             attrs=("depth", "color"), resolution=16, voxel_size=0.008, depth_scale=1000.0, depth_min=0.1,
+             depth_max=3.0, weight_threshold=3.0, trunc_voxel_multiplier=8.0, range_map_down_factor=8) -> dict:
+    """VoxelBlockGrid::RayCast on the oracle's buffers -> {attr: [h, w, c] array}."""
+    assert table_keys.dtype == np.int32 and table_keys.flags.c_contiguous
+    assert tsdf.dtype == np.float32 and weight.dtype == np.uint16
+    rng = _arr(range_map, np.float32)
+    K = _arr(intrinsic, np.float64).reshape(9)
+    E = _arr(extrinsic, np.float64).reshape(16)
+    out = {}
+    ptrs = []
+    for name in ("depth", "vertex", "color", "normal", "index", "mask", "interp_ratio", "interp_ratio_dx",
+                 "interp_ratio_dy", "interp_ratio_dz"):
+        if name in attrs:
+            c, dt = RAYCAST_ATTRS[name]
+            out[name] = np.full((height, width, c), 77, dt)
+            ptrs.append(out[name].ctypes.data)
+        else:
+            ptrs.append(None)
+    lib().orc_ray_cast(_p(table_keys, _i32p), int(size), _p(tsdf, _f32p), _p(weight, _u16p),
+                       None if color_buf is None else color_buf.ctypes.data, _p(rng, _f32p), _p(K, _f64p),
+                       _p(E, _f64p), int(height), int(width), int(resolution), float(voxel_size),
+                       float(depth_scale), float(depth_min), float(depth_max), float(weight_threshold),
+                       float(trunc_voxel_multiplier), int(range_map_down_factor), *ptrs)
+    if "mask" in out:
+        out["mask"] = out["mask"].astype(bool)
+    return out
 
 
 def hashmap_activate(table_keys, size, keys):

@@ -246,6 +246,30 @@ int orc_hashmap_activate(int32_t* table_keys, int64_t capacity, int64_t* size,
                          const int32_t* keys, int64_t n, int32_t* buf_indices,
                          uint8_t* masks);
 
+/* VoxelBlockGrid ray casting (t/geometry/kernel/VoxelBlockGridImpl.h:310-555,
+ * 578-1120; VoxelBlockGrid.cpp:328-402).  range: [h/down][w/down][2] f32 (min, max).
+ * PARITY UNPINNED against reference outputs: the reference's own test
+ * (tests/t/geometry/VoxelBlockGrid.cpp:352-410) needs downloaded data and only checks that the
+ * result keys exist; the camera primitives used are pinned bit-exactly through oracle/ref_shim
+ * (TransformIndexer), the loop itself through analytic properties (tests/test_oracle_raycast.py). */
+void orc_estimate_range(const int32_t* block_keys, int64_t n, const double K[9],
+                        const double E[16], int h, int w, int down_factor,
+                        int resolution, float voxel_size, float depth_min,
+                        float depth_max, float* range);
+/* Outputs (any may be NULL): depth [h][w], vertex/color/normal [h][w][3], index (int64) /
+ * mask (u8) / interp_ratio(_dx,_dy,_dz) [h][w][8].  table_keys: [size][3] block keys in slot
+ * order; tsdf/weight/color buffers in the slam::Model layout (see orc_tsdf_integrate). */
+void orc_ray_cast(const int32_t* table_keys, int64_t size, const float* tsdf_buf,
+                  const uint16_t* weight_buf, const uint16_t* color_buf,
+                  const float* range, const double K[9], const double E[16], int h,
+                  int w, int resolution, float voxel_size, float depth_scale,
+                  float depth_min, float depth_max, float weight_threshold,
+                  float trunc_voxel_multiplier, int range_map_down_factor,
+                  float* depth_out, float* vertex_out, float* color_out,
+                  float* normal_out, int64_t* index_out, uint8_t* mask_out,
+                  float* ratio_out, float* ratio_dx_out, float* ratio_dy_out,
+                  float* ratio_dz_out);
+
 int orc_num_threads(void);
 
 #ifdef __cplusplus

@@ -304,3 +304,306 @@ int orc_hashmap_activate(int32_t* table_keys, int64_t capacity, int64_t* size,
     free(next);
     return rc;
 }
+
+/* ------------------------------------------------- EstimateRange + RayCast */
+
+/* GeometryIndexer.h:81-97 Rotate */
+static inline void xi_rotate(const xform_indexer* t, float x, float y, float z,
+                             float* xo, float* yo, float* zo) {
+    x *= t->scale;
+    y *= t->scale;
+    z *= t->scale;
+    *xo = x * t->e[0][0] + y * t->e[0][1] + z * t->e[0][2];
+    *yo = x * t->e[1][0] + y * t->e[1][1] + z * t->e[1][2];
+    *zo = x * t->e[2][0] + y * t->e[2][1] + z * t->e[2][2];
+}
+
+static inline int imin(int a, int b) { return a < b ? a : b; }
+static inline int imax(int a, int b) { return a > b ? a : b; }
+
+/* t/geometry/kernel/VoxelBlockGridImpl.h:310-555 EstimateRangeCPU.  The 16x16 "fragments" of
+ * passes 0/1 only partition each block's screen rectangle; the min/max they scatter equals the
+ * min/max over the whole rectangle, which is what is computed here.  The reference's fragment
+ * buffer can overflow (:431-434, :458-468: a warning and a partial map); that failure mode is
+ * not restated — the map is always complete. */
+void orc_estimate_range(const int32_t* block_keys, int64_t n, const double K[9],
+                        const double E[16], int h, int w, int down_factor,
+                        int resolution, float voxel_size, float depth_min,
+                        float depth_max, float* range) {
+    const int h_down = h / down_factor, w_down = w / down_factor;
+    xform_indexer ti;
+    xi_init(&ti, K, E, 1.0f);
+    for (int64_t i = 0; i < (int64_t)h_down * w_down; ++i) { /* pass 0.5 (:472-484) */
+        range[2 * i] = depth_max;
+        range[2 * i + 1] = depth_min;
+    }
+    const int64_t block_resolution = resolution;
+    for (int64_t b = 0; b < n; ++b) {
+        const int32_t* key = block_keys + 3 * b;
+        int u_min = w_down - 1, v_min = h_down - 1, u_max = 0, v_max = 0;
+        float z_min = depth_max, z_max = depth_min;
+        for (int i = 0; i < 8; ++i) { /* :389-412 */
+            float xw = (key[0] + ((i & 1) > 0)) * block_resolution * voxel_size;
+            float yw = (key[1] + ((i & 2) > 0)) * block_resolution * voxel_size;
+            float zw = (key[2] + ((i & 4) > 0)) * block_resolution * voxel_size;
+            float xc, yc, zc, u, v;
+            xi_rigid(&ti, xw, yw, zw, &xc, &yc, &zc);
+            if (zc <= 0) continue;
+            xi_project(&ti, xc, yc, zc, &u, &v);
+            u /= down_factor;
+            v /= down_factor;
+            v_min = imin((int)floorf(v), v_min);
+            v_max = imax((int)ceilf(v), v_max);
+            u_min = imin((int)floorf(u), u_min);
+            u_max = imax((int)ceilf(u), u_max);
+            z_min = z_min < zc ? z_min : zc;
+            z_max = z_max > zc ? z_max : zc;
+        }
+        v_min = imax(0, v_min);
+        v_max = imin(h_down - 1, v_max);
+        u_min = imax(0, u_min);
+        u_max = imin(w_down - 1, u_max);
+        if (v_min >= v_max || u_min >= u_max || z_min >= z_max) continue; /* :420 */
+        for (int v = v_min; v <= v_max; ++v)
+            for (int u = u_min; u <= u_max; ++u) { /* pass 1 (:497-541) */
+                float* r = range + 2 * ((int64_t)v * w_down + u);
+                r[0] = z_min < r[0] ? z_min : r[0];
+                r[1] = z_max > r[1] ? z_max : r[1];
+            }
+    }
+}
+
+typedef struct {
+    const int32_t* keys;
+    int64_t* head;
+    int64_t* next;
+    int64_t nb;
+} block_lookup;
+
+static int lookup_build(block_lookup* m, const int32_t* keys, int64_t size) {
+    m->keys = keys;
+    m->nb = 16;
+    while (m->nb < 2 * size) m->nb <<= 1;
+    m->head = (int64_t*)malloc((size_t)m->nb * sizeof(int64_t));
+    m->next = (int64_t*)malloc((size_t)(size > 0 ? size : 1) * sizeof(int64_t));
+    if (!m->head || !m->next) return -1;
+    for (int64_t i = 0; i < m->nb; ++i) m->head[i] = -1;
+    for (int64_t s = 0; s < size; ++s) {
+        const int32_t* k = keys + 3 * s;
+        uint64_t hsh = orc_minivec_hash_i32x3(k[0], k[1], k[2]) & (uint64_t)(m->nb - 1);
+        m->next[s] = m->head[hsh];
+        m->head[hsh] = s;
+    }
+    return 0;
+}
+
+static inline int64_t lookup_find(const block_lookup* m, int x, int y, int z) {
+    uint64_t hsh = orc_minivec_hash_i32x3(x, y, z) & (uint64_t)(m->nb - 1);
+    for (int64_t s = m->head[hsh]; s >= 0; s = m->next[s]) {
+        const int32_t* k = m->keys + 3 * s;
+        if (k[0] == x && k[1] == y && k[2] == z) return s;
+    }
+    return -1;
+}
+
+static inline int isign(int x) { return (x > 0) ? 1 : ((x < 0) ? -1 : 0); } /* GeometryMacros.h:92-94 */
+
+/* t/geometry/kernel/VoxelBlockGridImpl.h:578-1120 RayCastCPU for <float, uint16_t, uint16_t>.
+ * The 1-entry MiniVecCache (:557-576) only short-cuts hash lookups and is omitted.
+ * One deliberate deviation: the voxel coordinate inside the block, index_t((x_g - x_b*block_size)
+ * / voxel_size) (:826-828), can round up to `resolution` when x_g sits a rounding error below a
+ * block face; upstream then indexes the next row of the block (or past the buffer).  It is
+ * clamped to resolution-1 here and in the CUDA kernel. */
+void orc_ray_cast(const int32_t* table_keys, int64_t size, const float* tsdf_buf,
+                  const uint16_t* weight_buf, const uint16_t* color_buf,
+                  const float* range, const double K[9], const double E[16], int h,
+                  int w, int resolution, float voxel_size, float depth_scale,
+                  float depth_min, float depth_max, float weight_threshold,
+                  float trunc_voxel_multiplier, int range_map_down_factor,
+                  float* depth_out, float* vertex_out, float* color_out,
+                  float* normal_out, int64_t* index_out, uint8_t* mask_out,
+                  float* ratio_out, float* ratio_dx_out, float* ratio_dy_out,
+                  float* ratio_dz_out) {
+    (void)depth_min;
+    (void)depth_max;
+    block_lookup map;
+    if (lookup_build(&map, table_keys, size) != 0) abort();
+    double Einv[16];
+    orc_inverse_transformation(E, Einv);
+    xform_indexer c2w, w2c;
+    xi_init(&c2w, K, Einv, 1.0f);
+    xi_init(&w2c, K, E, 1.0f);
+    const int block_resolution = resolution;
+    const float block_size = voxel_size * block_resolution;
+    const int resolution2 = block_resolution * block_resolution;
+    const int resolution3 = resolution2 * block_resolution;
+    const int w_down = w / range_map_down_factor;
+    const int render_color = color_buf != NULL && color_out != NULL;
+    const int visit_neighbors = render_color || normal_out || mask_out || index_out || ratio_out ||
+                                ratio_dx_out || ratio_dy_out || ratio_dz_out;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t workload = 0; workload < (int64_t)h * w; ++workload) {
+        const int y = (int)(workload / w), x = (int)(workload % w);
+        const float* rng = range + 2 * ((int64_t)(y / range_map_down_factor) * w_down + x / range_map_down_factor);
+        float* depth_ptr = depth_out ? depth_out + workload : NULL;
+        float* vertex_ptr = vertex_out ? vertex_out + 3 * workload : NULL;
+        float* color_ptr = render_color ? color_out + 3 * workload : NULL;
+        float* normal_ptr = normal_out ? normal_out + 3 * workload : NULL;
+        int64_t* index_ptr = index_out ? index_out + 8 * workload : NULL;
+        uint8_t* mask_ptr = mask_out ? mask_out + 8 * workload : NULL;
+        float* ratio_ptr = ratio_out ? ratio_out + 8 * workload : NULL;
+        float* rdx_ptr = ratio_dx_out ? ratio_dx_out + 8 * workload : NULL;
+        float* rdy_ptr = ratio_dy_out ? ratio_dy_out + 8 * workload : NULL;
+        float* rdz_ptr = ratio_dz_out ? ratio_dz_out + 8 * workload : NULL;
+        if (vertex_ptr) vertex_ptr[0] = vertex_ptr[1] = vertex_ptr[2] = 0;
+        if (depth_ptr) depth_ptr[0] = 0;
+        if (normal_ptr) normal_ptr[0] = normal_ptr[1] = normal_ptr[2] = 0;
+        if (color_out) color_out[3 * workload] = color_out[3 * workload + 1] = color_out[3 * workload + 2] = 0;
+        for (int i = 0; i < 8; ++i) {
+            if (mask_ptr) mask_ptr[i] = 0;
+            if (index_ptr) index_ptr[i] = 0;
+            if (ratio_ptr) ratio_ptr[i] = 0;
+            if (rdx_ptr) rdx_ptr[i] = 0;
+            if (rdy_ptr) rdy_ptr[i] = 0;
+            if (rdz_ptr) rdz_ptr[i] = 0;
+        }
+        float t = rng[0];
+        const float t_max = rng[1];
+        if (t >= t_max) continue;
+
+        float x_c = 0, y_c = 0, z_c = 0, x_g = 0, y_g = 0, z_g = 0, x_o = 0, y_o = 0, z_o = 0;
+        float t_prev = t;
+        float tsdf_prev = -1.0f;
+        float tsdf = 1.0;
+        const float sdf_trunc = voxel_size * trunc_voxel_multiplier;
+        float wgt = 0.0;
+        xi_rigid(&c2w, 0, 0, 0, &x_o, &y_o, &z_o);
+        xi_unproject(&c2w, (float)x, (float)y, 1.0f, &x_c, &y_c, &z_c);
+        xi_rigid(&c2w, x_c, y_c, z_c, &x_g, &y_g, &z_g);
+        const float x_d = (x_g - x_o), y_d = (y_g - y_o), z_d = (z_g - z_o);
+
+        int surface_found = 0;
+        while (t < t_max) {
+            /* GetLinearIdxAtT (:795-833) */
+            int64_t linear_idx = -1;
+            {
+                const float xg = x_o + t * x_d, yg = y_o + t * y_d, zg = z_o + t * z_d;
+                const int x_b = (int)floorf(xg / block_size);
+                const int y_b = (int)floorf(yg / block_size);
+                const int z_b = (int)floorf(zg / block_size);
+                const int64_t blk = lookup_find(&map, x_b, y_b, z_b);
+                if (blk >= 0) {
+                    int x_v = (int)((xg - x_b * block_size) / voxel_size);
+                    int y_v = (int)((yg - y_b * block_size) / voxel_size);
+                    int z_v = (int)((zg - z_b * block_size) / voxel_size);
+                    x_v = imin(x_v, block_resolution - 1);
+                    y_v = imin(y_v, block_resolution - 1);
+                    z_v = imin(z_v, block_resolution - 1);
+                    linear_idx = blk * resolution3 + z_v * resolution2 + y_v * block_resolution + x_v;
+                }
+            }
+            if (linear_idx < 0) {
+                t_prev = t;
+                t += block_size;
+            } else {
+                tsdf_prev = tsdf;
+                tsdf = tsdf_buf[linear_idx];
+                wgt = weight_buf[linear_idx];
+                if (tsdf_prev > 0 && wgt >= weight_threshold && tsdf <= 0) {
+                    surface_found = 1;
+                    break;
+                }
+                t_prev = t;
+                float delta = tsdf * sdf_trunc;
+                t += delta < voxel_size ? voxel_size : delta;
+            }
+        }
+        if (!surface_found) continue;
+
+        float t_intersect = (t * tsdf_prev - t_prev * tsdf) / (tsdf_prev - tsdf);
+        x_g = x_o + t_intersect * x_d;
+        y_g = y_o + t_intersect * y_d;
+        z_g = z_o + t_intersect * z_d;
+        if (depth_ptr) *depth_ptr = t_intersect * depth_scale;
+        if (vertex_ptr) xi_rigid(&w2c, x_g, y_g, z_g, vertex_ptr + 0, vertex_ptr + 1, vertex_ptr + 2);
+        if (!visit_neighbors) continue;
+
+        const int x_b = (int)floorf(x_g / block_size);
+        const int y_b = (int)floorf(y_g / block_size);
+        const int z_b = (int)floorf(z_g / block_size);
+        const float x_v = (x_g - (float)x_b * block_size) / voxel_size;
+        const float y_v = (y_g - (float)y_b * block_size) / voxel_size;
+        const float z_v = (z_g - (float)z_b * block_size) / voxel_size;
+        const int64_t block_buf_idx = lookup_find(&map, x_b, y_b, z_b);
+        if (block_buf_idx < 0) continue;
+        const int x_v_floor = (int)floorf(x_v), y_v_floor = (int)floorf(y_v), z_v_floor = (int)floorf(z_v);
+        const float ratio_x = x_v - (float)x_v_floor;
+        const float ratio_y = y_v - (float)y_v_floor;
+        const float ratio_z = z_v - (float)z_v_floor;
+        float sum_r = 0.0;
+        for (int k = 0; k < 8; ++k) {
+            const int dx_v = (k & 1) > 0 ? 1 : 0, dy_v = (k & 2) > 0 ? 1 : 0, dz_v = (k & 4) > 0 ? 1 : 0;
+            /* GetLinearIdxAtP (:748-793) */
+            int64_t lin;
+            {
+                const int xv = x_v_floor + dx_v, yv = y_v_floor + dy_v, zv = z_v_floor + dz_v;
+                const int x_vn = (xv + block_resolution) % block_resolution;
+                const int y_vn = (yv + block_resolution) % block_resolution;
+                const int z_vn = (zv + block_resolution) % block_resolution;
+                const int dx_b = isign(xv - x_vn), dy_b = isign(yv - y_vn), dz_b = isign(zv - z_vn);
+                if (dx_b == 0 && dy_b == 0 && dz_b == 0) {
+                    lin = block_buf_idx * resolution3 + zv * resolution2 + yv * block_resolution + xv;
+                } else {
+                    const int64_t nb = lookup_find(&map, x_b + dx_b, y_b + dy_b, z_b + dz_b);
+                    lin = nb < 0 ? -1 : nb * resolution3 + z_vn * resolution2 + y_vn * block_resolution + x_vn;
+                }
+            }
+            if (lin >= 0 && weight_buf[lin] > 0) {
+                const float rx = dx_v * (ratio_x) + (1 - dx_v) * (1 - ratio_x);
+                const float ry = dy_v * (ratio_y) + (1 - dy_v) * (1 - ratio_y);
+                const float rz = dz_v * (ratio_z) + (1 - dz_v) * (1 - ratio_z);
+                const float r = rx * ry * rz;
+                if (ratio_ptr) ratio_ptr[k] = r;
+                if (mask_ptr) mask_ptr[k] = 1;
+                if (index_ptr) index_ptr[k] = lin;
+                const float tsdf_k = tsdf_buf[lin];
+                const float idx_ = ry * rz * (2 * dx_v - 1);
+                const float idy_ = rx * rz * (2 * dy_v - 1);
+                const float idz_ = rx * ry * (2 * dz_v - 1);
+                if (rdx_ptr) rdx_ptr[k] = idx_;
+                if (rdy_ptr) rdy_ptr[k] = idy_;
+                if (rdz_ptr) rdz_ptr[k] = idz_;
+                if (normal_ptr) {
+                    normal_ptr[0] += idx_ * tsdf_k;
+                    normal_ptr[1] += idy_ * tsdf_k;
+                    normal_ptr[2] += idz_ * tsdf_k;
+                }
+                if (color_ptr) {
+                    const int64_t c = lin * 3;
+                    color_ptr[0] += r * color_buf[c + 0];
+                    color_ptr[1] += r * color_buf[c + 1];
+                    color_ptr[2] += r * color_buf[c + 2];
+                }
+                sum_r += r;
+            }
+        }
+        if (sum_r > 0) {
+            sum_r *= 255.0;
+            if (color_ptr) {
+                color_ptr[0] /= sum_r;
+                color_ptr[1] /= sum_r;
+                color_ptr[2] /= sum_r;
+            }
+            if (normal_ptr) {
+                const float EPSILON = 1e-5f;
+                float norm = sqrtf(normal_ptr[0] * normal_ptr[0] + normal_ptr[1] * normal_ptr[1] +
+                                   normal_ptr[2] * normal_ptr[2]);
+                norm = norm > EPSILON ? norm : EPSILON;
+                xi_rotate(&w2c, -normal_ptr[0] / norm, -normal_ptr[1] / norm, -normal_ptr[2] / norm,
+                          normal_ptr + 0, normal_ptr + 1, normal_ptr + 2);
+            }
+        }
+    }
+    free(map.head);
+    free(map.next);
+}
