@@ -355,6 +355,42 @@ int o3db_vbg_integrate_sequence(o3db_vbg* vbg, int64_t n_frames, const void* con
 int64_t o3db_vbg_last_frustum_blocks(o3db_vbg* vbg, int32_t* block_coords_dev, int64_t max_blocks,
                                      void* stream);
 
+/* ------------------------------------------------------------------------
+ * VoxelBlockGrid::RayCast (t/geometry/VoxelBlockGrid.cpp:328-402) = kernel::voxel_grid::EstimateRange
+ * (kernel/VoxelBlockGridImpl.h:310-555) + RayCast (:578-1120), the step after Integrate in
+ * slam::Model::SynthesizeModelFrame (slam/Model.cpp:38-66).
+ *
+ * block_coords_dev: [num_blocks,3] int32 keys that bound the rays (upstream: frustum_block_coords_),
+ *   or NULL = the blocks touched by the last o3db_vbg_integrate_frame (no host round trip).
+ * K: 3x3, E: 4x4 world->camera, both host f64 row-major.
+ * range_dev (optional for ray_cast): [height/down][width/down][2] f32 (min, max) — upstream's "range"
+ *   rendering.  Unlike upstream there is no fragment buffer and hence no overflow mode.
+ * Outputs are row-major [height][width][C]; every pointer may be NULL (attribute not requested).
+ * Rendering "color" from a grid created without colour yields zeros.
+ * ---------------------------------------------------------------------- */
+typedef struct {
+    float* depth;            /* C=1: t_intersect * depth_scale, 0 = no surface */
+    float* vertex;           /* C=3: camera-frame point */
+    float* color;            /* C=3: trilinear colour / 255 */
+    float* normal;           /* C=3: camera-frame, MINUS the normalised TSDF gradient (as upstream) */
+    int64_t* index;          /* C=8: linear voxel ids of the 8 interpolation corners */
+    uint8_t* mask;           /* C=8: corner valid (bool) */
+    float* interp_ratio;     /* C=8 */
+    float* interp_ratio_dx;  /* C=8 */
+    float* interp_ratio_dy;  /* C=8 */
+    float* interp_ratio_dz;  /* C=8 */
+} o3db_raycast_outputs;
+
+int o3db_vbg_estimate_range(o3db_vbg* vbg, const int32_t* block_coords_dev, int64_t num_blocks,
+                            const double intrinsic_host[9], const double extrinsic_host[16], int height,
+                            int width, int down_factor, float depth_min, float depth_max,
+                            float* range_dev, void* stream);
+int o3db_vbg_ray_cast(o3db_vbg* vbg, const int32_t* block_coords_dev, int64_t num_blocks,
+                      const double intrinsic_host[9], const double extrinsic_host[16], int width, int height,
+                      const o3db_raycast_outputs* outputs_host, float depth_scale, float depth_min,
+                      float depth_max, float weight_threshold, float trunc_voxel_multiplier,
+                      int range_map_down_factor, float* range_dev, void* stream);
+
 /* Measurement aid (bench.py): when enabled, CUDA events bracket the touch and the
  * integrate kernel of every o3db_vbg_integrate_frame call (up to 4096 frames per
  * read); o3db_vbg_profile_read synchronises and returns the summed device times. */

@@ -41,6 +41,12 @@ class IcpResult(C.Structure):
                 ("status", C.c_int), ("num_correspondences", C.c_int64)]
 
 
+class RaycastOutputs(C.Structure):
+    """o3db_raycast_outputs: device pointers, None = attribute not requested"""
+    _fields_ = [(n, C.c_void_p) for n in ("depth", "vertex", "color", "normal", "index", "mask", "interp_ratio",
+                                          "interp_ratio_dx", "interp_ratio_dy", "interp_ratio_dz")]
+
+
 _vp = C.c_void_p
 _i64 = C.c_int64
 _dbl = C.c_double
@@ -103,6 +109,9 @@ _SIGS = {
     "o3db_vbg_integrate_frame_host": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _dp, _dp, _f, _f, _f, _vp]),
     "o3db_vbg_integrate_sequence": (_i, [_vp, _i64, _vp, _i, _vp, _i, _i, _i, _dp, _dp, _f, _f, _f, _i, _vp]),
     "o3db_vbg_last_frustum_blocks": (_i64, [_vp, _vp, _i64, _vp]),
+    "o3db_vbg_estimate_range": (_i, [_vp, _vp, _i64, _dp, _dp, _i, _i, _i, _f, _f, _vp, _vp]),
+    "o3db_vbg_ray_cast": (_i, [_vp, _vp, _i64, _dp, _dp, _i, _i, C.POINTER(RaycastOutputs), _f, _f, _f, _f, _f, _i,
+                               _vp, _vp]),
     "o3db_vbg_profile": (_i, [_vp, _i]),
     "o3db_vbg_profile_read": (_i, [_vp, _dp, _dp, C.POINTER(_i64)]),
     "o3db_build_spatial_hash_table": (_i, [_vp, _i64, _dbl, C.c_uint32, _vp, _vp, _vp]),

@@ -335,6 +335,38 @@ class VoxelBlockGrid:
                                            dptr(E), float(depth_scale), float(depth_max),
                                            float(trunc_voxel_multiplier), current_stream_ptr()))
 
+    _RAYCAST_ATTRS = {"vertex": (3, torch.float32), "normal": (3, torch.float32), "depth": (1, torch.float32),
+                      "color": (3, torch.float32), "index": (8, torch.int64), "mask": (8, torch.bool),
+                      "interp_ratio": (8, torch.float32), "interp_ratio_dx": (8, torch.float32),
+                      "interp_ratio_dy": (8, torch.float32), "interp_ratio_dz": (8, torch.float32)}
+
+    def ray_cast(self, block_coords, intrinsic, extrinsic, width, height, render_attributes=("depth", "color"),
+                 depth_scale=1000.0, depth_min=0.1, depth_max=3.0, weight_threshold=3.0,
+                 trunc_voxel_multiplier=8.0, range_map_down_factor=8):
+        """VoxelBlockGrid::RayCast (VoxelBlockGrid.cpp:328-402; pybind voxel_block_grid.cpp ray_cast) ->
+        dict {"range": [h/d, w/d, 2], attr: [h, w, C]}.  block_coords=None takes the blocks touched by the
+        last fused integrate_frame without a host round trip (slam::Model::frustum_block_coords_)."""
+        from ..._lib import RaycastOutputs
+        K, E = _k9(intrinsic), as_host_f64_4x4(extrinsic, "extrinsic")
+        width, height, down = int(width), int(height), int(range_map_down_factor)
+        out = {}
+        ptrs = RaycastOutputs()
+        for name in render_attributes:
+            if name not in self._RAYCAST_ATTRS:
+                raise RuntimeError(f"Unsupported attribute {name}, please implement customized ray casting.")
+            ch, dt = self._RAYCAST_ATTRS[name]
+            out[name] = torch.empty((height, width, ch), dtype=dt, device="cuda")
+            setattr(ptrs, name, out[name].data_ptr())
+        rng = torch.empty((max(height // max(down, 1), 0), max(width // max(down, 1), 0), 2), dtype=torch.float32,
+                          device="cuda")
+        bc = None if block_coords is None else self.hashmap()._keys_arg(block_coords)
+        check(lib.o3db_vbg_ray_cast(self._h, None if bc is None else bc.data_ptr(), 0 if bc is None else bc.shape[0],
+                                    dptr(K), dptr(E), width, height, C.byref(ptrs), float(depth_scale),
+                                    float(depth_min), float(depth_max), float(weight_threshold),
+                                    float(trunc_voxel_multiplier), down, rng.data_ptr(), current_stream_ptr()))
+        out["range"] = rng
+        return out
+
     def last_frustum_block_coordinates(self):
         cap = 76800
         out = torch.empty((cap, 3), dtype=torch.int32, device="cuda")

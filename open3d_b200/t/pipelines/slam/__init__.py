@@ -47,6 +47,17 @@ class Frame:
         return Image(self.get_data(name))
 
 
+def _inverse_transformation(T):
+    """t::geometry::InverseTransformation (t/geometry/Utility.h:77-115), f64 on the host"""
+    E = np.eye(4)
+    R, t = T[:3, :3], T[:3, 3]
+    E[:3, :3] = R.T
+    E[0, 3] = -(E[0, 0] * t[0] + E[0, 1] * t[1] + E[0, 2] * t[2])
+    E[1, 3] = -(E[1, 0] * t[0] + E[1, 1] * t[1] + E[1, 2] * t[2])
+    E[2, 3] = -(E[2, 0] * t[0] + E[2, 1] * t[1] + E[2, 2] * t[2])
+    return E
+
+
 class Model:
     """slam::Model (slam/Model.cpp:23-36): owns a VoxelBlockGrid{tsdf f32, weight u16,
     color u16x3} and the current frame pose."""
@@ -75,13 +86,7 @@ class Model:
         depth = input_frame.get_data("depth")
         color = input_frame.get_data("color")
         T = self.transformation_frame_to_world
-        # t::geometry::InverseTransformation (t/geometry/Utility.h:77-115), f64 on the host
-        E = np.eye(4)
-        R, t = T[:3, :3], T[:3, 3]
-        E[:3, :3] = R.T
-        E[0, 3] = -(E[0, 0] * t[0] + E[0, 1] * t[1] + E[0, 2] * t[2])
-        E[1, 3] = -(E[1, 0] * t[0] + E[1, 1] * t[1] + E[1, 2] * t[2])
-        E[2, 3] = -(E[2, 0] * t[0] + E[2, 1] * t[1] + E[2, 2] * t[2])
+        E = _inverse_transformation(T)
         if isinstance(color, torch.Tensor) and color.numel() == 0:
             color = None
         self.voxel_grid.integrate_frame(depth, color, input_frame.get_intrinsics(), E, depth_scale, depth_max,
@@ -99,5 +104,20 @@ class Model:
     def track_frame_to_model(self, *args, **kwargs):
         raise RuntimeError("Model.track_frame_to_model (RGB-D odometry) is not built yet: SURVEY.md §8f next #2")
 
-    def synthesize_model_frame(self, *args, **kwargs):
-        raise RuntimeError("Model.synthesize_model_frame (ray casting) is not built yet: SURVEY.md §8f next #4")
+    def synthesize_model_frame(self, raycast_frame, depth_scale=1000.0, depth_min=0.1, depth_max=3.0,
+                               trunc_voxel_multiplier=8.0, enable_color=True, weight_threshold=-1.0):
+        """Model::SynthesizeModelFrame (slam/Model.cpp:38-66): ray-cast the blocks of the last integrated
+        frame from the current pose into raycast_frame's "depth" (and "color")."""
+        if weight_threshold < 0:
+            weight_threshold = min(self.frame_id * 1.0, 3.0)
+        T = self.transformation_frame_to_world
+        res = self.voxel_grid.ray_cast(None, raycast_frame.get_intrinsics(), _inverse_transformation(T),
+                                       raycast_frame.width(), raycast_frame.height(), ("depth", "color"), depth_scale,
+                                       depth_min, depth_max, weight_threshold, trunc_voxel_multiplier)
+        raycast_frame.set_data("depth", res["depth"])
+        if enable_color:
+            raycast_frame.set_data("color", res["color"])
+        elif raycast_frame.get_data("color").numel() == 0:
+            # a dummy RGB frame keeps RGB-D odometry usable in TrackFrameToModel (Model.cpp:58-64)
+            raycast_frame.set_data("color", torch.zeros((raycast_frame.height(), raycast_frame.width(), 3),
+                                                        dtype=torch.float32, device="cuda"))

@@ -318,6 +318,16 @@ static inline void xi_rotate(const xform_indexer* t, float x, float y, float z,
     *zo = x * t->e[2][0] + y * t->e[2][1] + z * t->e[2][2];
 }
 
+/* float -> int conversion of an out-of-range value is undefined in C++; the reference's CUDA build
+ * saturates (cvt.rzi.s32.f32), x86 yields INT_MIN.  A block corner just in front of the camera plane
+ * projects to |u|, |v| ~ 1e9+, so the choice matters for EstimateRange: the CUDA behaviour is restated. */
+static inline int sat_int(float x) {
+    if (x != x) return 0;
+    if (x >= 2147483648.0f) return 2147483647;
+    if (x <= -2147483648.0f) return (-2147483647 - 1);
+    return (int)x;
+}
+
 static inline int imin(int a, int b) { return a < b ? a : b; }
 static inline int imax(int a, int b) { return a > b ? a : b; }
 
@@ -352,10 +362,10 @@ void orc_estimate_range(const int32_t* block_keys, int64_t n, const double K[9],
             xi_project(&ti, xc, yc, zc, &u, &v);
             u /= down_factor;
             v /= down_factor;
-            v_min = imin((int)floorf(v), v_min);
-            v_max = imax((int)ceilf(v), v_max);
-            u_min = imin((int)floorf(u), u_min);
-            u_max = imax((int)ceilf(u), u_max);
+            v_min = imin(sat_int(floorf(v)), v_min);
+            v_max = imax(sat_int(ceilf(v)), v_max);
+            u_min = imin(sat_int(floorf(u)), u_min);
+            u_max = imax(sat_int(ceilf(u)), u_max);
             z_min = z_min < zc ? z_min : zc;
             z_max = z_max > zc ? z_max : zc;
         }
@@ -437,14 +447,18 @@ void orc_ray_cast(const int32_t* table_keys, int64_t size, const float* tsdf_buf
     const float block_size = voxel_size * block_resolution;
     const int resolution2 = block_resolution * block_resolution;
     const int resolution3 = resolution2 * block_resolution;
-    const int w_down = w / range_map_down_factor;
+    const int w_down = w / range_map_down_factor, h_down = h / range_map_down_factor;
     const int render_color = color_buf != NULL && color_out != NULL;
     const int visit_neighbors = render_color || normal_out || mask_out || index_out || ratio_out ||
                                 ratio_dx_out || ratio_dy_out || ratio_dz_out;
 #pragma omp parallel for schedule(dynamic, 64)
     for (int64_t workload = 0; workload < (int64_t)h * w; ++workload) {
         const int y = (int)(workload / w), x = (int)(workload % w);
-        const float* rng = range + 2 * ((int64_t)(y / range_map_down_factor) * w_down + x / range_map_down_factor);
+        /* :851-852 range_indexer(x / down, y / down): when the image size is not a multiple of the down
+         * factor the last partial row / column of cells does not exist (h_down = h / down) and upstream
+         * reads past the map; clamped to the last cell here and in the CUDA kernel. */
+        const float* rng = range + 2 * ((int64_t)imin(y / range_map_down_factor, h_down - 1) * w_down +
+                                        imin(x / range_map_down_factor, w_down - 1));
         float* depth_ptr = depth_out ? depth_out + workload : NULL;
         float* vertex_ptr = vertex_out ? vertex_out + 3 * workload : NULL;
         float* color_ptr = render_color ? color_out + 3 * workload : NULL;

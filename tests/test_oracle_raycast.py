@@ -121,3 +121,20 @@ def test_ray_cast_weight_threshold_and_depth_only(volume):
     # "color" requested without a colour buffer: zeros (upstream leaves the tensor unwritten)
     out = oracle.ray_cast(*args, ("depth", "color"), RES, VOXEL, SCALE, DMIN, DMAX, 1.0, TRUNC, 8)
     assert not out["color"].any() and np.array_equal(out["depth"], lo)
+
+
+def test_ray_cast_image_size_not_a_multiple_of_the_down_factor(volume):
+    """h_down = h / down drops the partial last row / column of range cells; pixels there use the last cell
+    (upstream indexes past the map)."""
+    T = camera_pose(volume["frames"][-1])
+    E = oracle.inverse_transformation(T)
+    rng = oracle.estimate_range(volume["frustum"], PRIMESENSE_K, E, 250, 333, 8, RES, VOXEL, DMIN, DMAX)
+    assert rng.shape == (31, 41, 2)
+    out = oracle.ray_cast(volume["keys"], volume["size"], volume["tsdf"], volume["wt"], None, rng, PRIMESENSE_K, E,
+                          250, 333, ("depth",), RES, VOXEL, SCALE, DMIN, DMAX, 1.0, TRUNC, 8)["depth"]
+    assert out.shape == (250, 333, 1) and (out[-2:, :] > 0).any() and (out[:, -5:] > 0).any()
+    full = oracle.ray_cast(volume["keys"], volume["size"], volume["tsdf"], volume["wt"], None,
+                           oracle.estimate_range(volume["frustum"], PRIMESENSE_K, E, 480, 640, 8, RES, VOXEL, DMIN, DMAX),
+                           PRIMESENSE_K, E, 480, 640, ("depth",), RES, VOXEL, SCALE, DMIN, DMAX, 1.0, TRUNC, 8)["depth"]
+    same = (out > 0) & (full[:250, :333] > 0)
+    assert np.abs(out - full[:250, :333])[same].max() < 1e-2      # same rays (same K): only the start t differs

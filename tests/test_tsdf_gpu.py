@@ -296,3 +296,162 @@ def test_integrate_sequence_equals_per_frame_calls(o3d):
         got = volume(use_seq, host)
         for a, b in zip(ref, got):
             assert np.array_equal(a, b)
+
+
+# ------------------------------------------- EstimateRange + RayCast
+
+DMIN = 0.1
+ALL_ATTRS = ("depth", "vertex", "color", "normal", "index", "mask", "interp_ratio", "interp_ratio_dx",
+             "interp_ratio_dy", "interp_ratio_dz")
+
+
+@pytest.fixture(scope="module")
+def fused_pair(o3d):
+    """The same 5 colour frames fused by slam.Model (CUDA) and by the oracle."""
+    slam = o3d.t.pipelines.slam
+    cap = 9000
+    model = slam.Model(VOXEL, RES, cap)
+    okeys, otsdf, owt, ocol = _oracle_volume(cap, True)
+    osize = 0
+    frames = (0, 2, 4, 6, 8)
+    for n, fid in enumerate(frames):
+        T, E, depth, col = _frame(fid, color=True)
+        frame = slam.Frame(480, 640, PRIMESENSE_K)
+        frame.set_data("depth", torch.from_numpy(depth).cuda())
+        frame.set_data("color", torch.from_numpy(col).cuda())
+        model.update_frame_pose(n, T)
+        model.integrate(frame, SCALE, DMAX, TRUNC_MULT)
+        want = oracle.depth_touch(depth, PRIMESENSE_K, E, RES, VOXEL, VOXEL * TRUNC_MULT, SCALE, DMAX, 4)
+        bi, _, osize, rc = oracle.hashmap_activate(okeys, osize, want)
+        assert rc == 0
+        oracle.tsdf_integrate(depth, col, bi, okeys, otsdf, owt, ocol, PRIMESENSE_K, PRIMESENSE_K, E, RES, VOXEL,
+                              VOXEL * TRUNC_MULT, SCALE, DMAX)
+    _compare_volumes(model.voxel_grid, okeys, otsdf, owt, ocol, osize)
+    return dict(model=model, okeys=okeys, otsdf=otsdf, owt=owt, ocol=ocol, osize=osize, frustum=want,
+                last_pose=camera_pose(frames[-1]))
+
+
+def _bits(a):
+    a = np.ascontiguousarray(a)
+    return a.view(np.uint32) if a.dtype == np.float32 else a
+
+
+@pytest.mark.parametrize("down", [8, 4])
+def test_estimate_range_bit_exact_vs_oracle(fused_pair, down):
+    vbg = fused_pair["model"].voxel_grid
+    T = fused_pair["last_pose"]
+    E = oracle.inverse_transformation(T)
+    want = oracle.estimate_range(fused_pair["frustum"], PRIMESENSE_K, E, 480, 640, down, RES, VOXEL, DMIN, DMAX)
+    # explicit block coordinates (VoxelBlockGrid::RayCast's argument) ...
+    bc = torch.from_numpy(fused_pair["frustum"]).cuda()
+    got = vbg.ray_cast(bc, PRIMESENSE_K, E, 640, 480, ("depth",), SCALE, DMIN, DMAX, 1.0, TRUNC_MULT, down)["range"]
+    assert got.shape == want.shape
+    assert np.array_equal(_bits(got.cpu().numpy()), _bits(want))
+    # ... and the frustum of the last fused frame taken on the device (slam::Model::frustum_block_coords_)
+    got2 = vbg.ray_cast(None, PRIMESENSE_K, E, 640, 480, ("depth",), SCALE, DMIN, DMAX, 1.0, TRUNC_MULT, down)["range"]
+    assert np.array_equal(_bits(got2.cpu().numpy()), _bits(want))
+    # a partially covered view, and a cloud of blocks all around the camera: corners behind the camera
+    # plane are skipped (:398), corners just in front of it project to |u|, |v| ~ 1e9 (saturating casts)
+    allk = vbg.hashmap().key_tensor()[: fused_pair["osize"]].contiguous()
+    rng_keys = np.random.default_rng(7).integers(-14, 15, (4000, 3)).astype(np.int32) + np.int32([8, 0, 11])
+    for T2, keys in ((camera_pose(100), allk.cpu().numpy()), (camera_pose(30), rng_keys)):
+        E2 = oracle.inverse_transformation(T2)
+        want2 = oracle.estimate_range(keys, PRIMESENSE_K, E2, 480, 640, down, RES, VOXEL, DMIN, DMAX)
+        got3 = vbg.ray_cast(torch.from_numpy(keys).cuda(), PRIMESENSE_K, E2, 640, 480, ("depth",), SCALE, DMIN, DMAX,
+                            1.0, TRUNC_MULT, down)["range"]
+        assert np.array_equal(_bits(got3.cpu().numpy()), _bits(want2))
+        covered = want2[..., 0] < want2[..., 1]
+        assert covered.any() and (keys is rng_keys or not covered.all())
+
+
+@pytest.mark.parametrize("fid,threshold", [(8, 3.0), (5, 1.0), (40, 1.0)])
+def test_ray_cast_bit_exact_vs_oracle(fused_pair, fid, threshold):
+    """All ten renderings of VoxelBlockGrid::RayCast from an integrated pose, an in-between pose and a pose
+    that sees the edge of the fused region.  The march is evaluated without FMA contraction: identical."""
+    vbg = fused_pair["model"].voxel_grid
+    osize = fused_pair["osize"]
+    T = camera_pose(fid)
+    E = oracle.inverse_transformation(T)
+    gkeys = vbg.hashmap().key_tensor()[:osize].contiguous()
+    res = vbg.ray_cast(gkeys, PRIMESENSE_K, E, 640, 480, ALL_ATTRS, SCALE, DMIN, DMAX, threshold, TRUNC_MULT, 8)
+    rng = oracle.estimate_range(gkeys.cpu().numpy(), PRIMESENSE_K, E, 480, 640, 8, RES, VOXEL, DMIN, DMAX)
+    assert np.array_equal(_bits(res["range"].cpu().numpy()), _bits(rng))
+    ref = oracle.ray_cast(fused_pair["okeys"], osize, fused_pair["otsdf"], fused_pair["owt"], fused_pair["ocol"],
+                          rng, PRIMESENSE_K, E, 480, 640, ALL_ATTRS, RES, VOXEL, SCALE, DMIN, DMAX, threshold,
+                          TRUNC_MULT, 8)
+    hit = ref["depth"][..., 0] > 0
+    assert hit.mean() > (0.5 if fid != 40 else 0.02)
+    for name in ("depth", "vertex", "normal", "color", "interp_ratio", "interp_ratio_dx", "interp_ratio_dy",
+                 "interp_ratio_dz"):
+        got = res[name].cpu().numpy()
+        np.testing.assert_allclose(got, ref[name], rtol=1e-5, atol=1e-6, err_msg=name)     # north_star bound
+        assert np.array_equal(_bits(got), _bits(ref[name])), name                           # in fact identical
+    gmask = res["mask"].cpu().numpy()
+    assert np.array_equal(gmask, ref["mask"])
+    # voxel indices: slot order differs between the two hash maps -> compare (block key, voxel-in-block)
+    gi, oi = res["index"].cpu().numpy(), ref["index"]
+    r3 = RES ** 3
+    gk = gkeys.cpu().numpy()[gi[gmask] // r3]
+    ok = fused_pair["okeys"][oi[gmask] // r3]
+    assert np.array_equal(gk, ok) and np.array_equal(gi[gmask] % r3, oi[gmask] % r3)
+    assert not gi[~gmask].any()
+    if fid == 8:   # against the analytic scene: the O(voxel) staircase of the nearest-voxel march
+        truth = render_depth(T).numpy().astype(np.float64)
+        d = res["depth"].cpu().numpy()[..., 0].astype(np.float64)
+        both = (d > 0) & (truth > 0)
+        assert np.median(np.abs(d - truth)[both]) < 0.75 * VOXEL * SCALE
+
+
+def test_ray_cast_attribute_subsets_and_errors(o3d, fused_pair):
+    vbg = fused_pair["model"].voxel_grid
+    T = fused_pair["last_pose"]
+    E = oracle.inverse_transformation(T)
+    full = vbg.ray_cast(None, PRIMESENSE_K, E, 640, 480, ("depth", "vertex", "normal", "color"), SCALE, DMIN, DMAX,
+                        1.0, TRUNC_MULT)
+    only = vbg.ray_cast(None, PRIMESENSE_K, E, 640, 480, ("depth", "vertex"), SCALE, DMIN, DMAX, 1.0, TRUNC_MULT)
+    assert set(only) == {"depth", "vertex", "range"}                       # the no-neighbour fast path (:1000)
+    assert torch.equal(only["depth"], full["depth"]) and torch.equal(only["vertex"], full["vertex"])
+    assert full["depth"].shape == (480, 640, 1) and full["color"].shape == (480, 640, 3)
+    assert not (vbg.ray_cast(None, PRIMESENSE_K, E, 640, 480, ("depth",), SCALE, DMIN, DMAX, 50.0)["depth"] > 0).any()
+    with pytest.raises(RuntimeError, match="Unsupported attribute"):
+        vbg.ray_cast(None, PRIMESENSE_K, E, 640, 480, ("albedo",))
+    # odd image sizes (partial tiles, range cells cut by integer division)
+    small = vbg.ray_cast(None, PRIMESENSE_K, E, 333, 250, ("depth", "normal"), SCALE, DMIN, DMAX, 1.0, TRUNC_MULT)
+    rng = oracle.estimate_range(fused_pair["frustum"], PRIMESENSE_K, E, 250, 333, 8, RES, VOXEL, DMIN, DMAX)
+    ref = oracle.ray_cast(fused_pair["okeys"], fused_pair["osize"], fused_pair["otsdf"], fused_pair["owt"], None, rng,
+                          PRIMESENSE_K, E, 250, 333, ("depth", "normal"), RES, VOXEL, SCALE, DMIN, DMAX, 1.0,
+                          TRUNC_MULT, 8)
+    assert np.array_equal(_bits(small["range"].cpu().numpy()), _bits(rng))
+    assert np.array_equal(_bits(small["depth"].cpu().numpy()), _bits(ref["depth"]))
+    assert np.array_equal(_bits(small["normal"].cpu().numpy()), _bits(ref["normal"]))
+    # a grid without colour renders zeros for "color"
+    plain = o3d.t.geometry.VoxelBlockGrid(("tsdf", "weight"), (torch.float32, torch.uint16), ((1,), (1,)), VOXEL, RES, 4000)
+    T0, E0, depth, _ = _frame(0)
+    bc = plain.compute_unique_block_coordinates(torch.from_numpy(depth), PRIMESENSE_K, E0, SCALE, DMAX, TRUNC_MULT)
+    plain.integrate(bc, torch.from_numpy(depth), None, PRIMESENSE_K, PRIMESENSE_K, E0, SCALE, DMAX, TRUNC_MULT)
+    out = plain.ray_cast(bc, PRIMESENSE_K, E0, 640, 480, ("depth", "color"), SCALE, DMIN, DMAX, 1.0, TRUNC_MULT)
+    assert (out["depth"] > 0).float().mean() > 0.8 and not out["color"].any()
+
+
+def test_model_synthesize_model_frame(o3d, fused_pair):
+    """slam::Model::SynthesizeModelFrame (Model.cpp:38-66)."""
+    slam = o3d.t.pipelines.slam
+    model = fused_pair["model"]
+    rc = slam.Frame(480, 640, PRIMESENSE_K)
+    model.synthesize_model_frame(rc, SCALE, DMIN, DMAX, TRUNC_MULT, True)     # weight_threshold = min(frame_id, 3)
+    d, c = rc.get_data("depth"), rc.get_data("color")
+    assert d.shape == (480, 640, 1) and c.shape == (480, 640, 3) and d.is_cuda
+    E = oracle.inverse_transformation(model.get_current_frame_pose())
+    rng = oracle.estimate_range(fused_pair["frustum"], PRIMESENSE_K, E, 480, 640, 8, RES, VOXEL, DMIN, DMAX)
+    ref = oracle.ray_cast(fused_pair["okeys"], fused_pair["osize"], fused_pair["otsdf"], fused_pair["owt"],
+                          fused_pair["ocol"], rng, PRIMESENSE_K, E, 480, 640, ("depth", "color"), RES, VOXEL, SCALE,
+                          DMIN, DMAX, 3.0, TRUNC_MULT, 8)
+    assert np.array_equal(_bits(d.cpu().numpy()), _bits(ref["depth"]))
+    assert np.array_equal(_bits(c.cpu().numpy()), _bits(ref["color"]))
+    truth = render_depth(model.get_current_frame_pose()).numpy().astype(np.float64)
+    got = d.cpu().numpy()[..., 0].astype(np.float64)
+    both = (got > 0) & (truth > 0)
+    assert both.mean() > 0.8 and np.median(np.abs(got - truth)[both]) < 0.75 * VOXEL * SCALE
+    rc2 = slam.Frame(480, 640, PRIMESENSE_K)
+    model.synthesize_model_frame(rc2, SCALE, DMIN, DMAX, TRUNC_MULT, False)
+    assert torch.equal(rc2.get_data("depth"), d) and not rc2.get_data("color").any()
