@@ -526,6 +526,39 @@ def bench_tsdf(args, rank, world, local_rank, L, torch, stream, barrier, max_ove
                                  "touch_kernel_avg_us": 1e3 * dev["touch_ms"] / max(dev["profiled_frames"], 1),
                                  "mean_touched_blocks_per_frame": mean_blocks, "peak_source": peak_src,
                                  "frame_frac_end_to_end": alg / (dev["ms_per_frame"] * 1e-3) / 1e9 / peak}
+    # slam::Model::SynthesizeModelFrame (EstimateRange + RayCast of the last frame's frustum, depth + colour),
+    # reported beside the integration numbers, not part of `value`
+    if rank == 0:
+        v = C.c_void_p()
+        L.check(L.lib.o3db_vbg_create(VOXEL, RES, 40000, 1, stream, C.byref(v)))
+        nseq = min(60, len(mine))
+        L.check(L.lib.o3db_vbg_integrate_sequence(v, nseq, dev_ptrs, L.DEPTH_U16, dev_cptrs, L.COLOR_U8, 480, 640,
+                                                  L.dptr(K), L.dptr(ext_all), DSCALE, DMAX, TRUNC_MULT, 0, stream))
+        rd = torch.empty((480, 640, 1), dtype=torch.float32, device="cuda")
+        rc = torch.empty((480, 640, 3), dtype=torch.float32, device="cuda")
+        ro = L.RaycastOutputs()
+        ro.depth, ro.color = rd.data_ptr(), rc.data_ptr()
+        E_last = exts[nseq - 1]
+        reps = 20
+
+        def cast():
+            L.check(L.lib.o3db_vbg_ray_cast(v, None, 0, L.dptr(K), L.dptr(E_last), 640, 480, C.byref(ro), DSCALE, 0.1, DMAX,
+                                            3.0, TRUNC_MULT, 8, None, stream))
+        for _ in range(3):
+            cast()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = L.launch_count()
+        a.record()
+        for _ in range(reps):
+            cast()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / reps
+        out["raycast"] = {"workload": "slam::Model::SynthesizeModelFrame 640x480 depth+color after 60 fused frames",
+                          "ms_per_frame": ms, "frames_per_sec": 1e3 / ms, "rays_per_sec": 640 * 480 / (ms * 1e-3),
+                          "hit_fraction": float((rd > 0).float().mean()), "gpu_launches_per_frame":
+                          (L.launch_count() - l0) / reps}
+        L.lib.o3db_vbg_destroy(v)
     out["metric"] = "tsdf_frames_per_sec_640x480"
     out["config"] = {"workload": "voxel_block_grid_tsdf_integrate", "frames": F, "image": "640x480 u16 depth (+u8 colour)",
                      "voxel_size": VOXEL, "block_resolution": RES, "trunc_voxel_multiplier": TRUNC_MULT,

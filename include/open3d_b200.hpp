@@ -10,6 +10,7 @@
 // INTEGRATION.md shows the forwarding stubs for a real Open3D build).
 #pragma once
 
+#include <algorithm>
 #include <array>
 #include <cstdint>
 #include <functional>
@@ -35,8 +36,20 @@ struct PointCloud {
     const float* positions = nullptr;  // device
     const float* normals = nullptr;    // device, may be null
     int64_t num_points = 0;
+    const float* colors = nullptr;     // device, may be null
+    const float* color_gradients = nullptr;   // device, may be null ("color_gradients" attribute)
     bool HasPointPositions() const { return positions != nullptr && num_points > 0; }
     bool HasPointNormals() const { return normals != nullptr && num_points > 0; }
+    bool HasPointColors() const { return colors != nullptr && num_points > 0; }
+
+    /// PointCloud::EstimateColorGradients (t/geometry/PointCloud.cpp:723-767, hybrid search) into a
+    /// caller-owned [N,3] device buffer, which becomes this cloud's color_gradients attribute.
+    void EstimateColorGradients(float* gradients_dev, int max_nn = 30, double radius = 0.0, void* stream = nullptr) {
+        if (!HasPointColors()) throw std::runtime_error("PointCloud must have colors attribute to estimate color gradients.");
+        if (!HasPointNormals()) throw std::runtime_error("PointCloud must have normals attribute to estimate color gradients.");
+        Check(o3db_estimate_color_gradients(positions, normals, colors, num_points, radius, max_nn, gradients_dev, stream));
+        color_gradients = gradients_dev;
+    }
 };
 
 }  // namespace geometry
@@ -112,6 +125,15 @@ public:
     RobustKernel kernel_;
 };
 
+/// TransformationEstimation.h:318-395 (lambda_geometric outside [0,1] falls back to 0.968, :337-340)
+class TransformationEstimationForColoredICP {
+public:
+    explicit TransformationEstimationForColoredICP(double lambda_geometric = 0.968, const RobustKernel& kernel = RobustKernel())
+        : lambda_geometric_((lambda_geometric < 0 || lambda_geometric > 1.0) ? 0.968 : lambda_geometric), kernel_(kernel) {}
+    double lambda_geometric_;
+    RobustKernel kernel_;
+};
+
 using IterationCallback = std::function<void(int iteration_index, double fitness, double inlier_rmse)>;
 
 /// registration::ICP (Registration.h:133-144, Registration.cpp:93-106) for
@@ -160,6 +182,53 @@ inline RegistrationResult ICP(const geometry::PointCloud& source, const geometry
     return out;
 }
 
+/// registration::ICP for TransformationEstimationForColoredICP.  The target needs color_gradients
+/// (PointCloud::EstimateColorGradients; upstream computes them with radius 2 * max_correspondence_distance
+/// when missing, Registration.cpp:243-263 — here the caller owns the buffer, so it is required).
+inline RegistrationResult ICP(const geometry::PointCloud& source, const geometry::PointCloud& target,
+                              double max_correspondence_distance, const std::array<double, 16>& init_source_to_target,
+                              const TransformationEstimationForColoredICP& estimation,
+                              const ICPConvergenceCriteria& criteria = ICPConvergenceCriteria(), double voxel_size = -1.0,
+                              const IterationCallback& callback_after_iteration = nullptr,
+                              int64_t* correspondences_dev = nullptr, void* stream = nullptr) {
+    if (!target.HasPointPositions() || !source.HasPointPositions())
+        throw std::runtime_error("Source and/or Target pointcloud is empty.");
+    if (!target.HasPointNormals()) throw std::runtime_error("ColoredICP requires target pointcloud to have normals.");
+    if (!target.HasPointColors()) throw std::runtime_error("ColoredICP requires target pointcloud to have colors.");
+    if (!source.HasPointColors()) throw std::runtime_error("ColoredICP requires source pointcloud to have colors.");
+    if (!target.color_gradients) throw std::runtime_error("Target pointcloud missing color_gradients attribute.");
+    if (max_correspondence_distance <= 0.0)
+        throw std::runtime_error(" Max correspondence distance must be greater than 0, but got " +
+                                 std::to_string(max_correspondence_distance) + " in scale: 0.");
+    if (voxel_size > 0)
+        throw std::runtime_error("voxel_size > 0: apply PointCloud::VoxelDownSample first (o3db_voxel_down_sample_attrs)");
+    o3db_icp_options opt{};
+    opt.max_correspondence_distance = max_correspondence_distance;
+    opt.max_iteration = criteria.max_iteration_;
+    opt.relative_fitness = criteria.relative_fitness_;
+    opt.relative_rmse = criteria.relative_rmse_;
+    opt.kernel = {static_cast<int>(estimation.kernel_.type_), estimation.kernel_.scaling_parameter_,
+                  estimation.kernel_.shape_parameter_};
+    o3db_icp_result r{};
+    std::vector<double> per(2 * static_cast<size_t>(criteria.max_iteration_ > 0 ? criteria.max_iteration_ : 1), 0.0);
+    Check(o3db_icp_colored(source.positions, source.colors, source.num_points, target.positions, target.normals,
+                           target.colors, target.color_gradients, target.num_points, init_source_to_target.data(), &opt,
+                           estimation.lambda_geometric_, &r, correspondences_dev, per.data(), stream));
+    RegistrationResult out;
+    for (int i = 0; i < 16; ++i) out.transformation_[i] = r.transformation[i];
+    out.correspondences_ = correspondences_dev;
+    out.fitness_ = r.fitness;
+    out.inlier_rmse_ = r.inlier_rmse;
+    out.converged_ = r.converged != 0;
+    out.num_iterations_ = r.num_iterations;
+    const int executed = r.num_iterations + (r.converged ? 1 : 0);
+    for (int k = 0; k < executed; ++k) {
+        out.per_iteration_.push_back({per[2 * k], per[2 * k + 1]});
+        if (callback_after_iteration) callback_after_iteration(k, per[2 * k], per[2 * k + 1]);
+    }
+    return out;
+}
+
 }  // namespace registration
 
 namespace slam {
@@ -196,21 +265,27 @@ public:
     /// Model::Integrate (Model.cpp:91-106)
     void Integrate(const Frame& f, float depth_scale = 1000.0f, float depth_max = 3.0f, float trunc_voxel_multiplier = 8.0f,
                    void* stream = nullptr) {
-        // t::geometry::InverseTransformation (t/geometry/Utility.h:77-115)
-        const auto& T = T_frame_to_world_;
-        std::array<double, 16> E{};
-        E[0] = T[0]; E[1] = T[4]; E[2] = T[8];
-        E[4] = T[1]; E[5] = T[5]; E[6] = T[9];
-        E[8] = T[2]; E[9] = T[6]; E[10] = T[10];
-        E[3] = -(E[0] * T[3] + E[1] * T[7] + E[2] * T[11]);
-        E[7] = -(E[4] * T[3] + E[5] * T[7] + E[6] * T[11]);
-        E[11] = -(E[8] * T[3] + E[9] * T[7] + E[10] * T[11]);
-        E[15] = 1;
+        const std::array<double, 16> E = Extrinsic();
         const int dd = f.depth_is_f32 ? O3DB_DEPTH_F32 : O3DB_DEPTH_U16;
         const int cd = f.color ? (f.depth_is_f32 ? O3DB_COLOR_F32 : O3DB_COLOR_U8) : O3DB_COLOR_NONE;
         Check((f.images_on_host ? o3db_vbg_integrate_frame_host : o3db_vbg_integrate_frame)(
                 vbg_, f.depth, dd, f.color, cd, f.height, f.width, f.intrinsics.data(), E.data(), depth_scale, depth_max,
                 trunc_voxel_multiplier, stream));
+    }
+
+    /// Model::SynthesizeModelFrame (Model.cpp:38-66): ray-cast the blocks of the last integrated frame from
+    /// the current pose.  depth_dev [h][w] f32 and color_dev [h][w][3] f32 are caller-owned device buffers
+    /// (color_dev may be null = enable_color false).
+    void SynthesizeModelFrame(int height, int width, const std::array<double, 9>& intrinsics, float* depth_dev,
+                              float* color_dev, float depth_scale = 1000.0f, float depth_min = 0.1f, float depth_max = 3.0f,
+                              float trunc_voxel_multiplier = 8.0f, float weight_threshold = -1.0f, void* stream = nullptr) {
+        if (weight_threshold < 0) weight_threshold = std::min(frame_id_ * 1.0f, 3.0f);
+        const std::array<double, 16> E = Extrinsic();
+        o3db_raycast_outputs out{};
+        out.depth = depth_dev;
+        out.color = color_dev;
+        Check(o3db_vbg_ray_cast(vbg_, nullptr, 0, intrinsics.data(), E.data(), width, height, &out, depth_scale, depth_min,
+                                depth_max, weight_threshold, trunc_voxel_multiplier, 8, nullptr, stream));
     }
 
     int64_t NumBlocks(void* stream = nullptr) {
@@ -223,6 +298,20 @@ public:
     int frame_id_ = -1;
 
 private:
+    /// t::geometry::InverseTransformation (t/geometry/Utility.h:77-115) of the current pose
+    std::array<double, 16> Extrinsic() const {
+        const auto& T = T_frame_to_world_;
+        std::array<double, 16> E{};
+        E[0] = T[0]; E[1] = T[4]; E[2] = T[8];
+        E[4] = T[1]; E[5] = T[5]; E[6] = T[9];
+        E[8] = T[2]; E[9] = T[6]; E[10] = T[10];
+        E[3] = -(E[0] * T[3] + E[1] * T[7] + E[2] * T[11]);
+        E[7] = -(E[4] * T[3] + E[5] * T[7] + E[6] * T[11]);
+        E[11] = -(E[8] * T[3] + E[9] * T[7] + E[10] * T[11]);
+        E[15] = 1;
+        return E;
+    }
+
     o3db_vbg* vbg_ = nullptr;
     std::array<double, 16> T_frame_to_world_;
 };

@@ -17,3 +17,15 @@ def pytest_configure(config):
 def kats():
     with open(os.path.join(ROOT, "tests", "golden", "reference_kats.json")) as f:
         return json.load(f)
+
+
+def pytest_collection_modifyitems(config, items):
+    """A wedged kernel must not hang the whole GPU run: every GPU test gets a hard limit (thread method:
+    a blocked CUDA call cannot be interrupted by a signal, the process is ended instead)."""
+    try:
+        import pytest_timeout  # noqa: F401
+    except ImportError:
+        return
+    for item in items:
+        if item.get_closest_marker("gpu") and not item.get_closest_marker("timeout"):
+            item.add_marker(pytest.mark.timeout(600, method="thread"))

@@ -44,8 +44,16 @@ static int host_mode() {
     EXPECT(throws_with([&] { reg::ICP(empty, tgt, 0.1); }, "empty"));
     EXPECT(throws_with([&] { reg::ICP(src, tgt_no_normals, 0.1); }, "normal"));
     EXPECT(throws_with([&] { reg::ICP(src, tgt, 0.0); }, "Max correspondence distance"));
-    EXPECT(throws_with([&] { reg::ICP(src, tgt, 0.1, {{1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}}, {}, {}, 0.02); },
+    EXPECT(throws_with([&] { reg::ICP(src, tgt, 0.1, {{1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}}, reg::TransformationEstimationPointToPlane(), {}, 0.02); },
                        "VoxelDownSample"));
+    // ColoredICP argument checks (Registration.cpp:160-176, TransformationEstimation.cpp:401-404)
+    const std::array<double, 16> eye{{1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}};
+    reg::TransformationEstimationForColoredICP colored;
+    geo::PointCloud csrc{dummy, nullptr, 1, dummy}, ctgt{dummy, dummy, 1, dummy};
+    EXPECT(throws_with([&] { reg::ICP(src, ctgt, 0.1, eye, colored); }, "source pointcloud to have colors"));
+    EXPECT(throws_with([&] { reg::ICP(csrc, tgt, 0.1, eye, colored); }, "target pointcloud to have colors"));
+    EXPECT(throws_with([&] { reg::ICP(csrc, ctgt, 0.1, eye, colored); }, "color_gradients"));
+    EXPECT(reg::TransformationEstimationForColoredICP(7.0).lambda_geometric_ == 0.968 && colored.lambda_geometric_ == 0.968);
     reg::ICPConvergenceCriteria c;
     EXPECT(c.relative_fitness_ == 1e-6 && c.relative_rmse_ == 1e-6 && c.max_iteration_ == 30);
     reg::RobustKernel k;
@@ -100,6 +108,41 @@ static int gpu_mode() {
     for (int i = 0; i < 16; ++i) EXPECT(std::fabs(res.transformation_[i] - ref.transformation[i]) < 2e-5);
     EXPECT(std::fabs(res.fitness_ - ref.fitness) < 2e-4 && std::fabs(res.inlier_rmse_ - ref.inlier_rmse) < 2e-6);
     EXPECT(res.per_iteration_.size() == 8 && res.per_iteration_[0][0] == per[0]);
+    // ColoredICP on the same pair: texture in the target frame, gradients from EstimateColorGradients
+    {
+        std::vector<float> sc(3 * n), tc(3 * n), grad(3 * n), grad_ref(3 * n);
+        auto tex = [](float x, float y, int c) { return 0.5f + 0.5f * std::sin((2.1f + 0.7f * c) * x + (1.3f + c) * y + c); };
+        for (int k = 0; k < n; ++k)
+            for (int ch = 0; ch < 3; ++ch) {
+                tc[3 * k + ch] = tex(tgt[3 * k], tgt[3 * k + 1], ch);
+                sc[3 * k + ch] = tex(src[3 * k] - 0.012f, src[3 * k + 1] + 0.008f, ch);   // colour of where it belongs
+            }
+        float *d_sc, *d_tc, *d_grad;
+        EXPECT(cudaMalloc(&d_sc, sizeof(float) * 3 * n) == cudaSuccess && cudaMalloc(&d_tc, sizeof(float) * 3 * n) == cudaSuccess &&
+               cudaMalloc(&d_grad, sizeof(float) * 3 * n) == cudaSuccess);
+        cudaMemcpy(d_sc, sc.data(), sizeof(float) * 3 * n, cudaMemcpyHostToDevice);
+        cudaMemcpy(d_tc, tc.data(), sizeof(float) * 3 * n, cudaMemcpyHostToDevice);
+        geo::PointCloud CS{d_src, nullptr, n, d_sc}, CT{d_tgt, d_nrm, n, d_tc};
+        CT.EstimateColorGradients(d_grad, 30, 0.1);
+        cudaMemcpy(grad.data(), d_grad, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost);
+        orc_estimate_color_gradients_f32(tgt.data(), nrm.data(), tc.data(), n, 0.1, 30, grad_ref.data());
+        double gmax = 0, gerr = 0;
+        for (int k = 0; k < 3 * n; ++k) {
+            gmax = std::fmax(gmax, std::fabs(grad_ref[k]));
+            gerr = std::fmax(gerr, std::fabs(grad[k] - grad_ref[k]));
+        }
+        EXPECT(gmax > 0.1 && gerr <= 1e-5 * gmax);
+        auto cres = reg::ICP(CS, CT, 0.05, {{1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}},
+                             reg::TransformationEstimationForColoredICP(0.968), reg::ICPConvergenceCriteria(0, 0, 6));
+        orc_icp_result cref;
+        EXPECT(orc_icp_colored_f32(src.data(), sc.data(), n, tgt.data(), nrm.data(), tc.data(), grad_ref.data(), n, 0.05, I, 6,
+                                   0, 0, 0.968, 0, 1.0, 1.0, &cref, per.data(), nullptr) == 0);
+        EXPECT(cres.num_iterations_ == 6);
+        for (int i = 0; i < 16; ++i) EXPECT(std::fabs(cres.transformation_[i] - cref.transformation[i]) < 2e-5);
+        cudaFree(d_sc);
+        cudaFree(d_tc);
+        cudaFree(d_grad);
+    }
     // robust kernel + singular system error text
     EXPECT(throws_with(
             [&] {
@@ -130,6 +173,22 @@ static int gpu_mode() {
     f.images_on_host = true;
     model.Integrate(f);   // same frame again through the host-image path: no new blocks
     EXPECT(model.NumBlocks() == want);
+    // Model::SynthesizeModelFrame: the wall comes back at 1.5 m (O(voxel) staircase of the march)
+    {
+        float* d_out;
+        EXPECT(cudaMalloc(&d_out, sizeof(float) * 480 * 640) == cudaSuccess);
+        model.SynthesizeModelFrame(480, 640, f.intrinsics, d_out, nullptr);
+        std::vector<float> out(480 * 640);
+        cudaMemcpy(out.data(), d_out, out.size() * sizeof(float), cudaMemcpyDeviceToHost);
+        int64_t hits = 0, close = 0;
+        for (float d : out)
+            if (d > 0) {
+                ++hits;
+                close += std::fabs(d - 1500.f) < 16.f;
+            }
+        EXPECT(hits > 0.9 * out.size() && close > 0.99 * hits);
+        cudaFree(d_out);
+    }
     std::printf("cpp gpu-mode ok: fitness %.4f rmse %.5f blocks %lld\n", res.fitness_, res.inlier_rmse_, (long long)want);
     return 0;
 }
