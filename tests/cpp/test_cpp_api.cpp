@@ -177,6 +177,9 @@ static int gpu_mode() {
     {
         float* d_out;
         EXPECT(cudaMalloc(&d_out, sizeof(float) * 480 * 640) == cudaSuccess);
+        // weight_threshold = min(frame_id, 3) (Model.cpp:45-47): at frame 0 it is 0 and never-observed voxels
+        // (tsdf 0, weight 0) count as surface, as upstream; the SLAM loop only synthesizes from frame 1 on
+        model.UpdateFramePose(1, {{1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}});
         model.SynthesizeModelFrame(480, 640, f.intrinsics, d_out, nullptr);
         std::vector<float> out(480 * 640);
         cudaMemcpy(out.data(), d_out, out.size() * sizeof(float), cudaMemcpyDeviceToHost);
