@@ -121,6 +121,35 @@ def _declare(L):
     L.orc_ray_cast.argtypes = [_i32p, C.c_int64, _f32p, _u16p, C.c_void_p, _f32p, _f64p, _f64p, C.c_int, C.c_int,
                                C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                C.c_int] + [C.c_void_p] * 10
+    L.orc_clip_transform.restype = None
+    L.orc_clip_transform.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
+                                     C.c_float, _f32p]
+    L.orc_pyr_down_depth.restype = None
+    L.orc_pyr_down_depth.argtypes = [_f32p, C.c_int, C.c_int, C.c_float, C.c_float, _f32p]
+    L.orc_create_vertex_map.restype = None
+    L.orc_create_vertex_map.argtypes = [_f32p, C.c_int, C.c_int, _f64p, C.c_float, _f32p]
+    L.orc_create_normal_map.restype = None
+    L.orc_create_normal_map.argtypes = [_f32p, C.c_int, C.c_int, C.c_float, _f32p]
+    L.orc_filter_bilateral_f32.restype = None
+    L.orc_filter_bilateral_f32.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _f32p]
+    L.orc_huber_deriv.restype = C.c_float
+    L.orc_huber_deriv.argtypes = [C.c_float, C.c_float]
+    L.orc_huber_loss.restype = C.c_float
+    L.orc_huber_loss.argtypes = [C.c_float, C.c_float]
+    L.orc_odometry_jacobian_p2plane.restype = C.c_int
+    L.orc_odometry_jacobian_p2plane.argtypes = [C.c_int, C.c_int, C.c_float, _f32p, _f32p, _f32p, C.c_int, C.c_int,
+                                                _f64p, _f64p, _f32p, _f32p]
+    L.orc_odometry_p2plane_sums.restype = None
+    L.orc_odometry_p2plane_sums.argtypes = [_f32p, _f32p, _f32p, C.c_int, C.c_int, _f64p, _f64p, C.c_float, C.c_float,
+                                            _f64p, _f64p]
+    L.orc_compute_odometry_result_p2plane.restype = C.c_int
+    L.orc_compute_odometry_result_p2plane.argtypes = [_f32p, _f32p, _f32p, C.c_int, C.c_int, _f64p, _f64p, C.c_float,
+                                                      C.c_float, _f64p, _f64p, _f64p]
+    L.orc_rgbd_odometry_multi_scale_p2plane.restype = C.c_int
+    L.orc_rgbd_odometry_multi_scale_p2plane.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, _f64p, _f64p,
+                                                        C.c_float, C.c_float, C.c_int, C.POINTER(C.c_int), _f64p,
+                                                        _f64p, C.c_float, C.c_float, _f64p, _f64p, _f64p, _f64p,
+                                                        C.POINTER(C.c_int)]
     L.orc_estimate_color_gradients_f32.restype = None
     L.orc_estimate_color_gradients_f32.argtypes = [_f32p, _f32p, _f32p, C.c_int64, C.c_double, C.c_int, _f32p]
     L.orc_solve_sym3x3_pinv.restype = None
@@ -485,3 +514,124 @@ def icp_colored(source, source_colors, target, target_normals, target_colors, ta
     return IcpResult(np.array(res.transformation, np.float64).reshape(4, 4), res.fitness, res.inlier_rmse,
                      bool(res.converged), res.num_iterations, per[:executed].copy(), corr, rc, res.loop_seconds,
                      res.build_seconds)
+
+
+# ---------------------------------------------------------------- RGB-D odometry (PointToPlane)
+
+def clip_transform(depth, scale=1000.0, min_value=0.0, max_value=3.0, clip_fill=float("nan")) -> np.ndarray:
+    d = np.ascontiguousarray(depth)
+    d = d.reshape(d.shape[0], d.shape[1])
+    f32 = d.dtype == np.float32
+    assert f32 or d.dtype == np.uint16
+    out = np.empty(d.shape, np.float32)
+    lib().orc_clip_transform(d.ctypes.data, int(f32), d.shape[0], d.shape[1], float(scale), float(min_value),
+                             float(max_value), float(clip_fill), _p(out, _f32p))
+    return out
+
+
+def pyr_down_depth(depth, depth_diff, invalid_fill=float("nan")) -> np.ndarray:
+    d = _arr(depth, np.float32)
+    d = d.reshape(d.shape[0], d.shape[1])
+    out = np.empty((d.shape[0] // 2, d.shape[1] // 2), np.float32)
+    lib().orc_pyr_down_depth(_p(d, _f32p), d.shape[0], d.shape[1], float(depth_diff), float(invalid_fill),
+                             _p(out, _f32p))
+    return out
+
+
+def create_vertex_map(depth, intrinsic, invalid_fill=float("nan")) -> np.ndarray:
+    d = _arr(depth, np.float32)
+    d = d.reshape(d.shape[0], d.shape[1])
+    K = _arr(intrinsic, np.float64).reshape(9)
+    out = np.empty(d.shape + (3,), np.float32)
+    lib().orc_create_vertex_map(_p(d, _f32p), d.shape[0], d.shape[1], _p(K, _f64p), float(invalid_fill),
+                                _p(out, _f32p))
+    return out
+
+
+def create_normal_map(vertex, invalid_fill=float("nan")) -> np.ndarray:
+    v = _arr(vertex, np.float32)
+    out = np.empty(v.shape, np.float32)
+    lib().orc_create_normal_map(_p(v, _f32p), v.shape[0], v.shape[1], float(invalid_fill), _p(out, _f32p))
+    return out
+
+
+def filter_bilateral(img, kernel_size=5, value_sigma=5.0, dist_sigma=10.0) -> np.ndarray:
+    a = _arr(img, np.float32)
+    a = a.reshape(a.shape[0], a.shape[1])
+    out = np.empty(a.shape, np.float32)
+    lib().orc_filter_bilateral_f32(_p(a, _f32p), a.shape[0], a.shape[1], int(kernel_size), float(value_sigma),
+                                   float(dist_sigma), _p(out, _f32p))
+    return out
+
+
+def huber_deriv(r, delta) -> float:
+    return float(lib().orc_huber_deriv(float(r), float(delta)))
+
+
+def huber_loss(r, delta) -> float:
+    return float(lib().orc_huber_loss(float(r), float(delta)))
+
+
+def odometry_jacobian_p2plane(x, y, source_vertex, target_vertex, target_normal, intrinsic, T, depth_outlier_trunc=0.07):
+    sv, tv, tn = (_arr(a, np.float32) for a in (source_vertex, target_vertex, target_normal))
+    K = _arr(intrinsic, np.float64).reshape(9)
+    Tm = _arr(T, np.float64).reshape(16)
+    J = np.zeros(6, np.float32)
+    r = np.zeros(1, np.float32)
+    ok = lib().orc_odometry_jacobian_p2plane(int(x), int(y), float(depth_outlier_trunc), _p(sv, _f32p), _p(tv, _f32p),
+                                             _p(tn, _f32p), sv.shape[0], sv.shape[1], _p(K, _f64p), _p(Tm, _f64p),
+                                             _p(J, _f32p), _p(r, _f32p))
+    return bool(ok), J, float(r[0])
+
+
+def odometry_p2plane_sums(source_vertex, target_vertex, target_normal, intrinsic, T, depth_outlier_trunc=0.07,
+                          depth_huber_delta=0.05) -> dict:
+    sv, tv, tn = (_arr(a, np.float32) for a in (source_vertex, target_vertex, target_normal))
+    K = _arr(intrinsic, np.float64).reshape(9)
+    Tm = _arr(T, np.float64).reshape(16)
+    s, a = np.zeros(29), np.zeros(29)
+    lib().orc_odometry_p2plane_sums(_p(sv, _f32p), _p(tv, _f32p), _p(tn, _f32p), sv.shape[0], sv.shape[1],
+                                    _p(K, _f64p), _p(Tm, _f64p), float(depth_outlier_trunc), float(depth_huber_delta),
+                                    _p(s, _f64p), _p(a, _f64p))
+    return {"sums64": s, "abs64": a}
+
+
+def compute_odometry_result_p2plane(source_vertex, target_vertex, target_normal, intrinsic, T,
+                                    depth_outlier_trunc=0.07, depth_huber_delta=0.05):
+    """-> (rc, delta 4x4, inlier_rmse, fitness)"""
+    sv, tv, tn = (_arr(a, np.float32) for a in (source_vertex, target_vertex, target_normal))
+    K = _arr(intrinsic, np.float64).reshape(9)
+    Tm = _arr(T, np.float64).reshape(16)
+    dT = np.zeros(16)
+    rmse, fit = C.c_double(0), C.c_double(0)
+    rc = lib().orc_compute_odometry_result_p2plane(_p(sv, _f32p), _p(tv, _f32p), _p(tn, _f32p), sv.shape[0],
+                                                   sv.shape[1], _p(K, _f64p), _p(Tm, _f64p),
+                                                   float(depth_outlier_trunc), float(depth_huber_delta), _p(dT, _f64p),
+                                                   C.byref(rmse), C.byref(fit))
+    return rc, dT.reshape(4, 4), rmse.value, fit.value
+
+
+def rgbd_odometry_multi_scale_p2plane(source_depth, target_depth, intrinsic, init=None, depth_scale=1000.0,
+                                      depth_max=3.0, criteria=((10, 1e-6, 1e-6), (5, 1e-6, 1e-6), (3, 1e-6, 1e-6)),
+                                      depth_outlier_trunc=0.07, depth_huber_delta=0.05) -> dict:
+    """criteria: (max_iteration, relative_rmse, relative_fitness) per level, coarse to fine."""
+    s, t = np.ascontiguousarray(source_depth), np.ascontiguousarray(target_depth)
+    s, t = s.reshape(s.shape[0], s.shape[1]), t.reshape(t.shape[0], t.shape[1])
+    assert s.dtype == t.dtype and s.shape == t.shape and s.dtype in (np.uint16, np.float32)
+    K = _arr(intrinsic, np.float64).reshape(9)
+    T0 = _arr(np.eye(4) if init is None else init, np.float64).reshape(16)
+    n = len(criteria)
+    it = (C.c_int * n)(*[int(c[0]) for c in criteria])
+    rr = np.array([c[1] for c in criteria], np.float64)
+    rf = np.array([c[2] for c in criteria], np.float64)
+    T = np.zeros(16)
+    rmse, fit, done = C.c_double(0), C.c_double(0), C.c_int(0)
+    per = np.zeros((max(sum(int(c[0]) for c in criteria), 1), 2))
+    rc = lib().orc_rgbd_odometry_multi_scale_p2plane(s.ctypes.data, t.ctypes.data, int(s.dtype == np.float32),
+                                                     s.shape[0], s.shape[1], _p(K, _f64p), _p(T0, _f64p),
+                                                     float(depth_scale), float(depth_max), n, it, _p(rr, _f64p),
+                                                     _p(rf, _f64p), float(depth_outlier_trunc),
+                                                     float(depth_huber_delta), _p(T, _f64p), C.byref(rmse),
+                                                     C.byref(fit), _p(per, _f64p), C.byref(done))
+    return {"status": rc, "transformation": T.reshape(4, 4), "inlier_rmse": rmse.value, "fitness": fit.value,
+            "per_iteration": per[: done.value].copy()}

@@ -270,6 +270,41 @@ void orc_ray_cast(const int32_t* table_keys, int64_t size, const float* tsdf_buf
                   float* ratio_out, float* ratio_dx_out, float* ratio_dy_out,
                   float* ratio_dz_out);
 
+/* ---------------------------------------------------------- RGB-D odometry
+ * t/pipelines/odometry/RGBDOdometry.cpp (driver), t/pipelines/kernel/RGBDOdometry{CPU.cpp,JacobianImpl.h}
+ * (PointToPlane method), t/geometry/kernel/ImageImpl.h (pyramid kernels); see odometry_oracle.c.
+ * Images are row-major [rows][cols](x3).  orc_filter_bilateral_f32 is PARITY UNPINNED (NPP/IPP). */
+void orc_clip_transform(const void* src, int src_is_f32, int rows, int cols, float scale,
+                        float min_value, float max_value, float clip_fill, float* dst);
+void orc_pyr_down_depth(const float* src, int rows, int cols, float depth_diff,
+                        float invalid_fill, float* dst /* [rows/2][cols/2] */);
+void orc_create_vertex_map(const float* depth, int rows, int cols, const double K[9],
+                           float invalid_fill, float* vertex);
+void orc_create_normal_map(const float* vertex, int rows, int cols, float invalid_fill, float* normal);
+void orc_filter_bilateral_f32(const float* src, int rows, int cols, int kernel_size,
+                              float value_sigma, float dist_sigma, float* dst);
+float orc_huber_deriv(float r, float delta);
+float orc_huber_loss(float r, float delta);
+int orc_odometry_jacobian_p2plane(int x, int y, float depth_outlier_trunc, const float* source_vertex,
+                                  const float* target_vertex, const float* target_normal, int rows, int cols,
+                                  const double K[9], const double T[16], float J[6], float* r);
+void orc_odometry_p2plane_sums(const float* source_vertex, const float* target_vertex,
+                               const float* target_normal, int rows, int cols, const double K[9],
+                               const double T[16], float depth_outlier_trunc, float depth_huber_delta,
+                               double sums29[29], double abs29[29]);
+int orc_compute_odometry_result_p2plane(const float* source_vertex, const float* target_vertex,
+                                        const float* target_normal, int rows, int cols,
+                                        const double K[9], const double T[16],
+                                        float depth_outlier_trunc, float depth_huber_delta,
+                                        double delta_T[16], double* inlier_rmse, double* fitness);
+int orc_rgbd_odometry_multi_scale_p2plane(const void* source_depth, const void* target_depth, int depth_is_f32,
+                                          int rows, int cols, const double K[9], const double init_T[16],
+                                          float depth_scale, float depth_max, int n_levels,
+                                          const int* max_iteration, const double* relative_rmse,
+                                          const double* relative_fitness, float depth_outlier_trunc,
+                                          float depth_huber_delta, double T_out[16], double* inlier_rmse,
+                                          double* fitness, double* per_iter, int* executed);
+
 int orc_num_threads(void);
 
 #ifdef __cplusplus

@@ -14,6 +14,9 @@
 //   DISPATCH_ROBUST_KERNEL_FUNCTION                                t/pipelines/registration/RobustKernelImpl.h:35-115
 //   TransformIndexer, ArrayIndexer                                 t/geometry/kernel/GeometryIndexer.h:25-144, 160-420
 //   solve_svd3x3<float> / <double>                                 core/linalg/kernel/SVD3x3.h:2170-2215
+//   odometry::GetJacobianPointToPlane, HuberDeriv, HuberLoss         t/pipelines/kernel/RGBDOdometryJacobianImpl.h:29-160
+//   image::ClipTransformCPU, PyrDownDepthCPU, CreateVertexMapCPU,
+//          CreateNormalMapCPU (whole functions, serial ParallelFor)  t/geometry/kernel/ImageImpl.h:86-315
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -30,6 +33,8 @@ using std::pow;
 #include "open3d/t/geometry/kernel/GeometryIndexer.h"
 #define OPEN3D_SKIP_TRANSFORM_MAIN   // TransformImpl.h:90: keep only the per-point kernels
 #include "open3d/t/geometry/kernel/TransformImpl.h"
+#include "open3d/t/geometry/kernel/ImageImpl.h"
+#include "open3d/t/pipelines/kernel/RGBDOdometryJacobianImpl.h"
 #include "open3d/t/pipelines/kernel/RegistrationImpl.h"
 #include "open3d/t/pipelines/kernel/TransformationConverterImpl.h"
 #include "open3d/t/pipelines/registration/RobustKernelImpl.h"
@@ -137,6 +142,49 @@ void ref_solve_svd3x3_f32(const float A[9], const float b[3], float x[3]) {
 }
 void ref_solve_svd3x3_f64(const double A[9], const double b[3], double x[3]) {
     open3d::core::linalg::kernel::solve_svd3x3<double>(A, b, x);
+}
+
+// ---- RGB-D odometry
+float ref_huber_deriv(float r, float delta) { return o3k::odometry::HuberDeriv(r, delta); }
+float ref_huber_loss(float r, float delta) { return o3k::odometry::HuberLoss(r, delta); }
+
+// One pixel of ComputeOdometryResultPointToPlane: vertex / normal maps are [rows][cols][3] f32.
+int ref_odometry_jacobian_p2plane(int x, int y, float depth_outlier_trunc, const float* source_vertex,
+                                  const float* target_vertex, const float* target_normal, int rows, int cols,
+                                  const double K[9], const double T[16], float J[6], float* r) {
+    using open3d::core::Tensor;
+    Tensor sv((void*)source_vertex, {rows, cols, 3}, open3d::core::Float32);
+    Tensor tv((void*)target_vertex, {rows, cols, 3}, open3d::core::Float32);
+    Tensor tn((void*)target_normal, {rows, cols, 3}, open3d::core::Float32);
+    Tensor Kt((void*)K, {3, 3}, open3d::core::Float64), Tt((void*)T, {4, 4}, open3d::core::Float64);
+    o3g::NDArrayIndexer svi(sv, 2), tvi(tv, 2), tni(tn, 2);
+    o3g::TransformIndexer ti(Kt, Tt);
+    return o3k::odometry::GetJacobianPointToPlane(x, y, depth_outlier_trunc, svi, tvi, tni, ti, J, *r) ? 1 : 0;
+}
+
+// Image kernels, whole functions.  depth_dtype: 0 = u16, 1 = f32 (ClipTransform's source).
+void ref_clip_transform(const void* src, int src_is_f32, int rows, int cols, float scale, float min_value,
+                        float max_value, float clip_fill, float* dst) {
+    open3d::core::Tensor s((void*)src, {rows, cols, 1}, src_is_f32 ? open3d::core::Float32 : open3d::core::UInt16);
+    open3d::core::Tensor d((void*)dst, {rows, cols, 1}, open3d::core::Float32);
+    o3g::image::ClipTransformCPU(s, d, scale, min_value, max_value, clip_fill);
+}
+void ref_pyr_down_depth(const float* src, int rows, int cols, float depth_diff, float invalid_fill, float* dst) {
+    open3d::core::Tensor s((void*)src, {rows, cols, 1}, open3d::core::Float32);
+    open3d::core::Tensor d((void*)dst, {rows / 2, cols / 2, 1}, open3d::core::Float32);
+    o3g::image::PyrDownDepthCPU(s, d, depth_diff, invalid_fill);
+}
+void ref_create_vertex_map(const float* depth, int rows, int cols, const double K[9], float invalid_fill,
+                           float* vertex) {
+    open3d::core::Tensor s((void*)depth, {rows, cols, 1}, open3d::core::Float32);
+    open3d::core::Tensor d((void*)vertex, {rows, cols, 3}, open3d::core::Float32);
+    open3d::core::Tensor Kt((void*)K, {3, 3}, open3d::core::Float64);
+    o3g::image::CreateVertexMapCPU(s, d, Kt, invalid_fill);
+}
+void ref_create_normal_map(const float* vertex, int rows, int cols, float invalid_fill, float* normal) {
+    open3d::core::Tensor s((void*)vertex, {rows, cols, 3}, open3d::core::Float32);
+    open3d::core::Tensor d((void*)normal, {rows, cols, 3}, open3d::core::Float32);
+    o3g::image::CreateNormalMapCPU(s, d, invalid_fill);
 }
 
 }  // extern "C"

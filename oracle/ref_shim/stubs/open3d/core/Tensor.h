@@ -25,7 +25,7 @@ public:
     bool operator==(const Dtype& o) const { return size_ == o.size_ && code_ == o.code_; }
     bool operator!=(const Dtype& o) const { return !(*this == o); }
     std::string ToString() const { return "Dtype"; }
-    static const Dtype Float32, Float64, UInt8, UInt16, Int32, Int64, Bool;
+    static const Dtype Float32, Float64, UInt8, UInt16, Int32, Int64, Bool, Int8, Int16, UInt32, UInt64;
 private:
     int64_t size_;
     int code_;
@@ -37,12 +37,20 @@ inline const Dtype Dtype::UInt16(2, 4);
 inline const Dtype Dtype::Int32(4, 5);
 inline const Dtype Dtype::Int64(8, 6);
 inline const Dtype Dtype::Bool(1, 7);
+inline const Dtype Dtype::Int8(1, 8);
+inline const Dtype Dtype::Int16(2, 9);
+inline const Dtype Dtype::UInt32(4, 10);
+inline const Dtype Dtype::UInt64(8, 11);
 static const Dtype Float32 = Dtype::Float32;
 static const Dtype Float64 = Dtype::Float64;
 static const Dtype UInt8 = Dtype::UInt8;
 static const Dtype UInt16 = Dtype::UInt16;
 static const Dtype Int32 = Dtype::Int32;
 static const Dtype Int64 = Dtype::Int64;
+static const Dtype Int8 = Dtype::Int8;
+static const Dtype Int16 = Dtype::Int16;
+static const Dtype UInt32 = Dtype::UInt32;
+static const Dtype UInt64 = Dtype::UInt64;
 
 class Device {
 public:

@@ -229,3 +229,115 @@ def test_sym3x3_pinv_vs_reference_svd_solver(ref):
     # the reference's f32 solver: finite, same order of magnitude, but far from exact (documented gap)
     assert 1e-3 < float(np.median(dev_ref)) < 0.5, np.median(dev_ref)
     assert float(np.median(res_ref)) > 100 * max(res_orc)
+
+
+# ------------------------------------------------ RGB-D odometry + image pyramid
+
+def _odometry_inputs(level_div=4):
+    from tests.synth import PRIMESENSE_K, camera_pose, render_depth
+    Ta, Tb = camera_pose(100), camera_pose(103)
+    da, db = render_depth(Ta).numpy(), render_depth(Tb).numpy()
+    da[40:60, 100:140] = 0            # holes -> NaN after ClipTransform
+    db[300:330, 200:260] = 0
+    return da, db, np.linalg.inv(Ta) @ Tb, np.ascontiguousarray(PRIMESENSE_K, dtype=np.float64)
+
+
+def _same(a, b):
+    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+    nan = np.isnan(a)
+    return a.shape == b.shape and np.array_equal(nan, np.isnan(b)) and \
+        np.array_equal(a[~nan].view(np.uint32), b[~nan].view(np.uint32))
+
+
+def test_image_pyramid_kernels_match_reference_functions(ref):
+    """ClipTransformCPU, PyrDownDepthCPU, CreateVertexMapCPU, CreateNormalMapCPU compiled from
+    t/geometry/kernel/ImageImpl.h:86-315 (whole functions, NaN fills) vs the oracle: bit-exact."""
+    vp = C.c_void_p
+    ref.ref_clip_transform.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, f32p]
+    ref.ref_pyr_down_depth.argtypes = [f32p, C.c_int, C.c_int, C.c_float, C.c_float, f32p]
+    ref.ref_create_vertex_map.argtypes = [f32p, C.c_int, C.c_int, f64p, C.c_float, f32p]
+    ref.ref_create_normal_map.argtypes = [f32p, C.c_int, C.c_int, C.c_float, f32p]
+    da, _, _, K = _odometry_inputs()
+    rows, cols = da.shape
+    nan = float("nan")
+    for src, is_f32 in ((da, 0), ((da.astype(np.float32) / 1000.0), 1)):
+        src = np.ascontiguousarray(src)
+        want = np.empty((rows, cols), np.float32)
+        scale = 1000.0 if not is_f32 else 1.0
+        ref.ref_clip_transform(src.ctypes.data, is_f32, rows, cols, scale, 0.0, 3.0, nan, _p(want, f32p))
+        got = oracle.clip_transform(src, scale, 0.0, 3.0, nan)
+        assert np.isnan(got).any() and _same(got, want)
+    depth = oracle.clip_transform(da)
+    r, c = rows, cols
+    Kp = K.copy()
+    for level in range(3):
+        v_want = np.empty((r, c, 3), np.float32)
+        ref.ref_create_vertex_map(_p(depth, f32p), r, c, _p(Kp.reshape(9), f64p), nan, _p(v_want, f32p))
+        v_got = oracle.create_vertex_map(depth, Kp)
+        assert _same(v_got, v_want)
+        n_want = np.empty((r, c, 3), np.float32)
+        ref.ref_create_normal_map(_p(v_want, f32p), r, c, nan, _p(n_want, f32p))
+        assert _same(oracle.create_normal_map(v_got), n_want)
+        d_want = np.empty((r // 2, c // 2), np.float32)
+        ref.ref_pyr_down_depth(_p(depth, f32p), r, c, 0.14, nan, _p(d_want, f32p))
+        depth = oracle.pyr_down_depth(depth, 0.14)
+        assert _same(depth, d_want) and np.isnan(depth).any() and np.isfinite(depth).mean() > 0.9
+        r, c = r // 2, c // 2
+        Kp = Kp / 2
+        Kp[2, 2] = 1
+    # a finite invalid_fill exercises the == branches of PyrDownDepth / CreateNormalMap / is_invalid
+    d0 = np.where(np.isnan(oracle.clip_transform(da)), np.float32(0), oracle.clip_transform(da))
+    v_want = np.empty((rows, cols, 3), np.float32)
+    ref.ref_create_vertex_map(_p(d0, f32p), rows, cols, _p(K.reshape(9), f64p), 0.0, _p(v_want, f32p))
+    assert _same(oracle.create_vertex_map(d0, K, 0.0), v_want)
+    n_want = np.empty((rows, cols, 3), np.float32)
+    ref.ref_create_normal_map(_p(v_want, f32p), rows, cols, 0.0, _p(n_want, f32p))
+    assert _same(oracle.create_normal_map(v_want, 0.0), n_want)
+    p_want = np.empty((rows // 2, cols // 2), np.float32)
+    ref.ref_pyr_down_depth(_p(d0, f32p), rows, cols, 0.14, 0.0, _p(p_want, f32p))
+    assert _same(oracle.pyr_down_depth(d0, 0.14, 0.0), p_want)
+
+
+def test_odometry_huber_and_jacobian_match_reference_header(ref):
+    """RGBDOdometryJacobianImpl.h:29-37 (HuberDeriv truncates the residual to int inside Sign()) and
+    :106-160 GetJacobianPointToPlane, every pixel of a 120x160 level."""
+    ref.ref_huber_deriv.restype = C.c_float
+    ref.ref_huber_deriv.argtypes = [C.c_float, C.c_float]
+    ref.ref_huber_loss.restype = C.c_float
+    ref.ref_huber_loss.argtypes = [C.c_float, C.c_float]
+    ref.ref_odometry_jacobian_p2plane.argtypes = [C.c_int, C.c_int, C.c_float, f32p, f32p, f32p, C.c_int, C.c_int,
+                                                  f64p, f64p, f32p, f32p]
+    rng = np.random.default_rng(4)
+    for r in np.concatenate([rng.normal(0, 0.05, 300), rng.normal(0, 2.0, 100), [0.0, 0.05, -0.05, 1.0, -1.0, 1.5]]):
+        for delta in (0.05, 0.1, 1.2):
+            a, b = np.float32(oracle.huber_deriv(r, delta)), np.float32(ref.ref_huber_deriv(r, delta))
+            assert a.view(np.uint32) == b.view(np.uint32), (r, delta)
+            a, b = np.float32(oracle.huber_loss(r, delta)), np.float32(ref.ref_huber_loss(r, delta))
+            assert a.view(np.uint32) == b.view(np.uint32), (r, delta)
+    assert oracle.huber_deriv(0.06, 0.05) == 0.0 and oracle.huber_deriv(1.5, 0.05) == np.float32(0.05)   # the int Sign()
+    da, db, T_gt, K = _odometry_inputs()
+    ds, dt = oracle.clip_transform(db), oracle.clip_transform(da)
+    Kp = K.copy()
+    for _ in range(2):
+        ds, dt = oracle.pyr_down_depth(ds, 0.14), oracle.pyr_down_depth(dt, 0.14)
+        Kp = Kp / 2
+        Kp[2, 2] = 1
+    sv, tv = oracle.create_vertex_map(ds, Kp), oracle.create_vertex_map(dt, Kp)
+    tn = oracle.create_normal_map(oracle.create_vertex_map(oracle.filter_bilateral(dt), Kp))
+    rows, cols = ds.shape
+    T = T_gt.copy()
+    T[:3, 3] += [0.01, -0.02, 0.015]     # not yet aligned: both inliers and truncated outliers
+    Kf, Tf = np.ascontiguousarray(Kp.reshape(9)), np.ascontiguousarray(T.reshape(16))
+    J, r = np.zeros(6, np.float32), np.zeros(1, np.float32)
+    valid = 0
+    for y in range(rows):
+        for x in range(cols):
+            ok = ref.ref_odometry_jacobian_p2plane(x, y, 0.07, _p(sv, f32p), _p(tv, f32p), _p(tn, f32p), rows, cols,
+                                                   _p(Kf, f64p), _p(Tf, f64p), _p(J, f32p), _p(r, f32p))
+            ok2, J2, r2 = oracle.odometry_jacobian_p2plane(x, y, sv, tv, tn, Kp, T, 0.07)
+            assert bool(ok) == ok2
+            if ok:
+                valid += 1
+                assert np.array_equal(J.view(np.uint32), J2.view(np.uint32))
+                assert np.float32(r[0]).view(np.uint32) == np.float32(r2).view(np.uint32)
+    assert 0.3 * rows * cols < valid < rows * cols
