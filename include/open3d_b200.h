@@ -39,7 +39,8 @@ typedef enum {
     O3DB_ERR_SINGULAR = -3,  /* singular 6x6 system (reference raises, TransformationConverter.cpp:219-225) */
     O3DB_ERR_CAPACITY = -4,  /* hash map / buffer capacity exceeded */
     O3DB_ERR_NO_BLOCKS = -5, /* "No block is touched in TSDF volume" (VoxelBlockGridCUDA.cu:193-198) */
-    O3DB_ERR_COMM = -6       /* NCCL not available / communicator failure */
+    O3DB_ERR_COMM = -6,      /* NCCL not available / communicator failure */
+    O3DB_ERR_NO_INLIERS = -7 /* "Invalid inlier_count value 0, must be > 0." (odometry/RGBDOdometry.cpp:449-452) */
 } o3db_status;
 
 const char* o3db_last_error(void);
@@ -390,6 +391,71 @@ int o3db_vbg_ray_cast(o3db_vbg* vbg, const int32_t* block_coords_dev, int64_t nu
                       const o3db_raycast_outputs* outputs_host, float depth_scale, float depth_min,
                       float depth_max, float weight_threshold, float trunc_voxel_multiplier,
                       int range_map_down_factor, float* range_dev, void* stream);
+
+/* ------------------------------------------------------------------------
+ * RGB-D odometry, PointToPlane method — slam::Model::TrackFrameToModel (slam/Model.cpp:68-89) ->
+ * odometry::RGBDOdometryMultiScale (odometry/RGBDOdometry.cpp:56-206).
+ *
+ * Image members used by the pyramid (t/geometry/Image.cpp:409-520 over t/geometry/kernel/ImageImpl.h:86-315),
+ * device buffers, row-major [rows][cols](x3), Float32 unless noted:
+ * ---------------------------------------------------------------------- */
+int o3db_image_clip_transform(const void* src_dev, int depth_dtype /* O3DB_DEPTH_U16 | _F32 */, int rows, int cols,
+                              float scale, float min_value, float max_value, float clip_fill, float* dst_dev,
+                              void* stream);
+int o3db_image_pyr_down_depth(const float* src_dev, int rows, int cols, float diff_threshold, float invalid_fill,
+                              float* dst_dev /* [rows/2][cols/2] */, void* stream);
+int o3db_image_create_vertex_map(const float* depth_dev, int rows, int cols, const double intrinsic_host[9],
+                                 float invalid_fill, float* vertex_dev /* [rows][cols][3] */, void* stream);
+int o3db_image_create_normal_map(const float* vertex_dev, int rows, int cols, float invalid_fill,
+                                 float* normal_dev /* [rows][cols][3] */, void* stream);
+/* Image::FilterBilateral (Image.cpp:248-285).  Upstream forwards to NPP's nppiFilterBilateralGaussBorder
+ * (kernel/NPPImage.cpp:319-376: radius kernel_size/2, nValSquareSigma = value_sigma^2, nPosSquareSigma =
+ * dist_sigma^2, replicated border), a closed-source library; this evaluates NPP's documented definition
+ *   out = sum(w v) / sum(w),  w = exp(-(dx^2+dy^2)/(2 dist_sigma^2)) * exp(-(v - v_center)^2/(2 value_sigma^2))
+ * in f32.  PARITY UNPINNED against NPP. */
+int o3db_image_filter_bilateral(const float* src_dev, int rows, int cols, int kernel_size, float value_sigma,
+                                float dist_sigma, float* dst_dev, void* stream);
+
+/* odometry::ComputeOdometryResultPointToPlane (RGBDOdometry.cpp:432-459) = kernel
+ * ComputeOdometryResultPointToPlaneCUDA (kernel/RGBDOdometryCUDA.cu:37-125) + DecodeAndSolve6x6 +
+ * PoseToTransformation: one Gauss-Newton step.  delta_transformation_host: 4x4 f64 row-major;
+ * inlier_rmse = sum(HuberLoss) / inlier_count, fitness = inlier_count / (rows*cols) (as upstream);
+ * sums29_host (optional): the 29 reduced scalars.  Errors: O3DB_ERR_SINGULAR, O3DB_ERR_NO_INLIERS. */
+int o3db_compute_odometry_result_point_to_plane(const float* source_vertex_map_dev,
+                                                const float* target_vertex_map_dev,
+                                                const float* target_normal_map_dev, int rows, int cols,
+                                                const double intrinsic_host[9],
+                                                const double init_source_to_target_host[16],
+                                                float depth_outlier_trunc, float depth_huber_delta,
+                                                double delta_transformation_host[16], double* inlier_rmse_host,
+                                                double* fitness_host, double* sums29_host, void* stream);
+
+typedef struct {
+    int max_iteration;        /* OdometryConvergenceCriteria (RGBDOdometry.h:33-52) */
+    double relative_rmse;
+    double relative_fitness;
+} o3db_odometry_criteria;
+
+typedef struct {
+    double transformation[16]; /* OdometryResult::transformation_ (source -> target, 4x4 f64) */
+    double inlier_rmse;        /* OdometryResult::inlier_rmse_ */
+    double fitness;            /* OdometryResult::fitness_ */
+    int status;                /* O3DB_OK, O3DB_ERR_SINGULAR or O3DB_ERR_NO_INLIERS */
+    int iterations;            /* Gauss-Newton steps executed over all levels */
+} o3db_odometry_result;
+
+/* RGBDOdometryMultiScale(..., Method::PointToPlane) with the whole coarse-to-fine loop on the device.
+ * criteria[0] applies to the coarsest level (upstream's criteria_list order); num_levels <= 8.
+ * Depth images may be UInt16 or Float32 independently (input frame vs. ray-cast model frame).
+ * per_iteration_host (optional): (inlier_rmse, fitness) of every executed step. */
+int o3db_rgbd_odometry_multi_scale_point_to_plane(const void* source_depth_dev, int source_dtype,
+                                                  const void* target_depth_dev, int target_dtype, int rows,
+                                                  int cols, const double intrinsic_host[9],
+                                                  const double init_source_to_target_host[16], float depth_scale,
+                                                  float depth_max, const o3db_odometry_criteria* criteria,
+                                                  int num_levels, float depth_outlier_trunc,
+                                                  float depth_huber_delta, o3db_odometry_result* result_host,
+                                                  double* per_iteration_host, void* stream);
 
 /* Measurement aid (bench.py): when enabled, CUDA events bracket the touch and the
  * integrate kernel of every o3db_vbg_integrate_frame call (up to 4096 frames per

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libo3db200.so")
 
 OK = 0
-ERR_INVALID, ERR_CUDA, ERR_SINGULAR, ERR_CAPACITY, ERR_NO_BLOCKS, ERR_COMM = -1, -2, -3, -4, -5, -6
+ERR_INVALID, ERR_CUDA, ERR_SINGULAR, ERR_CAPACITY, ERR_NO_BLOCKS, ERR_COMM, ERR_NO_INLIERS = -1, -2, -3, -4, -5, -6, -7
 DEPTH_U16, DEPTH_F32 = 0, 1
 COLOR_NONE, COLOR_U8, COLOR_F32 = 0, 1, 2
 UNIQUE_ID_BYTES = 128
@@ -39,6 +39,15 @@ class IcpResult(C.Structure):
     _fields_ = [("transformation", C.c_double * 16), ("fitness", C.c_double),
                 ("inlier_rmse", C.c_double), ("converged", C.c_int), ("num_iterations", C.c_int),
                 ("status", C.c_int), ("num_correspondences", C.c_int64)]
+
+
+class OdometryCriteria(C.Structure):
+    _fields_ = [("max_iteration", C.c_int), ("relative_rmse", C.c_double), ("relative_fitness", C.c_double)]
+
+
+class OdometryResult(C.Structure):
+    _fields_ = [("transformation", C.c_double * 16), ("inlier_rmse", C.c_double), ("fitness", C.c_double),
+                ("status", C.c_int), ("iterations", C.c_int)]
 
 
 class RaycastOutputs(C.Structure):
@@ -109,6 +118,16 @@ _SIGS = {
     "o3db_vbg_integrate_frame_host": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _dp, _dp, _f, _f, _f, _vp]),
     "o3db_vbg_integrate_sequence": (_i, [_vp, _i64, _vp, _i, _vp, _i, _i, _i, _dp, _dp, _f, _f, _f, _i, _vp]),
     "o3db_vbg_last_frustum_blocks": (_i64, [_vp, _vp, _i64, _vp]),
+    "o3db_image_clip_transform": (_i, [_vp, _i, _i, _i, _f, _f, _f, _f, _vp, _vp]),
+    "o3db_image_pyr_down_depth": (_i, [_vp, _i, _i, _f, _f, _vp, _vp]),
+    "o3db_image_create_vertex_map": (_i, [_vp, _i, _i, _dp, _f, _vp, _vp]),
+    "o3db_image_create_normal_map": (_i, [_vp, _i, _i, _f, _vp, _vp]),
+    "o3db_image_filter_bilateral": (_i, [_vp, _i, _i, _i, _f, _f, _vp, _vp]),
+    "o3db_compute_odometry_result_point_to_plane": (_i, [_vp, _vp, _vp, _i, _i, _dp, _dp, _f, _f, _dp, _dp, _dp, _dp,
+                                                         _vp]),
+    "o3db_rgbd_odometry_multi_scale_point_to_plane": (_i, [_vp, _i, _vp, _i, _i, _i, _dp, _dp, _f, _f,
+                                                           C.POINTER(OdometryCriteria), _i, _f, _f,
+                                                           C.POINTER(OdometryResult), _dp, _vp]),
     "o3db_vbg_estimate_range": (_i, [_vp, _vp, _i64, _dp, _dp, _i, _i, _i, _f, _f, _vp, _vp]),
     "o3db_vbg_ray_cast": (_i, [_vp, _vp, _i64, _dp, _dp, _i, _i, C.POINTER(RaycastOutputs), _f, _f, _f, _f, _f, _i,
                                _vp, _vp]),

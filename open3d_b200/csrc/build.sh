@@ -10,7 +10,7 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17
 cd "${HERE}"
 OBJS=()
 PIDS=()
-for f in common icp tsdf comm pointcloud raycast; do
+for f in common icp tsdf comm pointcloud raycast odometry; do
   "${NVCC}" "${FLAGS[@]}" -c "${f}.cu" -o "${f}.o" &
   PIDS+=($!)
   OBJS+=("${f}.o")

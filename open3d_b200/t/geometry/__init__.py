@@ -135,6 +135,80 @@ class Image:
     def columns(self):
         return int(self._t.shape[1])
 
+    @property
+    def channels(self):
+        return int(self._t.shape[2])
+
+    # ---- the depth-pyramid members RGB-D odometry uses (t/geometry/Image.cpp:248-285, 409-520)
+    def _f32_1ch(self, who):
+        t = self._t
+        if self.rows <= 0 or self.columns <= 0 or self.channels != 1:
+            raise RuntimeError(f"Invalid shape, expected a 1 channel image, but got ({self.rows}, {self.columns}, "
+                               f"{self.channels})")
+        if t.dtype != torch.float32:
+            raise RuntimeError(f"{who}: expected a Float32 image, got {t.dtype}")
+        return t.cuda().contiguous()
+
+    def clip_transform(self, scale, min_value, max_value, clip_fill=0.0):
+        """Image::ClipTransform (Image.cpp:426-456): UInt16/Float32 -> Float32, in / scale, clipped values filled."""
+        if self.rows <= 0 or self.columns <= 0 or self.channels != 1:
+            raise RuntimeError(f"Invalid shape, expected a 1 channel image, but got ({self.rows}, {self.columns}, "
+                               f"{self.channels})")
+        t = self._t.cuda().contiguous()
+        out = torch.empty((self.rows, self.columns, 1), dtype=torch.float32, device=t.device)
+        check(lib.o3db_image_clip_transform(t.data_ptr(), _depth_dtype(t), self.rows, self.columns, float(scale),
+                                            float(min_value), float(max_value), float(clip_fill), out.data_ptr(),
+                                            current_stream_ptr()))
+        return Image(out)
+
+    def pyr_down_depth(self, diff_threshold, invalid_fill=0.0):
+        """Image::PyrDownDepth (Image.cpp:409-424)."""
+        t = self._f32_1ch("PyrDownDepth")
+        out = torch.empty((self.rows // 2, self.columns // 2, 1), dtype=torch.float32, device=t.device)
+        check(lib.o3db_image_pyr_down_depth(t.data_ptr(), self.rows, self.columns, float(diff_threshold),
+                                            float(invalid_fill), out.data_ptr(), current_stream_ptr()))
+        return Image(out)
+
+    def create_vertex_map(self, intrinsics, invalid_fill=0.0):
+        """Image::CreateVertexMap (Image.cpp:458-480)."""
+        t = self._f32_1ch("CreateVertexMap")
+        out = torch.empty((self.rows, self.columns, 3), dtype=torch.float32, device=t.device)
+        check(lib.o3db_image_create_vertex_map(t.data_ptr(), self.rows, self.columns, dptr(_k9(intrinsics)),
+                                               float(invalid_fill), out.data_ptr(), current_stream_ptr()))
+        return Image(out)
+
+    def create_normal_map(self, invalid_fill=0.0):
+        """Image::CreateNormalMap (Image.cpp:482-500) of a vertex map."""
+        if self.channels != 3 or self._t.dtype != torch.float32:
+            raise RuntimeError(f"Invalid shape, expected a 3 channel Float32 image, but got ({self.rows}, "
+                               f"{self.columns}, {self.channels})")
+        t = self._t.cuda().contiguous()
+        out = torch.empty_like(t)
+        check(lib.o3db_image_create_normal_map(t.data_ptr(), self.rows, self.columns, float(invalid_fill),
+                                               out.data_ptr(), current_stream_ptr()))
+        return Image(out)
+
+    def filter_bilateral(self, kernel_size=3, value_sigma=20.0, dist_sigma=10.0):
+        """Image::FilterBilateral (Image.cpp:248-285) for 1-channel Float32 (NPP's documented definition; see
+        o3db_image_filter_bilateral)."""
+        if kernel_size < 3:
+            raise RuntimeError(f"Kernel size must be >= 3, but got {kernel_size}.")
+        t = self._f32_1ch("FilterBilateral")
+        out = torch.empty_like(t)
+        check(lib.o3db_image_filter_bilateral(t.data_ptr(), self.rows, self.columns, int(kernel_size),
+                                              float(value_sigma), float(dist_sigma), out.data_ptr(),
+                                              current_stream_ptr()))
+        return Image(out)
+
+
+class RGBDImage:
+    """t::geometry::RGBDImage (t/geometry/RGBDImage.h): a colour / depth image pair."""
+
+    def __init__(self, color=None, depth=None, aligned=True):
+        self.color = color if isinstance(color, Image) else Image(color)
+        self.depth = depth if isinstance(depth, Image) else Image(depth)
+        self.aligned = aligned
+
 
 def _image_tensor(img):
     if img is None:

@@ -1,1 +1,1 @@
-from . import registration, slam  # noqa: F401
+from . import odometry, registration, slam  # noqa: F401

@@ -4,15 +4,17 @@ cpp/pybind/t/pipelines/slam/slam.cpp:58-160).
 
 ``Model.integrate`` is the fused, host-sync-free pipeline
 ``o3db_vbg_integrate_frame`` (frustum touch + hash activate + TSDF fusion).
-``track_frame_to_model`` / ``synthesize_model_frame`` (RGB-D odometry, ray
-casting) are SURVEY.md §8f "next" rows and raise until built.
+``synthesize_model_frame`` is ``o3db_vbg_ray_cast`` on the last frame's frustum and
+``track_frame_to_model`` the device-resident PointToPlane RGB-D odometry of
+``open3d_b200.t.pipelines.odometry``: together the dense-SLAM loop of
+examples/python/t_reconstruction_system/dense_slam.py.
 """
 from __future__ import annotations
 
 import numpy as np
 import torch
 
-from ...geometry import Image, VoxelBlockGrid
+from ...geometry import Image, RGBDImage, VoxelBlockGrid
 from ....core import as_host_f64_4x4
 
 
@@ -101,8 +103,17 @@ class Model:
     def get_hashmap(self):
         return self.voxel_grid.hashmap()
 
-    def track_frame_to_model(self, *args, **kwargs):
-        raise RuntimeError("Model.track_frame_to_model (RGB-D odometry) is not built yet: SURVEY.md §8f next #2")
+    def track_frame_to_model(self, input_frame, model_frame, depth_scale=1000.0, depth_max=3.0, depth_diff=0.07,
+                             method=None, criteria=(6, 3, 1)):
+        """Model::TrackFrameToModel (slam/Model.cpp:68-89): multi-scale RGB-D odometry of the input frame against
+        the ray-cast model frame, identity initialisation; returns OdometryResult (source = input -> model)."""
+        from .. import odometry
+        method = odometry.Method.PointToPlane if method is None else method
+        return odometry.rgbd_odometry_multi_scale(
+            RGBDImage(input_frame.get_data_as_image("color"), input_frame.get_data_as_image("depth")),
+            RGBDImage(model_frame.get_data_as_image("color"), model_frame.get_data_as_image("depth")),
+            model_frame.get_intrinsics(), np.eye(4), depth_scale, depth_max, criteria, method,
+            odometry.OdometryLossParams(depth_diff))
 
     def synthesize_model_frame(self, raycast_frame, depth_scale=1000.0, depth_min=0.1, depth_max=3.0,
                                trunc_voxel_multiplier=8.0, enable_color=True, weight_threshold=-1.0):
