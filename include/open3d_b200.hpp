@@ -5,6 +5,7 @@
 //       RegistrationResult, RobustKernel, TransformationEstimationPointToPlane}
 //       (cpp/open3d/t/pipelines/registration/{Registration.h, TransformationEstimation.h, RobustKernel.h})
 //   open3d::t::pipelines::slam::{Model, Frame}            (cpp/open3d/t/pipelines/slam/{Model.h, Frame.h})
+//   open3d::t::pipelines::odometry::{RGBDOdometryMultiScale (PointToPlane), OdometryResult, ...}   (odometry/RGBDOdometry.h)
 //   open3d::t::geometry::{PointCloud, VoxelBlockGrid}     (the members this path touches)
 // core::Tensor is replaced by raw device pointers + sizes (the library has no tensor runtime;
 // INTEGRATION.md shows the forwarding stubs for a real Open3D build).
@@ -231,6 +232,75 @@ inline RegistrationResult ICP(const geometry::PointCloud& source, const geometry
 
 }  // namespace registration
 
+namespace odometry {
+
+/// RGBDOdometry.h:24-30
+enum class Method { PointToPlane, Intensity, Hybrid };
+
+/// RGBDOdometry.h:33-52 (implicitly constructible from an iteration count, like upstream's {10, 5, 3})
+class OdometryConvergenceCriteria {
+public:
+    OdometryConvergenceCriteria(int max_iteration, double relative_rmse = 1e-6, double relative_fitness = 1e-6)
+        : max_iteration_(max_iteration), relative_rmse_(relative_rmse), relative_fitness_(relative_fitness) {}
+    int max_iteration_;
+    double relative_rmse_;
+    double relative_fitness_;
+};
+
+/// RGBDOdometry.h:54-78
+class OdometryResult {
+public:
+    std::array<double, 16> transformation_{{1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}};
+    double inlier_rmse_ = 0.0;
+    double fitness_ = 0.0;
+};
+
+/// RGBDOdometry.h:80-114
+class OdometryLossParams {
+public:
+    OdometryLossParams(float depth_outlier_trunc = 0.07f, float depth_huber_delta = 0.05f, float intensity_huber_delta = 0.1f)
+        : depth_outlier_trunc_(depth_outlier_trunc), depth_huber_delta_(depth_huber_delta),
+          intensity_huber_delta_(intensity_huber_delta) {}
+    float depth_outlier_trunc_, depth_huber_delta_, intensity_huber_delta_;
+};
+
+/// A depth image on the device: UInt16 or Float32, [rows][cols].
+struct DepthImage {
+    const void* data = nullptr;
+    bool is_f32 = false;
+    int rows = 0, cols = 0;
+};
+
+/// RGBDOdometryMultiScale (RGBDOdometry.cpp:56-113) for Method::PointToPlane (only the depth images are read).
+inline OdometryResult RGBDOdometryMultiScale(const DepthImage& source, const DepthImage& target,
+                                             const std::array<double, 9>& intrinsics,
+                                             const std::array<double, 16>& init_source_to_target = {{1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}},
+                                             float depth_scale = 1000.0f, float depth_max = 3.0f,
+                                             const std::vector<OdometryConvergenceCriteria>& criteria_list = {10, 5, 3},
+                                             Method method = Method::Hybrid, const OdometryLossParams& params = OdometryLossParams(),
+                                             void* stream = nullptr) {
+    if (method != Method::PointToPlane)
+        throw std::runtime_error("open3d_b200 implements Method::PointToPlane; Intensity / Hybrid odometry are outside this build's scope.");
+    if (!source.data || !target.data || source.rows <= 0 || source.cols <= 0)
+        throw std::runtime_error("Invalid shape, expected a 1 channel image, but got an empty depth image");
+    if (source.rows != target.rows || source.cols != target.cols)
+        throw std::runtime_error("source and target depth images must have the same size");
+    std::vector<o3db_odometry_criteria> c;
+    for (const auto& k : criteria_list) c.push_back({k.max_iteration_, k.relative_rmse_, k.relative_fitness_});
+    o3db_odometry_result r{};
+    Check(o3db_rgbd_odometry_multi_scale_point_to_plane(
+            source.data, source.is_f32 ? O3DB_DEPTH_F32 : O3DB_DEPTH_U16, target.data, target.is_f32 ? O3DB_DEPTH_F32 : O3DB_DEPTH_U16,
+            source.rows, source.cols, intrinsics.data(), init_source_to_target.data(), depth_scale, depth_max, c.data(),
+            static_cast<int>(c.size()), params.depth_outlier_trunc_, params.depth_huber_delta_, &r, nullptr, stream));
+    OdometryResult out;
+    for (int i = 0; i < 16; ++i) out.transformation_[i] = r.transformation[i];
+    out.inlier_rmse_ = r.inlier_rmse;
+    out.fitness_ = r.fitness;
+    return out;
+}
+
+}  // namespace odometry
+
 namespace slam {
 
 /// slam::Frame (slam/Frame.h): intrinsics + device (or host) images.
@@ -271,6 +341,20 @@ public:
         Check((f.images_on_host ? o3db_vbg_integrate_frame_host : o3db_vbg_integrate_frame)(
                 vbg_, f.depth, dd, f.color, cd, f.height, f.width, f.intrinsics.data(), E.data(), depth_scale, depth_max,
                 trunc_voxel_multiplier, stream));
+    }
+
+    /// Model::TrackFrameToModel (Model.cpp:68-89): the input frame's depth against the ray-cast model depth
+    /// (Float32 device buffer filled by SynthesizeModelFrame), identity initialisation.
+    odometry::OdometryResult TrackFrameToModel(const Frame& input_frame, const float* raycast_depth_dev, float depth_scale = 1000.0f,
+                                               float depth_max = 3.0f, float depth_diff = 0.07f,
+                                               odometry::Method method = odometry::Method::PointToPlane,
+                                               const std::vector<odometry::OdometryConvergenceCriteria>& criteria = {6, 3, 1},
+                                               void* stream = nullptr) const {
+        if (input_frame.images_on_host) throw std::runtime_error("TrackFrameToModel: the input frame must be on the device");
+        odometry::DepthImage src{input_frame.depth, input_frame.depth_is_f32, input_frame.height, input_frame.width};
+        odometry::DepthImage tgt{raycast_depth_dev, true, input_frame.height, input_frame.width};
+        return odometry::RGBDOdometryMultiScale(src, tgt, input_frame.intrinsics, {{1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}},
+                                                depth_scale, depth_max, criteria, method, odometry::OdometryLossParams(depth_diff), stream);
     }
 
     /// Model::SynthesizeModelFrame (Model.cpp:38-66): ray-cast the blocks of the last integrated frame from

@@ -190,6 +190,27 @@ static int gpu_mode() {
                 close += std::fabs(d - 1500.f) < 16.f;
             }
         EXPECT(hits > 0.9 * out.size() && close > 0.99 * hits);
+        namespace odo = open3d_b200::t::pipelines::odometry;
+        EXPECT(throws_with([&] { odo::RGBDOdometryMultiScale({d_depth, false, 480, 640}, {d_out, true, 480, 640}, f.intrinsics); },
+                           "PointToPlane"));
+        // Model::TrackFrameToModel on a curved surface (all 6 DoF observable; a plane would leave x / y / roll free):
+        // the frame tracked against the model it was just fused into comes back as ~identity
+        std::vector<uint16_t> curved(480 * 640);
+        for (int v = 0; v < 480; ++v)
+            for (int u = 0; u < 640; ++u)
+                curved[v * 640 + u] = (uint16_t)std::lround(1500.0 + 220.0 * std::sin(u / 70.0) * std::cos(v / 55.0) + 0.25 * (v - 240));
+        cudaMemcpy(d_depth, curved.data(), curved.size() * 2, cudaMemcpyHostToDevice);
+        slam::Model m2(0.008f, 16, 6000);
+        slam::Frame f2;
+        f2.height = 480; f2.width = 640; f2.depth = d_depth;
+        m2.UpdateFramePose(0, {{1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}});
+        m2.Integrate(f2);
+        m2.UpdateFramePose(1, {{1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}});
+        m2.Integrate(f2);
+        m2.SynthesizeModelFrame(480, 640, f2.intrinsics, d_out, nullptr);
+        const auto tr = m2.TrackFrameToModel(f2, d_out);
+        EXPECT(tr.fitness_ > 0.8);
+        for (int i = 0; i < 16; ++i) EXPECT(std::fabs(tr.transformation_[i] - (i % 5 == 0 ? 1.0 : 0.0)) < 0.02);
         cudaFree(d_out);
     }
     std::printf("cpp gpu-mode ok: fitness %.4f rmse %.5f blocks %lld\n", res.fitness_, res.inlier_rmse_, (long long)want);
