@@ -225,6 +225,9 @@ def icp_config(n_gpus):
 # ----------------------------------------------------------------------------------------------
 
 def main():
+    # NCCL announces its version on stdout at VERSION level; keep stdout to the one JSON line
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

@@ -330,7 +330,7 @@ class VoxelBlockGrid:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h:
+        if h and lib is not None:     # (module globals are already torn down at interpreter exit)
             lib.o3db_vbg_destroy(h)
             self._h = None
 

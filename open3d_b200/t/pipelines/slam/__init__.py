@@ -122,8 +122,11 @@ class Model:
         if weight_threshold < 0:
             weight_threshold = min(self.frame_id * 1.0, 3.0)
         T = self.transformation_frame_to_world
+        # upstream always renders {"depth", "color"} and drops the colour when !enable_color (Model.cpp:49-55);
+        # the depth map does not depend on it, so the colour pass (8-corner trilinear gather) is skipped here
+        attrs = ("depth", "color") if enable_color else ("depth",)
         res = self.voxel_grid.ray_cast(None, raycast_frame.get_intrinsics(), _inverse_transformation(T),
-                                       raycast_frame.width(), raycast_frame.height(), ("depth", "color"), depth_scale,
+                                       raycast_frame.width(), raycast_frame.height(), attrs, depth_scale,
                                        depth_min, depth_max, weight_threshold, trunc_voxel_multiplier)
         raycast_frame.set_data("depth", res["depth"])
         if enable_color:

@@ -1,6 +1,6 @@
 """Short workload for ncu captures: 6 ICP iterations on the 2M-point bench clouds and
 40 fused TSDF frames (depth + colour); "colored" = colour gradients + 6 ColoredICP iterations at 500 k points;
-"raycast" = 5 SynthesizeModelFrame-style ray casts after the 40 frames.  Usage (under gpurun):
+"raycast" = 5 SynthesizeModelFrame-style ray casts after the 40 frames; "slam" = 6 frames of the dense-SLAM loop.  Usage (under gpurun):
   ncu --set full --clock-control none --import-source on -k regex:icp_iteration_kernel -s 3 -c 2 \
       -o gpurun_out/icp python profiles/profile_workload.py icp
 """
@@ -79,3 +79,23 @@ if what in ("tsdf", "raycast", "all"):
         torch.cuda.synchronize()
         print("raycast hit fraction", float((rd > 0).float().mean()))
     L.lib.o3db_vbg_destroy(v)
+if what in ("slam", "all"):
+    # 6 frames of the dense-SLAM loop (track_frame_to_model + integrate + synthesize_model_frame), public API
+    import open3d_b200
+    slam = open3d_b200.t.pipelines.slam
+    T0 = camera_pose(100)
+    model = slam.Model(0.008, 16, 12000, T0)
+    pose = T0.copy()
+    rc_frame = slam.Frame(480, 640, PRIMESENSE_K)
+    for n in range(6):
+        dep, col = render_depth(camera_pose(100 + n), device="cuda", with_color=True)
+        fr = slam.Frame(480, 640, PRIMESENSE_K)
+        fr.set_data("depth", dep.contiguous())
+        fr.set_data("color", col.contiguous())
+        if n > 0:
+            pose = pose @ model.track_frame_to_model(fr, rc_frame, 1000.0, 3.0, 0.07).transformation
+        model.update_frame_pose(n, pose)
+        model.integrate(fr, 1000.0, 3.0, 8.0)
+        model.synthesize_model_frame(rc_frame, 1000.0, 0.1, 3.0, 8.0, False)
+    torch.cuda.synchronize()
+    print("slam pose drift mm", 1e3 * float(np.linalg.norm(pose[:3, 3] - camera_pose(105)[:3, 3])))
