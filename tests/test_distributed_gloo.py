@@ -38,7 +38,17 @@ def _worker(rank, world, port, q):
     t = torch.from_numpy(part.copy())
     dist.all_reduce(t)
     full = oracle.pose_p2plane_sums(src, tgt, nrm, corr)["sums64"]
-    q.put((rank, got == bytes(range(128)), np.allclose(t.numpy(), full, rtol=1e-12, atol=1e-12),
+    # the same for ColoredICP (o3db_icp_create_colored takes the same communicator): the target side
+    # (colours, colour gradients) is replicated, the source colours are sharded with the source points
+    from tests.synth import make_colors
+    sc, tc = make_colors(src, 1), make_colors(tgt, 1)
+    grad = oracle.estimate_color_gradients(tgt, nrm, tc, 0.08, 30)
+    cpart = oracle.pose_colored_sums(src[b:e], sc[b:e], tgt, nrm, tc, grad, corr[b:e], 0.968)["sums64"]
+    ct = torch.from_numpy(cpart.copy())
+    dist.all_reduce(ct)
+    cfull = oracle.pose_colored_sums(src, sc, tgt, nrm, tc, grad, corr, 0.968)["sums64"]
+    colored_ok = np.allclose(ct.numpy(), cfull, rtol=1e-12, atol=1e-12)
+    q.put((rank, got == bytes(range(128)), colored_ok and np.allclose(t.numpy(), full, rtol=1e-12, atol=1e-12),
            d.reduce_max(float(rank + 1)), d.reduce_sum(float(e - b)), len(src)))
     dist.destroy_process_group()
 
