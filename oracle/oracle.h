@@ -210,7 +210,8 @@ void orc_inverse_transformation(const double T[16], double Tinv[16]);
  * (int32 triples) sorted lexicographically (x,y,z) into keys_out (capacity
  * max_keys triples) and returns their number, or -1 if capacity is exceeded.
  * The reference's output order is undefined; sorted here for set comparison.
- * parity unpinned offline (reference counts need the Redwood download). */
+ * PINNED: identical block set to the reference's own DepthTouchCPU compiled unmodified
+ * (oracle/ref_shim/ref_shim_vbg.cpp; tests/test_oracle_vs_ref_vbg.py). */
 int64_t orc_depth_touch(const void* depth, int is_f32, int rows, int cols,
                         const double K[9], const double extrinsic[16],
                         int resolution, float voxel_size, float sdf_trunc,
@@ -223,8 +224,8 @@ int64_t orc_depth_touch(const void* depth, int is_f32, int rows, int cols,
  * block_keys: capacity x 3 int32, buf_indices: n_blocks int32 into the value
  * buffers (tsdf [cap][res^3], weight [cap][res^3], color [cap][res^3][3]).
  * color / color_buf may be NULL (depth-only overload, VoxelBlockGrid.cpp:269-278).
- * parity unpinned offline (see above); cross-checked against the reference
- * header math via oracle/_ref where that compiles. */
+ * PINNED bit-exactly (tsdf, weight, colour; both input dtypes; with and without colour)
+ * against the reference's own IntegrateCPU compiled unmodified (tests/test_oracle_vs_ref_vbg.py). */
 void orc_tsdf_integrate(const void* depth, const void* color, int inputs_f32,
                         int rows, int cols, const int32_t* buf_indices,
                         int64_t n_blocks, const int32_t* block_keys,
@@ -248,10 +249,9 @@ int orc_hashmap_activate(int32_t* table_keys, int64_t capacity, int64_t* size,
 
 /* VoxelBlockGrid ray casting (t/geometry/kernel/VoxelBlockGridImpl.h:310-555,
  * 578-1120; VoxelBlockGrid.cpp:328-402).  range: [h/down][w/down][2] f32 (min, max).
- * PARITY UNPINNED against reference outputs: the reference's own test
- * (tests/t/geometry/VoxelBlockGrid.cpp:352-410) needs downloaded data and only checks that the
- * result keys exist; the camera primitives used are pinned bit-exactly through oracle/ref_shim
- * (TransformIndexer), the loop itself through analytic properties (tests/test_oracle_raycast.py). */
+ * PINNED bit-exactly against the reference's own EstimateRangeCPU / RayCastCPU<float,u16,u16>, compiled
+ * unmodified from /root/reference (oracle/ref_shim/ref_shim_vbg.cpp; tests/test_oracle_vs_ref_vbg.py),
+ * and through analytic properties of the rendered scene (tests/test_oracle_raycast.py). */
 void orc_estimate_range(const int32_t* block_keys, int64_t n, const double K[9],
                         const double E[16], int h, int w, int down_factor,
                         int resolution, float voxel_size, float depth_min,

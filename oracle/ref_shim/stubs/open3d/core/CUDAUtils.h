@@ -12,3 +12,6 @@
 #define OPEN3D_GET_LAST_CUDA_ERROR(message)
 #define CUDA_CALL(cuda_function, ...) throw std::runtime_error("no CUDA in ref_shim")
 #include "open3d/utility/Logging.h"
+
+#define OPEN3D_ASSERT_MSG(cond, msg) do { if (!(cond)) throw std::runtime_error(msg); } while (0)
+#define OPEN3D_ASSERT(cond) do { if (!(cond)) throw std::runtime_error(#cond); } while (0)

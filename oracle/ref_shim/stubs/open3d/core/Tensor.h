@@ -2,6 +2,8 @@
 // reference's *Impl.h headers touch, over caller-owned host memory.
 #pragma once
 #include <cstdint>
+#include <cstring>
+#include <memory>
 #include <initializer_list>
 #include <string>
 #include <unordered_map>
@@ -47,6 +49,7 @@ static const Dtype UInt8 = Dtype::UInt8;
 static const Dtype UInt16 = Dtype::UInt16;
 static const Dtype Int32 = Dtype::Int32;
 static const Dtype Int64 = Dtype::Int64;
+static const Dtype Bool = Dtype::Bool;
 static const Dtype Int8 = Dtype::Int8;
 static const Dtype Int16 = Dtype::Int16;
 static const Dtype UInt32 = Dtype::UInt32;
@@ -66,7 +69,26 @@ public:
 class Tensor {
 public:
     Tensor() : ptr_(nullptr) {}
+    // non-owning view of caller memory
     Tensor(void* ptr, SizeVector shape, Dtype dtype) : ptr_(ptr), shape_(shape), dtype_(dtype) {}
+    // owning, zero-initialised (upstream: uninitialised)
+    Tensor(const SizeVector& shape, Dtype dtype, const Device& = Device()) : shape_(shape), dtype_(dtype) {
+        int64_t n = 1;
+        for (auto s : shape_) n *= s;
+        own_ = std::shared_ptr<char>(new char[(size_t)(n > 0 ? n : 1) * dtype.ByteSize()](), std::default_delete<char[]>());
+        ptr_ = own_.get();
+    }
+    template <typename T>
+    Tensor(const std::vector<T>& init, const SizeVector& shape, Dtype dtype, const Device& d = Device())
+        : Tensor(shape, dtype, d) {
+        memcpy(ptr_, init.data(), init.size() * sizeof(T));
+    }
+    static Tensor Zeros(const SizeVector& shape, Dtype dtype, const Device& d = Device()) { return Tensor(shape, dtype, d); }
+    static Tensor Empty(const SizeVector& shape, Dtype dtype, const Device& d = Device()) { return Tensor(shape, dtype, d); }
+    static Tensor Eye(int64_t n, Dtype, const Device&) {
+        static double eye[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+        return Tensor(eye, {n, n}, Dtype::Float64);
+    }
     bool IsContiguous() const { return true; }
     SizeVector GetShape() const { return shape_; }
     int64_t GetShape(int i) const { return shape_[i]; }
@@ -86,14 +108,32 @@ public:
     T* GetDataPtr() { return static_cast<T*>(ptr_); }
     template <typename T>
     const T* GetDataPtr() const { return static_cast<const T*>(ptr_); }
-    static Tensor Eye(int64_t n, Dtype, const Device&) {
-        static double eye[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
-        return Tensor(eye, {n, n}, Dtype::Float64);
+    template <typename T>
+    T Item() const { return *static_cast<const T*>(ptr_); }
+    // sub-tensor along dim 0 (views share ownership)
+    Tensor operator[](int64_t i) const {
+        SizeVector sub(shape_.begin() + 1, shape_.end());
+        int64_t stride = dtype_.ByteSize();
+        for (auto s : sub) stride *= s;
+        Tensor t(static_cast<char*>(ptr_) + i * stride, sub, dtype_);
+        t.own_ = own_;
+        return t;
+    }
+    Tensor Slice(int64_t dim, int64_t start, int64_t stop) const {
+        if (dim != 0) utility::LogError("ref_shim Tensor::Slice: dim 0 only");
+        SizeVector shp = shape_;
+        shp[0] = stop - start;
+        int64_t stride = dtype_.ByteSize();
+        for (size_t k = 1; k < shape_.size(); ++k) stride *= shape_[k];
+        Tensor t(static_cast<char*>(ptr_) + start * stride, shp, dtype_);
+        t.own_ = own_;
+        return t;
     }
 private:
     void* ptr_;
     SizeVector shape_;
     Dtype dtype_;
+    std::shared_ptr<char> own_;
 };
 
 }  // namespace core

@@ -371,6 +371,7 @@ static inline int isign(int x) { return (x > 0) ? 1 : ((x < 0) ? -1 : 0); } /* G
 
 /* t/geometry/kernel/VoxelBlockGridImpl.h:578-1120 RayCastCPU for <float, uint16_t, uint16_t>.
  * The 1-entry MiniVecCache (:557-576) only short-cuts hash lookups and is omitted.
+ * Bit-exact against RayCastCPU<float,u16,u16> compiled from the reference (tests/test_oracle_vs_ref_vbg.py).
  * One deliberate deviation: the voxel coordinate inside the block, index_t((x_g - x_b*block_size)
  * / voxel_size) (:826-828), can round up to `resolution` when x_g sits a rounding error below a
  * block face; upstream then indexes the next row of the block (or past the buffer).  It is
