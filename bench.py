@@ -178,6 +178,54 @@ def cpu_tsdf_baseline(frames, color):
     return len(frames) / (time.perf_counter() - t0)
 
 
+def _ref_lib():
+    """oracle/_ref/libo3dref.so: the reference's own VoxelBlockGridCPU.cpp / VoxelBlockGridImpl.h compiled unmodified
+    (oracle/ref_shim/ref_shim_vbg.cpp; ParallelFor on OpenMP).  None if it was not built (no /root/reference)."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "oracle", "_ref", "libo3dref.so")
+    if not os.path.exists(path):
+        return None
+    try:
+        L = C.CDLL(path)
+        L.ref_depth_touch.restype = C.c_int64
+        L.ref_depth_touch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_float,
+                                      C.c_float, C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_int64]
+        L.ref_integrate.restype = None
+        L.ref_integrate.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p,
+                                    C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_int, C.c_float, C.c_float, C.c_float, C.c_float]
+        L.ref_num_threads.restype = C.c_int
+        return L
+    except (OSError, AttributeError):
+        return None
+
+
+def cpu_tsdf_reference(frames, color, R):
+    """frames/s of the REFERENCE's DepthTouchCPU + IntegrateCPU (compiled from /root/reference) on all host threads;
+    HashMap::Activate in between is the oracle's (upstream's is a TBB container, absent here)."""
+    import oracle
+    from tests.synth import PRIMESENSE_K
+    cap = 60000
+    keys = np.zeros((cap, 3), np.int32)
+    tsdf = np.zeros((cap, RES ** 3), np.float32)
+    wt = np.zeros((cap, RES ** 3), np.uint16)
+    colbuf = np.zeros((cap, RES ** 3, 3), np.uint16) if color else None
+    K9 = np.ascontiguousarray(np.asarray(PRIMESENSE_K, np.float64).reshape(9))
+    touched = np.zeros((76800, 3), np.int32)
+    size = 0
+    t0 = time.perf_counter()
+    for (E, depth, col) in frames:
+        Ef = np.ascontiguousarray(np.asarray(E, np.float64).reshape(16))
+        n = R.ref_depth_touch(depth.ctypes.data, 0, 480, 640, K9.ctypes.data, Ef.ctypes.data, RES, VOXEL,
+                              VOXEL * TRUNC_MULT, DSCALE, DMAX, 4, touched.ctypes.data, len(touched))
+        bi, _, size, _ = oracle.hashmap_activate(keys, size, touched[:n])
+        bi = np.ascontiguousarray(bi, np.int32)
+        R.ref_integrate(depth.ctypes.data, col.ctypes.data if color else None, 0, 480, 640, bi.ctypes.data, len(bi),
+                        keys.ctypes.data, cap, tsdf.ctypes.data, wt.ctypes.data,
+                        colbuf.ctypes.data if color else None, K9.ctypes.data, K9.ctypes.data, Ef.ctypes.data, RES,
+                        VOXEL, VOXEL * TRUNC_MULT, DSCALE, DMAX)
+    return len(frames) / (time.perf_counter() - t0)
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU implementation of the path cannot be built here
     (Eigen/TBB/nanoflann/stdgpu are download-time dependencies), so this arm
@@ -633,9 +681,21 @@ def bench_tsdf(args, rank, world, local_rank, L, torch, stream, barrier, max_ove
         for color in (False, True):
             fps = cpu_tsdf_baseline(frames, color)
             res["depth_color" if color else "depth_only"] = fps
-        return {"value": res["depth_only"], "value_with_color": res["depth_color"], "unit": "frames/s",
-                "cores": oracle_mod.num_threads(), "kind": "port",
-                "sample": f"{len(frames)} frames spread over the trajectory (touch + activate + integrate, OpenMP port)"}
+        out_cpu = {"value": res["depth_only"], "value_with_color": res["depth_color"], "unit": "frames/s",
+                   "cores": oracle_mod.num_threads(), "kind": "port",
+                   "sample": f"{len(frames)} frames spread over the trajectory (touch + activate + integrate, OpenMP port)"}
+        R = _ref_lib()
+        if R is not None:
+            # the same sample through the reference's OWN DepthTouchCPU / IntegrateCPU (oracle/_ref); reported as the
+            # baseline when available, the port's figure kept beside it
+            ref = {("depth_color" if c else "depth_only"): cpu_tsdf_reference(frames, c, R) for c in (False, True)}
+            out_cpu = {"value": ref["depth_only"], "value_with_color": ref["depth_color"], "unit": "frames/s",
+                       "cores": int(R.ref_num_threads()), "kind": "reference",
+                       "sample": f"{len(frames)} frames spread over the trajectory; DepthTouchCPU + IntegrateCPU compiled "
+                                 "unmodified from the reference (OpenMP ParallelFor stand-in for TBB), HashMap::Activate "
+                                 "from the oracle port",
+                       "port_value": res["depth_only"], "port_value_with_color": res["depth_color"]}
+        return out_cpu
 
     out["_cpu"] = cpu_part
     return out

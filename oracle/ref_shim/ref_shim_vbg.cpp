@@ -1,13 +1,16 @@
 // ref_shim_vbg.cpp — TEST INFRASTRUCTURE.  Compiles the reference's own CPU implementation of the voxel-block-grid
 // kernels — t/geometry/kernel/VoxelBlockGridCPU.cpp (DepthTouchCPU) together with the VoxelBlockGridImpl.h templates it
 // instantiates (IntegrateCPU, EstimateRangeCPU, RayCastCPU) — unmodified, from where the file lies under /root/reference,
-// against the stub core::Tensor / HashMap / TBB headers in stubs/ (serial ParallelFor, std:: containers instead of
-// tbb::), and exports them through a small C ABI so that the CPU oracle (oracle/tsdf_oracle.c) can be checked against
+// against the stub core::Tensor / HashMap / TBB headers in stubs/ (OpenMP ParallelFor as upstream, std:: containers
+// behind locks instead of tbb::), and exports them through a small C ABI so that the CPU oracle (oracle/tsdf_oracle.c) can be checked against
 // the real thing bit for bit.  No reference source is copied into this repository.
 #include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <memory>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 using std::abs;
 using std::max;
@@ -29,6 +32,14 @@ o3c::Tensor E_tensor(const double* E) { return o3c::Tensor((void*)E, {4, 4}, o3c
 }  // namespace
 
 extern "C" {
+
+int ref_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
 
 // DepthTouchCPU (VoxelBlockGridCPU.cpp:117-201): returns the number of touched blocks, keys in arbitrary order.
 int64_t ref_depth_touch(const void* depth, int is_f32, int rows, int cols, const double K[9], const double E[16],

@@ -1,5 +1,6 @@
-// ref_shim stub (test infrastructure): the reference's image kernels only need
-// core::ParallelFor from this include chain; run it serially on the host.
+// ref_shim stub (test infrastructure): core::ParallelFor (upstream: tbb::parallel_for over blocked ranges,
+// core/ParallelFor.h:76-110; here: an OpenMP static parallel for — TBB is absent) and the element-wise Indexer
+// of image::ToCPU.
 #pragma once
 #include <cstdint>
 #include <initializer_list>
@@ -24,6 +25,7 @@ private:
 
 template <typename func_t>
 void ParallelFor(const Device&, int64_t n, const func_t& func) {
+#pragma omp parallel for schedule(static) if (n > 4096)
     for (int64_t i = 0; i < n; ++i) func(i);
 }
 }  // namespace core

@@ -1,12 +1,21 @@
-// ref_shim stub (test infrastructure): the shim runs core::ParallelFor serially, so the lock is a no-op.
+// ref_shim stub (test infrastructure): a real spin lock (the shim's ParallelFor runs on OpenMP threads).
 #pragma once
+#include <atomic>
 namespace tbb {
 class spin_mutex {
 public:
     class scoped_lock {
     public:
-        explicit scoped_lock(spin_mutex&) {}
+        explicit scoped_lock(spin_mutex& m) : m_(m) {
+            while (m_.flag_.test_and_set(std::memory_order_acquire)) {
+            }
+        }
+        ~scoped_lock() { m_.flag_.clear(std::memory_order_release); }
+    private:
+        spin_mutex& m_;
     };
+private:
+    std::atomic_flag flag_ = ATOMIC_FLAG_INIT;
 };
 namespace profiling {
 template <typename T>
