@@ -684,7 +684,14 @@ def bench_tsdf(args, rank, world, local_rank, L, torch, stream, barrier, max_ove
         out_cpu = {"value": res["depth_only"], "value_with_color": res["depth_color"], "unit": "frames/s",
                    "cores": oracle_mod.num_threads(), "kind": "port",
                    "sample": f"{len(frames)} frames spread over the trajectory (touch + activate + integrate, OpenMP port)"}
-        R = _ref_lib()
+        R = None
+        try:
+            R = _ref_lib()
+            if R is not None:
+                cpu_tsdf_reference(frames[:1], False, R)       # (also the warm-up) must not take the bench down
+        except Exception as e:                                # noqa: BLE001
+            print(f"[bench] reference-compiled TSDF baseline unavailable: {e}", file=sys.stderr)
+            R = None
         if R is not None:
             # the same sample through the reference's OWN DepthTouchCPU / IntegrateCPU (oracle/_ref); reported as the
             # baseline when available, the port's figure kept beside it
