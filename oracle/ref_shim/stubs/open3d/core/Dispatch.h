@@ -18,3 +18,16 @@
             open3d::utility::LogError("Unsupported data type."); \
         }                                             \
     }()
+
+#define DISPATCH_FLOAT_DTYPE_TO_TEMPLATE(DTYPE, ...)  \
+    [&] {                                             \
+        if (DTYPE == open3d::core::Float32) {         \
+            using scalar_t = float;                   \
+            return __VA_ARGS__();                     \
+        } else if (DTYPE == open3d::core::Float64) {  \
+            using scalar_t = double;                  \
+            return __VA_ARGS__();                     \
+        } else {                                      \
+            open3d::utility::LogError("Unsupported data type."); \
+        }                                             \
+    }()

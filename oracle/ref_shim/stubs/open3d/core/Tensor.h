@@ -6,6 +6,7 @@
 #include <memory>
 #include <initializer_list>
 #include <string>
+#include <tuple>
 #include <unordered_map>
 #include <vector>
 
@@ -129,7 +130,23 @@ public:
         t.own_ = own_;
         return t;
     }
+    // ---- members that only have to COMPILE (ComputeRtPointToPointCPU etc. are never run in the shim)
+    Tensor To(const Dtype&) const { unsupported(); }
+    Tensor To(const Device&, const Dtype& = Dtype()) const {   // dtype conversion f32 -> f64 is what the kernels ask for
+        return *this;
+    }
+    std::tuple<Tensor, Tensor, Tensor> SVD() const { unsupported(); }
+    double Det() const { unsupported(); }
+    Tensor T() const { unsupported(); }
+    Tensor Matmul(const Tensor&) const { unsupported(); }
+    Tensor Reshape(const SizeVector&) const { unsupported(); }
+    Tensor Neg() const { unsupported(); }
+    Tensor operator-(const Tensor&) const { unsupported(); }
+    Tensor& operator=(double) { unsupported(); }
+    Tensor(const Tensor&) = default;
+    Tensor& operator=(const Tensor&) = default;
 private:
+    [[noreturn]] static void unsupported() { utility::LogError("ref_shim Tensor: member not available in the stub"); }
     void* ptr_;
     SizeVector shape_;
     Dtype dtype_;

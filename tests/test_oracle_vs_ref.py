@@ -341,3 +341,62 @@ def test_odometry_huber_and_jacobian_match_reference_header(ref):
                 assert np.array_equal(J.view(np.uint32), J2.view(np.uint32))
                 assert np.float32(r[0]).view(np.uint32) == np.float32(r2).view(np.uint32)
     assert 0.3 * rows * cols < valid < rows * cols
+
+
+# ------------------------------------------------ whole CPU reduction kernels of the reference (ref_shim_reg.cpp)
+
+def _check_sums(got64, abs64, want, rtol=2e-5):
+    """the reference accumulates Float32 terms in f32 (serially here, ~6 k terms: its own rounding noise is
+    ~sqrt(n) eps = 5e-6 of sum|term|, measured 3e-6); the oracle accumulates the same f32 terms in f64: equal inlier
+    count, every slot within rtol * sum|term|"""
+    want = np.asarray(want)
+    assert want[28] == got64[28] > 0
+    err = np.abs(want - got64)
+    assert (err <= rtol * abs64 + 1e-12).all(), (err / (abs64 + 1e-300)).max()
+
+
+@pytest.mark.parametrize("robust", [("L2Loss", 1.0, 1.0), ("L1Loss", 1.0, 1.0), ("HuberLoss", 0.01, 1.0),
+                                    ("TukeyLoss", 0.03, 1.0), ("GeneralizedLoss", 0.5, 1.3)])
+def test_pose_sums_match_reference_cpu_kernels(ref, robust):
+    """ComputePosePointToPlaneCPU and ComputePoseColoredICPCPU (t/pipelines/kernel/RegistrationCPU.cpp:30-218) as
+    whole functions — Jacobian, robust weight dispatch, slot layout, residual / count slots."""
+    from tests.synth import make_colors, make_icp_pair
+    ref.ref_pose_p2plane_sums_f32.argtypes = [f32p, f32p, f32p, i64p, C.c_int64, C.c_int64, C.c_int, C.c_double,
+                                              C.c_double, f64p]
+    ref.ref_pose_colored_sums_f32.argtypes = [f32p] * 6 + [i64p, C.c_int64, C.c_int64, C.c_int, C.c_double, C.c_double,
+                                                           C.c_double, f64p]
+    src, tgt, nrm, _ = make_icp_pair(6000, seed=12)
+    idx, _, _ = oracle.hybrid_search(tgt, src, 0.05, 1)
+    corr = np.ascontiguousarray(idx[:, 0].astype(np.int64))
+    method = oracle.ROBUST[robust[0]]
+    want = np.zeros(29)
+    ref.ref_pose_p2plane_sums_f32(_p(src, f32p), _p(tgt, f32p), _p(nrm, f32p), _p(corr, i64p), len(src), len(tgt),
+                                  method, robust[1], robust[2], _p(want, f64p))
+    o = oracle.pose_p2plane_sums(src, tgt, nrm, corr, robust)
+    _check_sums(o["sums64"], o["abs64"], want)
+    sc, tc = make_colors(src, 1), make_colors(tgt, 1)
+    grad = np.ascontiguousarray(np.random.default_rng(1).normal(0, 0.5, tgt.shape).astype(np.float32))
+    ref.ref_pose_colored_sums_f32(_p(src, f32p), _p(sc, f32p), _p(tgt, f32p), _p(nrm, f32p), _p(tc, f32p), _p(grad, f32p),
+                                  _p(corr, i64p), len(src), len(tgt), method, robust[1], robust[2], 0.968, _p(want, f64p))
+    o = oracle.pose_colored_sums(src, sc, tgt, nrm, tc, grad, corr, 0.968, robust)
+    _check_sums(o["sums64"], o["abs64"], want)
+
+
+def test_odometry_sums_match_reference_cpu_kernel(ref):
+    """odometry::ComputeOdometryResultPointToPlaneCPU (t/pipelines/kernel/RGBDOdometryCPU.cpp:286-362) as a whole
+    function on a 240x320 level."""
+    ref.ref_odometry_p2plane_sums.argtypes = [f32p, f32p, f32p, C.c_int, C.c_int, f64p, f64p, C.c_float, C.c_float, f64p]
+    da, db, T_gt, K = _odometry_inputs()
+    ds, dt = oracle.pyr_down_depth(oracle.clip_transform(db), 0.14), oracle.pyr_down_depth(oracle.clip_transform(da), 0.14)
+    Kp = K / 2
+    Kp[2, 2] = 1
+    sv, tv = oracle.create_vertex_map(ds, Kp), oracle.create_vertex_map(dt, Kp)
+    tn = oracle.create_normal_map(oracle.create_vertex_map(oracle.filter_bilateral(dt), Kp))
+    T = T_gt.copy()
+    T[:3, 3] += [0.01, -0.02, 0.015]
+    want = np.zeros(29)
+    Kf, Tf = np.ascontiguousarray(Kp.reshape(9)), np.ascontiguousarray(T.reshape(16))
+    ref.ref_odometry_p2plane_sums(_p(sv, f32p), _p(tv, f32p), _p(tn, f32p), sv.shape[0], sv.shape[1], _p(Kf, f64p),
+                                  _p(Tf, f64p), 0.07, 0.05, _p(want, f64p))
+    o = oracle.odometry_p2plane_sums(sv, tv, tn, Kp, T, 0.07, 0.05)
+    _check_sums(o["sums64"], o["abs64"], want, rtol=1e-4)   # ~70 k f32 terms upstream
