@@ -72,3 +72,59 @@ def test_shard_range_partitions():
         assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
         sizes = [e - b for b, e in spans]
         assert max(sizes) - min(sizes) <= 1
+
+
+def test_colored_icp_and_odometry_host_side():
+    """argument checks that run before any device work, and the defaults of the mirrored classes"""
+    from open3d_b200.t.pipelines import odometry as odo
+    src, tgt = _clouds()
+    est = reg.TransformationEstimationForColoredICP()
+    assert est.lambda_geometric == 0.968 and int(est.kernel.type) == 0
+    with pytest.raises(RuntimeError, match="target pointcloud to have colors"):        # Registration.cpp:160-176
+        reg.icp(src, tgt, 0.1, np.eye(4), est)
+    tgt.set_point_colors(np.zeros((64, 3), np.float32))
+    with pytest.raises(RuntimeError, match="source pointcloud to have colors"):
+        reg.icp(src, tgt, 0.1, np.eye(4), est)
+    with pytest.raises(RuntimeError, match="PointToPlane and"):
+        reg.icp(src, tgt, 0.1, np.eye(4), object())
+    p = odo.OdometryLossParams()
+    assert (p.depth_outlier_trunc, p.depth_huber_delta, p.intensity_huber_delta) == (0.07, 0.05, 0.1)   # RGBDOdometry.h:82-84
+    c = odo.OdometryConvergenceCriteria(7)
+    assert (c.max_iteration, c.relative_rmse, c.relative_fitness) == (7, 1e-6, 1e-6)                     # :35-37
+    assert [m.name for m in odo.Method] == ["PointToPlane", "Intensity", "Hybrid"]
+    assert [k.max_iteration for k in odo._criteria_list((6, 3, 1))] == [6, 3, 1]                          # Model.h:83-84
+    r = odo.OdometryResult()
+    assert np.array_equal(r.transformation, np.eye(4)) and r.inlier_rmse == 0.0 and r.fitness == 0.0
+    d = torch.zeros((8, 8), dtype=torch.uint16)
+    with pytest.raises(RuntimeError, match="PointToPlane"):                              # default method = Hybrid upstream
+        odo.rgbd_odometry_multi_scale(o3d.t.geometry.RGBDImage(None, d), o3d.t.geometry.RGBDImage(None, d), np.eye(3))
+    with pytest.raises(RuntimeError, match="Unsupported attribute"):
+        o3d.t.geometry.VoxelBlockGrid.ray_cast(object.__new__(o3d.t.geometry.VoxelBlockGrid), None, np.eye(3), np.eye(4),
+                                               8, 8, ("albedo",))
+
+
+@needs_no_gpu
+def test_no_cpu_fallback_new_entry_points():
+    """every C entry point added for the widened rows fails loudly without a device"""
+    import ctypes as C
+    from open3d_b200 import _lib as L
+    a = np.zeros((16, 16), np.float32)
+    out = np.zeros((16, 16, 3), np.float32)
+    K = np.ascontiguousarray(np.eye(3))
+    T = np.ascontiguousarray(np.eye(4))
+    calls = [
+        lambda: L.lib.o3db_image_clip_transform(a.ctypes.data, L.DEPTH_F32, 16, 16, 1.0, 0.0, 3.0, 0.0, out.ctypes.data, None),
+        lambda: L.lib.o3db_image_create_vertex_map(a.ctypes.data, 16, 16, L.dptr(K), 0.0, out.ctypes.data, None),
+        lambda: L.lib.o3db_image_filter_bilateral(a.ctypes.data, 16, 16, 5, 5.0, 10.0, out.ctypes.data, None),
+        lambda: L.lib.o3db_estimate_color_gradients(out.ctypes.data, out.ctypes.data, out.ctypes.data, 256, 0.1, 30,
+                                                    out.ctypes.data, None),
+    ]
+    for call in calls:
+        rc = call()
+        assert rc == L.ERR_CUDA and "cuda" in L.last_error().lower(), (rc, L.last_error())
+    res = L.OdometryResult()
+    crit = (L.OdometryCriteria * 1)(L.OdometryCriteria(1, 1e-6, 1e-6))
+    rc = L.lib.o3db_rgbd_odometry_multi_scale_point_to_plane(a.ctypes.data, L.DEPTH_F32, a.ctypes.data, L.DEPTH_F32, 16, 16,
+                                                             L.dptr(K), L.dptr(T), 1.0, 3.0, crit, 1, 0.07, 0.05,
+                                                             C.byref(res), None, None)
+    assert rc == L.ERR_CUDA
