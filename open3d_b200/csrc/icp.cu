@@ -24,6 +24,9 @@ static constexpr int kMaxCellsPerAxis = 4096;
 #define ICP_THIN_FACTOR 8
 #endif
 static constexpr double kThinFactor = ICP_THIN_FACTOR;   // grid-x (thin axis) cells are this much coarser
+#ifndef ICP_PREFETCH_SRC
+#define ICP_PREFETCH_SRC 0   // 1: prefetch the next chunk's source point (round-2 candidate; measure with profiles/tune_icp.sh)
+#endif
 #ifndef ICP_CELL_SCALE
 #define ICP_CELL_SCALE 0.5
 #endif
@@ -859,15 +862,36 @@ icp_iteration_kernel(IcpArgs a) {
     for (int k = 0; k < kNumSums; ++k) acc[k] = 0.f;
 #endif
     int since = 0;
+#if ICP_PREFETCH_SRC
+    // experimental (default off, unmeasured): issue the NEXT chunk's source load before this chunk's search so
+    // that its latency (10 % of the stall samples) hides behind the search; same values, same results
+    float4 p_next = make_float4(0.f, 0.f, 0.f, 0.f);
+    {
+        const int64_t i0 = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+        if (i0 < a.n) p_next = a.src[i0];
+    }
+#endif
     for (int64_t base = (int64_t)blockIdx.x * kThreads; base < a.n; base += (int64_t)gridDim.x * kThreads) {
         const int64_t i = base + threadIdx.x;
         const bool live = i < a.n;
         float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+#if ICP_PREFETCH_SRC
+        p = p_next;
+        {
+            const int64_t in = i + (int64_t)gridDim.x * kThreads;
+            if (in < a.n) p_next = a.src[in];
+        }
+        if (live) {
+            apply_transform(s_U, p.x, p.y, p.z);
+            a.src[i] = p;
+        }
+#else
         if (live) {
             p = a.src[i];
             apply_transform(s_U, p.x, p.y, p.z);   // Registration.cpp:322 (PointCloud::Transform), fused
             a.src[i] = p;
         }
+#endif
         Best b;
         b.j = -1;
         if (live) {

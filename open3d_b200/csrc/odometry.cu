@@ -30,6 +30,9 @@
 namespace o3db {
 
 static constexpr int kOT = 256;
+#ifndef ODO_BLOCKS_PER_SM
+#define ODO_BLOCKS_PER_SM 4   // blocks per SM of the iteration kernel; fewer = shorter serial tail in the last block (tunable)
+#endif
 
 // ------------------------------------------------------------ image kernels
 
@@ -439,7 +442,7 @@ static void odo_scratch_free(OdoScratch* s, cudaStream_t st) {
 
 static int odo_scratch_alloc(OdoScratch* s, int64_t pixels, int log_entries, const double* T, cudaStream_t st) {
     configure_memory_pool();
-    s->blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(pixels, kThreads), (int64_t)num_sms() * 4));
+    s->blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(pixels, kThreads), (int64_t)num_sms() * ODO_BLOCKS_PER_SM));
     static_assert(sizeof(OdoState) <= 4096, "OdoState must fit a pinned block");
     O3DB_CUDA_CHECK(cudaMallocAsync(&s->st, sizeof(OdoState), st));
     O3DB_CUDA_CHECK(cudaMallocAsync(&s->partials, (size_t)s->blocks * kSumStride * sizeof(double), st));
