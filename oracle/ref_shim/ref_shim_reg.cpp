@@ -1,7 +1,8 @@
 // ref_shim_reg.cpp — TEST INFRASTRUCTURE.  Compiles the reference's own CPU reduction kernels, unmodified, from where
 // they lie under /root/reference: t/pipelines/kernel/RegistrationCPU.cpp (ComputePosePointToPlaneCPU,
 // ComputePoseColoredICPCPU: Jacobian + robust weight + 29-slot accumulation as whole functions) and
-// t/pipelines/kernel/RGBDOdometryCPU.cpp (ComputeOdometryResultPointToPlaneCPU).  tbb::parallel_reduce is a stub that
+// t/pipelines/kernel/RGBDOdometryCPU.cpp (ComputeOdometryResultPointToPlaneCPU), plus the header-inline
+// EstimatePointWiseColorGradientKernel of t/geometry/kernel/PointCloudImpl.h.  tbb::parallel_reduce is a stub that
 // runs the body once over the whole range (the serial order); DecodeAndSolve6x6 — which upstream implements with
 // LAPACK — is replaced by a probe that hands the 29 reduced scalars back to the test.
 #include <cmath>
@@ -16,6 +17,7 @@ using std::pow;
 
 #include "open3d/t/pipelines/kernel/RegistrationCPU.cpp"   // from -I /root/reference/cpp
 #include "open3d/t/pipelines/kernel/RGBDOdometryCPU.cpp"
+#include "open3d/t/geometry/kernel/PointCloudImpl.h"        // EstimatePointWiseColorGradientKernel (:1066-1165)
 
 namespace {
 thread_local double g_sums[29];
@@ -83,6 +85,16 @@ void ref_odometry_p2plane_sums(const float* source_vertex, const float* target_v
     o3k::odometry::ComputeOdometryResultPointToPlaneCPU(sv, tv, tn, Kt, Tt, delta, residual, count, depth_outlier_trunc,
                                                         depth_huber_delta);
     memcpy(sums29, g_sums, sizeof(g_sums));
+}
+
+// EstimatePointWiseColorGradientKernel<float> (t/geometry/kernel/PointCloudImpl.h:1066-1165) for point i with its
+// neighbour list (indices[0] = the point itself, as the hybrid search returns it).  Ends in the reference's own
+// solve_svd3x3<float>.
+void ref_color_gradient_point_f32(const float* points, const float* normals, const float* colors, int64_t i,
+                                  const int32_t* indices, int32_t count, float* gradients) {
+    const int32_t off = (int32_t)(3 * i);
+    open3d::t::geometry::kernel::pointcloud::EstimatePointWiseColorGradientKernel<float>(points, normals, colors, off,
+                                                                                          indices, count, gradients);
 }
 
 }  // extern "C"

@@ -15,3 +15,13 @@
 
 #define OPEN3D_ASSERT_MSG(cond, msg) do { if (!(cond)) throw std::runtime_error(msg); } while (0)
 #define OPEN3D_ASSERT(cond) do { if (!(cond)) throw std::runtime_error(#cond); } while (0)
+
+namespace open3d {
+namespace core {
+class Device;
+namespace cuda {
+inline void Synchronize() {}
+inline void Synchronize(const Device&) {}
+}  // namespace cuda
+}  // namespace core
+}  // namespace open3d

@@ -141,6 +141,16 @@ public:
     Tensor Matmul(const Tensor&) const { unsupported(); }
     Tensor Reshape(const SizeVector&) const { unsupported(); }
     Tensor Neg() const { unsupported(); }
+    Tensor Div(double) const { unsupported(); }
+    Tensor Transpose(int64_t, int64_t) const { unsupported(); }
+    template <typename T>
+    static Tensor Full(const SizeVector&, T, Dtype, const Device& = Device()) { unsupported(); }
+    Tensor Contiguous() const { return *this; }
+    Tensor Clone() const {
+        Tensor t(shape_, dtype_);
+        memcpy(t.ptr_, ptr_, (size_t)NumElements() * dtype_.ByteSize());
+        return t;
+    }
     Tensor operator-(const Tensor&) const { unsupported(); }
     Tensor& operator=(double) { unsupported(); }
     Tensor(const Tensor&) = default;
