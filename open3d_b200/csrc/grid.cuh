@@ -97,6 +97,90 @@ __device__ __forceinline__ void scan_range(const float4* __restrict__ pts, unsig
     }
 }
 
+// ONE loop over the concatenation of up to NS slabs [s[k], s[k] + n[k]): a warp then runs
+// max_lane(sum n)/4 trips instead of sum_slabs(max_lane(n_slab)/4) — the lanes' slabs fill differently, and
+// padding every slab separately to the warp's worst lane left two thirds of the candidate slots idle (ncu,
+// DESIGN.md §4.1).  The running best is one 64-bit key (dist^2 bits : index) so that "closer, ties to the
+// lower index" is a single unsigned comparison; non-negative floats order like their bit patterns.
+// `best` / `bj` come in initialised ("nothing": thr:INT_MAX / 0xffffffff, or a seed candidate) and are only
+// replaced by keys <= best.
+static constexpr unsigned kNoPoint = 0xffffffffu;
+template <int NS>
+__device__ __forceinline__ void scan_slabs_flat(const float4* __restrict__ pts, const unsigned (&s)[NS],
+                                                const unsigned (&n)[NS], float qx, float qy, float qz,
+                                                unsigned long long& best, unsigned& bj) {
+    unsigned pre[NS], off[NS];   // slab k covers virtual indices [pre[k], pre[k] + n[k]); global = off[k] + virtual
+    unsigned total = 0;
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        pre[k] = total;
+        off[k] = s[k] - total;
+        total += n[k];
+    }
+    for (unsigned v = 0; v < total; v += 4) {
+        unsigned jj[4];
+        float4 t[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            // lanes that have run out of candidates issue no load (a warp's trip count is its longest lane's:
+            // the L1 data pipe, not the ALUs, is what this loop saturates — DESIGN.md §4.1)
+            const unsigned w = v + k;
+            unsigned o = off[0];
+#pragma unroll
+            for (int q = 1; q < NS; ++q) o = w >= pre[q] ? off[q] : o;
+            jj[k] = o + w;
+            t[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (w < total) t[k] = __ldg(&pts[jj[k]]);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float dx = t[k].x - qx, dy = t[k].y - qy, dz = t[k].z - qz;
+            const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));   // canonical (see scan_range)
+            unsigned long long key =
+                    ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_int(t[k].w);
+            if (v + k >= total) key = ~0ull;
+            if (key <= best) {   // d >= 0, so the bit patterns order like the values; NaN sorts last
+                best = key;
+                bj = jj[k];
+            }
+        }
+    }
+}
+
+// Every point whose (grid-y, grid-z) cell is touched by the box [q - rad, q + rad], over ALL grid-x cells,
+// as at most NS slabs in one flat loop.  For every grid-z of the box, the cells [all grid-x] x [y0..y1] are
+// ONE contiguous run of the table (x fastest, then y); grid-x is the cloud's thin direction, so for
+// surface-like data a run holds just the handful of points of a few cell columns, for two CSR loads.
+// All CSR loads are issued together, then all candidates four at a time: two dependent round trips whatever
+// the box size.  Returns false — nothing scanned, best / bj untouched — when the box spans more than NS
+// grid-z rows or a slab is long (volumetric data): the caller then prunes row by row (nn_search_from).
+template <int NS>
+__device__ __forceinline__ bool scan_box_flat(const Grid& g, const float4* __restrict__ pts,
+                                              const unsigned* __restrict__ cs, float gy, float gz, float qx,
+                                              float qy, float qz, float rad, unsigned long long& best,
+                                              unsigned& bj) {
+    const int y0 = cell1(lo_bound(gy, rad), g.oy, g.inv_c, g.ny), y1 = cell1(hi_bound(gy, rad), g.oy, g.inv_c, g.ny);
+    const int z0 = cell1(lo_bound(gz, rad), g.oz, g.inv_c, g.nz), z1 = cell1(hi_bound(gz, rad), g.oz, g.inv_c, g.nz);
+    if (z1 - z0 >= NS) return false;
+    unsigned s[NS], n[NS];
+    unsigned longest = 0;
+#pragma unroll
+    for (int dz = 0; dz < NS; ++dz) {
+        unsigned b0 = 0, b1 = 0;
+        if (z0 + dz <= z1) {
+            const int plane = (z0 + dz) * g.ny;
+            b0 = __ldg(&cs[(plane + y0) * g.nx]);
+            b1 = __ldg(&cs[(plane + y1 + 1) * g.nx]);
+        }
+        s[dz] = b0;
+        n[dz] = b1 - b0;
+        longest = max(longest, n[dz]);
+    }
+    if (longest > kSlabMax) return false;
+    scan_slabs_flat<NS>(pts, s, n, qx, qy, qz, best, bj);
+    return true;
+}
+
 // One (iy, iz) row of cells: visit only the x cells that can still hold a point at
 // distance <= best, given that every point of the row is at least sqrt(gap2) away in (y, z).
 // skip_cx >= 0: that cell was scanned already.
@@ -120,14 +204,13 @@ __device__ __forceinline__ void scan_row(const Grid& g, const float4* __restrict
 // other rows of the neighbourhood; a row (and the x cells inside it) is skipped as soon as its
 // distance lower bound exceeds the best distance found so far.  PRUNE = false visits everything
 // (used to validate the pruning).
+// nn_search_from: `b` is pre-initialised — either "nothing yet" (d = thr, j = -1, idx = INT_MAX) or an
+// actual candidate (a seed): every point that beats b lies within rr of the query, so rr may be the
+// seed's distance instead of the search radius.
 template <bool PRUNE>
-__device__ __forceinline__ void nn_search(const Grid& g, const float4* __restrict__ pts,
-                                          const unsigned* __restrict__ cs, float qx, float qy,
-                                          float qz, float rr, float thr, Best& b) {
-    b.d = thr;
-    b.j = -1;
-    b.idx = 0x7fffffff;
-    b.x = b.y = b.z = 0.f;
+__device__ __forceinline__ void nn_search_from(const Grid& g, const float4* __restrict__ pts,
+                                               const unsigned* __restrict__ cs, float qx, float qy,
+                                               float qz, float rr, Best& b) {
     float gx, gy, gz;                       // the query in grid axis order (cells / gaps only)
     to_grid(g, qx, qy, qz, gx, gy, gz);
     const float lx = lo_bound(gx, rr), hx = hi_bound(gx, rr);
@@ -175,109 +258,105 @@ __device__ __forceinline__ void nn_search(const Grid& g, const float4* __restric
     }
 }
 
-// Two-pass search for fine grids (cell < radius), the fused ICP kernel's default:
-//   pass 1  every point of the 3x3x3-ish box [q - r1, q + r1] (r1 = cell size), no pruning:
-//           all lanes run the same short loops (little divergence); if the best point
-//           found is within r1 it is the exact nearest neighbour (nothing closer can lie
-//           outside the box);
-//   pass 2  only for lanes that found nothing within r1: the general pruned search.
-// r1_accept2 = (r1 (1 - 1e-4))^2.
-__device__ __forceinline__ void nn_search_two_pass(const Grid& g, const float4* __restrict__ pts,
-                                                   const unsigned* __restrict__ cs, float qx, float qy, float qz,
-                                                   float r1, float r1_accept2, float rr, float thr, Best& b) {
+template <bool PRUNE>
+__device__ __forceinline__ void nn_search(const Grid& g, const float4* __restrict__ pts,
+                                          const unsigned* __restrict__ cs, float qx, float qy,
+                                          float qz, float rr, float thr, Best& b) {
     b.d = thr;
     b.j = -1;
     b.idx = 0x7fffffff;
     b.x = b.y = b.z = 0.f;
+    nn_search_from<PRUNE>(g, pts, cs, qx, qy, qz, rr, b);
+}
+
+// --------------------------------------------------------- searches of the fused ICP kernels
+//
+// Fast path (inline, scan_box_flat<3> from a seed) and slow path (nn_search_slow, deliberately NOT inlined:
+// it runs for a handful of queries per iteration once the clouds are roughly aligned, and keeping its loops
+// out of the iteration kernel's main body keeps that body's register allocation tight).
+//
+// Seeds (temporal coherence): `seed_j` is the sorted position of the point that won this query in the
+// previous iteration.  The seed is an ACTUAL candidate, so the exact nearest neighbour is either the seed or a
+// point with key (dist^2 : index) <= the seed's — and every such point lies within sqrt(dist^2_seed) of the
+// query per axis.  Scanning all cells that the box [q - rad, q + rad] touches (rad = that distance, inflated
+// by 1e-5 for the f32 rounding of the distance arithmetic; binning slack as in lo_bound / hi_bound) is
+// therefore exhaustive: same result, bit for bit, as the unseeded search, from ~4 candidates instead of ~16.
+
+// canonical dist^2 (bit-identical to oracle/icp_oracle.c dist2_f32)
+__device__ __forceinline__ float dist2_canonical(const float4 t, float qx, float qy, float qz) {
+    const float dx = t.x - qx, dy = t.y - qy, dz = t.z - qz;
+    return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+}
+
+// Seeded fast path, from a BOUND on the seed's distance instead of the seed point itself: the caller keeps,
+// per query, dist^2 to its winner of the previous iteration (`d2_prev`, computed from the stored f32 points)
+// and knows how far the query has moved since (`moved2` = |p_new - p_old|^2 of the stored f32 points).  By
+// the triangle inequality the old winner — an actual candidate — is now within sqrt(d2_prev) + sqrt(moved2),
+// so the exact nearest neighbour, and every point tying with it, lies inside that box: scanning it from
+// "nothing yet" returns the same winner, bit for bit, as the exhaustive search, without ever fetching the seed.
+// (Both roots come from the hardware reciprocal square root, 2 ulp; the 1e-4 margin also covers the f32
+// rounding of the two squared distances.)  Returns the winner's sorted position, or kNoPoint when nothing lies
+// within the radius; `handled` = false when the fast path does not apply (box taller than 3 cell rows,
+// long slabs): the caller then calls nn_search_slow.
+__device__ __forceinline__ unsigned nn_search_bounded_fast(const Grid& g, const float4* __restrict__ pts,
+                                                           const unsigned* __restrict__ cs, float qx, float qy,
+                                                           float qz, float rr, float thr, float d2_prev,
+                                                           float moved2, bool& handled) {
+    const float a = d2_prev > 0.f ? d2_prev * rsqrtf(d2_prev) : 0.f;
+    const float b = moved2 > 0.f ? moved2 * rsqrtf(moved2) : 0.f;
+    const float rad = fminf(rr, (a + b) * 1.0001f);
     float gx, gy, gz;
     to_grid(g, qx, qy, qz, gx, gy, gz);
-    if (hi_bound(gx, rr) < g.bmin[0] || lo_bound(gx, rr) > g.bmax[0] || hi_bound(gy, rr) < g.bmin[1] ||
-        lo_bound(gy, rr) > g.bmax[1] || hi_bound(gz, rr) < g.bmin[2] || lo_bound(gz, rr) > g.bmax[2] ||
-        !(qx == qx) || !(qy == qy) || !(qz == qz))
-        return;
-    const int x0 = cell1(lo_bound(gx, r1), g.ox, g.inv_cx, g.nx), x1 = cell1(hi_bound(gx, r1), g.ox, g.inv_cx, g.nx);
-    const int y0 = cell1(lo_bound(gy, r1), g.oy, g.inv_c, g.ny), y1 = cell1(hi_bound(gy, r1), g.oy, g.inv_c, g.ny);
-    const int z0 = cell1(lo_bound(gz, r1), g.oz, g.inv_c, g.nz), z1 = cell1(hi_bound(gz, r1), g.oz, g.inv_c, g.nz);
-    if (z1 - z0 <= 2) {
-        // SLABS.  For every grid-z of the box, the cells [all grid-x] x [y0..y1] are ONE contiguous
-        // run of the table (x fastest, then y).  Grid-x is the cloud's thin direction, so for
-        // surface-like data the run holds just the handful of points of 3 cell columns — the same
-        // candidates as nine per-row runs, in a third of the loops and a third of the CSR loads.
-        // A slab that turns out long (volumetric data) is scanned row by row over [x0..x1] instead.
-        unsigned ss[3], se[3];
-#pragma unroll
-        for (int dz = 0; dz < 3; ++dz) {
-            const bool on = z0 + dz <= z1;
-            const int plane = min(z0 + dz, z1) * g.ny;
-            const unsigned s = __ldg(&cs[(plane + y0) * g.nx]), e = __ldg(&cs[(plane + y1 + 1) * g.nx]);
-            ss[dz] = s;
-            se[dz] = on ? e : s;
+    unsigned long long best = ((unsigned long long)__float_as_uint(thr) << 32) | 0x7fffffffull;
+    unsigned bj = kNoPoint;
+    handled = scan_box_flat<3>(g, pts, cs, gy, gz, qx, qy, qz, rad, best, bj);
+    return bj;
+}
+
+// Everything else: no seed (first iteration, previously unmatched points), far seed, volumetric data.
+//   no seed:   pass 1 scans the box [q - r1, q + r1] (r1 = max(cell size, r / 2)); if the best point
+//              found is within r1 it is the exact nearest neighbour (nothing closer can lie outside the
+//              box); r1_accept2 = (r1 (1 - 1e-4))^2;
+//   then:      the full-radius box (or the seed-bounded one) as one flat 5-slab scan;
+//   otherwise: the pruned row-by-row search.
+// Returns the winner's sorted position or kNoPoint.
+__device__ __noinline__ unsigned nn_search_slow(const Grid* gp, const float4* __restrict__ pts,
+                                                const unsigned* __restrict__ cs, float qx, float qy, float qz,
+                                                float r1, float r1_accept2, float rr, float thr, int seed_j) {
+    const Grid& g = *gp;
+    unsigned long long best = ((unsigned long long)__float_as_uint(thr) << 32) | 0x7fffffffull;
+    unsigned bj = kNoPoint;
+    float rad = rr;
+    if (seed_j >= 0) {
+        const float4 ts = __ldg(&pts[seed_j]);
+        const float sd = dist2_canonical(ts, qx, qy, qz);
+        if (sd <= thr) {
+            best = ((unsigned long long)__float_as_uint(sd) << 32) | (unsigned)__float_as_int(ts.w);
+            bj = (unsigned)seed_j;
+            rad = fminf(rr, sqrtf(sd) * 1.00001f);
         }
-        const unsigned n0 = se[0] - ss[0], n1 = se[1] - ss[1], n2 = se[2] - ss[2];
-        if (n0 <= kSlabMax && n1 <= kSlabMax && n2 <= kSlabMax) {
-            // ONE loop over the concatenation of the three slabs: a warp then runs
-            // max_lane(n0+n1+n2)/4 trips instead of sum_slabs(max_lane(n_slab)/4) — the lanes'
-            // slabs fill differently, and padding every slab separately to the warp's worst lane
-            // left two thirds of the candidate slots idle (ncu).  The running best
-            // is one 64-bit key (dist^2 bits : index) so that "closer, ties to the lower index"
-            // is a single unsigned comparison; non-negative floats order like their bit patterns.
-            const unsigned total = n0 + n1 + n2;
-            const unsigned o1 = ss[1] - n0, o2 = ss[2] - n0 - n1;   // virtual index -> global index offsets
-            unsigned long long best = ((unsigned long long)__float_as_uint(thr) << 32) | 0x7fffffffull;
-            unsigned bj = 0xffffffffu;
-            for (unsigned v = 0; v < total; v += 4) {
-                unsigned jj[4];
-                float4 t[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const unsigned w = min(v + k, total - 1);
-                    jj[k] = w < n0 ? ss[0] + w : (w < n0 + n1 ? o1 + w : o2 + w);
-                    t[k] = __ldg(&pts[jj[k]]);
-                }
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float dx = t[k].x - qx, dy = t[k].y - qy, dz = t[k].z - qz;
-                    const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));   // canonical (see scan_range)
-                    const unsigned long long key =
-                            ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_int(t[k].w);
-                    if (key <= best) {   // d >= 0, so the bit patterns order like the values; NaN sorts last
-                        best = key;
-                        bj = jj[k];
-                    }
-                }
-            }
-            if (bj != 0xffffffffu) {
-                const float4 w = __ldg(&pts[bj]);
-                b.d = __uint_as_float((unsigned)(best >> 32));
-                b.idx = (int)(unsigned)(best & 0xffffffffull);
-                b.j = (int)bj;
-                b.x = w.x;
-                b.y = w.y;
-                b.z = w.z;
-            }
-        } else {
-#pragma unroll
-            for (int dz = 0; dz < 3; ++dz) {
-                if (se[dz] - ss[dz] <= kSlabMax) {
-                    scan_range(pts, ss[dz], se[dz], qx, qy, qz, b);
-                } else {
-                    const int plane = (z0 + dz) * g.ny;
-                    for (int iy = y0; iy <= y1; ++iy) {
-                        const int row = (plane + iy) * g.nx;
-                        scan_range(pts, cs[row + x0], cs[row + x1 + 1], qx, qy, qz, b);
-                    }
-                }
-            }
-        }
-    } else {
-        for (int iz = z0; iz <= z1; ++iz)
-            for (int iy = y0; iy <= y1; ++iy) {
-                const int row = (iz * g.ny + iy) * g.nx;
-                scan_range(pts, cs[row + x0], cs[row + x1 + 1], qx, qy, qz, b);
-            }
     }
-    if (b.j >= 0 && b.d <= r1_accept2) return;
-    nn_search<true>(g, pts, cs, qx, qy, qz, rr, thr, b);
+    float gx, gy, gz;
+    to_grid(g, qx, qy, qz, gx, gy, gz);
+    if (bj == kNoPoint) {
+        // entirely outside the bounding box (or NaN): no candidate can pass
+        if (hi_bound(gx, rr) < g.bmin[0] || lo_bound(gx, rr) > g.bmax[0] || hi_bound(gy, rr) < g.bmin[1] ||
+            lo_bound(gy, rr) > g.bmax[1] || hi_bound(gz, rr) < g.bmin[2] || lo_bound(gz, rr) > g.bmax[2] ||
+            !(qx == qx) || !(qy == qy) || !(qz == qz))
+            return kNoPoint;
+        if (r1 < rr && scan_box_flat<5>(g, pts, cs, gy, gz, qx, qy, qz, r1, best, bj) && bj != kNoPoint &&
+            __uint_as_float((unsigned)(best >> 32)) <= r1_accept2)
+            return bj;
+    }
+    if (scan_box_flat<5>(g, pts, cs, gy, gz, qx, qy, qz, rad, best, bj)) return bj;
+    if (scan_box_flat<9>(g, pts, cs, gy, gz, qx, qy, qz, rad, best, bj)) return bj;   // cells finer than r / 2
+    Best b;
+    b.d = __uint_as_float((unsigned)(best >> 32));
+    b.idx = (int)(unsigned)(best & 0xffffffffull);
+    b.j = bj == kNoPoint ? -1 : (int)bj;
+    b.x = b.y = b.z = 0.f;
+    nn_search_from<true>(g, pts, cs, qx, qy, qz, rad, b);
+    return b.j < 0 ? kNoPoint : (unsigned)b.j;
 }
 
 }  // namespace o3db

@@ -24,9 +24,10 @@ static constexpr int kMaxCellsPerAxis = 4096;
 #define ICP_THIN_FACTOR 8
 #endif
 static constexpr double kThinFactor = ICP_THIN_FACTOR;   // grid-x (thin axis) cells are this much coarser
-#ifndef ICP_PREFETCH_SRC
-#define ICP_PREFETCH_SRC 0   // 1: prefetch the next chunk's source point (round-2 candidate; measure with profiles/tune_icp.sh)
+#ifndef ICP_SEEDED
+#define ICP_SEEDED 1   // 1: seed every query's search with its winner of the previous iteration (exact; see nn_search_seeded)
 #endif
+static constexpr bool kSeeded = ICP_SEEDED != 0;
 #ifndef ICP_CELL_SCALE
 #define ICP_CELL_SCALE 0.5
 #endif
@@ -38,11 +39,8 @@ static constexpr bool kTwoPass = ICP_TWO_PASS != 0;
 #ifndef ICP_MIN_BLOCKS
 #define ICP_MIN_BLOCKS 3
 #endif
-#ifndef ICP_ACC_SMEM
-#define ICP_ACC_SMEM 0
-#endif
 #ifndef ICP_DEFAULT_VARIANT
-#define ICP_DEFAULT_VARIANT 1
+#define ICP_DEFAULT_VARIANT 2   // 1 = direct, 2 = staged (TMA + cp.async ring)
 #endif
 
 // --------------------------------------------------------------------- bbox
@@ -129,6 +127,40 @@ __global__ void count_kernel(const float* __restrict__ pts, int64_t n, Grid g, A
     const unsigned k = TRANSFORM ? cell_key_tiled(g, x, y, z) : cell_key(g, x, y, z);
     key[i] = k;
     rank[i] = atomicAdd(&count[k], 1u);
+}
+
+// Stable order inside a cell.  count_kernel's atomic rank is the ARRIVAL order of the points of a cell, which
+// differs from run to run; these two passes replace it by the canonical one (ascending original index), so that
+// the sorted arrays — and with them every sum taken over them — are bit-reproducible.  Cells hold a handful
+// of points, so ranking a point against its cell mates is cheaper than any general stable sort.
+__global__ void scatter_index_kernel(int64_t n, const unsigned* __restrict__ start, const unsigned* __restrict__ key,
+                                     const unsigned* __restrict__ rank, unsigned* __restrict__ idx_sorted) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) idx_sorted[start[key[i]] + rank[i]] = (unsigned)i;
+}
+static constexpr unsigned kCanonMaxRun = 2048;   // longer runs (absurd densities) keep the arrival order
+__global__ void canonical_rank_kernel(int64_t n, const unsigned* __restrict__ start, const unsigned* __restrict__ key,
+                                      const unsigned* __restrict__ idx_sorted, unsigned* __restrict__ rank) {
+    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const unsigned i = idx_sorted[j];
+    const unsigned k = key[i];
+    const unsigned s = start[k], e = start[k + 1];
+    if (e - s == 1 || e - s > kCanonMaxRun) return;
+    unsigned below = 0;
+    for (unsigned q = s; q < e; ++q) below += __ldg(&idx_sorted[q]) < i ? 1u : 0u;
+    rank[i] = below;
+}
+static int canonical_ranks(int64_t n, const unsigned* start, const unsigned* key, unsigned* rank, cudaStream_t st) {
+    unsigned* idx_sorted = nullptr;
+    O3DB_CUDA_CHECK(cudaMallocAsync(&idx_sorted, n * sizeof(unsigned), st));
+    const unsigned nb = (unsigned)ceil_div(n, 256);
+    scatter_index_kernel<<<nb, 256, 0, st>>>(n, start, key, rank, idx_sorted);
+    O3DB_LAUNCH_CHECK();
+    canonical_rank_kernel<<<nb, 256, 0, st>>>(n, start, key, idx_sorted, rank);
+    O3DB_LAUNCH_CHECK();
+    O3DB_CUDA_CHECK(cudaFreeAsync(idx_sorted, st));
+    return O3DB_OK;
 }
 
 template <bool TRANSFORM>
@@ -263,6 +295,7 @@ __global__ void ref_scatter_kernel(const float* __restrict__ pts, int64_t n, flo
 using namespace o3db;
 
 struct o3db_nns {
+    cudaStream_t stream = 0;   // creation stream (buffers are freed on it)
     Grid g{};
     double radius = 0;
     int64_t m = 0;
@@ -283,7 +316,10 @@ static void nns_free(o3db_nns* s, cudaStream_t st) {
     s->cell_start = nullptr;
 }
 
-static int grid_from_bbox(const float mn[3], const float mx[3], double radius, double cell_scale, Grid* g,
+#ifndef ICP_THIN_MERGE_MAX
+#define ICP_THIN_MERGE_MAX 8.0   // merge the whole thin axis into ONE cell while a (y, z) column holds at most this many points on average
+#endif
+static int grid_from_bbox(const float mn[3], const float mx[3], double radius, double cell_scale, int64_t m, Grid* g,
                           int64_t* ncell) {
     double c = radius * (cell_scale > 0 ? cell_scale : 1.0) * (1.0 + 1e-4);
     if (!(c > 0) || !std::isfinite(c)) c = 1.0;
@@ -298,12 +334,19 @@ static int grid_from_bbox(const float mn[3], const float mx[3], double radius, d
     int order[3] = {2, 1, 0};
     std::stable_sort(order, order + 3, [&](int a, int b) { return ext[a] < ext[b]; });
     for (int k = 0; k < 3; ++k) g->ax[k] = order[k];
+    double cx = c * kThinFactor;
     for (;;) {
         double n[3];
         bool ok = true;
         double prod = 1;
+        // Surface-like clouds: when a (y, z) column of cells holds only a handful of points over the WHOLE thin
+        // extent, the thin axis becomes a single cell (slab scans cross all of it anyway): the CSR table
+        // shrinks by nx and a slab boundary is one multiply-free lookup.  Volumetric clouds keep thin cells.
+        const double cols = (std::floor(ext[order[1]] / c) + 1) * (std::floor(ext[order[2]] / c) + 1);
+        cx = c * kThinFactor;
+        if ((double)m <= ICP_THIN_MERGE_MAX * cols) cx = std::max(cx, ext[order[0]] * (1.0 + 1e-3) + c);
         for (int k = 0; k < 3; ++k) {
-            n[k] = std::floor(ext[order[k]] / (k == 0 ? c * kThinFactor : c)) + 1;
+            n[k] = std::floor(ext[order[k]] / (k == 0 ? cx : c)) + 1;
             ok = ok && n[k] <= kMaxCellsPerAxis;
             prod *= n[k];
         }
@@ -317,7 +360,7 @@ static int grid_from_bbox(const float mn[3], const float mx[3], double radius, d
     }
     g->c = (float)c;
     g->inv_c = 1.0f / g->c;
-    g->cx = (float)(c * kThinFactor);
+    g->cx = (float)cx;
     g->inv_cx = 1.0f / g->cx;
     g->ox = mn[order[0]];
     g->oy = mn[order[1]];
@@ -336,6 +379,7 @@ static int grid_from_bbox(const float mn[3], const float mx[3], double radius, d
 static int nns_build(o3db_nns* s, const float* pts, const float* nrm, int64_t m, double radius,
                      double cell_scale, cudaStream_t st) {
     configure_memory_pool();
+    s->stream = st;
     s->m = m;
     s->radius = radius;
     unsigned* d_bbox = nullptr;
@@ -358,7 +402,7 @@ static int nns_build(o3db_nns* s, const float* pts, const float* nrm, int64_t m,
             return O3DB_ERR_INVALID;
         }
     }
-    grid_from_bbox(mn, mx, radius, cell_scale, &s->g, &s->ncell);
+    grid_from_bbox(mn, mx, radius, cell_scale, m, &s->g, &s->ncell);
 
     unsigned *key = nullptr, *rank = nullptr, *scratch = nullptr;
     O3DB_CUDA_CHECK(cudaMallocAsync(&s->cell_start, (s->ncell + 1) * sizeof(unsigned), st));
@@ -373,6 +417,8 @@ static int nns_build(o3db_nns* s, const float* pts, const float* nrm, int64_t m,
     count_kernel<false><<<nb, kThreads, 0, st>>>(pts, m, s->g, id, s->cell_start, key, rank);
     O3DB_LAUNCH_CHECK();
     int rc = exclusive_scan_u32(s->cell_start, s->ncell, scratch, st);
+    if (rc) return rc;
+    rc = canonical_ranks(m, s->cell_start, key, rank, st);
     if (rc) return rc;
     scatter_kernel<false><<<nb, kThreads, 0, st>>>(pts, nrm, m, id, s->cell_start, key, rank, s->pts4, s->nrm4);
     O3DB_LAUNCH_CHECK();
@@ -497,19 +543,9 @@ __device__ __forceinline__ float robust_weight(const Robust& k, float r) {
 
 // ------------------------------------------------- 29(+1)-scalar reduction (reduce.cuh)
 
-__device__ __forceinline__ void flush_acc_smem(float (*s_acc)[kThreads], double (*s_warp)[kSumStride]) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-#pragma unroll
-    for (int k = 0; k < kNumSums; ++k) {
-        const double v = warp_sum((double)s_acc[k][threadIdx.x]);
-        if (lane == 0) s_warp[w][k] += v;
-        s_acc[k][threadIdx.x] = 0.f;
-    }
-}
-
 // RegistrationImpl.h:251-287 + RegistrationCUDA.cu:29-79 slot layout.
-template <bool L2LOSS>
-__device__ __forceinline__ void accumulate_p2plane(float (&acc)[kNumSums], const Robust& rk, float sx, float sy,
+template <bool L2LOSS, int NACC>
+__device__ __forceinline__ void accumulate_p2plane(float (&acc)[NACC], const Robust& rk, float sx, float sy,
                                                    float sz, float tx, float ty, float tz, float nx, float ny,
                                                    float nz) {
     // r and J are evaluated without FMA contraction, in the reference's operation order, so
@@ -539,8 +575,8 @@ __device__ __forceinline__ void accumulate_p2plane(float (&acc)[kNumSums], const
 
 // ComputePoseColoredICP per-correspondence body (RegistrationImpl.h:337-425 / RegistrationCUDA.cu:119-183):
 // geometric + photometric Jacobian rows, two robust weights, same 29-slot layout.
-template <bool L2LOSS>
-__device__ __forceinline__ void accumulate_colored(float (&acc)[kNumSums], const Robust& rk, const float (&vs)[3],
+template <bool L2LOSS, int NACC>
+__device__ __forceinline__ void accumulate_colored(float (&acc)[NACC], const Robust& rk, const float (&vs)[3],
                                                    const float (&vt)[3], const float (&nt)[3], float is, float it,
                                                    const float (&dit)[3], float sqrt_lg, float sqrt_lp) {
     const float d = (vs[0] - vt[0]) * nt[0] + (vs[1] - vt[1]) * nt[1] + (vs[2] - vt[2]) * nt[2];
@@ -608,7 +644,7 @@ pose_p2plane_kernel(const float* __restrict__ src, const float* __restrict__ tgt
             if (c != -1) {
                 const float* t = tgt + 3 * c;
                 const float* m = nrm + 3 * c;
-                accumulate_p2plane<L2LOSS>(acc, rk, src[3 * i], src[3 * i + 1], src[3 * i + 2], t[0], t[1], t[2],
+                accumulate_p2plane<L2LOSS, kNumSums>(acc, rk, src[3 * i], src[3 * i + 1], src[3 * i + 2], t[0], t[1], t[2],
                                            m[0], m[1], m[2]);
             }
         }
@@ -656,7 +692,7 @@ pose_colored_kernel(const float* __restrict__ src, const float* __restrict__ src
             const float is = color_intensity(src_c[s], src_c[s + 1], src_c[s + 2]);
             const float it = color_intensity(tgt_c[t], tgt_c[t + 1], tgt_c[t + 2]);
             const float dit[3] = {tgt_g[t], tgt_g[t + 1], tgt_g[t + 2]};
-            accumulate_colored<L2LOSS>(acc, rk, vs, vt, nt, is, it, dit, sqrt_lg, sqrt_lp);
+            accumulate_colored<L2LOSS, kNumSums>(acc, rk, vs, vt, nt, is, it, dit, sqrt_lg, sqrt_lp);
         }
         if (++since == kFlushEvery) {
             flush_acc(acc, s_warp);
@@ -737,6 +773,8 @@ struct IcpArgs {
     const float4* nrm;
     const unsigned* cs;
     float4* src;          // working source, sorted, .w = original index bits
+    int* prev;            // per working source point: sorted target position of its last winner, -1 = none
+    float* dprev;         // per working source point: dist^2 to that winner (+inf = none)
     int64_t n;            // local source points
     double n_total;       // source points over all ranks (fitness denominator)
     float rr, thr;
@@ -753,6 +791,7 @@ struct IcpArgs {
     const float4* tcg;    // per sorted target point: colour gradient xyz, .w = intensity
     const float* sint;    // per sorted source point: intensity
     float sqrt_lg, sqrt_lp;
+    long long* dbg;       // -DICP_TIMING=1 builds only: 8 timestamps per block (see profiles/icp_timing.py)
 };
 
 __device__ void set_identity(double* T, float* Uf) {
@@ -763,56 +802,122 @@ __device__ void set_identity(double* T, float* Uf) {
     }
 }
 
-// Host part of DoSingleScaleICPIterations (Registration.cpp:293-358), on device,
-// run by one thread once per iteration.
-__device__ void icp_finalize_iteration(const IcpArgs& a, const double* sums) {
+#ifndef ICP_TRANSPOSE_SMEM
+#define ICP_TRANSPOSE_SMEM 0   // 1: the per-chunk transposed reduction goes through a shared-memory tile instead of shuffles
+#endif
+#ifndef ICP_TIMING
+#define ICP_TIMING 0   // 1: record per-block timestamps of the last iteration launch (diagnostics only)
+#endif
+__device__ __forceinline__ long long global_ns() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define ICP_STAMP(slot)                                                                            \
+    do {                                                                                           \
+        if (ICP_TIMING && a.dbg && threadIdx.x == 0) a.dbg[(size_t)blockIdx.x * 8 + (slot)] = global_ns(); \
+    } while (0)
+
+#ifndef ICP_PDL
+#define ICP_PDL 1   // 1: launch the iteration kernels with programmatic stream serialization (see pdl_wait)
+#endif
+__device__ __forceinline__ void pdl_wait() {
+#if ICP_PDL
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_launch_dependents() {
+#if ICP_PDL
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+
+// Host part of DoSingleScaleICPIterations (Registration.cpp:293-358), on device, run by ONE WARP once per
+// iteration (all 32 lanes must call it): the 6x6 solve is warp-parallel, the six sin / cos of the pose and the
+// sixteen entries of T <- U T are spread over lanes, lane 0 keeps the books.  `s_scratch`: 64 doubles of
+// shared memory.
+__device__ void icp_finalize_iteration(const IcpArgs& a, const double* sums, double* s_scratch) {
     IcpState* st = a.st;
+    const int lane = threadIdx.x & 31;
     const double count = sums[28];
     const double fitness = count / a.n_total;                       // Registration.cpp:47-50
     const double rmse = count > 0 ? sqrt(sums[29] / count) : 0.0;
-    st->fitness = fitness;
-    st->rmse = rmse;
-    st->count = count;
     if (!(fitness > DBL_MIN)) {  // :51-60, :300-306 — no correspondences
-        set_identity(st->T, st->Uf);
-        st->converged = 0;
-        st->done = 1;
-        return;
-    }
-    double pose[6];
-    if (!solve6x6(sums, pose)) {  // TransformationConverter.cpp:219-225 — the reference raises
-        set_identity(nullptr, st->Uf);
-        st->status = 1;
-        st->done = 1;
-        return;
-    }
-    double U[16], R[16];
-    pose_to_T(pose, U);
-    for (int i = 0; i < 4; ++i)          // :319  T <- U * T
-        for (int j = 0; j < 4; ++j) {
-            double s = 0;
-            for (int k = 0; k < 4; ++k) s += U[i * 4 + k] * st->T[k * 4 + j];
-            R[i * 4 + j] = s;
+        if (lane == 0) {
+            st->fitness = fitness;
+            st->rmse = rmse;
+            st->count = count;
+            set_identity(st->T, st->Uf);
+            st->converged = 0;
+            st->done = 1;
         }
-    for (int i = 0; i < 16; ++i) {
-        st->T[i] = R[i];
-        st->Uf[i] = (float)U[i];          // :322 applied by the next kernel's load
-    }
-    if (a.per_iter) {
-        a.per_iter[2 * st->executed] = fitness;
-        a.per_iter[2 * st->executed + 1] = rmse;
-    }
-    st->executed += 1;
-    if (st->iter != 0 && fabs(st->prev_fitness - fitness) < a.rel_fitness &&
-        fabs(st->prev_rmse - rmse) < a.rel_rmse) {  // :348-355
-        st->converged = 1;
-        st->done = 1;
         return;
     }
-    st->prev_fitness = fitness;
-    st->prev_rmse = rmse;
-    st->iter += 1;
-    if (st->iter >= a.max_iteration) st->done = 1;
+    double* pose = s_scratch;            // [6]
+    double* trig = s_scratch + 8;        // cos a, cos b, cos g, sin a, sin b, sin g
+    double* U = s_scratch + 16;          // [16]
+    const bool ok = solve6x6_warp(sums, s_scratch + 16, pose);   // (Ms aliases U: dead before U is written)
+    if (!ok) {  // TransformationConverter.cpp:219-225 — the reference raises
+        if (lane == 0) {
+            st->fitness = fitness;
+            st->rmse = rmse;
+            st->count = count;
+            set_identity(nullptr, st->Uf);
+            st->status = 1;
+            st->done = 1;
+        }
+        return;
+    }
+    if (lane < 3) trig[lane] = cos(pose[lane]);
+    else if (lane < 6) trig[lane] = sin(pose[lane - 3]);
+    __syncwarp();
+    if (lane == 0) {   // TransformationConverterImpl.h:22-42 (same expressions as pose_to_T)
+        const double ca = trig[0], cb = trig[1], cg = trig[2], sa = trig[3], sb = trig[4], sg = trig[5];
+        U[0] = cg * cb;
+        U[1] = -1 * sg * ca + cg * sb * sa;
+        U[2] = sg * sa + cg * sb * ca;
+        U[3] = pose[3];
+        U[4] = sg * cb;
+        U[5] = cg * ca + sg * sb * sa;
+        U[6] = -1 * cg * sa + sg * sb * ca;
+        U[7] = pose[4];
+        U[8] = -1 * sb;
+        U[9] = cb * sa;
+        U[10] = cb * ca;
+        U[11] = pose[5];
+        U[12] = U[13] = U[14] = 0.0;
+        U[15] = 1.0;
+    }
+    __syncwarp();
+    if (lane < 16) {                     // :319  T <- U * T
+        const int i = lane >> 2, j = lane & 3;
+        double v = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v += U[i * 4 + k] * st->T[k * 4 + j];
+        __syncwarp(0xffffu);             // every lane has read the old T
+        st->T[lane] = v;
+        st->Uf[lane] = (float)U[lane];   // :322 applied by the next kernel's load
+    }
+    if (lane == 0) {
+        st->fitness = fitness;
+        st->rmse = rmse;
+        st->count = count;
+        if (a.per_iter) {
+            a.per_iter[2 * st->executed] = fitness;
+            a.per_iter[2 * st->executed + 1] = rmse;
+        }
+        st->executed += 1;
+        if (st->iter != 0 && fabs(st->prev_fitness - fitness) < a.rel_fitness &&
+            fabs(st->prev_rmse - rmse) < a.rel_rmse) {  // :348-355
+            st->converged = 1;
+            st->done = 1;
+        } else {
+            st->prev_fitness = fitness;
+            st->prev_rmse = rmse;
+            st->iter += 1;
+            if (st->iter >= a.max_iteration) st->done = 1;
+        }
+    }
 }
 
 // Final ComputeRegistrationResult (Registration.cpp:424-431).
@@ -832,157 +937,180 @@ __device__ void icp_finalize_evaluate(const IcpArgs& a, const double* sums) {
     set_identity(nullptr, st->Uf);
 }
 
-// One ICP iteration in ONE kernel: apply the pending update to the working
-// source in place, exact 1-NN within the radius through the grid, Jacobian,
-// 30-scalar reduction, and (last block) solve + pose update + convergence test.
-// MODE 0 = iterate, MODE 1 = evaluate (no Jacobian; writes correspondences).
-template <bool L2LOSS, int MODE, bool COLORED = false>
-__global__ void __launch_bounds__(kThreads, ICP_MIN_BLOCKS)
-icp_iteration_kernel(IcpArgs a) {
-    __shared__ double s_warp[kThreads / 32][kSumStride];
-    __shared__ double s_final[kSumStride];
-    __shared__ float s_U[16];
-    __shared__ int s_done;
-    if (threadIdx.x == 0) s_done = *(volatile int*)&a.st->done;
-    if (threadIdx.x < 16) s_U[threadIdx.x] = a.st->Uf[threadIdx.x];
-    for (int k = threadIdx.x; k < (kThreads / 32) * kSumStride; k += kThreads) (&s_warp[0][0])[k] = 0.0;
-    __syncthreads();
-    if (MODE == 0 && s_done) return;
+// ------------------------------------------------------- one query of one iteration
 
-#if ICP_ACC_SMEM
-    // per-thread accumulators live in shared memory (column tid of s_acc): the 30 values are
-    // only in registers while one correspondence is being expanded, which leaves the search
-    // the whole register budget and lets one more block fit per SM
-    __shared__ float s_acc[kNumSums][kThreads];
-#pragma unroll
-    for (int k = 0; k < kNumSums; ++k) s_acc[k][threadIdx.x] = 0.f;
-#else
-    float acc[kNumSums];
-#pragma unroll
-    for (int k = 0; k < kNumSums; ++k) acc[k] = 0.f;
-#endif
-    int since = 0;
-#if ICP_PREFETCH_SRC
-    // experimental (default off, unmeasured): issue the NEXT chunk's source load before this chunk's search so
-    // that its latency (10 % of the stall samples) hides behind the search; same values, same results
-    float4 p_next = make_float4(0.f, 0.f, 0.f, 0.f);
-    {
-        const int64_t i0 = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-        if (i0 < a.n) p_next = a.src[i0];
+// Everything one working source point does in one iteration: apply the pending update (the reference's
+// separate PointCloud::Transform pass, Registration.cpp:322) and store it back, exact 1-NN within the radius
+// (seeded by last iteration's winner `jp` when there is one: ts / nn / cg are that target point, its normal and
+// its colour row, fetched by the caller), Jacobian + 30 partial sums, new seed.
+// MODE 0 = iterate, MODE 1 = evaluate (no Jacobian; writes correspondences in the caller's order).
+template <bool L2LOSS, int MODE, bool COLORED>
+__device__ __forceinline__ bool icp_process_query(const IcpArgs& a, const float* s_U, int i, float4 p, int jp,
+                                                  float d2_prev, const float4* seed_nn, const float4* seed_cg,
+                                                  float (&acc)[32]) {
+    const float ox = p.x, oy = p.y, oz = p.z;
+    apply_transform(s_U, p.x, p.y, p.z);
+    a.src[i] = p;
+    unsigned bj = kNoPoint;
+    bool handled = false;
+    if (jp >= 0) {
+        const float mx = p.x - ox, my = p.y - oy, mz = p.z - oz;
+        bj = nn_search_bounded_fast(a.g, a.tgt, a.cs, p.x, p.y, p.z, a.rr, a.thr, d2_prev,
+                                    fmaf(mz, mz, fmaf(my, my, mx * mx)), handled);
     }
-#endif
-    for (int64_t base = (int64_t)blockIdx.x * kThreads; base < a.n; base += (int64_t)gridDim.x * kThreads) {
-        const int64_t i = base + threadIdx.x;
-        const bool live = i < a.n;
-        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-#if ICP_PREFETCH_SRC
-        p = p_next;
-        {
-            const int64_t in = i + (int64_t)gridDim.x * kThreads;
-            if (in < a.n) p_next = a.src[in];
-        }
-        if (live) {
-            apply_transform(s_U, p.x, p.y, p.z);
-            a.src[i] = p;
-        }
-#else
-        if (live) {
-            p = a.src[i];
-            apply_transform(s_U, p.x, p.y, p.z);   // Registration.cpp:322 (PointCloud::Transform), fused
-            a.src[i] = p;
-        }
-#endif
-        Best b;
-        b.j = -1;
-        if (live) {
-            if (kTwoPass) nn_search_two_pass(a.g, a.tgt, a.cs, p.x, p.y, p.z, a.r1, a.r1_accept2, a.rr, a.thr, b);
-            else nn_search<true>(a.g, a.tgt, a.cs, p.x, p.y, p.z, a.rr, a.thr, b);
-        }
-        if (live) {
-            if (b.j >= 0) {
-#if ICP_ACC_SMEM
-                if (MODE == 0) {
-                    float term[kNumSums];
-#pragma unroll
-                    for (int k = 0; k < kNumSums; ++k) term[k] = 0.f;
-                    const float4 nn = __ldg(&a.nrm[b.j]);
-                    accumulate_p2plane<L2LOSS>(term, a.rk, p.x, p.y, p.z, b.x, b.y, b.z, nn.x, nn.y, nn.z);
-                    term[29] = b.d;
-#pragma unroll
-                    for (int k = 0; k < kNumSums; ++k) s_acc[k][threadIdx.x] += term[k];
-                } else {
-                    s_acc[28][threadIdx.x] += 1.0f;
-                    s_acc[29][threadIdx.x] += b.d;
-                }
-#else
-                if (MODE == 0) {
-                    const float4 nn = __ldg(&a.nrm[b.j]);
-                    if (COLORED) {
-                        const float4 cg = __ldg(&a.tcg[b.j]);
-                        const float vs[3] = {p.x, p.y, p.z}, vt[3] = {b.x, b.y, b.z}, nt[3] = {nn.x, nn.y, nn.z};
-                        const float dit[3] = {cg.x, cg.y, cg.z};
-                        accumulate_colored<L2LOSS>(acc, a.rk, vs, vt, nt, __ldg(&a.sint[i]), cg.w, dit, a.sqrt_lg,
-                                                   a.sqrt_lp);
-                    } else {
-                        accumulate_p2plane<L2LOSS>(acc, a.rk, p.x, p.y, p.z, b.x, b.y, b.z, nn.x, nn.y, nn.z);
-                    }
-                } else {
-                    acc[28] += 1.0f;
-                }
-                acc[29] += b.d;
-#endif
+    if (!handled)
+        bj = nn_search_slow(&a.g, a.tgt, a.cs, p.x, p.y, p.z, kTwoPass ? a.r1 : a.rr, a.r1_accept2, a.rr, a.thr, jp);
+    if (kSeeded && (int)bj != jp) a.prev[i] = (int)bj;
+    int widx = -1;
+    if (kSeeded && bj == kNoPoint && jp >= 0) a.dprev[i] = __int_as_float(0x7f7f7f7f);
+    if (bj != kNoPoint) {
+        const float4 t = __ldg(&a.tgt[bj]);                  // (just scanned: an L1 hit)
+        const float d = dist2_canonical(t, p.x, p.y, p.z);   // the same arithmetic as inside the scan: same bits
+        if (kSeeded) a.dprev[i] = d;
+        widx = __float_as_int(t.w);
+        if (MODE == 0) {
+            // the seed's normal / colour row were fetched ahead (the winner rarely changes once the clouds
+            // are roughly aligned); they are only read now, so that they hold no registers during the search
+            const float4 nn = (int)bj == jp ? *seed_nn : __ldg(&a.nrm[bj]);
+            if (COLORED) {
+                const float4 cg = (int)bj == jp ? *seed_cg : __ldg(&a.tcg[bj]);
+                const float vs[3] = {p.x, p.y, p.z}, vt[3] = {t.x, t.y, t.z}, nt[3] = {nn.x, nn.y, nn.z};
+                const float dit[3] = {cg.x, cg.y, cg.z};
+                accumulate_colored<L2LOSS, 32>(acc, a.rk, vs, vt, nt, __ldg(&a.sint[i]), cg.w, dit, a.sqrt_lg, a.sqrt_lp);
+            } else {
+                accumulate_p2plane<L2LOSS, 32>(acc, a.rk, p.x, p.y, p.z, t.x, t.y, t.z, nn.x, nn.y, nn.z);
             }
-            if (MODE == 1 && a.corr_out) a.corr_out[__float_as_int(p.w)] = b.j >= 0 ? (int64_t)b.idx : (int64_t)-1;
+        } else {
+            acc[28] += 1.0f;
         }
-        if (++since == kFlushEvery) {
-#if ICP_ACC_SMEM
-            flush_acc_smem(s_acc, s_warp);
-#else
-            flush_acc(acc, s_warp);
-#endif
-            since = 0;
-        }
+        acc[29] += d;
     }
-#if ICP_ACC_SMEM
-    flush_acc_smem(s_acc, s_warp);
-#else
-    flush_acc(acc, s_warp);
-#endif
-    if (!block_reduce_to_global(s_warp, a.partials, &a.st->ticket, s_final)) return;
+    if (MODE == 1 && a.corr_out) a.corr_out[__float_as_int(p.w)] = (int64_t)widx;
+    return bj != kNoPoint;
+}
+
+// One chunk's contribution to the 30 sums: transposed warp reduction of the lanes' terms (f32 tree over 32
+// queries), added to the warp's running totals — one f64 per lane, lane l = slot l.
+__device__ __forceinline__ void icp_accumulate_chunk(float (&term)[32], bool matched, double& acc64) {
+    if (__any_sync(0xffffffffu, matched)) acc64 += (double)warp_transpose_sum32(term);
+}
+
+// The same through a per-warp shared-memory tile (30 conflict-free STS + 8 LDS.128 + a 31-add tree instead of
+// 31 shuffles + 62 selects + 31 adds): rows are 36 floats apart, so that the 8 lanes of an LDS.128 phase hit
+// 8 different bank quads.  Same f32 association as a balanced binary tree over the lanes.
+static constexpr int kTrStride = 36;
+static constexpr int kTrFloats = kNumSums * kTrStride;
+__device__ __forceinline__ void icp_accumulate_chunk_smem(float (&term)[32], bool matched, float* tr, double& acc64) {
+    if (!__any_sync(0xffffffffu, matched)) return;
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < kNumSums; ++k) tr[k * kTrStride + lane] = term[k];
+    __syncwarp();
+    if (lane < kNumSums) {
+        const float4* row = reinterpret_cast<const float4*>(tr + lane * kTrStride);
+        float q[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float4 v = row[k];
+            q[k] = (v.x + v.y) + (v.z + v.w);
+        }
+        acc64 += (double)(((q[0] + q[1]) + (q[2] + q[3])) + ((q[4] + q[5]) + (q[6] + q[7])));
+    }
+    __syncwarp();   // the tile is rewritten by the next chunk
+}
+
+// Block epilogue shared by both iteration kernels: block partial -> (last block) grand total, solve,
+// pose update, convergence test.
+template <int MODE>
+__device__ __forceinline__ void icp_block_epilogue(const IcpArgs& a, double (*s_warp)[kSumStride], double* s_final) {
+    ICP_STAMP(2);   // this block's first warp is through its loop
+    long long* stamps = (ICP_TIMING && a.dbg) ? a.dbg + (size_t)blockIdx.x * 8 + 3 : nullptr;   // [3] all warps done, [4] ticket = last
+    if (!block_reduce_to_global(s_warp, a.partials, &a.st->ticket, s_final, stamps)) return;
+    ICP_STAMP(5);   // last block: grand total ready
     if (a.fuse_finalize) {
-        if (threadIdx.x == 0) {
-            if (MODE == 0) icp_finalize_iteration(a, s_final);
-            else icp_finalize_evaluate(a, s_final);
+        if (threadIdx.x < 32) {
+            if (MODE == 0) icp_finalize_iteration(a, s_final, &s_warp[0][0]);   // (s_warp is dead: reused as scratch)
+            else if (threadIdx.x == 0) icp_finalize_evaluate(a, s_final);
         }
     } else if (threadIdx.x < kNumSums) {
         a.st->sums[threadIdx.x] = s_final[threadIdx.x];
     }
+    ICP_STAMP(7);   // last block: solve + pose update done
 }
 
+// ------------------------------------------------ direct variant (search_variant = 1)
 
-// ------------------------------------------------ TMA-staged tile variant
+// One ICP iteration in ONE kernel, every load issued where it is needed (source point, seed, seed's
+// normal, CSR offsets, candidates: four dependent round trips per query).  Kept as the A/B baseline of the
+// staged kernel below; same results bit for bit.
+template <bool L2LOSS, int MODE, bool COLORED = false>
+__global__ void __launch_bounds__(kThreads, ICP_MIN_BLOCKS)
+icp_iteration_direct_kernel(const __grid_constant__ IcpArgs a) {
+    __shared__ double s_warp[kThreads / 32][kSumStride];
+    __shared__ double s_final[kSumStride];
+    __shared__ float s_U[16];
+    __shared__ int s_done;
+    for (int k = threadIdx.x; k < (kThreads / 32) * kSumStride; k += kThreads) (&s_warp[0][0])[k] = 0.0;
+    ICP_STAMP(0);   // block resident
+    if (ICP_TIMING && a.dbg && threadIdx.x == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        a.dbg[(size_t)blockIdx.x * 8 + 6] = smid;
+    }
+    pdl_wait();
+    pdl_launch_dependents();
+    ICP_STAMP(1);   // predecessor complete
+    if (threadIdx.x == 0) s_done = *(volatile int*)&a.st->done;
+    if (threadIdx.x < 16) s_U[threadIdx.x] = a.st->Uf[threadIdx.x];
+    __syncthreads();
+    if (MODE == 0 && s_done) return;
 
-// Shared-memory tile of one 256-query chunk: the candidate rows of the chunk's cell box are
-// brought in with cp.async.bulk (TMA, one bulk copy per non-empty (y,z) row — a row of cells
-// is one contiguous run of float4 points) and the matching cell_start segments with coalesced
-// loads; the per-query scan then touches shared memory only.
-static constexpr int kTilePts = 2560;   // float4 candidates  (40 KB)
-static constexpr int kTileCs = 4096;    // staged cell_start entries (16 KB)
-static constexpr int kTileRows = 256;   // (y,z) rows of the box (one per thread)
+    double acc64 = 0.0;      // lane l: running total of slot l over this warp's queries
+    const int n = (int)a.n;
+    for (int base = blockIdx.x * kThreads; base < n; base += gridDim.x * kThreads) {
+        const int i = base + threadIdx.x;
+        float term[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) term[k] = 0.f;
+        bool matched = false;
+        if (i < n) {
+            const float4 p = a.src[i];
+            const int jp = kSeeded ? a.prev[i] : -1;
+            const float d2_prev = kSeeded ? a.dprev[i] : 0.f;
+            matched = icp_process_query<L2LOSS, MODE, COLORED>(a, s_U, i, p, jp, d2_prev, a.nrm + max(jp, 0),
+                                                               COLORED ? a.tcg + max(jp, 0) : nullptr, term);
+        }
+        icp_accumulate_chunk(term, matched, acc64);
+    }
+    if ((threadIdx.x & 31) < kNumSums) s_warp[threadIdx.x >> 5][threadIdx.x & 31] = acc64;
+    icp_block_epilogue<MODE>(a, s_warp, s_final);
+}
 
-struct __align__(16) TileSmem {
-    float4 pts[kTilePts];
-    unsigned cs[kTileCs];
-    int row_delta[kTileRows];            // smem index minus global index of the row's points
-    unsigned long long mbar;
-    int bbox[6];
-    int ok;
+// ------------------------------------------ staged variant (default): TMA + cp.async ring
+
+// Per warp, a two-slot ring in shared memory holds what a 32-query chunk needs before its search can
+// start, fetched while the PREVIOUS chunk is being searched:
+//   A  the chunk's source points and seeds: two TMA bulk copies (cp.async.bulk, completion on the slot's
+//      mbarrier) issued by lane 0 two chunks ahead — 512 B + 128 B, contiguous because the working source
+//      is stored sorted;
+//   B  the seeds' target points, normals (and colour rows): one 16-byte cp.async gather per lane and
+//      array, issued one chunk ahead as soon as A has landed (the gather address IS the seed).
+// A query therefore starts with p, seed, seed point and seed normal already on chip, and its dependent
+// chain shrinks from four global round trips (source -> seed point -> CSR offsets -> candidates) to two.
+// There is no block-wide barrier in the loop: slots are private to a warp (lane 0 produces, __syncwarp
+// hands a consumed slot back), accumulator flushes are warp-local.
+template <bool COLORED>
+struct __align__(16) IcpStage {
+    float4 p[32];      // A
+    float4 ns[32];     // B
+    float4 cg[COLORED ? 32 : 1];   // B
+    int jp[32];        // A
+    float d2[32];      // A
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* b, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
@@ -1003,200 +1131,121 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity
                 : "memory");
     } while (!done);
 }
-__device__ __forceinline__ float4 lds128(unsigned addr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-    return v;
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// scan_range() over candidates staged in shared memory; `base` is the shared address that
-// global index 0 of this row would have (may wrap below the window; only [s, e) is touched).
-__device__ __forceinline__ void scan_range_smem(unsigned base, unsigned s, unsigned e, float qx, float qy, float qz,
-                                                Best& b) {
-    for (unsigned j = s; j < e; j += 4) {
-        float4 t[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) t[k] = lds128(base + min(j + k, e - 1) * 16u);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float dx = t[k].x - qx, dy = t[k].y - qy, dz = t[k].z - qz;
-            const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-            const int idx = __float_as_int(t[k].w);
-            if (d < b.d || (d == b.d && idx < b.idx)) {
-                b.d = d;
-                b.j = (int)min(j + k, e - 1);
-                b.idx = idx;
-                b.x = t[k].x;
-                b.y = t[k].y;
-                b.z = t[k].z;
-            }
-        }
-    }
-}
+template <bool COLORED>
+struct IcpStagedSmem {   // dynamic shared memory of icp_iteration_kernel
+    IcpStage<COLORED> stage[kThreads / 32][2];
+#if ICP_TRANSPOSE_SMEM
+    float tr[kThreads / 32][kTrFloats];
+#endif
+};
 
-template <bool L2LOSS, int MODE>
+template <bool L2LOSS, int MODE, bool COLORED = false>
 __global__ void __launch_bounds__(kThreads, ICP_MIN_BLOCKS)
-icp_iteration_tile_kernel(IcpArgs a) {
+icp_iteration_kernel(const __grid_constant__ IcpArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    TileSmem& sm = *reinterpret_cast<TileSmem*>(smem_raw);
+    IcpStagedSmem<COLORED>& sm = *reinterpret_cast<IcpStagedSmem<COLORED>*>(smem_raw);
     __shared__ double s_warp[kThreads / 32][kSumStride];
     __shared__ double s_final[kSumStride];
     __shared__ float s_U[16];
     __shared__ int s_done;
-    if (threadIdx.x == 0) {
-        s_done = *(volatile int*)&a.st->done;
-        mbar_init(&sm.mbar, 1);
-    }
-    if (threadIdx.x < 16) s_U[threadIdx.x] = a.st->Uf[threadIdx.x];
+    __shared__ __align__(8) unsigned long long s_mbar[kThreads / 32][2];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     for (int k = threadIdx.x; k < (kThreads / 32) * kSumStride; k += kThreads) (&s_warp[0][0])[k] = 0.0;
+    if (threadIdx.x < 2 * (kThreads / 32)) mbar_init(&s_mbar[0][0] + threadIdx.x, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // Programmatic dependent launch: this grid may become resident while the previous iteration's last
+    // block is still in its serial epilogue; nothing produced by that kernel is read before the wait.
+    ICP_STAMP(0);   // block resident
+    if (ICP_TIMING && a.dbg && threadIdx.x == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        a.dbg[(size_t)blockIdx.x * 8 + 6] = smid;
+    }
+    pdl_wait();
+    pdl_launch_dependents();
+    ICP_STAMP(1);   // predecessor complete
+    if (threadIdx.x == 0) s_done = *(volatile int*)&a.st->done;
+    if (threadIdx.x < 16) s_U[threadIdx.x] = a.st->Uf[threadIdx.x];
     __syncthreads();
     if (MODE == 0 && s_done) return;
 
-    const Grid& g = a.g;
-    const int kBig = 0x3fffffff;
-    unsigned phase = 0;
-    float acc[kNumSums];
+    // chunk c of this warp covers working-source positions [q0(c), q0(c) + 32); the arrays are padded to
+    // a multiple of 256 entries, so a chunk that starts below n can always be copied whole
+    const int n = (int)a.n;
+    const int stride = gridDim.x * kThreads;
+    const int first = blockIdx.x * kThreads + w * 32;
+    constexpr unsigned kBytesA = 32 * sizeof(float4) + 32 * sizeof(int) + 32 * sizeof(float);
+    auto issue_a = [&](int c, int q0) {        // lane 0: TMA bulk copies of chunk c into slot c & 1
+        if (lane == 0 && q0 < n) {
+            IcpStage<COLORED>& sl = sm.stage[w][c & 1];
+            unsigned long long* mb = &s_mbar[w][c & 1];
+            mbar_expect_tx(mb, kBytesA);
+            bulk_g2s(sl.p, a.src + q0, 32 * sizeof(float4), mb);
+            bulk_g2s(sl.jp, a.prev + q0, 32 * sizeof(int), mb);
+            bulk_g2s(sl.d2, a.dprev + q0, 32 * sizeof(float), mb);
+        }
+    };
+    auto issue_b = [&](int c, int q0) {        // every lane: gather its seed's rows of chunk c (needs A(c))
+        if (q0 < n) {
+            IcpStage<COLORED>& sl = sm.stage[w][c & 1];
+            mbar_wait(&s_mbar[w][c & 1], (unsigned)(c >> 1) & 1u);
+            const int jp = kSeeded ? sl.jp[lane] : -1;
+            if (MODE == 0 && jp >= 0) {
+                cp_async16(&sl.ns[lane], a.nrm + jp);
+                if (COLORED) cp_async16(&sl.cg[lane], a.tcg + jp);
+            }
+        }
+        cp_async_commit();
+    };
+
+    double acc64 = 0.0;      // lane l: running total of slot l over this warp's queries
+    issue_a(0, first);
+    issue_a(1, first + stride);
+    issue_b(0, first);
+    int c = 0;
+    for (int q0 = first; q0 < n; q0 += stride, ++c) {
+        IcpStage<COLORED>& sl = sm.stage[w][c & 1];
+        // A(c) has landed: every lane waited on its mbarrier in issue_b(c), one trip ago (or in the prologue)
+        cp_async_wait_all();                                       // B(c)
+        const float4 p = sl.p[lane];
+        const int jp = kSeeded ? sl.jp[lane] : -1;
+        const float d2_prev = sl.d2[lane];
+        __syncwarp();          // every lane has read p / jp / d2 of slot c & 1: hand that part back to the producer
+        issue_a(c + 2, q0 + 2 * stride);
+        issue_b(c + 1, q0 + stride);
+        // (ns / cg of slot c & 1 are rewritten by issue_b(c + 2), i.e. in the NEXT trip: still valid below)
+        const int i = q0 + lane;
+        float term[32];
 #pragma unroll
-    for (int k = 0; k < kNumSums; ++k) acc[k] = 0.f;
-    int since = 0;
-    for (int64_t base = (int64_t)blockIdx.x * kThreads; base < a.n; base += (int64_t)gridDim.x * kThreads) {
-        const int64_t i = base + threadIdx.x;
-        const bool live = i < a.n;
-        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (live) {
-            p = a.src[i];
-            apply_transform(s_U, p.x, p.y, p.z);   // Registration.cpp:322 (PointCloud::Transform), fused
-            a.src[i] = p;
-        }
-        // ---- this query's pass-1 cell box and the block's union of them
-        float gx, gy, gz;   // the query in grid axis order
-        to_grid(g, p.x, p.y, p.z, gx, gy, gz);
-        const bool inside = live && !(hi_bound(gx, a.rr) < g.bmin[0] || lo_bound(gx, a.rr) > g.bmax[0] ||
-                                      hi_bound(gy, a.rr) < g.bmin[1] || lo_bound(gy, a.rr) > g.bmax[1] ||
-                                      hi_bound(gz, a.rr) < g.bmin[2] || lo_bound(gz, a.rr) > g.bmax[2] ||
-                                      !(p.x == p.x) || !(p.y == p.y) || !(p.z == p.z));
-        int x0 = kBig, x1 = -kBig, y0 = kBig, y1 = -kBig, z0 = kBig, z1 = -kBig;
-        if (inside) {
-            x0 = cell1(lo_bound(gx, a.r1), g.ox, g.inv_cx, g.nx);
-            x1 = cell1(hi_bound(gx, a.r1), g.ox, g.inv_cx, g.nx);
-            y0 = cell1(lo_bound(gy, a.r1), g.oy, g.inv_c, g.ny);
-            y1 = cell1(hi_bound(gy, a.r1), g.oy, g.inv_c, g.ny);
-            z0 = cell1(lo_bound(gz, a.r1), g.oz, g.inv_c, g.nz);
-            z1 = cell1(hi_bound(gz, a.r1), g.oz, g.inv_c, g.nz);
-        }
-        if (threadIdx.x < 6) sm.bbox[threadIdx.x] = (threadIdx.x & 1) ? -kBig : kBig;
-        __syncthreads();
-        {
-            int mn[3] = {x0, y0, z0}, mx[3] = {x1, y1, z1};
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    mn[k] = min(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
-                    mx[k] = max(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
-                }
-            }
-            if ((threadIdx.x & 31) == 0) {
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    atomicMin(&sm.bbox[2 * k], mn[k]);
-                    atomicMax(&sm.bbox[2 * k + 1], mx[k]);
-                }
-            }
-        }
-        __syncthreads();
-        const int BX0 = sm.bbox[0], BX1 = sm.bbox[1], BY0 = sm.bbox[2], BY1 = sm.bbox[3], BZ0 = sm.bbox[4],
-                  BZ1 = sm.bbox[5];
-        const int ty = BY1 - BY0 + 1, tz = BZ1 - BZ0 + 1, W = BX1 - BX0 + 2;   // W entries per row
-        const int rows = ty * tz;
-        bool tile_ok = BX0 <= BX1 && rows <= kTileRows && (int64_t)rows * W <= kTileCs;
-        // ---- stage the cell_start segments of every row of the box (coalesced)
-        if (tile_ok) {
-            for (int e = threadIdx.x; e < rows * W; e += kThreads) {
-                const int r = e / W, k = e - r * W;
-                const int iy = BY0 + r % ty, iz = BZ0 + r / ty;
-                sm.cs[e] = __ldg(&a.cs[(iz * g.ny + iy) * g.nx + BX0 + k]);
-            }
-        }
-        __syncthreads();
-        // ---- per-row candidate runs -> shared offsets; one bulk copy per non-empty row
-        unsigned cnt = 0, gstart = 0;
-        if (tile_ok && threadIdx.x < rows) {
-            gstart = sm.cs[threadIdx.x * W];
-            cnt = sm.cs[threadIdx.x * W + W - 1] - gstart;
-        }
-        unsigned total;
-        const unsigned off = block_exclusive_scan(cnt, total);
-        tile_ok = tile_ok && total <= (unsigned)kTilePts;
-        if (tile_ok) {
-            if (threadIdx.x < rows) sm.row_delta[threadIdx.x] = (int)off - (int)gstart;
-            if (threadIdx.x == 0) mbar_expect_tx(&sm.mbar, total * 16u);
-        }
-        __syncthreads();
-        if (tile_ok) {
-            if (cnt > 0) bulk_g2s(&sm.pts[off], a.tgt + gstart, cnt * 16u, &sm.mbar);
-            mbar_wait(&sm.mbar, phase);
-            phase ^= 1u;
-        }
-        // ---- search
-        Best b;
-        b.d = a.thr;
-        b.j = -1;
-        b.idx = 0x7fffffff;
-        b.x = b.y = b.z = 0.f;
-        if (inside) {
-            bool need_global = !tile_ok;
-            if (tile_ok) {
-                const unsigned pts_base = smem_u32(sm.pts);
-                for (int iz = z0; iz <= z1; ++iz)
-                    for (int iy = y0; iy <= y1; ++iy) {
-                        const int r = (iz - BZ0) * ty + (iy - BY0);
-                        const unsigned s = sm.cs[r * W + (x0 - BX0)], e = sm.cs[r * W + (x1 - BX0) + 1];
-                        scan_range_smem(pts_base + (unsigned)sm.row_delta[r] * 16u, s, e, p.x, p.y, p.z, b);
-                    }
-                need_global = !(b.j >= 0 && b.d <= a.r1_accept2) && a.r1 < a.rr;
-            }
-            if (need_global) nn_search_two_pass(g, a.tgt, a.cs, p.x, p.y, p.z, a.r1, a.r1_accept2, a.rr, a.thr, b);
-        }
-        if (live) {
-            if (b.j >= 0) {
-                if (MODE == 0) {
-                    const float4 nn = __ldg(&a.nrm[b.j]);
-                    accumulate_p2plane<L2LOSS>(acc, a.rk, p.x, p.y, p.z, b.x, b.y, b.z, nn.x, nn.y, nn.z);
-                } else {
-                    acc[28] += 1.0f;
-                }
-                acc[29] += b.d;
-            }
-            if (MODE == 1 && a.corr_out) a.corr_out[__float_as_int(p.w)] = b.j >= 0 ? (int64_t)b.idx : (int64_t)-1;
-        }
-        if (++since == kFlushEvery) {
-            flush_acc(acc, s_warp);
-            since = 0;
-        }
-        __syncthreads();   // everyone is done with the tile before the next chunk overwrites it
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int k = 0; k < 32; ++k) term[k] = 0.f;
+        bool matched = false;
+        if (i < n)
+            matched = icp_process_query<L2LOSS, MODE, COLORED>(a, s_U, i, p, jp, d2_prev, &sl.ns[lane],
+                                                               &sl.cg[COLORED ? lane : 0], term);
+#if ICP_TRANSPOSE_SMEM
+        icp_accumulate_chunk_smem(term, matched, sm.tr[w], acc64);
+#else
+        icp_accumulate_chunk(term, matched, acc64);
+#endif
     }
-    flush_acc(acc, s_warp);
-    if (!block_reduce_to_global(s_warp, a.partials, &a.st->ticket, s_final)) return;
-    if (a.fuse_finalize) {
-        if (threadIdx.x == 0) {
-            if (MODE == 0) icp_finalize_iteration(a, s_final);
-            else icp_finalize_evaluate(a, s_final);
-        }
-    } else if (threadIdx.x < kNumSums) {
-        a.st->sums[threadIdx.x] = s_final[threadIdx.x];
-    }
+    if (lane < kNumSums) s_warp[w][lane] = acc64;
+    icp_block_epilogue<MODE>(a, s_warp, s_final);
 }
 
 // Multi-GPU: runs after the all-reduce of st->sums.
 template <int MODE>
-__global__ void icp_finalize_kernel(IcpArgs a) {
-    if (threadIdx.x != 0) return;
+__global__ void icp_finalize_kernel(IcpArgs a) {   // <<<1, 32>>>
+    __shared__ double s_scratch[64];
     if (MODE == 0) {
         if (a.st->done) return;
-        icp_finalize_iteration(a, a.st->sums);
-    } else {
+        icp_finalize_iteration(a, a.st->sums, s_scratch);
+    } else if (threadIdx.x == 0) {
         icp_finalize_evaluate(a, a.st->sums);
     }
 }
@@ -1209,11 +1258,16 @@ __global__ void icp_finalize_kernel(IcpArgs a) {
 struct o3db_icp {
     o3db_nns nns;
     o3db_icp_options opt{};
+    cudaStream_t stream = 0;         // creation stream: allocations are freed on it (o3db_icp_destroy)
     const float* src_user = nullptr;
     int64_t n = 0;
+    int64_t n_pad = 0;               // n rounded up to whole 256-entry chunks (allocation size of src4 / prev)
     double n_total = 0;
     double init_T[16];
     float4* src4 = nullptr;
+    int* prev = nullptr;             // search seeds (see IcpArgs::prev)
+    float* dprev = nullptr;          // dist^2 to the seed (see IcpArgs::dprev)
+    long long* dbg = nullptr;        // ICP_TIMING builds only
     unsigned* src_key = nullptr;     // cell key of every source point (sort order)
     unsigned* src_rank = nullptr;
     unsigned* src_start = nullptr;   // CSR offsets of the source sort
@@ -1223,7 +1277,7 @@ struct o3db_icp {
     IcpState* h_st = nullptr;        // pinned
     o3db_comm* comm = nullptr;
     int grid_blocks = 0;
-    int variant = 2;                 // 1 = direct global search, 2 = TMA-staged tiles
+    int variant = 2;                 // 1 = direct loads, 2 = staged (TMA + cp.async ring; default)
     int64_t src_keys = 0;            // size of the source sort key space
     int launched = 0;
     bool l2loss = true;
@@ -1237,6 +1291,40 @@ struct o3db_icp {
 
 namespace o3db {
 
+typedef void (*IcpKernel)(IcpArgs);
+// mode 0 = iterate (loss / colour / variant of the handle), 1 = final evaluation (no Jacobian)
+static IcpKernel icp_kernel_for(const o3db_icp* c, int mode) {
+    if (c->variant == 1) {
+        if (mode == 1) return icp_iteration_direct_kernel<true, 1, false>;
+        if (c->colored) return c->l2loss ? icp_iteration_direct_kernel<true, 0, true> : icp_iteration_direct_kernel<false, 0, true>;
+        return c->l2loss ? icp_iteration_direct_kernel<true, 0, false> : icp_iteration_direct_kernel<false, 0, false>;
+    }
+    if (mode == 1) return icp_iteration_kernel<true, 1, false>;
+    if (c->colored) return c->l2loss ? icp_iteration_kernel<true, 0, true> : icp_iteration_kernel<false, 0, true>;
+    return c->l2loss ? icp_iteration_kernel<true, 0, false> : icp_iteration_kernel<false, 0, false>;
+}
+
+// Launch with the programmatic-stream-serialization attribute: the kernel's griddepcontrol.wait orders it
+// after the previous kernel on the stream; everything before that wait may overlap the predecessor's tail.
+// dynamic shared memory of the handle's iteration kernels (the staged variant: stage ring + transpose tile)
+static size_t icp_smem_bytes(const o3db_icp* c, int mode) {
+    if (c->variant == 1) return 0;
+    return (c->colored && mode == 0) ? sizeof(IcpStagedSmem<true>) : sizeof(IcpStagedSmem<false>);
+}
+
+static cudaError_t launch_icp(IcpKernel kernel, int blocks, size_t smem, cudaStream_t st, const IcpArgs& a) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)blocks);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = ICP_PDL ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, a);
+}
 static IcpArgs make_args(o3db_icp* c) {
     IcpArgs a{};
     a.g = c->nns.g;
@@ -1244,12 +1332,16 @@ static IcpArgs make_args(o3db_icp* c) {
     a.nrm = c->nns.nrm4;
     a.cs = c->nns.cell_start;
     a.src = c->src4;
+    a.prev = c->prev;
+    a.dprev = c->dprev;
+    a.dbg = c->dbg;
     a.n = c->n;
     a.n_total = c->n_total;
     const float r = (float)c->opt.max_correspondence_distance;
     a.thr = r * r;                       // FixedRadiusSearchImpl.cuh:692: T(radius) * T(radius)
     a.rr = r * (1.0f + 1e-6f);
-    a.r1 = fminf(c->nns.g.c, a.rr);
+    // unseeded first pass: a box of at least half the radius (and at least one cell)
+    a.r1 = fminf(fmaxf(c->nns.g.c, 0.5f * (1.0f + 1e-4f) * r), a.rr);
     a.r1_accept2 = (a.r1 * (1.0f - 1e-4f)) * (a.r1 * (1.0f - 1e-4f));
     a.rk.method = c->opt.kernel.method;
     a.rk.scale = (float)c->opt.kernel.scale;
@@ -1277,6 +1369,8 @@ static int icp_init_state(o3db_icp* c, cudaStream_t st) {
     }
     memcpy(c->h_st, &h, sizeof(h));
     O3DB_CUDA_CHECK(cudaMemcpyAsync(c->st, c->h_st, sizeof(IcpState), cudaMemcpyHostToDevice, st));
+    O3DB_CUDA_CHECK(cudaMemsetAsync(c->prev, 0xff, (size_t)c->n_pad * sizeof(int), st));   // no seeds yet
+    O3DB_CUDA_CHECK(cudaMemsetAsync(c->dprev, 0x7f, (size_t)c->n_pad * sizeof(float), st)); // 0x7f7f7f7f = 3.4e38: no bound
     c->launched = 0;
     return O3DB_OK;
 }
@@ -1315,7 +1409,8 @@ int o3db_nns_create(const float* points_dev, int64_t num_points, double radius, 
 
 void o3db_nns_destroy(o3db_nns* nns) {
     if (!nns) return;
-    nns_free(nns, 0);
+    cudaStreamSynchronize(nns->stream);   // searches may still be in flight on the creation stream
+    nns_free(nns, nns->stream);
     delete nns;
 }
 
@@ -1504,16 +1599,23 @@ int o3db_compute_pose_colored_icp(const float* source_dev, const float* source_c
 
 void o3db_icp_destroy(o3db_icp* c) {
     if (!c) return;
-    nns_free(&c->nns, 0);
-    if (c->src4) cudaFreeAsync(c->src4, 0);
-    if (c->src_key) cudaFreeAsync(c->src_key, 0);
-    if (c->src_rank) cudaFreeAsync(c->src_rank, 0);
-    if (c->src_start) cudaFreeAsync(c->src_start, 0);
-    if (c->partials) cudaFreeAsync(c->partials, 0);
-    if (c->per_iter) cudaFreeAsync(c->per_iter, 0);
-    if (c->st) cudaFreeAsync(c->st, 0);
-    if (c->tcg4) cudaFreeAsync(c->tcg4, 0);
-    if (c->sint) cudaFreeAsync(c->sint, 0);
+    // Every buffer was allocated, and all work on it enqueued, on the handle's stream: drain it, then
+    // free in stream order on the same stream (the pinned block may still be the target of a D2H copy).
+    cudaStream_t st = c->stream;
+    cudaStreamSynchronize(st);
+    nns_free(&c->nns, st);
+    if (c->src4) cudaFreeAsync(c->src4, st);
+    if (c->prev) cudaFreeAsync(c->prev, st);
+    if (c->dprev) cudaFreeAsync(c->dprev, st);
+    if (c->dbg) cudaFreeAsync(c->dbg, st);
+    if (c->src_key) cudaFreeAsync(c->src_key, st);
+    if (c->src_rank) cudaFreeAsync(c->src_rank, st);
+    if (c->src_start) cudaFreeAsync(c->src_start, st);
+    if (c->partials) cudaFreeAsync(c->partials, st);
+    if (c->per_iter) cudaFreeAsync(c->per_iter, st);
+    if (c->st) cudaFreeAsync(c->st, st);
+    if (c->tcg4) cudaFreeAsync(c->tcg4, st);
+    if (c->sint) cudaFreeAsync(c->sint, st);
     if (c->h_st) pinned_release(c->h_st);
     delete c;
 }
@@ -1538,13 +1640,14 @@ static int icp_create_impl(const float* source_dev, int64_t n, const float* targ
     // Registration.cpp:119-219 AssertInputMultiScaleICP
     O3DB_REQUIRE(source_dev && target_dev && n > 0 && m > 0, "Source and/or Target pointcloud is empty.");
     O3DB_REQUIRE(target_normals_dev != nullptr, "Target pointcloud missing normals attribute.");
-    O3DB_REQUIRE(n < INT_MAX && m < INT_MAX, "o3db_icp_create: too many points");
+    O3DB_REQUIRE(n < INT_MAX - 2048 && m < INT_MAX - 2048, "o3db_icp_create: too many points");
     O3DB_REQUIRE(options->max_correspondence_distance > 0, "max_correspondence_distance must be positive");
     O3DB_REQUIRE(options->max_iteration >= 0, "max_iteration must be non-negative");
     cudaStream_t st = (cudaStream_t)stream;
     o3db_icp* c = new (std::nothrow) o3db_icp();
     O3DB_REQUIRE(c != nullptr, "out of host memory");
     c->opt = *options;
+    c->stream = st;
     c->src_user = source_dev;
     c->n = n;
     c->comm = comm;
@@ -1580,38 +1683,31 @@ static int icp_create_impl(const float* source_dev, int64_t n, const float* targ
     } while (0)
     // fitness denominator over all ranks
     c->n_total = (double)n;
-    // 1 = direct (two-pass search straight from global/L1), 2 = TMA-staged shared-memory tiles.
-    // Default: whichever measured faster on B200 — currently the direct kernel.
-    c->variant = options->search_variant == 2 ? 2 : (options->search_variant == 1 ? 1 : ICP_DEFAULT_VARIANT);
-    if (c->colored) c->variant = 1;   // the tile-staged kernel has no coloured instantiation
+    // 1 = direct (every load where it is needed), 2 = staged (TMA bulk copies + cp.async gathers one chunk
+    // ahead).  Default: whichever measured faster on B200.
+    c->variant = options->search_variant == 1 ? 1 : (options->search_variant == 2 ? 2 : ICP_DEFAULT_VARIANT);
     int occ = 1;
-    if (c->colored) {
-        if (c->l2loss)
-            ICP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, icp_iteration_kernel<true, 0, true>, kThreads, 0));
-        else
-            ICP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, icp_iteration_kernel<false, 0, true>, kThreads, 0));
-    } else if (c->variant == 2) {
-        const int smem = (int)sizeof(TileSmem);
-        ICP_CUDA(cudaFuncSetAttribute(icp_iteration_tile_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        ICP_CUDA(cudaFuncSetAttribute(icp_iteration_tile_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        ICP_CUDA(cudaFuncSetAttribute(icp_iteration_tile_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        if (c->l2loss)
-            ICP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, icp_iteration_tile_kernel<true, 0>, kThreads, smem));
-        else
-            ICP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, icp_iteration_tile_kernel<false, 0>, kThreads, smem));
-    } else if (c->l2loss) {
-        ICP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, icp_iteration_kernel<true, 0>, kThreads, 0));
-    } else {
-        ICP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, icp_iteration_kernel<false, 0>, kThreads, 0));
-    }
+    for (int mode = 0; mode < 2; ++mode)
+        ICP_CUDA(cudaFuncSetAttribute(icp_kernel_for(c, mode), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)icp_smem_bytes(c, mode)));
+    ICP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, icp_kernel_for(c, 0), kThreads, icp_smem_bytes(c, 0)));
     c->grid_blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, kThreads), (int64_t)num_sms() * std::max(occ, 1)));
     const int64_t ncell = tiled_key_space(c->nns.g.nx, c->nns.g.ny, c->nns.g.nz);   // tile-major source keys
     c->src_keys = ncell;
-    ICP_CUDA(cudaMallocAsync(&c->src4, n * sizeof(float4), st));
+    // padded to whole 256-entry chunks: the staged kernel copies 32-entry chunks with TMA bulk copies
+    c->n_pad = ceil_div(n, kThreads) * kThreads;
+    ICP_CUDA(cudaMallocAsync(&c->src4, c->n_pad * sizeof(float4), st));
+    ICP_CUDA(cudaMallocAsync(&c->prev, c->n_pad * sizeof(int), st));
+    ICP_CUDA(cudaMallocAsync(&c->dprev, c->n_pad * sizeof(float), st));
+    ICP_CUDA(cudaMemsetAsync(c->src4 + n, 0, (c->n_pad - n) * sizeof(float4), st));
     ICP_CUDA(cudaMallocAsync(&c->src_key, n * sizeof(unsigned), st));
     ICP_CUDA(cudaMallocAsync(&c->src_rank, n * sizeof(unsigned), st));
     ICP_CUDA(cudaMallocAsync(&c->src_start, (ncell + 1) * sizeof(unsigned), st));
     ICP_CUDA(cudaMallocAsync(&c->partials, (size_t)c->grid_blocks * kSumStride * sizeof(double), st));
+#if ICP_TIMING
+    ICP_CUDA(cudaMallocAsync(&c->dbg, (size_t)c->grid_blocks * 8 * sizeof(long long), st));
+    ICP_CUDA(cudaMemsetAsync(c->dbg, 0, (size_t)c->grid_blocks * 8 * sizeof(long long), st));
+#endif
     ICP_CUDA(cudaMallocAsync(&c->per_iter, (size_t)std::max(1, options->max_iteration) * 2 * sizeof(double), st));
     ICP_CUDA(cudaMallocAsync(&c->st, sizeof(IcpState), st));
     static_assert(sizeof(IcpState) <= 4096, "IcpState must fit a pinned block");
@@ -1635,6 +1731,7 @@ static int icp_create_impl(const float* source_dev, int64_t n, const float* targ
     ICP_CUDA(cudaGetLastError());
     ICP_TRY(exclusive_scan_u32(c->src_start, ncell, scratch, st));
     ICP_CUDA(cudaFreeAsync(scratch, st));
+    ICP_TRY(canonical_ranks(n, c->src_start, c->src_key, c->src_rank, st));
     ICP_TRY(icp_gather_source(c, st));
     if (c->colored) {
         ICP_CUDA(cudaMallocAsync(&c->tcg4, m * sizeof(float4), st));
@@ -1693,6 +1790,16 @@ int o3db_icp_create_colored(const float* source_dev, const float* source_colors_
     return icp_create_impl(source_dev, n, target_dev, target_normals_dev, m, init_T, options, comm, col, stream, out);
 }
 
+#if ICP_TIMING
+// diagnostics build only: copies the per-block timestamps of the most recent iteration launch (8 per block)
+int o3db_icp_debug_timing(o3db_icp* c, long long* out_host, int max_blocks, int* blocks) {
+    cudaStreamSynchronize(c->stream);
+    const int nb = std::min(max_blocks, c->grid_blocks);
+    if (blocks) *blocks = c->grid_blocks;
+    return cudaMemcpy(out_host, c->dbg, (size_t)nb * 8 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? O3DB_OK : O3DB_ERR_CUDA;
+}
+#endif
+
 int o3db_icp_reset(o3db_icp* c, void* stream) {
     O3DB_REQUIRE(c != nullptr, "o3db_icp_reset: null handle");
     cudaStream_t st = (cudaStream_t)stream;
@@ -1707,16 +1814,7 @@ int o3db_icp_iterate(o3db_icp* c, int iterations, void* stream) {
     const int todo = std::min(iterations, c->opt.max_iteration - c->launched);
     IcpArgs a = make_args(c);
     for (int k = 0; k < todo; ++k) {
-        if (c->variant == 2) {
-            if (c->l2loss) icp_iteration_tile_kernel<true, 0><<<c->grid_blocks, kThreads, sizeof(TileSmem), st>>>(a);
-            else icp_iteration_tile_kernel<false, 0><<<c->grid_blocks, kThreads, sizeof(TileSmem), st>>>(a);
-        } else if (c->colored) {
-            if (c->l2loss) icp_iteration_kernel<true, 0, true><<<c->grid_blocks, kThreads, 0, st>>>(a);
-            else icp_iteration_kernel<false, 0, true><<<c->grid_blocks, kThreads, 0, st>>>(a);
-        } else {
-            if (c->l2loss) icp_iteration_kernel<true, 0><<<c->grid_blocks, kThreads, 0, st>>>(a);
-            else icp_iteration_kernel<false, 0><<<c->grid_blocks, kThreads, 0, st>>>(a);
-        }
+        launch_icp(icp_kernel_for(c, 0), c->grid_blocks, icp_smem_bytes(c, 0), st, a);
         O3DB_LAUNCH_CHECK();
         if (c->comm) {
             int rc = o3db_comm_allreduce_f64(c->comm, (double*)((char*)c->st + offsetof(IcpState, sums)), kNumSums, st);
@@ -1735,8 +1833,7 @@ int o3db_icp_finish(o3db_icp* c, o3db_icp_result* result, int64_t* correspondenc
     cudaStream_t st = (cudaStream_t)stream;
     IcpArgs a = make_args(c);
     a.corr_out = correspondences_dev;
-    if (c->variant == 2) icp_iteration_tile_kernel<true, 1><<<c->grid_blocks, kThreads, sizeof(TileSmem), st>>>(a);
-    else icp_iteration_kernel<true, 1><<<c->grid_blocks, kThreads, 0, st>>>(a);
+    launch_icp(icp_kernel_for(c, 1), c->grid_blocks, icp_smem_bytes(c, 1), st, a);
     O3DB_LAUNCH_CHECK();
     if (c->comm) {
         int rc = o3db_comm_allreduce_f64(c->comm, (double*)((char*)c->st + offsetof(IcpState, sums)), kNumSums, st);

@@ -30,27 +30,86 @@ __device__ __forceinline__ void flush_acc(float (&acc)[kNumSums], double (*s_war
     }
 }
 
+// Transposed warp reduction (the fused ICP kernels): every lane brings one query's 30 terms, lane l leaves
+// with the sum over the warp of term l.  Five exchange steps; in step `half` a lane keeps one half of its
+// remaining terms and trades the other half with lane ^ half, so a term costs one shuffle in total
+// (16 + 8 + 4 + 2 + 1 = 31 shuffles for 32 slots) instead of five, and the running totals of a warp live in
+// ONE register per lane instead of 30: the search keeps the register file.  The association is a fixed
+// binary tree over the lanes: deterministic.
+__device__ __forceinline__ float warp_transpose_sum32(float (&v)[32]) {
+    const unsigned lane = threadIdx.x & 31u;
+#pragma unroll
+    for (int half = 16; half >= 1; half >>= 1) {
+        const bool up = (lane & half) != 0;
+#pragma unroll
+        for (int k = 0; k < half; ++k) {
+            const float keep = up ? v[k + half] : v[k];
+            const float send = up ? v[k] : v[k + half];
+            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+        }
+    }
+    return v[0];
+}
+
+#ifndef O3DB_FENCE_ACQREL
+#define O3DB_FENCE_ACQREL 0
+#endif
+// release of the block partial before the ticket / acquire of everybody's partials after it
+__device__ __forceinline__ void reduce_fence() {
+#if O3DB_FENCE_ACQREL
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+#else
+    __threadfence();
+#endif
+}
+
 // Block epilogue: per-warp slots -> block partial -> (last block) grand total in
 // block-index order.  Returns true in the last block, with s_final[] filled.
 __device__ __forceinline__ bool block_reduce_to_global(double (*s_warp)[kSumStride], double* __restrict__ partials,
-                                                       unsigned* ticket, double* s_final) {
+                                                       unsigned* ticket, double* s_final,
+                                                       long long* stamps = nullptr) {
     __shared__ bool s_last;
     __syncthreads();
+    if (stamps && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(stamps[0]));
     if (threadIdx.x < kNumSums) {
         double v = 0;
 #pragma unroll
         for (int w = 0; w < kThreads / 32; ++w) v += s_warp[w][threadIdx.x];
         partials[(size_t)blockIdx.x * kSumStride + threadIdx.x] = v;
     }
-    __threadfence();
+    reduce_fence();
     __syncthreads();
     if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
     __syncthreads();
     if (!s_last) return false;
-    __threadfence();
+    if (stamps && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(stamps[1]));
+    reduce_fence();
+    // Grand total by the WHOLE block (round 1 had 30 threads walk all per-block partials one dependent
+    // L2 round trip at a time: ~130k cycles for 444 blocks, a third of the kernel): warp w sums the blocks
+    // b = w, w + 8, ... for all 30 columns (lane = column, 256-byte coalesced rows, 8 loads in flight),
+    // then thread k adds the 8 per-warp totals in warp order.  The association is fixed by the launch
+    // shape, so the result is still deterministic for a given grid.
+    __shared__ double s_part[kThreads / 32][kSumStride];
+    {
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        constexpr int kW = kThreads / 32, kU = 8;
+        double v = 0;
+        unsigned b = w;
+        for (; b + (kU - 1) * kW < gridDim.x; b += kU * kW) {
+            double t[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) t[u] = __ldcg(&partials[(size_t)(b + u * kW) * kSumStride + lane]);
+#pragma unroll
+            for (int u = 0; u < kU; ++u) v += t[u];
+        }
+        for (; b < gridDim.x; b += kW) v += __ldcg(&partials[(size_t)b * kSumStride + lane]);
+        s_part[w][lane] = v;
+    }
+    __syncthreads();
     if (threadIdx.x < kNumSums) {
         double v = 0;
-        for (unsigned b = 0; b < gridDim.x; ++b) v += __ldcg(&partials[(size_t)b * kSumStride + threadIdx.x]);
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) v += s_part[w][threadIdx.x];
         s_final[threadIdx.x] = v;
     }
     if (threadIdx.x == 0) *ticket = 0;
@@ -97,6 +156,70 @@ __device__ __host__ inline bool solve6x6(const double* A, double* x) {
         x[r] = s / M[r][r];
     }
     return true;
+}
+
+// The same factorisation by one warp (the fused loops run it in the serial tail of every iteration, where
+// a single thread walking a 6 x 7 array in local memory cost ~5 us): lane c < 7 owns column c of the augmented
+// matrix in registers; per elimination step the pivot choice and the five multipliers are computed by the
+// owner of the pivot column and broadcast, every lane updates its own column.  Same operations on the same
+// operands as solve6x6 up to the back substitution, which runs column-oriented (as LAPACK's dtrsv does) from
+// shared memory on lane 0.  Must be called by all 32 lanes of a warp; `Ms` is 42 doubles of shared memory.
+// Returns false (on every lane) for a singular system.
+__device__ __forceinline__ bool solve6x6_warp(const double* __restrict__ A, double* __restrict__ Ms, double* x) {
+    const int lane = threadIdx.x & 31;
+    const int c_own = lane < 7 ? lane : 6;
+    double col[6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+        const int hi = r > c_own ? r : c_own, lo = r > c_own ? c_own : r;
+        col[r] = c_own == 6 ? -A[21 + r] : A[(hi * (hi + 1)) / 2 + lo];
+    }
+    bool ok = true;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+        int piv = c;
+        double best = fabs(col[c]);
+#pragma unroll
+        for (int r = c + 1; r < 6; ++r)
+            if (fabs(col[r]) > best) {
+                best = fabs(col[r]);
+                piv = r;
+            }
+        piv = __shfl_sync(0xffffffffu, piv, c);
+        best = __shfl_sync(0xffffffffu, best, c);
+        if (!(best > 0.0)) ok = false;
+#pragma unroll
+        for (int r = c + 1; r < 6; ++r)
+            if (piv == r) {
+                const double t = col[c];
+                col[c] = col[r];
+                col[r] = t;
+            }
+#pragma unroll
+        for (int r = c + 1; r < 6; ++r) {
+            const double f = __shfl_sync(0xffffffffu, col[r] / col[c], c);
+            col[r] -= f * col[c];
+        }
+    }
+    if (lane < 7) {
+#pragma unroll
+        for (int r = 0; r < 6; ++r) Ms[r * 7 + lane] = col[r];
+    }
+    __syncwarp();
+    if (lane == 0 && ok) {
+        double b[6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) b[r] = Ms[r * 7 + 6];
+#pragma unroll
+        for (int k = 5; k >= 0; --k) {
+            const double xk = b[k] / Ms[k * 7 + k];
+            x[k] = xk;
+#pragma unroll
+            for (int r = 0; r < k; ++r) b[r] -= Ms[r * 7 + k] * xk;
+        }
+    }
+    __syncwarp();
+    return ok;
 }
 
 // TransformationConverterImpl.h:22-42 + TransformationConverter.cpp:81-104.

@@ -162,6 +162,8 @@ def _declare(L):
     L.orc_voxel_down_sample_f32.argtypes = [_f32p, _f32p, _f32p, C.c_int64, C.c_double, _f32p, _f32p, _f32p, _i32p]
     L.orc_num_threads.restype = C.c_int
     L.orc_num_threads.argtypes = []
+    L.orc_set_num_threads.restype = None
+    L.orc_set_num_threads.argtypes = [C.c_int]
 
 
 def _arr(a, dtype):
@@ -179,6 +181,20 @@ ROBUST = {"L2Loss": 0, "L1Loss": 1, "HuberLoss": 2, "CauchyLoss": 3, "GMLoss": 4
 
 def num_threads() -> int:
     return lib().orc_num_threads()
+
+
+def set_num_threads(n: int) -> int:
+    """OpenMP threads of the CPU legs (process-wide ICV: also covers oracle/_ref, which links the same libgomp)."""
+    lib().orc_set_num_threads(int(n))
+    return num_threads()
+
+
+def host_cores() -> int:
+    import os
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 def minivec_hash(keys) -> np.ndarray:

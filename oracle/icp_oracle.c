@@ -27,6 +27,16 @@ int orc_num_threads(void) {
 #endif
 }
 
+/* bench.py's CPU legs call this with the host's core count: launchers such as torchrun export
+ * OMP_NUM_THREADS=1, which would otherwise time the "all host threads" baseline on one core. */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* ------------------------------------------------------------------ hashes */
 
 /* core/hashmap/Dispatch.h:67-81 */

@@ -306,6 +306,7 @@ int orc_rgbd_odometry_multi_scale_p2plane(const void* source_depth, const void* 
                                           double* fitness, double* per_iter, int* executed);
 
 int orc_num_threads(void);
+void orc_set_num_threads(int n);
 
 #ifdef __cplusplus
 }

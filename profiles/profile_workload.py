@@ -22,14 +22,16 @@ if what in ("icp", "all"):
     src, tgt, nrm, _ = make_icp_pair(n, seed=2)
     d = [torch.from_numpy(a).cuda() for a in (src, tgt, nrm)]
     opt = L.IcpOptions()
-    opt.max_correspondence_distance, opt.max_iteration = 0.05, 6
+    icp_iters = int(os.environ.get("ICP_ITERS", 6))
+    opt.max_correspondence_distance, opt.max_iteration = 0.05, icp_iters
     opt.kernel = L.RobustKernel(0, 1.0, 1.0)
     opt.cell_scale = float(os.environ.get("CELL_SCALE", 0))
+    opt.search_variant = int(os.environ.get("ICP_VARIANT", 0))
     h = C.c_void_p()
     T0 = np.eye(4)
     L.check(L.lib.o3db_icp_create(d[0].data_ptr(), n, d[1].data_ptr(), d[2].data_ptr(), n, L.dptr(T0), C.byref(opt), None,
                                   stream, C.byref(h)))
-    L.check(L.lib.o3db_icp_iterate(h, 6, stream))
+    L.check(L.lib.o3db_icp_iterate(h, icp_iters, stream))
     res = L.IcpResult()
     L.check(L.lib.o3db_icp_finish(h, C.byref(res), None, None, stream))
     print("icp", res.fitness, res.inlier_rmse, res.num_iterations)

@@ -258,9 +258,11 @@ def test_icp_loop_vs_oracle(o3d, n, iters):
     assert res.num_iterations == ref.num_iterations == iters and res.converged == ref.converged
     assert len(log) == iters and [c["iteration_index"] for c in log] == list(range(iters))
     per = np.array([[c["fitness"], c["inlier_rmse"]] for c in log])
-    # iteration 0 sees bit-identical inputs: fitness must match exactly, rmse to f64 summation order
+    # iteration 0 sees bit-identical inputs: fitness must match exactly, rmse to summation order
     assert per[0, 0] == ref.per_iteration[0, 0]
-    assert abs(per[0, 1] - ref.per_iteration[0, 1]) < 1e-12
+    # (each warp sums its 32 squared distances as an f32 tree before the f64 accumulation: <= 5 * 2^-24 relative on
+    # the sum — the reference itself sums an f32 tensor, Registration.cpp:47-50)
+    assert abs(per[0, 1] - ref.per_iteration[0, 1]) < 3e-7 * ref.per_iteration[0, 1]
     # later iterations differ only through the f32 accumulation order of the update
     np.testing.assert_allclose(per[:, 0], ref.per_iteration[:, 0], atol=2e-4)
     np.testing.assert_allclose(per[:, 1], ref.per_iteration[:, 1], atol=2e-6)
@@ -478,7 +480,8 @@ def test_colored_icp_loop_vs_oracle(o3d, n, iters, robust):
                              relative_rmse=0, lambda_geometric=0.968, robust=robust or ("L2Loss", 1.0, 1.0))
     assert ref.status == 0 and res.num_iterations == ref.num_iterations == iters
     per = np.array([[c["fitness"], c["inlier_rmse"]] for c in log])
-    assert per[0, 0] == ref.per_iteration[0, 0] and abs(per[0, 1] - ref.per_iteration[0, 1]) < 1e-12
+    # (rmse: each warp sums its 32 terms as an f32 tree before the f64 accumulation, see test_icp_loop_vs_oracle)
+    assert per[0, 0] == ref.per_iteration[0, 0] and abs(per[0, 1] - ref.per_iteration[0, 1]) < 3e-7 * ref.per_iteration[0, 1]
     np.testing.assert_allclose(per[:, 0], ref.per_iteration[:, 0], atol=2e-4)
     np.testing.assert_allclose(per[:, 1], ref.per_iteration[:, 1], atol=2e-6)
     np.testing.assert_allclose(res.transformation, ref.transformation, atol=1e-7 if iters == 1 else 2e-5)
