@@ -105,10 +105,12 @@ __device__ __forceinline__ void scan_range(const float4* __restrict__ pts, unsig
 // `best` / `bj` come in initialised ("nothing": thr:INT_MAX / 0xffffffff, or a seed candidate) and are only
 // replaced by keys <= best.
 static constexpr unsigned kNoPoint = 0xffffffffu;
-template <int NS>
+// TRACK2: also keep d2nd = the smallest dist^2 among the scanned candidates that did NOT end up best (the
+// caller derives from it how far every point other than the winner is: see nn_search_seeded_fast).
+template <int NS, bool TRACK2>
 __device__ __forceinline__ void scan_slabs_flat(const float4* __restrict__ pts, const unsigned (&s)[NS],
                                                 const unsigned (&n)[NS], float qx, float qy, float qz,
-                                                unsigned long long& best, unsigned& bj) {
+                                                unsigned long long& best, unsigned& bj, float& d2nd) {
     unsigned pre[NS], off[NS];   // slab k covers virtual indices [pre[k], pre[k] + n[k]); global = off[k] + virtual
     unsigned total = 0;
 #pragma unroll
@@ -122,24 +124,29 @@ __device__ __forceinline__ void scan_slabs_flat(const float4* __restrict__ pts, 
         float4 t[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            // lanes that have run out of candidates issue no load (a warp's trip count is its longest lane's:
-            // the L1 data pipe, not the ALUs, is what this loop saturates — DESIGN.md §4.1)
-            const unsigned w = v + k;
+            const unsigned w = min(v + k, total - 1);   // the tail re-reads the last candidate (cannot change the result)
             unsigned o = off[0];
 #pragma unroll
             for (int q = 1; q < NS; ++q) o = w >= pre[q] ? off[q] : o;
             jj[k] = o + w;
-            t[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (w < total) t[k] = __ldg(&pts[jj[k]]);
+            t[k] = __ldg(&pts[jj[k]]);
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const float dx = t[k].x - qx, dy = t[k].y - qy, dz = t[k].z - qz;
             const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));   // canonical (see scan_range)
-            unsigned long long key =
+            const unsigned long long key =
                     ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_int(t[k].w);
-            if (v + k >= total) key = ~0ull;
-            if (key <= best) {   // d >= 0, so the bit patterns order like the values; NaN sorts last
+            if (TRACK2) {
+                // (a re-read of the current best — the loop's tail padding — must not count as a second point)
+                if (key < best) {
+                    d2nd = fminf(d2nd, __uint_as_float((unsigned)(best >> 32)));
+                    best = key;
+                    bj = jj[k];
+                } else if (key != best) {
+                    d2nd = fminf(d2nd, d);
+                }
+            } else if (key <= best) {   // d >= 0, so the bit patterns order like the values; NaN sorts last
                 best = key;
                 bj = jj[k];
             }
@@ -154,11 +161,11 @@ __device__ __forceinline__ void scan_slabs_flat(const float4* __restrict__ pts, 
 // All CSR loads are issued together, then all candidates four at a time: two dependent round trips whatever
 // the box size.  Returns false — nothing scanned, best / bj untouched — when the box spans more than NS
 // grid-z rows or a slab is long (volumetric data): the caller then prunes row by row (nn_search_from).
-template <int NS>
+template <int NS, bool TRACK2 = false>
 __device__ __forceinline__ bool scan_box_flat(const Grid& g, const float4* __restrict__ pts,
                                               const unsigned* __restrict__ cs, float gy, float gz, float qx,
                                               float qy, float qz, float rad, unsigned long long& best,
-                                              unsigned& bj) {
+                                              unsigned& bj, float* d2nd = nullptr) {
     const int y0 = cell1(lo_bound(gy, rad), g.oy, g.inv_c, g.ny), y1 = cell1(hi_bound(gy, rad), g.oy, g.inv_c, g.ny);
     const int z0 = cell1(lo_bound(gz, rad), g.oz, g.inv_c, g.nz), z1 = cell1(hi_bound(gz, rad), g.oz, g.inv_c, g.nz);
     if (z1 - z0 >= NS) return false;
@@ -177,7 +184,8 @@ __device__ __forceinline__ bool scan_box_flat(const Grid& g, const float4* __res
         longest = max(longest, n[dz]);
     }
     if (longest > kSlabMax) return false;
-    scan_slabs_flat<NS>(pts, s, n, qx, qy, qz, best, bj);
+    float dummy = 0.f;
+    scan_slabs_flat<NS, TRACK2>(pts, s, n, qx, qy, qz, best, bj, TRACK2 ? *d2nd : dummy);
     return true;
 }
 
@@ -288,28 +296,28 @@ __device__ __forceinline__ float dist2_canonical(const float4 t, float qx, float
     return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
 }
 
-// Seeded fast path, from a BOUND on the seed's distance instead of the seed point itself: the caller keeps,
-// per query, dist^2 to its winner of the previous iteration (`d2_prev`, computed from the stored f32 points)
-// and knows how far the query has moved since (`moved2` = |p_new - p_old|^2 of the stored f32 points).  By
-// the triangle inequality the old winner — an actual candidate — is now within sqrt(d2_prev) + sqrt(moved2),
-// so the exact nearest neighbour, and every point tying with it, lies inside that box: scanning it from
-// "nothing yet" returns the same winner, bit for bit, as the exhaustive search, without ever fetching the seed.
-// (Both roots come from the hardware reciprocal square root, 2 ulp; the 1e-4 margin also covers the f32
-// rounding of the two squared distances.)  Returns the winner's sorted position, or kNoPoint when nothing lies
-// within the radius; `handled` = false when the fast path does not apply (box taller than 3 cell rows,
-// long slabs): the caller then calls nn_search_slow.
-__device__ __forceinline__ unsigned nn_search_bounded_fast(const Grid& g, const float4* __restrict__ pts,
-                                                           const unsigned* __restrict__ cs, float qx, float qy,
-                                                           float qz, float rr, float thr, float d2_prev,
-                                                           float moved2, bool& handled) {
-    const float a = d2_prev > 0.f ? d2_prev * rsqrtf(d2_prev) : 0.f;
-    const float b = moved2 > 0.f ? moved2 * rsqrtf(moved2) : 0.f;
-    const float rad = fminf(rr, (a + b) * 1.0001f);
+// Seeded fast path.  ts = pts[seed_j] and sd = its canonical dist^2 <= thr (the caller has both: the staged
+// kernel fetched the seed one chunk ahead and needs the distance for its certificate).  The box [q - rad,
+// q + rad], rad = sqrt(sd) (hardware reciprocal square root, 2 ulp, with a 1e-4 margin), is scanned from
+// "nothing yet": it contains the seed, hence the exact winner and every point tying with it.
+// On return `handled` = false when the fast path does not apply (box taller than 3 cell rows, long slabs:
+// the caller then calls nn_search_slow); otherwise the winner's sorted position is returned and
+// `clearance` = a lower bound on the distance from the query to EVERY target point other than the winner:
+// min(sqrt(d2nd), rad) — a point that was not scanned lies outside the box, i.e. farther than rad along
+// grid-y or grid-z (binning is monotone; lo_bound / hi_bound only widen the box).
+__device__ __forceinline__ unsigned nn_search_seeded_fast(const Grid& g, const float4* __restrict__ pts,
+                                                          const unsigned* __restrict__ cs, float qx, float qy,
+                                                          float qz, float rr, float thr, float sd, bool& handled,
+                                                          float& clearance) {
+    const float rad = sd > 0.f ? fminf(rr, sd * rsqrtf(sd) * 1.0001f) : 0.f;
     float gx, gy, gz;
     to_grid(g, qx, qy, qz, gx, gy, gz);
     unsigned long long best = ((unsigned long long)__float_as_uint(thr) << 32) | 0x7fffffffull;
     unsigned bj = kNoPoint;
-    handled = scan_box_flat<3>(g, pts, cs, gy, gz, qx, qy, qz, rad, best, bj);
+    float d2nd = __int_as_float(0x7f7fffff);
+    handled = scan_box_flat<3, true>(g, pts, cs, gy, gz, qx, qy, qz, rad, best, bj, &d2nd);
+    // rounded down: 2 ulp of the reciprocal square root and the f32 rounding of d2nd are inside the 1e-5
+    clearance = fminf(rad, d2nd * rsqrtf(fmaxf(d2nd, 1e-37f)) * 0.99999f);
     return bj;
 }
 
@@ -326,28 +334,36 @@ __device__ __noinline__ unsigned nn_search_slow(const Grid* gp, const float4* __
     const Grid& g = *gp;
     unsigned long long best = ((unsigned long long)__float_as_uint(thr) << 32) | 0x7fffffffull;
     unsigned bj = kNoPoint;
+    unsigned long long seed_key = ~0ull;
     float rad = rr;
     if (seed_j >= 0) {
         const float4 ts = __ldg(&pts[seed_j]);
         const float sd = dist2_canonical(ts, qx, qy, qz);
         if (sd <= thr) {
-            best = ((unsigned long long)__float_as_uint(sd) << 32) | (unsigned)__float_as_int(ts.w);
-            bj = (unsigned)seed_j;
+            seed_key = ((unsigned long long)__float_as_uint(sd) << 32) | (unsigned)__float_as_int(ts.w);
             rad = fminf(rr, sqrtf(sd) * 1.00001f);
         }
     }
     float gx, gy, gz;
     to_grid(g, qx, qy, qz, gx, gy, gz);
-    if (bj == kNoPoint) {
+    if (seed_key == ~0ull) {
         // entirely outside the bounding box (or NaN): no candidate can pass
         if (hi_bound(gx, rr) < g.bmin[0] || lo_bound(gx, rr) > g.bmax[0] || hi_bound(gy, rr) < g.bmin[1] ||
             lo_bound(gy, rr) > g.bmax[1] || hi_bound(gz, rr) < g.bmin[2] || lo_bound(gz, rr) > g.bmax[2] ||
             !(qx == qx) || !(qy == qy) || !(qz == qz))
             return kNoPoint;
-        if (r1 < rr && scan_box_flat<5>(g, pts, cs, gy, gz, qx, qy, qz, r1, best, bj) && bj != kNoPoint &&
-            __uint_as_float((unsigned)(best >> 32)) <= r1_accept2)
-            return bj;
     }
+    // A seed farther than r1 bounds a box larger than pass 1's (typical right after a large first update:
+    // the old winner is a motion's length away while the true neighbour is millimetres away): pass 1 first.
+    if (r1 < rad && scan_box_flat<5>(g, pts, cs, gy, gz, qx, qy, qz, r1, best, bj) && bj != kNoPoint &&
+        __uint_as_float((unsigned)(best >> 32)) <= r1_accept2)
+        return bj;
+    if (seed_key < best) {   // the seed is an actual candidate: it bounds whatever comes next
+        best = seed_key;
+        bj = (unsigned)seed_j;
+    }
+    // every point that can still win lies within the distance of the best candidate known so far
+    if (bj != kNoPoint) rad = fminf(rad, sqrtf(__uint_as_float((unsigned)(best >> 32))) * 1.00001f);
     if (scan_box_flat<5>(g, pts, cs, gy, gz, qx, qy, qz, rad, best, bj)) return bj;
     if (scan_box_flat<9>(g, pts, cs, gy, gz, qx, qy, qz, rad, best, bj)) return bj;   // cells finer than r / 2
     Best b;

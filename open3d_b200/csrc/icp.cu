@@ -28,6 +28,10 @@ static constexpr double kThinFactor = ICP_THIN_FACTOR;   // grid-x (thin axis) c
 #define ICP_SEEDED 1   // 1: seed every query's search with its winner of the previous iteration (exact; see nn_search_seeded)
 #endif
 static constexpr bool kSeeded = ICP_SEEDED != 0;
+#ifndef ICP_CERTIFY
+#define ICP_CERTIFY 1   // 1: skip the scan when the triangle inequality proves last iteration's winner is still the winner
+#endif
+static constexpr bool kCertify = ICP_CERTIFY != 0;
 #ifndef ICP_CELL_SCALE
 #define ICP_CELL_SCALE 0.5
 #endif
@@ -774,7 +778,8 @@ struct IcpArgs {
     const unsigned* cs;
     float4* src;          // working source, sorted, .w = original index bits
     int* prev;            // per working source point: sorted target position of its last winner, -1 = none
-    float* dprev;         // per working source point: dist^2 to that winner (+inf = none)
+    float* dprev;         // per working source point: clearance of that winner (lower bound on the distance to every OTHER
+                          // target point, minus the motion since it was established); 0 = unknown
     int64_t n;            // local source points
     double n_total;       // source points over all ranks (fitness denominator)
     float rr, thr;
@@ -946,27 +951,51 @@ __device__ void icp_finalize_evaluate(const IcpArgs& a, const double* sums) {
 // MODE 0 = iterate, MODE 1 = evaluate (no Jacobian; writes correspondences in the caller's order).
 template <bool L2LOSS, int MODE, bool COLORED>
 __device__ __forceinline__ bool icp_process_query(const IcpArgs& a, const float* s_U, int i, float4 p, int jp,
-                                                  float d2_prev, const float4* seed_nn, const float4* seed_cg,
-                                                  float (&acc)[32]) {
+                                                  float clear_prev, const float4* seed_ts, const float4* seed_nn,
+                                                  const float4* seed_cg, float (&acc)[32]) {
     const float ox = p.x, oy = p.y, oz = p.z;
     apply_transform(s_U, p.x, p.y, p.z);
     a.src[i] = p;
     unsigned bj = kNoPoint;
     bool handled = false;
+    float clear_new = 0.f;      // what is known about the distance to every point other than the winner
+    float4 ts = make_float4(0.f, 0.f, 0.f, 0.f);
     if (jp >= 0) {
+        // "Still the winner" certificate (the Elkan / Hamerly bound of accelerated k-means, applied to ICP
+        // correspondences): when this query was last searched, every target point other than its winner was at
+        // least `clearance` away; since then the query has moved by at most the accumulated |p_new - p_old|
+        // (triangle inequality), which clear_prev already has subtracted.  If the old winner is now strictly
+        // closer than that bound, it is the exact nearest neighbour — no table lookup, no candidate scan.
+        // All roundings go against the certificate (round-down subtraction, 1e-5 margins on both roots).
+        ts = *seed_ts;
+        const float sd = dist2_canonical(ts, p.x, p.y, p.z);
         const float mx = p.x - ox, my = p.y - oy, mz = p.z - oz;
-        bj = nn_search_bounded_fast(a.g, a.tgt, a.cs, p.x, p.y, p.z, a.rr, a.thr, d2_prev,
-                                    fmaf(mz, mz, fmaf(my, my, mx * mx)), handled);
+        const float m2 = fmaf(mz, mz, fmaf(my, my, mx * mx));
+        const float moved = m2 > 0.f ? __fmul_ru(m2 * rsqrtf(m2), 1.00001f) : 0.f;
+        const float clear = __fsub_rd(clear_prev, moved);
+        const float r1 = sd > 0.f ? __fmul_ru(sd * rsqrtf(sd), 1.00001f) : 0.f;
+        if (sd <= a.thr) {
+            if (kCertify && r1 < clear) {
+                bj = (unsigned)jp;
+                clear_new = clear;
+                handled = true;
+            } else {
+                bj = nn_search_seeded_fast(a.g, a.tgt, a.cs, p.x, p.y, p.z, a.rr, a.thr, sd, handled, clear_new);
+            }
+        }
     }
-    if (!handled)
+    if (!handled) {
         bj = nn_search_slow(&a.g, a.tgt, a.cs, p.x, p.y, p.z, kTwoPass ? a.r1 : a.rr, a.r1_accept2, a.rr, a.thr, jp);
-    if (kSeeded && (int)bj != jp) a.prev[i] = (int)bj;
+        clear_new = 0.f;
+    }
+    if (kSeeded) {
+        if ((int)bj != jp) a.prev[i] = (int)bj;
+        a.dprev[i] = clear_new;
+    }
     int widx = -1;
-    if (kSeeded && bj == kNoPoint && jp >= 0) a.dprev[i] = __int_as_float(0x7f7f7f7f);
     if (bj != kNoPoint) {
-        const float4 t = __ldg(&a.tgt[bj]);                  // (just scanned: an L1 hit)
+        const float4 t = (int)bj == jp ? ts : __ldg(&a.tgt[bj]);   // (just scanned: an L1 hit)
         const float d = dist2_canonical(t, p.x, p.y, p.z);   // the same arithmetic as inside the scan: same bits
-        if (kSeeded) a.dprev[i] = d;
         widx = __float_as_int(t.w);
         if (MODE == 0) {
             // the seed's normal / colour row were fetched ahead (the winner rarely changes once the clouds
@@ -1076,8 +1105,8 @@ icp_iteration_direct_kernel(const __grid_constant__ IcpArgs a) {
         if (i < n) {
             const float4 p = a.src[i];
             const int jp = kSeeded ? a.prev[i] : -1;
-            const float d2_prev = kSeeded ? a.dprev[i] : 0.f;
-            matched = icp_process_query<L2LOSS, MODE, COLORED>(a, s_U, i, p, jp, d2_prev, a.nrm + max(jp, 0),
+            const float clear_prev = kSeeded ? a.dprev[i] : 0.f;
+            matched = icp_process_query<L2LOSS, MODE, COLORED>(a, s_U, i, p, jp, clear_prev, a.tgt + max(jp, 0), a.nrm + max(jp, 0),
                                                                COLORED ? a.tcg + max(jp, 0) : nullptr, term);
         }
         icp_accumulate_chunk(term, matched, acc64);
@@ -1101,11 +1130,12 @@ icp_iteration_direct_kernel(const __grid_constant__ IcpArgs a) {
 // hands a consumed slot back), accumulator flushes are warp-local.
 template <bool COLORED>
 struct __align__(16) IcpStage {
-    float4 p[32];      // A
-    float4 ns[32];     // B
-    float4 cg[COLORED ? 32 : 1];   // B
-    int jp[32];        // A
-    float d2[32];      // A
+    float4 p[32];      // A: working source points
+    float4 ts[32];     // B: the seeds' target points
+    float4 ns[32];     // B: their normals
+    float4 cg[COLORED ? 32 : 1];   // B: their colour rows
+    int jp[32];        // A: seeds
+    float d2[32];      // A: clearances
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -1196,9 +1226,10 @@ icp_iteration_kernel(const __grid_constant__ IcpArgs a) {
             IcpStage<COLORED>& sl = sm.stage[w][c & 1];
             mbar_wait(&s_mbar[w][c & 1], (unsigned)(c >> 1) & 1u);
             const int jp = kSeeded ? sl.jp[lane] : -1;
-            if (MODE == 0 && jp >= 0) {
-                cp_async16(&sl.ns[lane], a.nrm + jp);
-                if (COLORED) cp_async16(&sl.cg[lane], a.tcg + jp);
+            if (jp >= 0) {
+                cp_async16(&sl.ts[lane], a.tgt + jp);
+                if (MODE == 0) cp_async16(&sl.ns[lane], a.nrm + jp);
+                if (MODE == 0 && COLORED) cp_async16(&sl.cg[lane], a.tcg + jp);
             }
         }
         cp_async_commit();
@@ -1215,18 +1246,18 @@ icp_iteration_kernel(const __grid_constant__ IcpArgs a) {
         cp_async_wait_all();                                       // B(c)
         const float4 p = sl.p[lane];
         const int jp = kSeeded ? sl.jp[lane] : -1;
-        const float d2_prev = sl.d2[lane];
+        const float clear_prev = sl.d2[lane];
         __syncwarp();          // every lane has read p / jp / d2 of slot c & 1: hand that part back to the producer
         issue_a(c + 2, q0 + 2 * stride);
         issue_b(c + 1, q0 + stride);
-        // (ns / cg of slot c & 1 are rewritten by issue_b(c + 2), i.e. in the NEXT trip: still valid below)
+        // (ts / ns / cg of slot c & 1 are rewritten by issue_b(c + 2), i.e. in the NEXT trip: still valid below)
         const int i = q0 + lane;
         float term[32];
 #pragma unroll
         for (int k = 0; k < 32; ++k) term[k] = 0.f;
         bool matched = false;
         if (i < n)
-            matched = icp_process_query<L2LOSS, MODE, COLORED>(a, s_U, i, p, jp, d2_prev, &sl.ns[lane],
+            matched = icp_process_query<L2LOSS, MODE, COLORED>(a, s_U, i, p, jp, clear_prev, &sl.ts[lane], &sl.ns[lane],
                                                                &sl.cg[COLORED ? lane : 0], term);
 #if ICP_TRANSPOSE_SMEM
         icp_accumulate_chunk_smem(term, matched, sm.tr[w], acc64);
@@ -1370,7 +1401,7 @@ static int icp_init_state(o3db_icp* c, cudaStream_t st) {
     memcpy(c->h_st, &h, sizeof(h));
     O3DB_CUDA_CHECK(cudaMemcpyAsync(c->st, c->h_st, sizeof(IcpState), cudaMemcpyHostToDevice, st));
     O3DB_CUDA_CHECK(cudaMemsetAsync(c->prev, 0xff, (size_t)c->n_pad * sizeof(int), st));   // no seeds yet
-    O3DB_CUDA_CHECK(cudaMemsetAsync(c->dprev, 0x7f, (size_t)c->n_pad * sizeof(float), st)); // 0x7f7f7f7f = 3.4e38: no bound
+    O3DB_CUDA_CHECK(cudaMemsetAsync(c->dprev, 0, (size_t)c->n_pad * sizeof(float), st));     // no clearance known
     c->launched = 0;
     return O3DB_OK;
 }

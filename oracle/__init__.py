@@ -189,12 +189,55 @@ def set_num_threads(n: int) -> int:
     return num_threads()
 
 
+def _cgroup_cpu_quota():
+    """CPUs granted by the cgroup (v2 cpu.max / v1 cfs quota), or None."""
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            return max(1, int(float(q) / float(per)))
+    except (OSError, ValueError):
+        pass
+    try:
+        q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+        per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+        if q > 0 and per > 0:
+            return max(1, q // per)
+    except (OSError, ValueError):
+        pass
+    return None
+
+
 def host_cores() -> int:
+    """Hardware threads this process may run on: the affinity mask, capped by the cgroup CPU quota."""
     import os
     try:
-        return len(os.sched_getaffinity(0))
+        n = len(os.sched_getaffinity(0))
     except AttributeError:
-        return os.cpu_count() or 1
+        n = os.cpu_count() or 1
+    q = _cgroup_cpu_quota()
+    return max(1, min(n, q) if q else n)
+
+
+def physical_cores() -> int:
+    """Distinct physical cores inside the affinity mask (SMT siblings counted once), capped like host_cores()."""
+    import os
+    try:
+        cpus = sorted(os.sched_getaffinity(0))
+    except AttributeError:
+        return host_cores()
+    seen = set()
+    for c in cpus:
+        try:
+            sib = open(f"/sys/devices/system/cpu/cpu{c}/topology/thread_siblings_list").read().strip()
+        except OSError:
+            sib = str(c)
+        seen.add(sib)
+    return max(1, min(len(seen), host_cores()))
+
+
+def thread_candidates():
+    """Thread counts worth timing for an "all host cores" CPU leg: every hardware thread, and one per physical core."""
+    return sorted({host_cores(), physical_cores()}, reverse=True)
 
 
 def minivec_hash(keys) -> np.ndarray:

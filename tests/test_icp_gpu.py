@@ -560,5 +560,6 @@ def test_colored_icp_argument_errors(o3d):
     one = reg.icp(s, t, 0.05, np.eye(4), est, reg.ICPConvergenceCriteria(0, 0, 1))
     idx, _, _ = oracle.hybrid_search(tgt, src, 0.05, 1)
     T = est.compute_transformation(s, t, torch.from_numpy(idx[:, 0].astype(np.int64)))
-    np.testing.assert_allclose(T, one.transformation, atol=1e-9)
+    # (the stand-alone pose kernel and the fused loop add the same f32 terms in different association orders)
+    np.testing.assert_allclose(T, one.transformation, atol=1e-7)
     assert est.compute_rmse(s, t, torch.from_numpy(idx[:, 0].astype(np.int64))) > 0
