@@ -157,12 +157,22 @@ int o3db_voxel_down_sample_attrs(const float* positions_dev, const float* const*
 /* t::geometry::PointCloud::EstimateColorGradients with the hybrid search (t/geometry/PointCloud.cpp:
  * 723-767, kernel/PointCloudImpl.h:1066-1165 EstimateColorGradientsUsingHybridSearchCUDA): the
  * "color_gradients" attribute ColoredICP reads on the target.  Normal equations accumulated in f32 in
- * the reference's order; solved with the exact pseudo-inverse (singular values < 1e-10 dropped as
- * core/linalg/kernel/SVD3x3.h:2184-2187) — the reference's approximate f32 SVD is not reproduced
- * (DESIGN.md).  max_nn in 1..32 (reference default 30).  Points with < 4 neighbours get a zero gradient. */
+ * the reference's order, then the 3x3 solve:
+ *   O3DB_GRADIENT_SOLVER_REFERENCE (what o3db_estimate_color_gradients uses): the reference's own
+ *     solve_svd3x3<float> (core/linalg/kernel/SVD3x3.h:1131-2215, 4-sweep fast SVD, singular values
+ *     < 1e-10 dropped) — bit-identical to the reference's CPU kernel on identical inputs;
+ *   O3DB_GRADIENT_SOLVER_EXACT: exact pseudo-inverse of the same f32 system (f64 Jacobi), for callers
+ *     who want the mathematically exact least-squares gradient (the fast SVD is off by a median 12 %
+ *     on these condition-1e5 systems).
+ * max_nn in 1..32 (reference default 30).  Points with < 4 neighbours get a zero gradient. */
+#define O3DB_GRADIENT_SOLVER_REFERENCE 0
+#define O3DB_GRADIENT_SOLVER_EXACT 1
 int o3db_estimate_color_gradients(const float* positions_dev, const float* normals_dev, const float* colors_dev,
                                   int64_t n, double radius, int max_nn, float* color_gradients_dev /* [n,3] */,
                                   void* stream);
+int o3db_estimate_color_gradients_solver(const float* positions_dev, const float* normals_dev,
+                                         const float* colors_dev, int64_t n, double radius, int max_nn,
+                                         int solver, float* color_gradients_dev /* [n,3] */, void* stream);
 
 /* ------------------------------------------------------------------------
  * Fused, device-resident ICP loop — replaces

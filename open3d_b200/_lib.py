@@ -81,6 +81,7 @@ _SIGS = {
     "o3db_voxel_down_sample_attrs": (_i, [_vp, C.POINTER(_vp), _i, _i64, _dbl, _vp, C.POINTER(_vp), C.POINTER(_i64),
                                           _vp]),
     "o3db_estimate_color_gradients": (_i, [_vp, _vp, _vp, _i64, _dbl, _i, _vp, _vp]),
+    "o3db_estimate_color_gradients_solver": (_i, [_vp, _vp, _vp, _i64, _dbl, _i, _i, _vp, _vp]),
     "o3db_icp_create_colored": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _dp, C.POINTER(IcpOptions), _dbl, _vp,
                                      _vp, C.POINTER(_vp)]),
     "o3db_icp_colored": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _dp, C.POINTER(IcpOptions), _dbl,

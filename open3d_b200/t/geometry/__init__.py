@@ -83,9 +83,13 @@ class PointCloud:
             out.point[k] = v[: m.value].contiguous()
         return out
 
-    def estimate_color_gradients(self, max_nn=30, radius=None):
+    def estimate_color_gradients(self, max_nn=30, radius=None, solver="reference"):
         """PointCloud::EstimateColorGradients (t/geometry/PointCloud.cpp:723-767), hybrid search: sets
-        the "color_gradients" attribute ColoredICP reads on the target."""
+        the "color_gradients" attribute ColoredICP reads on the target.  solver="reference" (default)
+        reproduces upstream's solve_svd3x3<float> bit for bit; "exact" is the exact pseudo-inverse of
+        the same f32 normal equations (an extension, not upstream behaviour)."""
+        if solver not in ("reference", "exact"):
+            raise ValueError("solver must be 'reference' or 'exact'")
         if not self.has_point_colors():
             raise RuntimeError("PointCloud must have colors attribute to estimate color gradients.")
         if not self.has_point_normals():
@@ -95,8 +99,9 @@ class PointCloud:
                                "radius-only variants are outside this build's scope).")
         p, nrm, col = self.point["positions"], self.point["normals"], self.point["colors"]
         g = torch.empty_like(p)
-        check(lib.o3db_estimate_color_gradients(p.data_ptr(), nrm.data_ptr(), col.data_ptr(), int(p.shape[0]),
-                                                float(radius), int(max_nn), g.data_ptr(), current_stream_ptr()))
+        check(lib.o3db_estimate_color_gradients_solver(p.data_ptr(), nrm.data_ptr(), col.data_ptr(), int(p.shape[0]),
+                                                       float(radius), int(max_nn), 0 if solver == "reference" else 1,
+                                                       g.data_ptr(), current_stream_ptr()))
         self.point["color_gradients"] = g
         return self
 

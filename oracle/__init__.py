@@ -152,6 +152,12 @@ def _declare(L):
                                                         C.POINTER(C.c_int)]
     L.orc_estimate_color_gradients_f32.restype = None
     L.orc_estimate_color_gradients_f32.argtypes = [_f32p, _f32p, _f32p, C.c_int64, C.c_double, C.c_int, _f32p]
+    L.orc_estimate_color_gradients_solver_f32.restype = None
+    L.orc_estimate_color_gradients_solver_f32.argtypes = [_f32p, _f32p, _f32p, C.c_int64, C.c_double, C.c_int, C.c_int, _f32p]
+    L.orc_svd3x3_f32.restype = None
+    L.orc_svd3x3_f32.argtypes = [_f32p, _f32p, _f32p, _f32p]
+    L.orc_solve_svd3x3_f32.restype = None
+    L.orc_solve_svd3x3_f32.argtypes = [_f32p, _f32p, _f32p]
     L.orc_solve_sym3x3_pinv.restype = None
     L.orc_solve_sym3x3_pinv.argtypes = [_f64p, _f64p, _f64p]
     L.orc_icp_colored_f32.restype = C.c_int
@@ -536,14 +542,36 @@ def voxel_down_sample(positions, voxel_size, normals=None, colors=None):
             "colors": None if co is None else co[:m].copy(), "keys": keys[:m].copy()}
 
 
-def estimate_color_gradients(points, normals, colors, radius, max_nn=30) -> np.ndarray:
+GRADIENT_SOLVERS = {"reference": 0, "exact": 1}
+
+
+def estimate_color_gradients(points, normals, colors, radius, max_nn=30, solver="reference") -> np.ndarray:
+    """solver="reference": upstream's solve_svd3x3<float> (bit-identical to the reference kernel);
+    "exact": exact pseudo-inverse of the same f32 normal equations."""
     p = _arr(points, np.float32).reshape(-1, 3)
     nr = _arr(normals, np.float32).reshape(-1, 3)
     c = _arr(colors, np.float32).reshape(-1, 3)
     out = np.zeros_like(p)
-    lib().orc_estimate_color_gradients_f32(_p(p, _f32p), _p(nr, _f32p), _p(c, _f32p), p.shape[0], float(radius),
-                                           int(max_nn), _p(out, _f32p))
+    lib().orc_estimate_color_gradients_solver_f32(_p(p, _f32p), _p(nr, _f32p), _p(c, _f32p), p.shape[0], float(radius),
+                                                  int(max_nn), GRADIENT_SOLVERS[solver], _p(out, _f32p))
     return out
+
+
+def svd3x3(A):
+    """(U, S, V) of upstream's svd3x3<float> (SVD3x3.h:1131-2168), f32, row-major."""
+    A = _arr(A, np.float32).reshape(9)
+    U, S, V = np.zeros(9, np.float32), np.zeros(3, np.float32), np.zeros(9, np.float32)
+    lib().orc_svd3x3_f32(_p(A, _f32p), _p(U, _f32p), _p(S, _f32p), _p(V, _f32p))
+    return U.reshape(3, 3), S, V.reshape(3, 3)
+
+
+def solve_svd3x3(A, b) -> np.ndarray:
+    """upstream's solve_svd3x3<float> (SVD3x3.h:2170-2215)."""
+    A = _arr(A, np.float32).reshape(9)
+    b = _arr(b, np.float32).reshape(3)
+    x = np.zeros(3, np.float32)
+    lib().orc_solve_svd3x3_f32(_p(A, _f32p), _p(b, _f32p), _p(x, _f32p))
+    return x
 
 
 def solve_sym3x3_pinv(A, b) -> np.ndarray:

@@ -930,7 +930,7 @@ void orc_solve_sym3x3_pinv(const double Ain[9], const double b[3], double x[3]) 
 
 /* PointCloudImpl.h:1066-1165 for one point; idx: its neighbour list (count valid entries). */
 static void color_gradient_point(const float* pts, const float* nrm, const float* col, int64_t i,
-                                 const int32_t* idx, int count, float* out) {
+                                 const int32_t* idx, int count, int solver, float* out) {
     const int64_t o = 3 * i;
     if (count < 4) {
         out[o] = out[o + 1] = out[o + 2] = 0;
@@ -971,7 +971,11 @@ static void color_gradient_point(const float* pts, const float* nrm, const float
     AtA[3] = AtA[1];
     AtA[6] = AtA[2];
     AtA[7] = AtA[5];
-    double Ad[9], bd[3], xd[3];
+    if (solver == ORC_GRADIENT_SOLVER_REFERENCE) { /* PointCloudImpl.h:1163: solve_svd3x3 (svd3_oracle.c) */
+        orc_solve_svd3x3_f32(AtA, Atb, out + o);
+        return;
+    }
+    double Ad[9], bd[3], xd[3]; /* option: exact pseudo-inverse of the same f32 system */
     for (int q = 0; q < 9; ++q) Ad[q] = AtA[q];
     for (int q = 0; q < 3; ++q) bd[q] = Atb[q];
     orc_solve_sym3x3_pinv(Ad, bd, xd);
@@ -982,6 +986,11 @@ static void color_gradient_point(const float* pts, const float* nrm, const float
 
 void orc_estimate_color_gradients_f32(const float* pts, const float* nrm, const float* col, int64_t n,
                                       double radius, int max_nn, float* out) {
+    orc_estimate_color_gradients_solver_f32(pts, nrm, col, n, radius, max_nn, ORC_GRADIENT_SOLVER_REFERENCE, out);
+}
+
+void orc_estimate_color_gradients_solver_f32(const float* pts, const float* nrm, const float* col, int64_t n,
+                                             double radius, int max_nn, int solver, float* out) {
     if (max_nn > ORC_MAX_KNN) max_nn = ORC_MAX_KNN;
     int32_t* idx = (int32_t*)malloc((size_t)n * max_nn * sizeof(int32_t));
     float* d2 = (float*)malloc((size_t)n * max_nn * sizeof(float));
@@ -989,7 +998,7 @@ void orc_estimate_color_gradients_f32(const float* pts, const float* nrm, const 
     if (!idx || !d2 || !cnt) abort();
     orc_hybrid_search_f32(pts, n, pts, n, radius, max_nn, idx, d2, cnt);
 #pragma omp parallel for schedule(static)
-    for (int64_t i = 0; i < n; ++i) color_gradient_point(pts, nrm, col, i, idx + i * max_nn, cnt[i], out);
+    for (int64_t i = 0; i < n; ++i) color_gradient_point(pts, nrm, col, i, idx + i * max_nn, cnt[i], solver, out);
     free(idx);
     free(d2);
     free(cnt);

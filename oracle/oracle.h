@@ -164,16 +164,28 @@ int orc_icp_p2plane_f32(const float* source, int64_t n, const float* target,
 /* t/geometry/kernel/PointCloudImpl.h:1066-1165 EstimatePointWiseColorGradientKernel driven by
  * EstimateColorGradientsUsingHybridSearch (:1167-1222): hybrid search of the cloud on itself
  * (radius, max_nn), skip neighbour 0, project neighbours on the tangent plane, 3x3 normal
- * equations + the orthogonality row, x = pinv(AtA) Atb.  The per-neighbour arithmetic is f32 as
- * upstream; the final 3x3 pseudo-inverse is evaluated in f64 by Jacobi eigen-decomposition
- * (upstream: core/linalg/kernel/SVD3x3.h fast f32 SVD, singular values < 1e-10 dropped) —
- * agreement with the real solve_svd3x3 is checked in tests/test_oracle_vs_ref.py.
- * SURVEY.md 8f #3; parity unpinned offline beyond that check. */
+ * equations + the orthogonality row (all f32, upstream's order), then the 3x3 solve:
+ *   ORC_GRADIENT_SOLVER_REFERENCE (default): upstream's solve_svd3x3<float> (core/linalg/kernel/SVD3x3.h — the
+ *     4-sweep fast f32 SVD) restated in svd3_oracle.c, bit-identical to the reference's own function compiled in
+ *     oracle/_ref (tests/test_oracle_vs_ref.py) — so the whole per-point kernel equals the reference's bit for bit;
+ *   ORC_GRADIENT_SOLVER_EXACT: the exact pseudo-inverse of the same f32 system (f64 Jacobi), the option the
+ *     product also offers (the fast SVD is off by a median 12 % on these condition-1e5 systems).
+ * SURVEY.md 8f #3. */
+#define ORC_GRADIENT_SOLVER_REFERENCE 0
+#define ORC_GRADIENT_SOLVER_EXACT 1
 void orc_estimate_color_gradients_f32(const float* points, const float* normals, const float* colors,
                                       int64_t n, double radius, int max_nn, float* gradients_out);
+void orc_estimate_color_gradients_solver_f32(const float* points, const float* normals, const float* colors,
+                                             int64_t n, double radius, int max_nn, int solver,
+                                             float* gradients_out);
 
 /* pinv(A) b for a symmetric 3x3 A (row-major), f64 Jacobi; singular values < 1e-10 dropped. */
 void orc_solve_sym3x3_pinv(const double A[9], const double b[3], double x[3]);
+
+/* svd3_oracle.c: core/linalg/kernel/SVD3x3.h:1131-2168 svd3x3<float> (A = U diag(S) V^T, row-major) and
+ * :2170-2215 solve_svd3x3<float>, the host build's operation sequence. */
+void orc_svd3x3_f32(const float A[9], float U[9], float S[3], float V[9]);
+void orc_solve_svd3x3_f32(const float A[9], const float b[3], float x[3]);
 
 /* Registration.cpp:275-444 with TransformationEstimationForColoredICP
  * (TransformationEstimation.cpp:382-432 -> ComputePoseColoredICP, kernel/Registration.cpp:137-191). */

@@ -59,7 +59,8 @@ if what in ("colored", "all"):
     L.lib.o3db_icp_destroy(h)
 if what in ("tsdf", "raycast", "all"):
     v = C.c_void_p()
-    L.check(L.lib.o3db_vbg_create(0.008, 16, 40000, 1, stream, C.byref(v)))
+    with_color = int(os.environ.get("TSDF_COLOR", 1))
+    L.check(L.lib.o3db_vbg_create(0.008, 16, 40000, with_color, stream, C.byref(v)))
     K = np.ascontiguousarray(PRIMESENSE_K)
     for i in range(40):
         T = camera_pose(i * 5)
@@ -67,7 +68,8 @@ if what in ("tsdf", "raycast", "all"):
         E[:3, :3] = T[:3, :3].T
         E[:3, 3] = -(T[:3, :3].T @ T[:3, 3])
         dep, col = render_depth(T, device="cuda", with_color=True)
-        L.check(L.lib.o3db_vbg_integrate_frame(v, dep.data_ptr(), L.DEPTH_U16, col.data_ptr(), L.COLOR_U8, 480, 640, L.dptr(K),
+        L.check(L.lib.o3db_vbg_integrate_frame(v, dep.data_ptr(), L.DEPTH_U16, col.data_ptr() if with_color else None,
+                                               L.COLOR_U8 if with_color else 0, 480, 640, L.dptr(K),
                                                L.dptr(np.ascontiguousarray(E)), 1000.0, 3.0, 8.0, stream))
     print("tsdf blocks", L.lib.o3db_vbg_size(v, stream))
     if what in ("raycast", "all"):

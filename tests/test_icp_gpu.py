@@ -434,8 +434,11 @@ def _colored_pair(n, seed):
 
 @pytest.mark.parametrize("n,radius,max_nn", [(20000, 0.08, 30), (20000, 0.03, 30), (5000, 0.025, 8)])
 def test_color_gradients_vs_oracle(o3d, n, radius, max_nn):
-    """EstimateColorGradients, hybrid search (PointCloudImpl.h:1066-1165): the f32 normal equations are
-    accumulated in the reference's order, so the solve sees bit-identical systems."""
+    """EstimateColorGradients, hybrid search (PointCloudImpl.h:1066-1165).  Default solver = the reference's
+    solve_svd3x3<float>: BIT-EXACT vs the oracle, which is itself bit-exact vs the reference's own
+    EstimatePointWiseColorGradientKernel compiled in oracle/_ref (tests/test_oracle_vs_ref.py) — identical neighbour
+    lists, identical f32 normal equations, identical 4-sweep SVD.  solver="exact" (extension): 1e-5 of the oracle's
+    exact pseudo-inverse."""
     _, _, tgt, nrm, tc, _ = _colored_pair(n, 21)
     pc = o3d.t.geometry.PointCloud(tgt).set_point_normals(nrm).set_point_colors(tc)
     pc.estimate_color_gradients(max_nn, radius)
@@ -446,8 +449,12 @@ def test_color_gradients_vs_oracle(o3d, n, radius, max_nn):
     assert np.array_equal(zero, ~g.any(axis=1))           # < 4 neighbours -> exactly zero, same points
     if radius < 0.03:
         assert zero.any() and not zero.all()
+    assert g.tobytes() == ref.tobytes(), float(np.abs(g - ref).max())
+    pc.estimate_color_gradients(max_nn, radius, solver="exact")
+    g = pc.point["color_gradients"].cpu().numpy()
+    ref = oracle.estimate_color_gradients(tgt, nrm, tc, radius, max_nn, solver="exact")
     np.testing.assert_allclose(g, ref, rtol=1e-5, atol=1e-5 * np.abs(ref).max())
-    # the gradient is tangential: the orthogonality row drives g . n to ~0
+    # the exact gradient is tangential: the orthogonality row drives g . n to ~0
     assert np.abs((g * nrm).sum(1)).max() < 1e-3 * max(np.abs(g).max(), 1.0)
     with pytest.raises(RuntimeError, match="colors"):
         o3d.t.geometry.PointCloud(tgt).set_point_normals(nrm).estimate_color_gradients(30, radius)
