@@ -10,6 +10,8 @@
 // agree bit for bit; TSDF values then agree bit for bit as well.
 //
 // No CPU fallback: every entry point needs a CUDA device.
+#include <cuda.h>   // CUtensorMap (types only: the encoder is resolved through cudaGetDriverEntryPoint)
+
 #include <climits>
 #include <cmath>
 #include <new>
@@ -25,6 +27,41 @@ static constexpr int kT = 256;
 static constexpr int kStepSize = 3;                 // VoxelBlockGridCUDA.cu:125 step_size
 static constexpr int kSamples = kStepSize + 1;      // est_multipler_factor
 static constexpr int kStride = 4;                   // VoxelBlockGrid.cpp:221 down_factor
+
+// Programmatic dependent launch (both frame kernels are launched with the attribute): the grid may become
+// resident while its predecessor on the stream drains; nothing the predecessor wrote is read before the wait.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* b, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
+    unsigned done;
+    do {
+        asm volatile(
+                "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(smem_addr(b)), "r"(parity)
+                : "memory");
+    } while (!done);
+}
+// 2-D tiled TMA load (cp.async.bulk.tensor, SASS UTMALDG): box of the descriptor at element (x, y) of the image;
+// out-of-image elements are zero-filled by the copy engine, completion is signalled on the mbarrier.
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, unsigned long long* b) {
+    asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                    smem_addr(dst)),
+            "l"(map), "r"(smem_addr(b)), "r"(x), "r"(y)
+            : "memory");
+}
 
 // ------------------------------------------------------------------ touch
 
@@ -51,6 +88,8 @@ __global__ void __launch_bounds__(kT) touch_kernel(TouchArgs a) {
     // One thread per (strided pixel, ray sample): 4x the threads of the reference's launch
     // (VoxelBlockGridCUDA.cu:145) and a 4x shorter dependent chain per thread — the kernel is
     // pure latency (a few table round trips), so parallelism is what buys time.
+    pdl_wait();                 // the previous frame's integrate kernel: table, stamps, counters
+    pdl_launch_dependents();
     const int cols_s = a.cols / kStride, rows_s = a.rows / kStride;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int w = tid / kSamples, step = tid % kSamples;
@@ -226,8 +265,16 @@ struct IntegrateArgs {
     int* frame_slots;        // [max] slots of this frame's frustum blocks (Model::frustum_block_coords_)
     int* frame_count;
     int* max_new;            // running max of blocks first seen in one frame
+    int* dropped;            // [0] capacity the dropped frame needed, [1] id of the first dropped frame (0 = none)
     int frame_id;
     int capacity;
+    int max_list;            // size of exist_list / new_list
+    // 16^3 fast path (integrate16_kernel)
+    const float* inv_w;      // [65536] 1 / (w + 1), the reference's inv_wsum (VoxelBlockGridImpl.h:274) per u16 weight
+    float inv_scale;         // RN(1 / depth_scale), used only when fast_scale
+    int fast_scale;          // u16 depth: depth / depth_scale through a verified 3-FMA division (see depth_metres)
+    int same_k;              // colour intrinsics == depth intrinsics: interior pixels map to themselves (see below)
+    int use_tile;            // the depth image has a TMA descriptor: stage the projected tile in shared memory
 };
 
 // VoxelBlockGridImpl.h:226-303 for one voxel.  Returns false if the voxel is not updated.
@@ -357,12 +404,20 @@ template <typename depth_t, typename color_in_t, bool HAS_COLOR>
 __global__ void __launch_bounds__(kT) integrate_kernel(IntegrateArgs a) {
     __shared__ int s_slot, s_key[3];
     const bool fused = a.counters != nullptr;
-    int n_exist = 0, n_total = a.n_blocks, size0 = 0;
-    if (fused) {
+    int n_exist = 0, n_new = 0, n_total = a.n_blocks, size0 = 0;
+    bool drop = false;
+    pdl_wait();
+    pdl_launch_dependents();
+    if (fused) {   // same whole-frame drop rule as integrate16_kernel
         n_exist = a.counters[0];
-        n_total = n_exist + a.counters[1];
+        n_new = a.counters[1];
         size0 = *a.size;
-        if (a.counters[2]) n_total = 0;   // overflow: the host reports it; nothing is integrated
+        drop = a.counters[2] != 0 || size0 + n_new > a.capacity;
+        n_total = drop ? 0 : n_exist + n_new;
+        if (drop) {
+            const int n_roll = min(n_new, a.max_list);
+            for (int i = blockIdx.x * kT + threadIdx.x; i < n_roll; i += gridDim.x * kT) a.table[a.new_list[i].x] = kEmpty;
+        }
     }
     // work unit = one quarter of a 16^3 block (whole block for other resolutions)
     const int upb = a.resolution == 16 ? 4 : 1;
@@ -382,13 +437,7 @@ __global__ void __launch_bounds__(kT) integrate_kernel(IntegrateArgs a) {
                 const int2 nl = a.new_list[b - n_exist];
                 slot = size0 + (b - n_exist);
                 k = a.cand_keys + 3 * (size_t)nl.y;
-                if (slot >= a.capacity) {
-                    slot = -1;
-                    if (unit == 0) {
-                        a.table[nl.x] = kTomb;
-                        a.counters[2] = 1;
-                    }
-                } else if (unit == 0) {
+                if (unit == 0) {
                     a.keys_rw[3 * (size_t)slot] = k[0];
                     a.keys_rw[3 * (size_t)slot + 1] = k[1];
                     a.keys_rw[3 * (size_t)slot + 2] = k[2];
@@ -420,10 +469,17 @@ __global__ void __launch_bounds__(kT) integrate_kernel(IntegrateArgs a) {
         if (threadIdx.x == 0) s_last = atomicAdd(&a.counters[3], 1) == (int)gridDim.x - 1;
         __syncthreads();
         if (s_last && threadIdx.x == 0) {
-            const int n_new = a.counters[1];
-            const int ns = min(size0 + n_new, a.capacity);
-            *a.frame_count = a.counters[2] ? 0 : n_total;
-            *a.size = ns;
+            if (drop) {
+                *a.frame_count = 0;
+                if (a.dropped[1] == 0) {
+                    a.dropped[0] = size0 + n_new;
+                    a.dropped[1] = a.frame_id;
+                }
+                a.counters[2] = 1;
+            } else {
+                *a.frame_count = n_total;
+                *a.size = size0 + n_new;
+            }
             if (n_new > *a.max_new) *a.max_new = n_new;
             a.counters[0] = 0;
             a.counters[1] = 0;
@@ -431,6 +487,295 @@ __global__ void __launch_bounds__(kT) integrate_kernel(IntegrateArgs a) {
             // counters[2] (overflow) is sticky until the host reads it
         }
     }
+}
+
+
+// ------------------------------------------ integrate, 16^3 blocks: TMA-staged depth tile
+
+static constexpr int kTileRows = 96;        // rows of the staged depth tile
+static constexpr int kTileRowBytes = 256;   // 128 u16 / 64 f32 pixels per row
+static constexpr unsigned kTileBytes = kTileRows * kTileRowBytes;
+
+// depth / depth_scale (VoxelBlockGridImpl.h:253).  For u16 images the quotient has only 65536 possible
+// numerators: the host checks ONCE per scale, over all of them, that the division-free sequence
+// q = d y, r = fma(-q, s, d), q' = fma(r, y, q) with y = RN(1/s) returns exactly RN(d / s) (Markstein's
+// correction step; same IEEE operations on host and device), and only then sets fast_scale.
+template <typename depth_t>
+__device__ __forceinline__ float depth_metres(const IntegrateArgs& a, depth_t raw) {
+    const float d = (float)raw;
+    if (sizeof(depth_t) == 2 && a.fast_scale) {
+        const float q = __fmul_rn(d, a.inv_scale);
+        const float r = __fmaf_rn(-q, a.depth_scale, d);
+        return __fmaf_rn(r, a.inv_scale, q);
+    }
+    return dvd(d, a.depth_scale);
+}
+
+// One launch integrates a frame into 16^3 blocks.  Work unit = a quarter block (4 z-slices, 1024 voxels, 4
+// consecutive x voxels per thread).  Per unit and CTA:
+//   * thread 32 fetches the NEXT unit's slot / block key (and commits the block if this frame created it)
+//     while the current unit is computed: the list -> key dependent loads are off the critical path;
+//   * warp 0 projects the unit's 8 corners, and lane 0 issues ONE 2-D TMA load of the bounding pixel rectangle of
+//     the depth image into shared memory (out-of-image parts zero-filled), completion on an mbarrier;
+//   * every thread first issues its tsdf / weight (/ colour) loads, then does the voxel -> pixel geometry
+//     (the IEEE divisions that make the result bit-exact) while the tile and the voxel values are in flight,
+//     then waits on the mbarrier and reads its 4 depths from shared memory;
+//   * one __syncthreads per unit (tile / metadata hand-over).
+// Rectangles that do not fit the tile (very close blocks), units with a corner behind the camera and images
+// without a descriptor read the depth image directly; every tile read is bounds-checked against the staged
+// rectangle, so the staging can never change a result.
+template <typename depth_t, typename color_in_t, bool HAS_COLOR>
+__global__ void __launch_bounds__(kT) integrate16_kernel(const __grid_constant__ IntegrateArgs a,
+                                                         const __grid_constant__ CUtensorMap dmap) {
+    __shared__ __align__(128) unsigned char s_tile[kTileBytes];
+    __shared__ __align__(8) unsigned long long s_mbar;
+    __shared__ int s_meta[2][4];   // slot, block key
+    __shared__ int s_rect[4];      // x0, y0 of the staged rectangle, staged?
+    __shared__ bool s_last;
+    constexpr int kTileCols = kTileRowBytes / (int)sizeof(depth_t);
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(&s_mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    pdl_wait();                 // the touch kernel's lists / counters, the previous frame's size
+    pdl_launch_dependents();
+    const bool fused = a.counters != nullptr;
+    int n_exist = 0, n_new = 0, n_total = a.n_blocks, size0 = 0;
+    bool drop = false;
+    if (fused) {
+        n_exist = a.counters[0];
+        n_new = a.counters[1];
+        size0 = *a.size;
+        // ONE decision for every CTA (all four values are final once the touch kernel has finished): a frame
+        // whose new blocks do not fit, whose lists overflowed, or that follows a dropped frame, is dropped as
+        // a whole — nothing integrated, its provisional table entries released — and reported by the host.
+        drop = a.counters[2] != 0 || size0 + n_new > a.capacity;
+        n_total = drop ? 0 : n_exist + n_new;
+        if (drop) {
+            // no committed key's probe chain passes over a bucket that was empty when the frame began, so
+            // emptying every bucket this frame claimed restores the table exactly
+            const int n_roll = min(n_new, a.max_list);
+            for (int i = blockIdx.x * kT + tid; i < n_roll; i += gridDim.x * kT) a.table[a.new_list[i].x] = kEmpty;
+        }
+    }
+    const int n_units = n_total * 4;
+
+    auto fetch = [&](int wu, int buf) {    // one thread: metadata of work unit wu
+        const int b = wu >> 2, unit = wu & 3;
+        int slot;
+        const int* k;
+        if (!fused) {
+            slot = a.buf_indices[b];
+            k = a.block_keys + 3 * (size_t)slot;
+        } else if (b < n_exist) {
+            slot = a.exist_list[b];
+            k = a.block_keys + 3 * (size_t)slot;
+        } else {
+            // a block first seen in this frame: slot = old size + rank; its unit 0 commits it
+            const int2 nl = a.new_list[b - n_exist];
+            slot = size0 + (b - n_exist);
+            k = a.cand_keys + 3 * (size_t)nl.y;
+            if (unit == 0) {
+                a.keys_rw[3 * (size_t)slot] = k[0];
+                a.keys_rw[3 * (size_t)slot + 1] = k[1];
+                a.keys_rw[3 * (size_t)slot + 2] = k[2];
+                a.stamp[slot] = a.frame_id;
+                a.table[nl.x] = slot;
+            }
+        }
+        if (fused && unit == 0) a.frame_slots[b] = slot;
+        s_meta[buf][0] = slot;
+        s_meta[buf][1] = k[0];
+        s_meta[buf][2] = k[1];
+        s_meta[buf][3] = k[2];
+    };
+    if (tid == 32 && (int)blockIdx.x < n_units) fetch(blockIdx.x, 0);
+
+    int it = 0;
+    for (int wu = blockIdx.x; wu < n_units; wu += gridDim.x, ++it) {
+        __syncthreads();   // metadata of this unit published; every thread is done with the previous tile / rect
+        const int slot = s_meta[it & 1][0];
+        const int xb = s_meta[it & 1][1], yb = s_meta[it & 1][2], zb = s_meta[it & 1][3];
+        const int unit = wu & 3;
+        const int quad = unit * kT + tid;
+        const int xq = (quad & 3) * 4, yv = (quad >> 2) & 15, zv = quad >> 6;
+        const int lin = quad * 4;
+        float* tsdf = a.tsdf + (size_t)slot * 4096 + lin;
+        uint16_t* wt = a.weight + (size_t)slot * 4096 + lin;
+        uint16_t* cb = HAS_COLOR ? a.color_buf + ((size_t)slot * 4096 + lin) * 3 : nullptr;
+        // voxel values first: their DRAM latency overlaps the geometry below
+        const float4 t4 = *reinterpret_cast<const float4*>(tsdf);
+        const ushort4 w4 = *reinterpret_cast<const ushort4*>(wt);
+        uint2 c2[3];
+        if (HAS_COLOR) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) c2[k] = reinterpret_cast<const uint2*>(cb)[k];
+        }
+        if (tid < 32) {
+            // bounding pixel rectangle of the unit's voxels: perspective projection maps the convex hull of
+            // the 8 extreme voxels (all in front of the camera) into the hull of their projections
+            const int c = tid & 7;
+            float xc, yc, zc, u = 0.f, v = 0.f;
+            rigid(a.dcam, (float)(xb * 16 + ((c & 1) ? 15 : 0)), (float)(yb * 16 + ((c & 2) ? 15 : 0)),
+                  (float)(zb * 16 + unit * 4 + ((c & 4) ? 3 : 0)), xc, yc, zc);
+            bool ok = zc > 1e-3f;
+            if (ok) project(a.dcam, xc, yc, zc, u, v);
+            ok = ok && fabsf(u) < 1e6f && fabsf(v) < 1e6f;
+            float umin = u, umax = u, vmin = v, vmax = v;
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+                umin = fminf(umin, __shfl_xor_sync(0xffffffffu, umin, o));
+                umax = fmaxf(umax, __shfl_xor_sync(0xffffffffu, umax, o));
+                vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+                vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+            }
+            ok = __all_sync(0xffffffffu, ok);
+            if (tid == 0) {
+                const int x0 = (int)floorf(umin) - 1, x1 = (int)floorf(umax) + 1;
+                const int y0 = (int)floorf(vmin) - 1, y1 = (int)floorf(vmax) + 1;
+                const bool stage = a.use_tile && ok && x1 - x0 < kTileCols && y1 - y0 < kTileRows && x1 >= 0 && y1 >= 0 &&
+                                   x0 < a.cols && y0 < a.rows;
+                s_rect[0] = x0;
+                s_rect[1] = y0;
+                s_rect[2] = stage ? 1 : 0;
+                if (stage) {
+                    mbar_arrive_expect_tx(&s_mbar, kTileBytes);
+                    tma_load_2d(s_tile, &dmap, x0, y0, &s_mbar);
+                } else {
+                    mbar_arrive(&s_mbar);   // (release: s_rect is visible to every waiter)
+                }
+            }
+        } else if (tid == 32) {
+            const int next = wu + (int)gridDim.x;
+            if (next < n_units) fetch(next, (it + 1) & 1);
+        }
+        // VoxelBlockGridImpl.h:226-247: voxel -> camera -> pixel, uncontracted, reference order; the y / z
+        // products are shared by the thread's 4 voxels
+        const float ys = mul((float)(yb * 16 + yv), a.dcam.scale), zs = mul((float)(zb * 16 + zv), a.dcam.scale);
+        float py[3], pz[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            py[r] = mul(ys, a.dcam.e[r][1]);
+            pz[r] = mul(zs, a.dcam.e[r][2]);
+        }
+        float zc[4];
+        int pix[4];       // ui | vi << 16, -1 = outside the image
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float xs = mul((float)(xb * 16 + xq + k), a.dcam.scale);
+            const float xc = add(add(add(mul(xs, a.dcam.e[0][0]), py[0]), pz[0]), a.dcam.e[0][3]);
+            const float yc = add(add(add(mul(xs, a.dcam.e[1][0]), py[1]), pz[1]), a.dcam.e[1][3]);
+            zc[k] = add(add(add(mul(xs, a.dcam.e[2][0]), py[2]), pz[2]), a.dcam.e[2][3]);
+            float u, v;
+            project(a.dcam, xc, yc, zc[k], u, v);
+            pix[k] = in_boundary(u, v, a.rows, a.cols) ? ((int)u | ((int)v << 16)) : -1;
+        }
+        mbar_wait(&s_mbar, (unsigned)it & 1u);
+        const int rx0 = s_rect[0], ry0 = s_rect[1];
+        const bool staged = s_rect[2] != 0;
+        const depth_t* tile = reinterpret_cast<const depth_t*>(s_tile);
+        float tv[4] = {t4.x, t4.y, t4.z, t4.w};
+        unsigned short wv[4] = {w4.x, w4.y, w4.z, w4.w};
+        unsigned short cv[12];
+        if (HAS_COLOR) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                cv[4 * k + 0] = (unsigned short)(c2[k].x & 0xffffu);
+                cv[4 * k + 1] = (unsigned short)(c2[k].x >> 16);
+                cv[4 * k + 2] = (unsigned short)(c2[k].y & 0xffffu);
+                cv[4 * k + 3] = (unsigned short)(c2[k].y >> 16);
+            }
+        }
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (pix[k] < 0) continue;
+            const int ui = pix[k] & 0xffff, vi = pix[k] >> 16;
+            const int tx = ui - rx0, ty = vi - ry0;
+            const depth_t raw = (staged && (unsigned)tx < (unsigned)kTileCols && (unsigned)ty < (unsigned)kTileRows)
+                                        ? tile[ty * kTileCols + tx]
+                                        : __ldg(&((const depth_t*)a.depth)[(size_t)vi * a.cols + ui]);
+            const float depth = depth_metres<depth_t>(a, raw);                      // :253
+            float sdf = sub(depth, zc[k]);
+            if (depth <= 0 || depth > a.depth_max || zc[k] <= 0 || sdf < -a.sdf_trunc) continue;   // :256-258
+            sdf = sdf < a.sdf_trunc ? sdf : a.sdf_trunc;
+            sdf = dvd(sdf, a.sdf_trunc);
+            any = true;
+            const float inv_wsum = __ldg(&a.inv_w[wv[k]]);                           // :274, 1 / (w + 1) per u16 weight
+            const float weight = (float)wv[k];
+            tv[k] = mul(add(mul(weight, tv[k]), sdf), inv_wsum);                    // :276
+            if (HAS_COLOR) {
+                int cu, cw;
+                bool inb;
+                if (a.same_k && ui >= 1 && vi >= 1 && ui <= a.cols - 2 && vi <= a.rows - 2) {
+                    // :283-290 with identical intrinsics: uf = (fx ((ui - cx) / fx)) + cx differs from ui by
+                    // a few ulps of the image width (<< 0.5), so round(uf) == ui and an INTERIOR pixel is
+                    // always inside the boundary; border pixels take the general path below
+                    cu = ui;
+                    cw = vi;
+                    inb = true;
+                } else {
+                    float px, pyy, pzz, uf, vf;
+                    unproject(a.dcam, (float)ui, (float)vi, 1.0f, px, pyy, pzz);   // :283
+                    project(a.ccam, px, pyy, pzz, uf, vf);                           // :286
+                    inb = in_boundary(uf, vf, a.rows, a.cols);
+                    cu = (int)roundf(uf);
+                    cw = (int)roundf(vf);
+                }
+                if (inb) {
+                    const color_in_t* in = (const color_in_t*)a.color + ((size_t)cw * a.cols + cu) * 3;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const float v = mul(add(mul(weight, (float)cv[3 * k + c]),
+                                                mul((float)__ldg(&in[c]), a.color_multiplier)),
+                                            inv_wsum);                              // :295-298
+                        cv[3 * k + c] = (unsigned short)v;
+                    }
+                }
+            }
+            wv[k] = (unsigned short)add(weight, 1.0f);                              // :302
+        }
+        if (any) {
+            *reinterpret_cast<float4*>(tsdf) = make_float4(tv[0], tv[1], tv[2], tv[3]);
+            *reinterpret_cast<ushort4*>(wt) = make_ushort4(wv[0], wv[1], wv[2], wv[3]);
+            if (HAS_COLOR) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    reinterpret_cast<uint2*>(cb)[k] = make_uint2((unsigned)cv[4 * k] | ((unsigned)cv[4 * k + 1] << 16),
+                                                                 (unsigned)cv[4 * k + 2] | ((unsigned)cv[4 * k + 3] << 16));
+            }
+        }
+    }
+    if (fused) {
+        // last CTA publishes the new size and re-arms the per-frame counters
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_last = atomicAdd(&a.counters[3], 1) == (int)gridDim.x - 1;
+        __syncthreads();
+        if (s_last && tid == 0) {
+            if (drop) {
+                *a.frame_count = 0;
+                if (a.dropped[1] == 0) {          // first dropped frame: what it needed, and which one it was
+                    a.dropped[0] = size0 + n_new;
+                    a.dropped[1] = a.frame_id;
+                }
+                a.counters[2] = 1;                // sticky: later frames are dropped too until the host reserves
+            } else {
+                *a.frame_count = n_total;
+                *a.size = size0 + n_new;
+            }
+            if (n_new > *a.max_new) *a.max_new = n_new;
+            a.counters[0] = 0;
+            a.counters[1] = 0;
+            a.counters[3] = 0;
+        }
+    }
+}
+
+__global__ void inv_weight_table_kernel(float* __restrict__ out) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w < 65536) out[w] = dvd(1.0f, (float)(w + 1));   // VoxelBlockGridImpl.h:274 inv_wsum for weight w
 }
 
 __global__ void gather_keys_kernel(const int* __restrict__ keys, const int* __restrict__ slots, int n,
@@ -449,6 +794,73 @@ using namespace o3db;
 
 
 namespace o3db {
+
+
+// cuTensorMapEncodeTiled, resolved at run time through the runtime API (no link against libcuda).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        (void)cudaGetLastError();
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+// TMA descriptor of a row-major [rows][cols] depth image for kTileRowBytes x kTileRows boxes.  Returns false when
+// the image cannot be described (unaligned base / pitch, tiny image, no driver entry point): the kernel then
+// reads the image directly.
+static bool make_depth_tensor_map(CUtensorMap* map, const void* depth, int depth_dtype, int rows, int cols) {
+    memset(map, 0, sizeof(*map));
+    const size_t es = depth_dtype == O3DB_DEPTH_U16 ? 2 : 4;
+    const int box_cols = (int)(kTileRowBytes / es);
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc || ((uintptr_t)depth & 15) || ((size_t)cols * es) % 16 || cols < box_cols || rows < kTileRows) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)cols * es};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)kTileRows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(map, depth_dtype == O3DB_DEPTH_U16 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                           2, const_cast<void*>(depth), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+// Is q' = fma(fma(-d y, s, d), y, d y), y = RN(1 / s), equal to RN(d / s) for EVERY u16 d?  (See depth_metres.)
+static bool verify_fast_scale(float s) {
+    if (!(s > 0.f) || !std::isfinite(s)) return false;
+    const float y = 1.0f / s;
+    for (int i = 0; i < 65536; ++i) {
+        const float d = (float)i;
+        const float q = d * y;
+        const float r = fmaf(-q, s, d);
+        if (fmaf(r, y, q) != d / s) return false;
+    }
+    return true;
+}
+
+// Launch with the programmatic-stream-serialization attribute (the kernels call griddepcontrol.wait before they
+// touch anything a predecessor wrote).
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned grid, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kT);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 static unsigned pow2_at_least(int64_t v) {
     unsigned p = 16;

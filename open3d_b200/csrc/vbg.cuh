@@ -97,6 +97,9 @@ struct o3db_vbg {
     int2* new_list = nullptr;
     int* frame_slots = nullptr;
     int* frame_count = nullptr;
+    float* inv_w = nullptr;        // [65536] 1 / (w + 1) per u16 weight (integrate16_kernel)
+    float checked_scale = 0.f;     // depth_scale the 3-FMA u16 division was last verified for ...
+    bool checked_scale_ok = false; // ... and whether it reproduces d / scale for all 65536 u16 values
     // frustum-only table for the stand-alone GetUniqueBlockCoordinates
     int* ftable = nullptr;
     unsigned fbuckets = 0;
