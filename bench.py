@@ -388,6 +388,43 @@ def icp_config(n_gpus):
 # this repo's arm
 # ----------------------------------------------------------------------------------------------
 
+def bench_config3(args, rank, world, comm, torch, barrier, max_over_ranks):
+    """BASELINE configs[3]: MultiScaleICP with TransformationEstimationForColoredICP, 3 scales, a 5M-point pair; with N
+    ranks the source of every level is split by rows, one 30-double exchange per iteration.  One run,
+    through the public API (open3d_b200.t.pipelines.registration.multi_scale_icp)."""
+    import open3d_b200 as o3d
+    from tests.synth import make_colors, make_icp_pair
+    reg = o3d.t.pipelines.registration
+    n = int(args.config3_points)
+    src, tgt, nrm, T_gt = make_icp_pair(n, seed=11)
+    sc = make_colors((np.c_[src.astype(np.float64), np.ones(len(src))] @ T_gt.T)[:, :3], 1)
+    tc = make_colors(tgt, 1)
+    s = o3d.t.geometry.PointCloud(src).set_point_colors(sc)
+    t = o3d.t.geometry.PointCloud(tgt).set_point_normals(nrm).set_point_colors(tc)
+    voxels, radii, iters = [0.08, 0.04, 0.02], [0.16, 0.08, 0.05], [20, 15, 10]
+    crits = [reg.ICPConvergenceCriteria(0, 0, k) for k in iters]
+    est = reg.TransformationEstimationForColoredICP()
+    levels = []
+    runs = []
+    for rep in range(2):                      # first run warms allocator pools / NCCL / IPC mappings
+        torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        res = reg.multi_scale_icp(s, t, voxels, crits, radii, np.eye(4), est, None, comm)
+        torch.cuda.synchronize()
+        runs.append(max_over_ranks(time.perf_counter() - t0))
+    total_iters = int(res.num_iterations)
+    return {"workload": "multi-scale ColoredICP, 3 scales (voxel 0.08 / 0.04 / 0.02, radius 0.16 / 0.08 / 0.05, "
+                        f"{iters} iterations), {len(src)} source x {len(tgt)} target points, source rows split over "
+                        f"{world} GPU(s), pyramid + colour gradients built inside the call",
+            "baseline_config": "configs[3]", "n_gpus": world, "seconds_total": runs[-1], "seconds_first_run": runs[0],
+            "iterations": total_iters, "iters_per_sec_end_to_end": total_iters / runs[-1],
+            "fitness": float(res.fitness), "inlier_rmse": float(res.inlier_rmse),
+            "transformation_error_vs_ground_truth": float(np.abs(np.asarray(res.transformation) - T_gt).max()),
+            "timing": "wall clock around multi_scale_icp (voxel pyramid, colour gradients, index builds, all iterations, "
+                      "final evaluation), max over ranks"}
+
+
 def main():
     # NCCL announces its version on stdout at VERSION level; keep stdout to the one JSON line
     if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
@@ -404,6 +441,10 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--tsdf-frames", type=int, default=TSDF_FRAMES)
     ap.add_argument("--cell-scale", type=float, default=0.0)
+    ap.add_argument("--config3", action="store_true",
+                    help="also run BASELINE configs[3] once (multi-scale ColoredICP, 3 scales, 5M points, source split over the "
+                         "ranks); always on for N > 1")
+    ap.add_argument("--config3-points", type=int, default=5_000_000)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -555,6 +596,51 @@ def main():
                    "ms_per_step": e2e_ms / args.steps,
                    "path": "per rank: pinned H2D of shard + target, o3db_icp_create(comm) + iterate + finish, D2H result"}
 
+    # ------------------------------------------- multi-GPU extras: transport, strong scaling, configs[3]
+    multi = None
+    if world > 1:
+        transport = ("in-kernel exchange over NVLink peer memory (one kernel per iteration)"
+                     if L.lib.o3db_comm_uses_peer_memory(comm.handle) else
+                     "ncclAllReduce(30 x f64) + finalize kernel per iteration")
+        # strong scaling (SURVEY 8e's actual partition): ONE 2M-point registration, its source split over the ranks
+        from open3d_b200.distributed import shard_range
+        full = make_icp_pair(ICP_POINTS, seed=2)[0]
+        b, e = shard_range(len(full), rank, world)
+        d_shard = torch.from_numpy(np.ascontiguousarray(full[b:e])).cuda()
+        hs_ = C.c_void_p()
+        L.check(L.lib.o3db_icp_create(d_shard.data_ptr(), e - b, d_tgt.data_ptr(), d_nrm.data_ptr(), m, L.dptr(T0), C.byref(opt),
+                                      comm.handle, stream, C.byref(hs_)))
+        rs = L.IcpResult()
+
+        def strong_step():
+            L.check(L.lib.o3db_icp_reset(hs_, stream))
+            flush_l2()
+            a, c = ev(), ev()
+            a.record()
+            L.check(L.lib.o3db_icp_iterate(hs_, ICP_ITERS, stream))
+            L.check(L.lib.o3db_icp_finish(hs_, C.byref(rs), None, None, stream))
+            c.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(c)
+        for _ in range(args.warmup):
+            strong_step()
+        barrier()
+        strong_ms = max_over_ranks(sum(strong_step() for _ in range(args.steps)))
+        L.lib.o3db_icp_destroy(hs_)
+        multi = {"transport": transport,
+                 "strong_scaling": {"value": ICP_ITERS * args.steps / (strong_ms * 1e-3), "unit": "iters/s",
+                                    "ms_per_step": strong_ms / args.steps, "points_source_total": int(len(full)),
+                                    "points_source_per_gpu": int(e - b), "scaling": "strong",
+                                    "workload": "ONE 2M-point registration (BASELINE configs[1]), source rows split over the ranks, "
+                                                "target replicated",
+                                    "fitness": rs.fitness, "inlier_rmse": rs.inlier_rmse}}
+    if world > 1 or args.config3:
+        try:
+            cfg3 = bench_config3(args, rank, world, comm, torch, barrier, max_over_ranks)
+        except Exception as exc:   # reported, never hidden; the primary line must survive
+            cfg3 = {"error": f"{type(exc).__name__}: {exc}"}
+        multi = dict(multi or {}, config3=cfg3)
+
     # ----------------------------------------------------------------- TSDF
     tsdf = None
     if not args.skip_tsdf:
@@ -581,6 +667,8 @@ def main():
                     "index_build_ms": build_ms, "result": final, "roofline": icp_roof, "cpu_baseline": cpu,
                     "e2e": icp_e2e, "gpu_launches": int(icp_launches), "clocks": clocks.summary(),
                     "wall_s_timed_region": icp_wall}
+        if multi is not None:
+            icp_line["multi_gpu"] = multi
         if args.metric == "tsdf" and tsdf is not None:
             # same one-line schema, BASELINE configs[2] on top: depth-only integration is `value` (the config names
             # depth frames), the depth+colour run and everything else sit beside it; the ICP line rides along nested

@@ -233,6 +233,10 @@ int o3db_icp_iterate(o3db_icp* icp, int iterations, void* stream);
  * per_iteration_host (optional): 2 doubles (fitness, inlier_rmse) per executed iteration. */
 int o3db_icp_finish(o3db_icp* icp, o3db_icp_result* result_host, int64_t* correspondences_dev,
                     double* per_iteration_host, void* stream);
+/* The loop's state after the last executed iteration WITHOUT the final evaluation pass: transformation, and the
+ * fitness / inlier_rmse that iteration's own search measured.  What MultiScaleICP keeps between scales
+ * (Registration.cpp:406-431 re-runs ComputeRegistrationResult only after the last scale). */
+int o3db_icp_state(o3db_icp* icp, o3db_icp_result* result_host, double* per_iteration_host, void* stream);
 void o3db_icp_destroy(o3db_icp* icp);
 
 /* One-shot convenience: create + iterate(max_iteration) + finish + destroy. */
@@ -264,6 +268,10 @@ int o3db_icp_point_to_plane_host(const float* source_host, int64_t n, const floa
 int o3db_comm_get_unique_id(uint8_t id_out[O3DB_UNIQUE_ID_BYTES]);
 int o3db_comm_create(const uint8_t id[O3DB_UNIQUE_ID_BYTES], int rank, int world_size, o3db_comm** out);
 int o3db_comm_allreduce_f64(o3db_comm* comm, double* buf_dev, int count, void* stream);
+/* 1 when the ranks exchange the per-iteration system INSIDE the iteration kernel over NVLink / NVSwitch peer memory
+ * (every rank could map every other rank's mailbox through CUDA IPC at o3db_comm_create), 0 when each iteration is
+ * kernel + ncclAllReduce + finalize kernel.  Identical on all ranks.  (Set O3DB_COMM_NO_PEER to force NCCL.) */
+int o3db_comm_uses_peer_memory(const o3db_comm* comm);
 void o3db_comm_destroy(o3db_comm* comm);
 
 /* ------------------------------------------------------------------------
@@ -335,14 +343,44 @@ int o3db_vbg_integrate(o3db_vbg* vbg, const int32_t* block_coords_dev, int64_t n
                        float depth_scale, float depth_max, float trunc_voxel_multiplier, void* stream);
 
 /* slam::Model::Integrate (t/pipelines/slam/Model.cpp:91-106) as ONE fused,
- * host-sync-free pipeline: frustum touch + global activate + integrate.
- * num_blocks_host (optional) receives the frame's frustum block count of the
- * PREVIOUS call unless `sync` is non-zero. */
+ * host-sync-free pipeline: frustum touch + global activate + integrate (two launches per frame).
+ *
+ * Capacity: the reference grows the map inside HashMap::Activate (HashMap.cpp:166-181).  Here the FIRST frame of a
+ * handle (and the first one after o3db_vbg_reserve) sizes the map synchronously from the touch kernel's own count;
+ * later frames run asynchronously and the map is grown ahead of need from what earlier frames added (3 frames x
+ * twice the largest per-frame increase seen, at least 3 x 2048 blocks).  A frame that still does not fit (a camera
+ * jump adding more blocks than that) is DROPPED AS A WHOLE on the device, together with every later frame: nothing
+ * is integrated, the table is restored, the volume is exactly the state before that frame.  The next call that can
+ * see it (at most two calls later; o3db_vbg_size / _last_frustum_blocks see it immediately) returns
+ * O3DB_ERR_CAPACITY with "fused frame #K needed N blocks" in o3db_last_error(); call o3db_vbg_reserve(>= N) — which
+ * also re-arms the handle — and resubmit frames K, K+1, ... (K counts fused frames of this handle from 0). */
 int o3db_vbg_integrate_frame(o3db_vbg* vbg, const void* depth_dev, int depth_dtype,
                              const void* color_dev, int color_dtype, int rows, int cols,
                              const double intrinsic_host[9], const double extrinsic_host[16],
                              float depth_scale, float depth_max, float trunc_voxel_multiplier,
                              void* stream);
+/* Stateless twins of the reference's DepthTouchCUDA / IntegrateCUDA<...> (t/geometry/kernel/VoxelBlockGrid.h:345-381,
+ * VoxelBlockGridCUDA.cu:106-244) for an integration that keeps the reference's own core::HashMap: nothing but the
+ * arguments of those functions is needed — block indices / keys / value buffers are the reference hash map's tensors.
+ *   o3db_depth_touch: unique block coordinates of a depth frame (stride must be 4, VoxelBlockGrid.cpp:221); sdf_trunc
+ *     is passed as the reference passes it.  Synchronises the stream (the count sizes the output, as upstream).
+ *   o3db_integrate_blocks: per-voxel fusion of the listed blocks.  value_layout selects the reference's two value
+ *     layouts: O3DB_VALUES_U16 (weight UInt16, colour UInt16 — the slam::Model layout, fast path) or O3DB_VALUES_F32
+ *     (weight Float32, colour Float32); tsdf is Float32 in both.  All four IntegrateCUDA instantiations are covered
+ *     by {u16 depth + u8 colour, f32 depth + f32 colour} x {U16, F32}. */
+#define O3DB_VALUES_U16 0
+#define O3DB_VALUES_F32 1
+int o3db_depth_touch(const void* depth_dev, int depth_dtype, int rows, int cols, const double intrinsic_host[9],
+                     const double extrinsic_host[16], int block_resolution, float voxel_size, float sdf_trunc,
+                     float depth_scale, float depth_max, int stride, int32_t* block_coords_dev, int64_t max_blocks,
+                     int64_t* num_blocks_host, void* stream);
+int o3db_integrate_blocks(const void* depth_dev, int depth_dtype, const void* color_dev, int color_dtype, int rows,
+                          int cols, const int32_t* block_indices_dev, int64_t num_blocks,
+                          const int32_t* block_keys_dev, float* tsdf_dev, void* weight_dev, void* color_buf_dev,
+                          int value_layout, const double depth_intrinsic_host[9], const double color_intrinsic_host[9],
+                          const double extrinsic_host[16], int block_resolution, float voxel_size, float sdf_trunc,
+                          float depth_scale, float depth_max, void* stream);
+
 /* Same through HOST images (pinned recommended): H2D copies included. */
 int o3db_vbg_integrate_frame_host(o3db_vbg* vbg, const void* depth_host, int depth_dtype,
                                   const void* color_host, int color_dtype, int rows, int cols,

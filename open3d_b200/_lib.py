@@ -90,6 +90,7 @@ _SIGS = {
     "o3db_icp_reset": (_i, [_vp, _vp]),
     "o3db_icp_iterate": (_i, [_vp, _i, _vp]),
     "o3db_icp_finish": (_i, [_vp, C.POINTER(IcpResult), _vp, _dp, _vp]),
+    "o3db_icp_state": (_i, [_vp, C.POINTER(IcpResult), _dp, _vp]),
     "o3db_icp_destroy": (None, [_vp]),
     "o3db_icp_point_to_plane": (_i, [_vp, _i64, _vp, _vp, _i64, _dp, C.POINTER(IcpOptions), C.POINTER(IcpResult),
                                      _vp, _dp, _vp]),
@@ -97,11 +98,15 @@ _SIGS = {
                                           C.POINTER(IcpResult), _vp, _dp]),
     "o3db_comm_get_unique_id": (_i, [_vp]),
     "o3db_comm_create": (_i, [_vp, _i, _i, C.POINTER(_vp)]),
+    "o3db_comm_uses_peer_memory": (_i, [_vp]),
     "o3db_comm_allreduce_f64": (_i, [_vp, _vp, _i, _vp]),
     "o3db_comm_destroy": (None, [_vp]),
     "o3db_vbg_create": (_i, [_f, _i, _i64, _i, _vp, C.POINTER(_vp)]),
     "o3db_vbg_destroy": (None, [_vp]),
     "o3db_vbg_size": (_i64, [_vp, _vp]),
+    "o3db_depth_touch": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _f, _f, _f, _f, _i, _vp, _i64, _vp, _vp]),
+    "o3db_integrate_blocks": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _i64, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _f, _f,
+                                   _f, _f, _vp]),
     "o3db_vbg_capacity": (_i64, [_vp]),
     "o3db_vbg_reserve": (_i, [_vp, _i64, _vp]),
     "o3db_vbg_activate": (_i, [_vp, _vp, _i64, _vp, _vp, _vp]),

@@ -7,8 +7,10 @@
 // library.  Declarations below restate the stable NCCL 2.x C ABI (nccl.h).
 #include <dlfcn.h>
 
+#include <cstdlib>
 #include <mutex>
 #include <new>
+#include <vector>
 
 #include "comm.h"
 #include "common.cuh"
@@ -23,6 +25,7 @@ struct NcclApi {
     int (*GetUniqueId)(nccl_unique_id*) = nullptr;
     int (*CommInitRank)(nccl_comm_t*, int, nccl_unique_id, int) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, nccl_comm_t, cudaStream_t) = nullptr;
     int (*CommDestroy)(nccl_comm_t) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
     bool ok = false;
@@ -38,6 +41,7 @@ void load_nccl() {
     g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(h, "ncclGetUniqueId");
     g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(h, "ncclCommInitRank");
     g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(h, "ncclAllReduce");
+    g_nccl.AllGather = (decltype(g_nccl.AllGather))dlsym(h, "ncclAllGather");
     g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(h, "ncclCommDestroy");
     g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(h, "ncclGetErrorString");
     g_nccl.ok = g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllReduce && g_nccl.CommDestroy;
@@ -63,7 +67,73 @@ int nccl_check(int rc, const char* what) {
 struct o3db_comm {
     nccl_comm_t comm = nullptr;
     int rank = 0, world = 1;
+    // in-kernel exchange over peer memory (see icp.cu: peer_all_reduce); absent => NCCL all-reduce
+    bool peer = false;
+    double* my_box = nullptr;                 // cudaMalloc'ed, exported through CUDA IPC
+    void* opened[o3db::kMaxPeers] = {};       // peers' mailboxes as opened here
+    unsigned long long* seq = nullptr;
+    o3db::PeerView view{};
 };
+
+namespace {
+
+// Maps every rank's mailbox into every other rank's address space.  All ranks take the same decision (the
+// last all-gather carries each rank's success flag), so either every rank uses the in-kernel exchange or none.
+void setup_peer_exchange(o3db_comm* c) {
+    using namespace o3db;
+    if (c->world < 2 || c->world > kMaxPeers || !g_nccl.AllGather || getenv("O3DB_COMM_NO_PEER")) return;
+    const size_t box_bytes = (size_t)2 * c->world * kBoxDoubles * sizeof(double);
+    struct Msg {
+        cudaIpcMemHandle_t h;
+        int ok;
+        int pad[15];
+    };
+    static_assert(sizeof(Msg) == 128, "Msg layout");
+    Msg mine{}, *all_dev = nullptr, *mine_dev = nullptr;
+    std::vector<Msg> all((size_t)c->world);
+    bool ok = cudaMalloc(&c->my_box, box_bytes) == cudaSuccess && cudaMemset(c->my_box, 0, box_bytes) == cudaSuccess &&
+              cudaMalloc(&c->seq, sizeof(unsigned long long)) == cudaSuccess &&
+              cudaMemset(c->seq, 0, sizeof(unsigned long long)) == cudaSuccess &&
+              cudaIpcGetMemHandle(&mine.h, c->my_box) == cudaSuccess;
+    mine.ok = ok ? 1 : 0;
+    auto gather = [&]() -> bool {
+        return cudaMemcpy(mine_dev, &mine, sizeof(Msg), cudaMemcpyHostToDevice) == cudaSuccess &&
+               g_nccl.AllGather(mine_dev, all_dev, sizeof(Msg), /*ncclInt8*/ 0, c->comm, (cudaStream_t)0) == 0 &&
+               cudaStreamSynchronize(0) == cudaSuccess &&
+               cudaMemcpy(all.data(), all_dev, sizeof(Msg) * c->world, cudaMemcpyDeviceToHost) == cudaSuccess;
+    };
+    if (cudaMalloc(&all_dev, sizeof(Msg) * c->world) != cudaSuccess || cudaMalloc(&mine_dev, sizeof(Msg)) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return;   // (cannot even run the agreement round: every rank that fails here fails alike — out of memory)
+    }
+    bool all_ok = gather();
+    for (int p = 0; all_ok && p < c->world; ++p) all_ok = all[p].ok != 0;
+    if (all_ok) {
+        for (int p = 0; p < c->world && ok; ++p) {
+            if (p == c->rank) {
+                c->view.box[p] = c->my_box;
+            } else if (cudaIpcOpenMemHandle(&c->opened[p], all[p].h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess) {
+                c->view.box[p] = (double*)c->opened[p];
+            } else {
+                ok = false;
+            }
+        }
+    }
+    // second round: did every rank manage to open every mailbox?
+    mine.ok = (all_ok && ok) ? 1 : 0;
+    all_ok = gather();
+    for (int p = 0; all_ok && p < c->world; ++p) all_ok = all[p].ok != 0;
+    cudaFree(all_dev);
+    cudaFree(mine_dev);
+    (void)cudaGetLastError();
+    if (!all_ok) return;
+    c->view.seq = c->seq;
+    c->view.rank = c->rank;
+    c->view.world = c->world;
+    c->peer = true;
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -95,9 +165,12 @@ int o3db_comm_create(const uint8_t id_bytes[O3DB_UNIQUE_ID_BYTES], int rank, int
         delete c;
         return rc;
     }
+    setup_peer_exchange(c);
     *out = c;
     return O3DB_OK;
 }
+
+int o3db_comm_uses_peer_memory(const o3db_comm* comm) { return comm && comm->peer ? 1 : 0; }
 
 int o3db_comm_allreduce_f64(o3db_comm* comm, double* buf_dev, int count, void* stream) {
     O3DB_REQUIRE(comm != nullptr && buf_dev != nullptr && count > 0, "o3db_comm_allreduce_f64: bad arguments");
@@ -108,8 +181,15 @@ int o3db_comm_allreduce_f64(o3db_comm* comm, double* buf_dev, int count, void* s
 
 void o3db_comm_destroy(o3db_comm* comm) {
     if (!comm) return;
+    cudaDeviceSynchronize();
+    for (void* p : comm->opened)
+        if (p) cudaIpcCloseMemHandle(p);
+    if (comm->my_box) cudaFree(comm->my_box);
+    if (comm->seq) cudaFree(comm->seq);
     if (comm->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm->comm);
     delete comm;
 }
 
 }  // extern "C"
+
+const o3db::PeerView* o3db_comm_peer_view(const o3db_comm* comm) { return comm && comm->peer ? &comm->view : nullptr; }

@@ -797,6 +797,9 @@ struct IcpArgs {
     const float* sint;    // per sorted source point: intensity
     float sqrt_lg, sqrt_lp;
     long long* dbg;       // -DICP_TIMING=1 builds only: 8 timestamps per block (see profiles/icp_timing.py)
+    // multi-GPU, in-kernel exchange (use_peer != 0): every rank's mailbox as mapped into this process
+    PeerView peer;
+    int use_peer;
 };
 
 __device__ void set_identity(double* T, float* Uf) {
@@ -1048,6 +1051,62 @@ __device__ __forceinline__ void icp_accumulate_chunk_smem(float (&term)[32], boo
     __syncwarp();   // the tile is rewritten by the next chunk
 }
 
+// The exchange step of the source-sharded loop, done INSIDE the iteration kernel over NVLink /
+// NVSwitch peer memory instead of kernel -> ncclAllReduce -> finalize kernel: warp 0 of each rank's last block
+// stores its 30 local sums into slot [parity][rank] of EVERY rank's mailbox (plain peer stores), publishes them
+// with a system-scope release store of the sequence number, then waits until all `world` slots of its own
+// mailbox carry that number and adds them in rank order — so every rank computes bit-identical totals and the
+// identical pose update, with no broadcast.  Two slot parities suffice: rank r reuses a slot two collectives
+// later, which it can only reach after every peer has published the collective in between, i.e. after every peer
+// has finished reading the older one.  All 32 lanes of the warp must call it.  Returns false on a timeout (a
+// peer died): the caller flags a communication error instead of hanging the GPU.
+__device__ __forceinline__ bool peer_all_reduce(const PeerView& pv, double* s_final) {
+    const int lane = threadIdx.x & 31;
+    unsigned long long seq = 0;
+    if (lane == 0) seq = *pv.seq + 1;
+    seq = __shfl_sync(0xffffffffu, seq, 0);
+    const size_t par = (size_t)(seq & 1ull) * pv.world;
+    const double mine = lane < kNumSums ? s_final[lane] : 0.0;
+    for (int p = 0; p < pv.world; ++p)
+        if (lane < kNumSums) pv.box[p][(par + pv.rank) * kBoxDoubles + lane] = mine;
+    __threadfence_system();
+    __syncwarp();
+    if (lane < pv.world) {
+        unsigned long long* flag = reinterpret_cast<unsigned long long*>(pv.box[lane] + (par + pv.rank) * kBoxDoubles + kNumSums);
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(seq) : "memory");
+    }
+    double acc = 0.0;
+    bool ok = true;
+    long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (int r = 0; r < pv.world; ++r) {
+        const double* slot = pv.box[pv.rank] + (par + r) * kBoxDoubles;
+        if (lane == 0) {
+            const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(slot + kNumSums);
+            unsigned long long seen;
+            for (;;) {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flag) : "memory");
+                if (seen == seq) break;
+                long long t;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                if (t - t0 > 4000000000ll) {   // 4 s
+                    ok = false;
+                    break;
+                }
+            }
+        }
+        ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;   // (also orders the other lanes' loads after lane 0's acquire)
+        if (!ok) break;
+        double v = 0.0;
+        if (lane < kNumSums) asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(slot + lane) : "memory");
+        acc += v;
+    }
+    if (lane < kNumSums) s_final[lane] = acc;
+    if (lane == 0) *pv.seq = seq;
+    __syncwarp();
+    return ok;
+}
+
 // Block epilogue shared by both iteration kernels: block partial -> (last block) grand total, solve,
 // pose update, convergence test.
 template <int MODE>
@@ -1058,6 +1117,13 @@ __device__ __forceinline__ void icp_block_epilogue(const IcpArgs& a, double (*s_
     ICP_STAMP(5);   // last block: grand total ready
     if (a.fuse_finalize) {
         if (threadIdx.x < 32) {
+            if (a.use_peer && !peer_all_reduce(a.peer, s_final)) {
+                if (threadIdx.x == 0) {        // a peer never answered: stop the loop, the host reports O3DB_ERR_COMM
+                    a.st->status = 2;
+                    a.st->done = 1;
+                }
+                return;
+            }
             if (MODE == 0) icp_finalize_iteration(a, s_final, &s_warp[0][0]);   // (s_warp is dead: reused as scratch)
             else if (threadIdx.x == 0) icp_finalize_evaluate(a, s_final);
         }
@@ -1384,7 +1450,10 @@ static IcpArgs make_args(o3db_icp* c) {
     a.rel_fitness = c->opt.relative_fitness;
     a.rel_rmse = c->opt.relative_rmse;
     a.max_iteration = c->opt.max_iteration;
-    a.fuse_finalize = c->comm ? 0 : 1;
+    const PeerView* pv = o3db_comm_peer_view(c->comm);
+    a.use_peer = pv ? 1 : 0;
+    if (pv) a.peer = *pv;
+    a.fuse_finalize = (c->comm && !pv) ? 0 : 1;   // NCCL transport: all-reduce + finalize kernel follow the launch
     a.tcg = c->tcg4;
     a.sint = c->sint;
     a.sqrt_lg = (float)sqrt(c->lambda_geometric);          // RegistrationCUDA.cu:205-208
@@ -1847,7 +1916,7 @@ int o3db_icp_iterate(o3db_icp* c, int iterations, void* stream) {
     for (int k = 0; k < todo; ++k) {
         launch_icp(icp_kernel_for(c, 0), c->grid_blocks, icp_smem_bytes(c, 0), st, a);
         O3DB_LAUNCH_CHECK();
-        if (c->comm) {
+        if (!a.fuse_finalize) {
             int rc = o3db_comm_allreduce_f64(c->comm, (double*)((char*)c->st + offsetof(IcpState, sums)), kNumSums, st);
             if (rc) return rc;
             icp_finalize_kernel<0><<<1, 32, 0, st>>>(a);
@@ -1858,20 +1927,7 @@ int o3db_icp_iterate(o3db_icp* c, int iterations, void* stream) {
     return O3DB_OK;
 }
 
-int o3db_icp_finish(o3db_icp* c, o3db_icp_result* result, int64_t* correspondences_dev, double* per_iteration_host,
-                    void* stream) {
-    O3DB_REQUIRE(c != nullptr && result != nullptr, "o3db_icp_finish: null argument");
-    cudaStream_t st = (cudaStream_t)stream;
-    IcpArgs a = make_args(c);
-    a.corr_out = correspondences_dev;
-    launch_icp(icp_kernel_for(c, 1), c->grid_blocks, icp_smem_bytes(c, 1), st, a);
-    O3DB_LAUNCH_CHECK();
-    if (c->comm) {
-        int rc = o3db_comm_allreduce_f64(c->comm, (double*)((char*)c->st + offsetof(IcpState, sums)), kNumSums, st);
-        if (rc) return rc;
-        icp_finalize_kernel<1><<<1, 32, 0, st>>>(a);
-        O3DB_LAUNCH_CHECK();
-    }
+static int icp_read_state(o3db_icp* c, o3db_icp_result* result, double* per_iteration_host, cudaStream_t st) {
     O3DB_CUDA_CHECK(cudaMemcpyAsync(c->h_st, c->st, sizeof(IcpState), cudaMemcpyDeviceToHost, st));
     O3DB_CUDA_CHECK(cudaStreamSynchronize(st));
     const IcpState& h = *c->h_st;
@@ -1881,6 +1937,10 @@ int o3db_icp_finish(o3db_icp* c, o3db_icp_result* result, int64_t* correspondenc
     result->converged = h.converged;
     result->num_iterations = h.iter;
     result->num_correspondences = (int64_t)h.count;
+    if (h.status == 2) {
+        set_last_error("multi-GPU exchange timed out: a peer rank did not publish its sums (in-kernel NVLink exchange)");
+        return O3DB_ERR_COMM;
+    }
     result->status = h.status ? O3DB_ERR_SINGULAR : O3DB_OK;
     if (per_iteration_host && h.executed > 0) {
         O3DB_CUDA_CHECK(cudaMemcpyAsync(per_iteration_host, c->per_iter, (size_t)h.executed * 2 * sizeof(double),
@@ -1892,6 +1952,29 @@ int o3db_icp_finish(o3db_icp* c, o3db_icp_result* result, int64_t* correspondenc
         return O3DB_ERR_SINGULAR;
     }
     return O3DB_OK;
+}
+
+
+int o3db_icp_finish(o3db_icp* c, o3db_icp_result* result, int64_t* correspondences_dev, double* per_iteration_host,
+                    void* stream) {
+    O3DB_REQUIRE(c != nullptr && result != nullptr, "o3db_icp_finish: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    IcpArgs a = make_args(c);
+    a.corr_out = correspondences_dev;
+    launch_icp(icp_kernel_for(c, 1), c->grid_blocks, icp_smem_bytes(c, 1), st, a);
+    O3DB_LAUNCH_CHECK();
+    if (!a.fuse_finalize) {
+        int rc = o3db_comm_allreduce_f64(c->comm, (double*)((char*)c->st + offsetof(IcpState, sums)), kNumSums, st);
+        if (rc) return rc;
+        icp_finalize_kernel<1><<<1, 32, 0, st>>>(a);
+        O3DB_LAUNCH_CHECK();
+    }
+    return icp_read_state(c, result, per_iteration_host, st);
+}
+
+int o3db_icp_state(o3db_icp* c, o3db_icp_result* result, double* per_iteration_host, void* stream) {
+    O3DB_REQUIRE(c != nullptr && result != nullptr, "o3db_icp_state: null argument");
+    return icp_read_state(c, result, per_iteration_host, (cudaStream_t)stream);
 }
 
 int o3db_icp_point_to_plane(const float* source_dev, int64_t n, const float* target_dev,

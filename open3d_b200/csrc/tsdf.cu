@@ -14,6 +14,7 @@
 
 #include <climits>
 #include <cmath>
+#include <cstdlib>
 #include <new>
 #include <vector>
 
@@ -136,18 +137,36 @@ __global__ void __launch_bounds__(kT) touch_kernel(TouchArgs a) {
         __threadfence();   // the candidate key must be visible before its marker is
         r = probe<true>(a.tab, a.cand_keys, cand, kx, ky, kz, &bucket);
     }
-    if (r >= 0) {
-        if (a.stamp && __ldcg(&a.stamp[r]) != a.frame_id && atomicExch(&a.stamp[r], a.frame_id) != a.frame_id) {
-            const int p = atomicAdd(&a.counters[0], 1);
+    // (the exchange alone decides who is first in this frame: one round trip less than checking the stamp first;
+    // only one lane per distinct key and warp gets here)
+    const bool first_exist = r >= 0 && a.stamp && atomicExch(&a.stamp[r], a.frame_id) != a.frame_id;
+    const bool first_new = r == kResInserted;
+    if (r == kResFull) a.counters[2] = 1;
+    // warp-aggregated list appends: one atomic per warp and list instead of one per block key
+    const unsigned active = __activemask();
+    const unsigned me = __ballot_sync(active, first_exist), mn = __ballot_sync(active, first_new);
+    const unsigned lt = (1u << lane) - 1u;
+    if (me) {
+        const int lead = __ffs(me) - 1;
+        int base = 0;
+        if (lane == lead) base = atomicAdd(&a.counters[0], __popc(me));
+        base = __shfl_sync(active, base, lead);
+        if (first_exist) {
+            const int p = base + __popc(me & lt);
             if (p < a.max_list) a.exist_list[p] = r;
             else a.counters[2] = 1;
         }
-    } else if (r == kResInserted) {
-        const int p = atomicAdd(&a.counters[1], 1);
-        if (p < a.max_list) a.new_list[p] = make_int2((int)bucket, cand);
-        else a.counters[2] = 1;
-    } else if (r == kResFull) {
-        a.counters[2] = 1;
+    }
+    if (mn) {
+        const int lead = __ffs(mn) - 1;
+        int base = 0;
+        if (lane == lead) base = atomicAdd(&a.counters[1], __popc(mn));
+        base = __shfl_sync(active, base, lead);
+        if (first_new) {
+            const int p = base + __popc(mn & lt);
+            if (p < a.max_list) a.new_list[p] = make_int2((int)bucket, cand);
+            else a.counters[2] = 1;
+        }
     }
 }
 
@@ -265,8 +284,9 @@ struct IntegrateArgs {
     int* frame_slots;        // [max] slots of this frame's frustum blocks (Model::frustum_block_coords_)
     int* frame_count;
     int* max_new;            // running max of blocks first seen in one frame
-    int* dropped;            // [0] capacity the dropped frame needed, [1] id of the first dropped frame (0 = none)
+    int* dropped;            // [0] capacity the first dropped frame needed, [1] its frame index + 1 (0 = none)
     int frame_id;
+    int frame_index;         // 0-based index of the fused frame (reported when a frame is dropped)
     int capacity;
     int max_list;            // size of exist_list / new_list
     // 16^3 fast path (integrate16_kernel)
@@ -369,18 +389,22 @@ __device__ __forceinline__ void integrate_block16(const IntegrateArgs& a, int sl
     }
 }
 
-// Generic resolution (any res, scalar accesses) — parity path for res != 16.
-template <typename depth_t, typename color_in_t, bool HAS_COLOR>
+// Generic resolution (any res, scalar accesses) and generic value layout — the parity path for res != 16 and for
+// the reference's Float32 weight / Float32 colour instantiations (VoxelBlockGridCUDA.cu:238-244).
+template <typename depth_t, typename color_in_t, bool HAS_COLOR, typename weight_t, typename color_t>
 __device__ __forceinline__ void integrate_block_generic(const IntegrateArgs& a, int slot, int xb, int yb, int zb) {
     const int res = a.resolution, res3 = res * res * res;
+    weight_t* wbuf = reinterpret_cast<weight_t*>(a.weight);
+    color_t* cbuf = reinterpret_cast<color_t*>(a.color_buf);
     for (int vox = threadIdx.x; vox < res3; vox += kT) {
         const int xv = vox % res, yv = (vox / res) % res, zv = vox / (res * res);
         float sdf;
         int ui, vi;
         if (!voxel_sdf<depth_t>(a, xb * res + xv, yb * res + yv, zb * res + zv, sdf, ui, vi)) continue;
         const size_t lin = (size_t)slot * res3 + vox;
-        const unsigned short w = a.weight[lin];
-        const float inv_wsum = dvd(1.0f, (float)((int)w + 1));
+        const weight_t w = wbuf[lin];
+        // :274  1.0f / (*weight_ptr + 1): an int sum for UInt16 weights, a float sum for Float32 weights
+        const float inv_wsum = sizeof(weight_t) == 2 ? dvd(1.0f, (float)((int)w + 1)) : dvd(1.0f, add((float)w, 1.0f));
         const float weight = (float)w;
         a.tsdf[lin] = mul(add(mul(weight, a.tsdf[lin]), sdf), inv_wsum);
         if (HAS_COLOR) {
@@ -391,16 +415,15 @@ __device__ __forceinline__ void integrate_block_generic(const IntegrateArgs& a, 
                 const int cu = (int)roundf(uf), cw = (int)roundf(vf);
                 const color_in_t* in = (const color_in_t*)a.color + ((size_t)cw * a.cols + cu) * 3;
                 for (int c = 0; c < 3; ++c)
-                    a.color_buf[3 * lin + c] = (unsigned short)mul(
-                            add(mul(weight, (float)a.color_buf[3 * lin + c]), mul((float)in[c], a.color_multiplier)),
-                            inv_wsum);
+                    cbuf[3 * lin + c] = (color_t)mul(
+                            add(mul(weight, (float)cbuf[3 * lin + c]), mul((float)in[c], a.color_multiplier)), inv_wsum);
             }
         }
-        a.weight[lin] = (unsigned short)add(weight, 1.0f);
+        wbuf[lin] = (weight_t)add(weight, 1.0f);
     }
 }
 
-template <typename depth_t, typename color_in_t, bool HAS_COLOR>
+template <typename depth_t, typename color_in_t, bool HAS_COLOR, typename weight_t = uint16_t, typename color_t = uint16_t>
 __global__ void __launch_bounds__(kT) integrate_kernel(IntegrateArgs a) {
     __shared__ int s_slot, s_key[3];
     const bool fused = a.counters != nullptr;
@@ -420,7 +443,8 @@ __global__ void __launch_bounds__(kT) integrate_kernel(IntegrateArgs a) {
         }
     }
     // work unit = one quarter of a 16^3 block (whole block for other resolutions)
-    const int upb = a.resolution == 16 ? 4 : 1;
+    constexpr bool kVec = sizeof(weight_t) == 2;     // the vectorised quarter-block path is the u16 / u16 layout's
+    const int upb = (kVec && a.resolution == 16) ? 4 : 1;
     for (int wu = blockIdx.x; wu < n_total * upb; wu += gridDim.x) {
         const int b = wu / upb, unit = wu % upb;
         if (threadIdx.x == 0) {
@@ -456,8 +480,8 @@ __global__ void __launch_bounds__(kT) integrate_kernel(IntegrateArgs a) {
         __syncthreads();
         const int slot = s_slot;
         if (slot >= 0) {
-            if (a.resolution == 16) integrate_block16<depth_t, color_in_t, HAS_COLOR>(a, slot, unit, s_key[0], s_key[1], s_key[2]);
-            else integrate_block_generic<depth_t, color_in_t, HAS_COLOR>(a, slot, s_key[0], s_key[1], s_key[2]);
+            if (kVec && a.resolution == 16) integrate_block16<depth_t, color_in_t, HAS_COLOR>(a, slot, unit, s_key[0], s_key[1], s_key[2]);
+            else integrate_block_generic<depth_t, color_in_t, HAS_COLOR, weight_t, color_t>(a, slot, s_key[0], s_key[1], s_key[2]);
         }
         __syncthreads();
     }
@@ -473,7 +497,7 @@ __global__ void __launch_bounds__(kT) integrate_kernel(IntegrateArgs a) {
                 *a.frame_count = 0;
                 if (a.dropped[1] == 0) {
                     a.dropped[0] = size0 + n_new;
-                    a.dropped[1] = a.frame_id;
+                    a.dropped[1] = a.frame_index + 1;
                 }
                 a.counters[2] = 1;
             } else {
@@ -632,7 +656,8 @@ __global__ void __launch_bounds__(kT) integrate16_kernel(const __grid_constant__
             }
             ok = __all_sync(0xffffffffu, ok);
             if (tid == 0) {
-                const int x0 = (int)floorf(umin) - 1, x1 = (int)floorf(umax) + 1;
+                // the box must start on a 16-byte boundary of the image row (TMA requirement): round x0 down
+                const int x0 = ((int)floorf(umin) - 1) & ~(16 / (int)sizeof(depth_t) - 1), x1 = (int)floorf(umax) + 1;
                 const int y0 = (int)floorf(vmin) - 1, y1 = (int)floorf(vmax) + 1;
                 const bool stage = a.use_tile && ok && x1 - x0 < kTileCols && y1 - y0 < kTileRows && x1 >= 0 && y1 >= 0 &&
                                    x0 < a.cols && y0 < a.rows;
@@ -758,7 +783,7 @@ __global__ void __launch_bounds__(kT) integrate16_kernel(const __grid_constant__
                 *a.frame_count = 0;
                 if (a.dropped[1] == 0) {          // first dropped frame: what it needed, and which one it was
                     a.dropped[0] = size0 + n_new;
-                    a.dropped[1] = a.frame_id;
+                    a.dropped[1] = a.frame_index + 1;
                 }
                 a.counters[2] = 1;                // sticky: later frames are dropped too until the host reserves
             } else {
@@ -843,6 +868,26 @@ static bool verify_fast_scale(float s) {
         if (fmaf(r, y, q) != d / s) return false;
     }
     return true;
+}
+
+// 1 / (w + 1) for every u16 weight: one table per device, built once (and synchronised once), shared by all
+// handles and by the stateless entry points.
+static const float* inv_weight_table() {
+    static float* tab[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!tab[dev]) {
+        float* p = nullptr;
+        if (cudaMalloc(&p, 65536 * sizeof(float)) != cudaSuccess) return nullptr;
+        inv_weight_table_kernel<<<65536 / kT, kT>>>(p);
+        count_launch();
+        if (cudaGetLastError() != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
+            cudaFree(p);
+            return nullptr;
+        }
+        tab[dev] = p;
+    }
+    return tab[dev];
 }
 
 // Launch with the programmatic-stream-serialization attribute (the kernels call griddepcontrol.wait before they
@@ -943,37 +988,76 @@ static int absorb_status(o3db_vbg* v, const int* h) {
     v->known_size = h[0];
     v->max_new_seen = std::max<int64_t>(v->max_new_seen, h[9]);
     if (h[6]) {
-        set_last_error("voxel block hash map capacity (%lld blocks) exceeded; call o3db_vbg_reserve with a larger capacity",
-                       (long long)v->capacity);
+        // Frames are atomic and ordered on the device: a frame whose new blocks did not fit (HashMap::Activate would
+        // have grown the map, HashMap.cpp:166-181) and every frame after it were dropped whole — nothing integrated,
+        // the table restored — so the volume is exactly the state before that frame.
+        set_last_error("voxel block hash map capacity (%lld blocks) exceeded: fused frame #%d needed %d blocks; that frame "
+                       "and all later ones were dropped (volume unchanged).  Call o3db_vbg_reserve with a larger capacity "
+                       "and resubmit from that frame.",
+                       (long long)v->capacity, h[11] - 1, h[10]);
         return O3DB_ERR_CAPACITY;
     }
     return O3DB_OK;
 }
 
-// size_dev layout: [0] size, [4] n_exist [5] n_new [6] overflow [7] ticket, [8] frame_count, [9] max_new
+// size_dev layout: [0] size, [4] n_exist [5] n_new [6] overflow [7] ticket, [8] frame_count, [9] max_new,
+// [10] blocks the first dropped frame needed, [11] its frame id (0 = no frame dropped)
 static int read_status(o3db_vbg* v, cudaStream_t st) {
     O3DB_CUDA_CHECK(cudaMemcpyAsync(v->h_pinned, v->size_dev, 16 * sizeof(int), cudaMemcpyDeviceToHost, st));
     O3DB_CUDA_CHECK(cudaStreamSynchronize(st));
     return absorb_status(v, v->h_pinned);
 }
 
-template <typename F>
-static int dispatch_integrate(int depth_dtype, int color_dtype, bool has_color, F&& f) {
-    // instantiations of VoxelBlockGridCUDA.cu:238-244 restricted to the slam::Model value layout
+// Launches the integrate kernel for the input dtypes (VoxelBlockGridCUDA.cu:238-244, value layout u16 weight /
+// u16 colour): the 16^3 fast path with its TMA-staged depth tile, or the generic-resolution kernel.
+template <typename depth_t, typename color_in_t, bool HAS_COLOR>
+static int launch_integrate_typed(o3db_vbg* v, IntegrateArgs& a, int depth_dtype, unsigned grid, cudaStream_t st) {
+    cudaError_t e;
+    if (v->resolution == 16 && a.rows <= 32767 && a.cols <= 65535) {
+        CUtensorMap map;
+        static const bool no_tile = getenv("O3DB_TSDF_NO_TILE") != nullptr;   // A/B knob: read the depth image directly
+        a.use_tile = (!no_tile && make_depth_tensor_map(&map, a.depth, depth_dtype, a.rows, a.cols)) ? 1 : 0;
+        if (!a.use_tile) memset(&map, 0, sizeof(map));
+        e = launch_pdl(integrate16_kernel<depth_t, color_in_t, HAS_COLOR>, grid, st, a, map);
+    } else {
+        e = launch_pdl(integrate_kernel<depth_t, color_in_t, HAS_COLOR>, grid, st, a);
+    }
+    count_launch();
+    if (e != cudaSuccess) {
+        set_last_error("integrate kernel launch failed: %s", cudaGetErrorString(e));
+        return O3DB_ERR_CUDA;
+    }
+    return O3DB_OK;
+}
+
+static int launch_integrate(o3db_vbg* v, IntegrateArgs& a, int depth_dtype, int color_dtype, bool has_color, unsigned grid,
+                            cudaStream_t st) {
     if (depth_dtype == O3DB_DEPTH_U16) {
-        if (!has_color) return f(integrate_kernel<uint16_t, uint8_t, false>);
-        if (color_dtype == O3DB_COLOR_U8) return f(integrate_kernel<uint16_t, uint8_t, true>);
+        if (!has_color) return launch_integrate_typed<uint16_t, uint8_t, false>(v, a, depth_dtype, grid, st);
+        if (color_dtype == O3DB_COLOR_U8) return launch_integrate_typed<uint16_t, uint8_t, true>(v, a, depth_dtype, grid, st);
         set_last_error("u16 depth requires u8 color (kernel/VoxelBlockGrid.cpp:107-146)");
         return O3DB_ERR_INVALID;
     }
     if (depth_dtype == O3DB_DEPTH_F32) {
-        if (!has_color) return f(integrate_kernel<float, float, false>);
-        if (color_dtype == O3DB_COLOR_F32) return f(integrate_kernel<float, float, true>);
+        if (!has_color) return launch_integrate_typed<float, float, false>(v, a, depth_dtype, grid, st);
+        if (color_dtype == O3DB_COLOR_F32) return launch_integrate_typed<float, float, true>(v, a, depth_dtype, grid, st);
         set_last_error("f32 depth requires f32 color (kernel/VoxelBlockGrid.cpp:107-146)");
         return O3DB_ERR_INVALID;
     }
     set_last_error("Unsupported depth dtype");
     return O3DB_ERR_INVALID;
+}
+
+// Resident CTAs per SM of the integrate kernels (the persistent grids are sized from it).
+static unsigned integrate_grid() {
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, integrate16_kernel<uint16_t, uint8_t, true>, kT, 0) != cudaSuccess || n <= 0)
+            n = 4;
+        per_sm = n;
+    }
+    return (unsigned)(num_sms() * per_sm);
 }
 
 static IntegrateArgs base_integrate_args(o3db_vbg* v, const void* depth, const void* color, int color_dtype, int rows,
@@ -997,6 +1081,21 @@ static IntegrateArgs base_integrate_args(o3db_vbg* v, const void* depth, const v
     a.weight = v->weight;
     a.color_buf = v->color;
     a.capacity = (int)v->capacity;
+    a.max_list = (int)v->frustum_cap;
+    a.dropped = v->size_dev + 10;
+    a.inv_w = v->inv_w;
+    if (v->checked_scale != depth_scale) {     // one 65536-value host check per scale (see depth_metres)
+        v->checked_scale = depth_scale;
+        v->checked_scale_ok = verify_fast_scale(depth_scale);
+    }
+    a.fast_scale = v->checked_scale_ok ? 1 : 0;
+    a.inv_scale = 1.0f / depth_scale;
+    // colour intrinsics identical to the depth intrinsics (what slam::Model passes) and sane: interior pixels map to
+    // themselves (integrate16_kernel); anything else takes the reference's unproject / project per voxel
+    a.same_k = (a.ccam.fx == a.dcam.fx && a.ccam.fy == a.dcam.fy && a.ccam.cx == a.dcam.cx && a.ccam.cy == a.dcam.cy &&
+                a.dcam.fx > 1e-3f && a.dcam.fy > 1e-3f && std::isfinite(a.dcam.fx) && std::isfinite(a.dcam.fy) &&
+                fabsf(a.dcam.cx) < 1e5f && fabsf(a.dcam.cy) < 1e5f && rows <= 16384 && cols <= 16384)
+                       ? 1 : 0;
     return a;
 }
 
@@ -1068,6 +1167,12 @@ int o3db_vbg_create(float voxel_size, int block_resolution, int64_t block_count,
     v->counters = v->size_dev + 4;
     v->frame_count = v->size_dev + 8;
     memset(v->h_pinned, 0, 48 * sizeof(int));
+    v->inv_w = inv_weight_table();
+    if (!v->inv_w) {
+        set_last_error("o3db_vbg_create: could not build the weight table: %s", cudaGetErrorString(cudaGetLastError()));
+        o3db_vbg_destroy(v);
+        return O3DB_ERR_CUDA;
+    }
     *out = v;
     return O3DB_OK;
 }
@@ -1104,8 +1209,19 @@ int64_t o3db_vbg_capacity(const o3db_vbg* v) { return v ? v->capacity : 0; }
 
 int o3db_vbg_reserve(o3db_vbg* v, int64_t capacity, void* stream) {
     O3DB_REQUIRE(v != nullptr, "o3db_vbg_reserve: null handle");
-    if (capacity <= v->capacity) return O3DB_OK;
-    return grow(v, capacity, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = O3DB_OK;
+    if (capacity > v->capacity) rc = grow(v, capacity, st);
+    if (rc) return rc;
+    // a reserve acknowledges dropped frames (absorb_status): re-arm the device flag and forget the stale
+    // read-backs, so that the caller can resubmit from the first dropped frame
+    O3DB_CUDA_CHECK(cudaStreamSynchronize(st));
+    O3DB_CUDA_CHECK(cudaMemsetAsync(v->counters + 2, 0, sizeof(int), st));
+    O3DB_CUDA_CHECK(cudaMemsetAsync(v->size_dev + 10, 0, 2 * sizeof(int), st));
+    for (int i = 0; i < 48; ++i)
+        if (i % 16 == 6 || i % 16 == 10 || i % 16 == 11) v->h_pinned[i] = 0;
+    v->sync_next_frame = true;
+    return O3DB_OK;
 }
 
 int32_t* o3db_vbg_key_buffer(o3db_vbg* v) { return v ? v->keys : nullptr; }
@@ -1251,14 +1367,147 @@ int o3db_vbg_integrate(o3db_vbg* v, const int32_t* block_coords_dev, int64_t num
                                           E, depth_scale, depth_max, trunc_mult);
     a.buf_indices = buf;
     a.n_blocks = (int)num_blocks;
-    const unsigned grid = (unsigned)std::min<int64_t>(num_blocks * 4, (int64_t)num_sms() * 8);
-    rc = dispatch_integrate(depth_dtype, color_dtype, has_color, [&](auto kern) -> int {
-        kern<<<grid, kT, 0, st>>>(a);
-        O3DB_LAUNCH_CHECK();
-        return (int)O3DB_OK;
-    });
+    const unsigned grid = (unsigned)std::min<int64_t>(num_blocks * 4, (int64_t)integrate_grid());
+    rc = launch_integrate(v, a, depth_dtype, color_dtype, has_color, grid, st);
     cudaFreeAsync(buf, st);
     return rc;
+}
+
+/* Stateless twins of DepthTouchCUDA / IntegrateCUDA for the case where the hash map and its buffers stay the
+ * reference's own (integration/o3d_forwarders.cpp). */
+int o3db_depth_touch(const void* depth_dev, int depth_dtype, int rows, int cols, const double K[9], const double E[16],
+                     int block_resolution, float voxel_size, float sdf_trunc, float depth_scale, float depth_max,
+                     int stride, int32_t* block_coords_dev, int64_t max_blocks, int64_t* num_blocks_host, void* stream) {
+    O3DB_REQUIRE(K && E && voxel_size > 0 && block_resolution >= 1, "o3db_depth_touch: bad arguments");
+    O3DB_REQUIRE(stride == kStride, "o3db_depth_touch: stride must be 4 (VoxelBlockGrid.cpp:221 down_factor)");
+    int rc = check_images(depth_dev, depth_dtype, nullptr, 0, rows, cols);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    // scratch of one call: candidate keys, winners, a frustum-sized table (VoxelBlockGrid.cpp:225-234)
+    const int64_t need = (int64_t)(rows / kStride) * (cols / kStride) * kSamples;
+    const unsigned fbuckets = pow2_at_least(2 * need);
+    int *cand = nullptr, *ftable = nullptr, *counters = nullptr;
+    int2* winners = nullptr;
+    cudaError_t e = cudaMallocAsync(&cand, (size_t)need * 3 * sizeof(int), st);
+    if (e == cudaSuccess) e = cudaMallocAsync(&winners, (size_t)need * sizeof(int2), st);
+    if (e == cudaSuccess) e = cudaMallocAsync(&ftable, (size_t)fbuckets * sizeof(int), st);
+    if (e == cudaSuccess) e = cudaMallocAsync(&counters, 4 * sizeof(int), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ftable, 0xff, (size_t)fbuckets * sizeof(int), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(counters, 0, 4 * sizeof(int), st);
+    int h[2] = {0, 0};
+    if (e == cudaSuccess) {
+        TouchArgs t{};
+        double pose[16];
+        inverse_transformation(E, pose);
+        t.depth = depth_dev;
+        t.rows = rows;
+        t.cols = cols;
+        t.cam = make_cam(K, pose, 1.0f);
+        t.block_size = voxel_size * block_resolution;
+        t.sdf_trunc = sdf_trunc;
+        t.depth_scale = depth_scale;
+        t.depth_max = depth_max;
+        t.cand_keys = cand;
+        t.new_list = winners;
+        t.counters = counters;
+        t.max_list = (int)need;
+        t.tab = Table{ftable, fbuckets - 1, nullptr};
+        const unsigned nb = (unsigned)std::max<int64_t>(1, ceil_div(need, kT));
+        if (depth_dtype == O3DB_DEPTH_U16) touch_kernel<uint16_t><<<nb, kT, 0, st>>>(t);
+        else touch_kernel<float><<<nb, kT, 0, st>>>(t);
+        count_launch();
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h, counters, sizeof(h), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    rc = O3DB_OK;
+    const int64_t n = h[1];
+    if (e == cudaSuccess) {
+        if (num_blocks_host) *num_blocks_host = n;
+        if (n == 0) {
+            set_last_error("No block is touched in TSDF volume, abort integration. Please check specified parameters, "
+                           "especially depth_scale and voxel_size");
+            rc = O3DB_ERR_NO_BLOCKS;
+        } else if (block_coords_dev) {
+            if (max_blocks < n) {
+                set_last_error("block_coords buffer too small: %lld < %lld", (long long)max_blocks, (long long)n);
+                rc = O3DB_ERR_INVALID;
+            } else {
+                emit_unique_keys_kernel<<<(unsigned)ceil_div(n, kT), kT, 0, st>>>(winners, counters, cand, block_coords_dev,
+                                                                                  (int)max_blocks);
+                count_launch();
+                e = cudaGetLastError();
+            }
+        }
+    }
+    for (void* p : {(void*)cand, (void*)winners, (void*)ftable, (void*)counters})
+        if (p) cudaFreeAsync(p, st);
+    if (e != cudaSuccess) {
+        set_last_error("o3db_depth_touch: %s", cudaGetErrorString(e));
+        return O3DB_ERR_CUDA;
+    }
+    return rc;
+}
+
+int o3db_integrate_blocks(const void* depth_dev, int depth_dtype, const void* color_dev, int color_dtype, int rows,
+                          int cols, const int32_t* block_indices_dev, int64_t num_blocks,
+                          const int32_t* block_keys_dev, float* tsdf_dev, void* weight_dev, void* color_buf_dev,
+                          int value_layout, const double dK[9], const double cK[9], const double E[16],
+                          int block_resolution, float voxel_size, float sdf_trunc, float depth_scale, float depth_max,
+                          void* stream) {
+    O3DB_REQUIRE(dK && E && block_indices_dev && block_keys_dev && tsdf_dev && weight_dev && num_blocks > 0 &&
+                         num_blocks < INT_MAX && voxel_size > 0 && block_resolution >= 1,
+                 "o3db_integrate_blocks: bad arguments");
+    O3DB_REQUIRE(value_layout == O3DB_VALUES_U16 || value_layout == O3DB_VALUES_F32,
+                 "Unsupported value data type combination. Expected (float, float) or (uint16, uint16)");
+    int rc = check_images(depth_dev, depth_dtype, color_dev, color_dtype, rows, cols);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool has_color = color_dev != nullptr && color_buf_dev != nullptr;     // VoxelBlockGridImpl.h:202-203
+    o3db_vbg tmp;                 // only a carrier for base_integrate_args: nothing is owned
+    tmp.voxel_size = voxel_size;
+    tmp.resolution = block_resolution;
+    tmp.keys = const_cast<int*>(block_keys_dev);
+    tmp.tsdf = tsdf_dev;
+    tmp.weight = (uint16_t*)weight_dev;
+    tmp.color = (uint16_t*)color_buf_dev;
+    tmp.inv_w = inv_weight_table();
+    O3DB_REQUIRE(tmp.inv_w != nullptr, "o3db_integrate_blocks: could not build the weight table");
+    static float s_scale = 0.f;   // (benign race: both values are recomputed from depth_scale alone)
+    static bool s_ok = false;
+    tmp.checked_scale = s_scale;
+    tmp.checked_scale_ok = s_ok;
+    IntegrateArgs a = base_integrate_args(&tmp, depth_dev, has_color ? color_dev : nullptr, color_dtype, rows, cols, dK, cK, E,
+                                          depth_scale, depth_max, 1.0f);
+    s_scale = tmp.checked_scale;
+    s_ok = tmp.checked_scale_ok;
+    a.sdf_trunc = sdf_trunc;      // the reference passes the truncation itself (VoxelBlockGrid.h:369-381)
+    a.capacity = INT_MAX;
+    a.buf_indices = block_indices_dev;
+    a.n_blocks = (int)num_blocks;
+    if (value_layout == O3DB_VALUES_U16) {
+        const unsigned grid = (unsigned)std::min<int64_t>(num_blocks * 4, (int64_t)integrate_grid());
+        return launch_integrate(&tmp, a, depth_dtype, color_dtype, has_color, grid, st);
+    }
+    // Float32 weight / Float32 colour (VoxelBlockGridCUDA.cu:238-244, second and fourth instantiation)
+    const unsigned grid = (unsigned)std::min<int64_t>(num_blocks, (int64_t)num_sms() * 8);
+    cudaError_t e = cudaErrorInvalidValue;
+    if (depth_dtype == O3DB_DEPTH_U16 && (!has_color || color_dtype == O3DB_COLOR_U8)) {
+        e = has_color ? launch_pdl(integrate_kernel<uint16_t, uint8_t, true, float, float>, grid, st, a)
+                      : launch_pdl(integrate_kernel<uint16_t, uint8_t, false, float, float>, grid, st, a);
+    } else if (depth_dtype == O3DB_DEPTH_F32 && (!has_color || color_dtype == O3DB_COLOR_F32)) {
+        e = has_color ? launch_pdl(integrate_kernel<float, float, true, float, float>, grid, st, a)
+                      : launch_pdl(integrate_kernel<float, float, false, float, float>, grid, st, a);
+    } else {
+        set_last_error("Unsupported input data type combination. Expected (float, float) or (uint16, uint8)");
+        return O3DB_ERR_INVALID;
+    }
+    count_launch();
+    if (e != cudaSuccess) {
+        set_last_error("integrate kernel launch failed: %s", cudaGetErrorString(e));
+        return O3DB_ERR_CUDA;
+    }
+    return O3DB_OK;
 }
 
 int o3db_vbg_integrate_frame(o3db_vbg* v, const void* depth_dev, int depth_dtype, const void* color_dev,
@@ -1290,18 +1539,49 @@ int o3db_vbg_integrate_frame(o3db_vbg* v, const void* depth_dev, int depth_dtype
         }
     }
     const bool has_color = color_dev != nullptr && v->with_color;
-    v->frame_id += 1;
-    TouchArgs t = make_touch_args(v, depth_dev, rows, cols, K, E, depth_scale, depth_max, trunc_mult);
-    t.tab = Table{v->table, v->nbuckets - 1, v->keys};
-    t.stamp = v->stamp;
-    t.frame_id = v->frame_id;
     const int nthreads = (rows / kStride) * (cols / kStride) * kSamples;
     const unsigned nb = (unsigned)std::max<int64_t>(1, ceil_div(nthreads, kT));
     const bool prof = v->prof_on && (size_t)(3 * v->prof_frames + 2) < v->prof_ev.size();
     if (prof) cudaEventRecord(v->prof_ev[3 * v->prof_frames], st);
-    if (depth_dtype == O3DB_DEPTH_U16) touch_kernel<uint16_t><<<nb, kT, 0, st>>>(t);
-    else touch_kernel<float><<<nb, kT, 0, st>>>(t);
-    O3DB_LAUNCH_CHECK();
+    auto touch = [&]() -> int {
+        v->frame_id += 1;
+        TouchArgs t = make_touch_args(v, depth_dev, rows, cols, K, E, depth_scale, depth_max, trunc_mult);
+        t.tab = Table{v->table, v->nbuckets - 1, v->keys};
+        t.stamp = v->stamp;
+        t.frame_id = v->frame_id;
+        const cudaError_t e = depth_dtype == O3DB_DEPTH_U16 ? launch_pdl(touch_kernel<uint16_t>, nb, st, t)
+                                                            : launch_pdl(touch_kernel<float>, nb, st, t);
+        count_launch();
+        if (e != cudaSuccess) {
+            set_last_error("touch kernel launch failed: %s", cudaGetErrorString(e));
+            return O3DB_ERR_CUDA;
+        }
+        return O3DB_OK;
+    };
+    static const bool host_only = getenv("O3DB_TSDF_HOST_ONLY") != nullptr;   // diagnostics: everything but the launches
+    if (host_only) {
+        v->frames += 1;
+        return O3DB_OK;
+    }
+    rc = touch();
+    if (rc) return rc;
+    if (v->frames == 0 || v->sync_next_frame) {
+        // Nothing is known yet about how many blocks a frame of this sequence adds (first frame, or the first one
+        // after a reserve that followed a dropped frame): size the map from the touch kernel's own count before
+        // integrating, as HashMap::Activate does (HashMap.cpp:166-181).  One host synchronisation, once.
+        v->sync_next_frame = false;
+        O3DB_CUDA_CHECK(cudaMemcpyAsync(v->h_pinned, v->size_dev, 16 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        O3DB_CUDA_CHECK(cudaStreamSynchronize(st));
+        const int64_t need = (int64_t)v->h_pinned[0] + v->h_pinned[5];
+        if (need > v->capacity && !v->h_pinned[6]) {
+            rc = grow(v, std::max<int64_t>(2 * v->capacity, need + std::max<int64_t>(need / 2, 2048)), st);
+            if (rc) return rc;
+            // the provisional entries lived in the old table: discover the frame again in the new one
+            O3DB_CUDA_CHECK(cudaMemsetAsync(v->counters, 0, 2 * sizeof(int), st));
+            rc = touch();
+            if (rc) return rc;
+        }
+    }
     if (prof) cudaEventRecord(v->prof_ev[3 * v->prof_frames + 1], st);
     IntegrateArgs a = base_integrate_args(v, depth_dev, has_color ? color_dev : nullptr, color_dtype, rows, cols, K, K, E,
                                           depth_scale, depth_max, trunc_mult);
@@ -1317,12 +1597,8 @@ int o3db_vbg_integrate_frame(o3db_vbg* v, const void* depth_dev, int depth_dtype
     a.frame_count = v->frame_count;
     a.max_new = v->size_dev + 9;
     a.frame_id = v->frame_id;
-    const unsigned grid = (unsigned)num_sms() * 8;
-    rc = dispatch_integrate(depth_dtype, color_dtype, has_color, [&](auto kern) -> int {
-        kern<<<grid, kT, 0, st>>>(a);
-        O3DB_LAUNCH_CHECK();
-        return (int)O3DB_OK;
-    });
+    a.frame_index = (int)v->frames;
+    rc = launch_integrate(v, a, depth_dtype, color_dtype, has_color, integrate_grid(), st);
     if (rc) return rc;
     if (prof) {
         cudaEventRecord(v->prof_ev[3 * v->prof_frames + 2], st);

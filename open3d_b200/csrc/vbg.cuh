@@ -97,9 +97,10 @@ struct o3db_vbg {
     int2* new_list = nullptr;
     int* frame_slots = nullptr;
     int* frame_count = nullptr;
-    float* inv_w = nullptr;        // [65536] 1 / (w + 1) per u16 weight (integrate16_kernel)
+    const float* inv_w = nullptr;  // [65536] 1 / (w + 1) per u16 weight (integrate16_kernel); per-device table, not owned
     float checked_scale = 0.f;     // depth_scale the 3-FMA u16 division was last verified for ...
     bool checked_scale_ok = false; // ... and whether it reproduces d / scale for all 65536 u16 values
+    bool sync_next_frame = false;  // the next fused frame sizes the map synchronously (after a reserve)
     // frustum-only table for the stand-alone GetUniqueBlockCoordinates
     int* ftable = nullptr;
     unsigned fbuckets = 0;

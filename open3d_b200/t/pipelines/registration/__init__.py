@@ -224,7 +224,7 @@ def _options(max_correspondence_distance, criteria, kernel):
     return o
 
 
-def _assert_inputs(source, target, estimation_method, max_correspondence_distance):
+def _assert_inputs(source, target, estimation_method, max_correspondence_distance, scale_idx=0):
     # Registration.cpp:119-219 AssertInputMultiScaleICP
     colored = isinstance(estimation_method, TransformationEstimationForColoredICP)
     if not colored and not isinstance(estimation_method, TransformationEstimationPointToPlane):
@@ -245,10 +245,16 @@ def _assert_inputs(source, target, estimation_method, max_correspondence_distanc
                            "PointCloud.")
     if max_correspondence_distance <= 0.0:
         raise RuntimeError(" Max correspondence distance must be greater than 0, but got "
-                           f"{max_correspondence_distance} in scale: 0.")
+                           f"{max_correspondence_distance} in scale: {scale_idx}.")
 
 
-def _run_single_scale(source, target, max_dist, init, estimation, criteria, callback, iteration_offset, scale_idx):
+def _run_single_scale(source, target, max_dist, init, estimation, criteria, callback, iteration_offset, scale_idx,
+                      final_evaluation=True, comm=None):
+    """DoSingleScaleICPIterations (Registration.cpp:275-360) as one device-resident loop.  final_evaluation: also
+    run ComputeRegistrationResult for the final transformation (MultiScaleICP does so after the LAST scale only,
+    Registration.cpp:424-431; between scales the last iteration's own fitness / rmse / transformation are kept).
+    comm: this process holds a SHARD of the source (rows shard_range(n, rank, world) of the cloud every rank has in
+    full); the target is replicated and every iteration exchanges the 30-double system."""
     s = source.point["positions"]
     t = target.point["positions"]
     n = target.point["normals"]
@@ -259,18 +265,29 @@ def _run_single_scale(source, target, max_dist, init, estimation, criteria, call
     if isinstance(estimation, TransformationEstimationForColoredICP):
         estimation._check(source, target)
         sc, tc, tg = source.point["colors"], target.point["colors"], target.point["color_gradients"]
+        if comm is not None:
+            b, e = _shard(s.shape[0], comm)
+            s, sc = s[b:e].contiguous(), sc[b:e].contiguous()
         check(lib.o3db_icp_create_colored(s.data_ptr(), sc.data_ptr(), s.shape[0], t.data_ptr(), n.data_ptr(),
                                           tc.data_ptr(), tg.data_ptr(), t.shape[0], dptr(T0), C.byref(opt),
-                                          float(estimation.lambda_geometric), None, stream, C.byref(handle)))
+                                          float(estimation.lambda_geometric), comm.handle if comm is not None else None,
+                                          stream, C.byref(handle)))
     else:
+        if comm is not None:
+            b, e = _shard(s.shape[0], comm)
+            s = s[b:e].contiguous()
         check(lib.o3db_icp_create(s.data_ptr(), s.shape[0], t.data_ptr(), n.data_ptr(), t.shape[0], dptr(T0),
-                                  C.byref(opt), None, stream, C.byref(handle)))
+                                  C.byref(opt), comm.handle if comm is not None else None, stream, C.byref(handle)))
     try:
         check(lib.o3db_icp_iterate(handle, opt.max_iteration, stream))
         res = IcpResult()
         corr = torch.empty(s.shape[0], dtype=torch.int64, device=s.device)
         per_iter = np.zeros((max(opt.max_iteration, 1), 2), np.float64)
-        rc = lib.o3db_icp_finish(handle, C.byref(res), corr.data_ptr(), dptr(per_iter), stream)
+        if final_evaluation:
+            rc = lib.o3db_icp_finish(handle, C.byref(res), corr.data_ptr(), dptr(per_iter), stream)
+        else:
+            corr = None
+            rc = lib.o3db_icp_state(handle, C.byref(res), dptr(per_iter), stream)
         if rc == ERR_SINGULAR:
             raise O3DBError(rc, "Singular 6x6 linear system detected, tracking failed.")
         check(rc)
@@ -304,16 +321,42 @@ def evaluate_registration(source, target, max_correspondence_distance, transform
 
 
 def icp(source, target, max_correspondence_distance, init_source_to_target=None,
-        estimation_method=None, criteria=None, voxel_size=-1.0, callback_after_iteration=None):
+        estimation_method=None, criteria=None, voxel_size=-1.0, callback_after_iteration=None, comm=None):
     """ICP() (Registration.cpp:93-106) == MultiScaleICP with one scale."""
     return multi_scale_icp(source, target, [voxel_size], [criteria or ICPConvergenceCriteria()],
                            [max_correspondence_distance], init_source_to_target, estimation_method,
-                           callback_after_iteration)
+                           callback_after_iteration, comm)
+
+
+def _shard(n, comm):
+    from ....distributed import shard_range
+    return shard_range(int(n), comm.rank, comm.world)
+
+
+def _replicate_from_rank0(cloud, comm):
+    """Every rank built the same pyramid level, but VoxelDownSample's output ORDER is unspecified (hash-map slot
+    order, as upstream) and its f32 means depend on the atomics' order: rank 0's level is broadcast so that all ranks
+    shard one and the same cloud.  One-off per level, outside the iteration loop."""
+    import torch.distributed as dist
+    n = torch.tensor([cloud.point["positions"].shape[0]], dtype=torch.int64, device="cuda")
+    dist.broadcast(n, src=0)
+    out = type(cloud)()
+    for key in sorted(cloud.point):
+        v = cloud.point[key]
+        buf = v.contiguous() if comm.rank == 0 else torch.empty((int(n.item()),) + tuple(v.shape[1:]), dtype=v.dtype, device=v.device)
+        dist.broadcast(buf, src=0)
+        out.point[key] = buf
+    return out
 
 
 def multi_scale_icp(source, target, voxel_sizes, criteria_list, max_correspondence_distances,
-                    init_source_to_target=None, estimation_method=None, callback_after_iteration=None):
-    """MultiScaleICP (Registration.cpp:362-444)."""
+                    init_source_to_target=None, estimation_method=None, callback_after_iteration=None, comm=None):
+    """MultiScaleICP (Registration.cpp:362-444).
+
+    comm (extension; upstream is single-device): an open3d_b200.distributed.Communicator.  Every rank passes the SAME
+    full clouds; the voxel pyramid and the colour gradients are built once (rank 0's levels are broadcast), each
+    level's source is split by rows over the ranks and every iteration exchanges the 30-double system, so all ranks
+    return the same transformation / fitness / rmse (correspondence_set covers the rank's own rows)."""
     if estimation_method is None:
         raise RuntimeError("open3d_b200 implements TransformationEstimationPointToPlane and ...ForColoredICP; pass "
                            "one explicitly (the reference default is PointToPoint, outside this build's scope).")
@@ -324,9 +367,9 @@ def multi_scale_icp(source, target, voxel_sizes, criteria_list, max_corresponden
     T = as_host_f64_4x4(np.eye(4) if init_source_to_target is None else init_source_to_target,
                         "init_source_to_target")
     for i, d in enumerate(max_correspondence_distances):
-        _assert_inputs(source, target, estimation_method, d)
-    for i in range(n_scales - 1):   # Registration.cpp:190-200
-        if voxel_sizes[i] < voxel_sizes[i + 1]:
+        _assert_inputs(source, target, estimation_method, d, i)
+    for i in range(n_scales - 1):   # Registration.cpp:190-200: voxel_sizes[i + 1] >= voxel_sizes[i] is an error
+        if voxel_sizes[i + 1] >= voxel_sizes[i]:
             raise RuntimeError(" [MultiScaleICP]: Voxel sizes must be in strictly decreasing order.")
     # InitializePointCloudPyramidForMultiScaleICP (Registration.cpp:221-273)
     src_pyr, tgt_pyr = [None] * n_scales, [None] * n_scales
@@ -344,12 +387,18 @@ def multi_scale_icp(source, target, voxel_sizes, criteria_list, max_corresponden
     for k in range(n_scales - 2, -1, -1):
         src_pyr[k] = src_pyr[k + 1].voxel_down_sample(voxel_sizes[k])
         tgt_pyr[k] = tgt_pyr[k + 1].voxel_down_sample(voxel_sizes[k])
+    if comm is not None and comm.world > 1:
+        src_pyr = [_replicate_from_rank0(c, comm) for c in src_pyr]
+        tgt_pyr = [_replicate_from_rank0(c, comm) for c in tgt_pyr]
+    else:
+        comm = None
     result = RegistrationResult(T)
     total = 0
     for s_idx in range(n_scales):
         result, executed, _ = _run_single_scale(src_pyr[s_idx], tgt_pyr[s_idx], max_correspondence_distances[s_idx],
                                                 result.transformation, estimation_method, criteria_list[s_idx],
-                                                callback_after_iteration, total, s_idx)
+                                                callback_after_iteration, total, s_idx,
+                                                final_evaluation=(s_idx == n_scales - 1), comm=comm)
         total += result.num_iterations
         if result.fitness <= np.finfo(np.float64).tiny:   # Registration.cpp:434-438
             result.converged = False

@@ -111,6 +111,11 @@ def _declare(L):
                                      _i32p, C.c_int64, _i32p, _f32p, _u16p, _u16p,
                                      _f64p, _f64p, _f64p, C.c_int, C.c_float, C.c_float,
                                      C.c_float, C.c_float]
+    L.orc_tsdf_integrate_f32_values.restype = None
+    L.orc_tsdf_integrate_f32_values.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                                _i32p, C.c_int64, _i32p, _f32p, _f32p, _f32p,
+                                                _f64p, _f64p, _f64p, C.c_int, C.c_float, C.c_float,
+                                                C.c_float, C.c_float]
     L.orc_hashmap_activate.restype = C.c_int
     L.orc_hashmap_activate.argtypes = [_i32p, C.c_int64, _i64p, _i32p, C.c_int64,
                                        _i32p, _u8p]
@@ -446,16 +451,19 @@ def tsdf_integrate(depth, color, buf_indices, block_keys, tsdf, weight, color_bu
     bi = _arr(buf_indices, np.int32).reshape(-1)
     assert block_keys.dtype == np.int32 and block_keys.flags.c_contiguous
     assert tsdf.dtype == np.float32 and tsdf.flags.c_contiguous
-    assert weight.dtype == np.uint16 and weight.flags.c_contiguous
+    values_f32 = weight.dtype == np.float32         # the reference's (Float32, Float32) value layout
+    assert weight.dtype in (np.uint16, np.float32) and weight.flags.c_contiguous
     if color_buf is not None:
-        assert color_buf.dtype == np.uint16 and color_buf.flags.c_contiguous
+        assert color_buf.dtype == weight.dtype and color_buf.flags.c_contiguous
     dK = _arr(depth_K, np.float64).reshape(9)
     cK = _arr(color_K if color_K is not None else depth_K, np.float64).reshape(9)
     E = _arr(extrinsic, np.float64).reshape(16)
-    lib().orc_tsdf_integrate(depth.ctypes.data, None if color is None else color.ctypes.data,
+    fn = lib().orc_tsdf_integrate_f32_values if values_f32 else lib().orc_tsdf_integrate
+    vp = _f32p if values_f32 else _u16p
+    fn(depth.ctypes.data, None if color is None else color.ctypes.data,
                              int(f32), rows, cols, _p(bi, _i32p), bi.shape[0],
-                             _p(block_keys, _i32p), _p(tsdf, _f32p), _p(weight, _u16p),
-                             None if color_buf is None else _p(color_buf, _u16p),
+                             _p(block_keys, _i32p), _p(tsdf, _f32p), _p(weight, vp),
+                             None if color_buf is None else _p(color_buf, vp),
                              _p(dK, _f64p), _p(cK, _f64p), _p(E, _f64p), int(resolution),
                              float(voxel_size), float(sdf_trunc), float(depth_scale),
                              float(depth_max))

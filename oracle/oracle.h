@@ -246,6 +246,16 @@ void orc_tsdf_integrate(const void* depth, const void* color, int inputs_f32,
                         const double color_K[9], const double extrinsic[16],
                         int resolution, float voxel_size, float sdf_trunc,
                         float depth_scale, float depth_max);
+/* The same for the reference's second value layout (weight Float32, colour Float32: the other two IntegrateCPU /
+ * IntegrateCUDA instantiations); pinned bit-exactly against IntegrateCPU<.., float, float> in oracle/_ref. */
+void orc_tsdf_integrate_f32_values(const void* depth, const void* color, int inputs_f32,
+                                   int rows, int cols, const int32_t* buf_indices,
+                                   int64_t n_blocks, const int32_t* block_keys,
+                                   float* tsdf_buf, float* weight_buf,
+                                   float* color_buf, const double depth_K[9],
+                                   const double color_K[9], const double extrinsic[16],
+                                   int resolution, float voxel_size, float sdf_trunc,
+                                   float depth_scale, float depth_max);
 
 /* Set-semantics activate, core/hashmap/HashMap.cpp:166-197 +
  * CPU/TBBHashBackend.h:173-227: keys n x 3; masks[i] = 1 for exactly one

@@ -31,6 +31,31 @@ o3c::Tensor K_tensor(const double* K) { return o3c::Tensor((void*)K, {3, 3}, o3c
 o3c::Tensor E_tensor(const double* E) { return o3c::Tensor((void*)E, {4, 4}, o3c::Float64); }
 }  // namespace
 
+// IntegrateCPU<u16,u8,f32,W,C> / <f32,f32,f32,W,C> (VoxelBlockGridImpl.h:151-308) for both value layouts the
+// reference instantiates: (W, C) = (uint16_t, uint16_t) — the slam::Model layout — and (float, float).
+template <typename W>
+static void integrate_layout(const void* depth, const void* color, int inputs_f32, int rows, int cols, const int32_t* buf_indices,
+                             int64_t n_blocks, const int32_t* block_keys, int64_t capacity, float* tsdf, W* weight, W* color_buf,
+                             const double dK[9], const double cK[9], const double E[16], int resolution, float voxel_size,
+                             float sdf_trunc, float depth_scale, float depth_max) {
+    const o3c::Dtype vdt = sizeof(W) == 2 ? o3c::UInt16 : o3c::Float32;
+    const int64_t r3 = (int64_t)resolution * resolution * resolution;
+    o3c::Tensor d((void*)depth, {rows, cols, 1}, inputs_f32 ? o3c::Float32 : o3c::UInt16);
+    o3c::Tensor c = color ? o3c::Tensor((void*)color, {rows, cols, 3}, inputs_f32 ? o3c::Float32 : o3c::UInt8) : o3c::Tensor();
+    o3c::Tensor idx((void*)buf_indices, {n_blocks}, o3c::Int32);
+    o3c::Tensor keys((void*)block_keys, {capacity, 3}, o3c::Int32);
+    TensorMap vm("tsdf");
+    vm["tsdf"] = o3c::Tensor(tsdf, {capacity * r3, 1}, o3c::Float32);
+    vm["weight"] = o3c::Tensor(weight, {capacity * r3, 1}, vdt);
+    if (color_buf) vm["color"] = o3c::Tensor(color_buf, {capacity * r3, 3}, vdt);
+    if (inputs_f32)
+        o3v::IntegrateCPU<float, float, float, W, W>(d, c, idx, keys, vm, K_tensor(dK), K_tensor(cK), E_tensor(E), resolution,
+                                                     voxel_size, sdf_trunc, depth_scale, depth_max);
+    else
+        o3v::IntegrateCPU<uint16_t, uint8_t, float, W, W>(d, c, idx, keys, vm, K_tensor(dK), K_tensor(cK), E_tensor(E), resolution,
+                                                          voxel_size, sdf_trunc, depth_scale, depth_max);
+}
+
 extern "C" {
 
 int ref_num_threads(void) {
@@ -55,28 +80,20 @@ int64_t ref_depth_touch(const void* depth, int is_f32, int rows, int cols, const
     return n;
 }
 
-// IntegrateCPU<u16,u8,f32,u16,u16> / <f32,f32,f32,u16,u16> (VoxelBlockGridImpl.h:151-308), slam::Model layout.
 void ref_integrate(const void* depth, const void* color, int inputs_f32, int rows, int cols, const int32_t* buf_indices,
                    int64_t n_blocks, const int32_t* block_keys, int64_t capacity, float* tsdf, uint16_t* weight,
                    uint16_t* color_buf, const double dK[9], const double cK[9], const double E[16], int resolution,
                    float voxel_size, float sdf_trunc, float depth_scale, float depth_max) {
-    const int64_t r3 = (int64_t)resolution * resolution * resolution;
-    o3c::Tensor d((void*)depth, {rows, cols, 1}, inputs_f32 ? o3c::Float32 : o3c::UInt16);
-    o3c::Tensor c = color ? o3c::Tensor((void*)color, {rows, cols, 3}, inputs_f32 ? o3c::Float32 : o3c::UInt8) : o3c::Tensor();
-    o3c::Tensor idx((void*)buf_indices, {n_blocks}, o3c::Int32);
-    o3c::Tensor keys((void*)block_keys, {capacity, 3}, o3c::Int32);
-    TensorMap vm("tsdf");
-    vm["tsdf"] = o3c::Tensor(tsdf, {capacity * r3, 1}, o3c::Float32);
-    vm["weight"] = o3c::Tensor(weight, {capacity * r3, 1}, o3c::UInt16);
-    if (color_buf) vm["color"] = o3c::Tensor(color_buf, {capacity * r3, 3}, o3c::UInt16);
-    if (inputs_f32)
-        o3v::IntegrateCPU<float, float, float, uint16_t, uint16_t>(d, c, idx, keys, vm, K_tensor(dK), K_tensor(cK),
-                                                                   E_tensor(E), resolution, voxel_size, sdf_trunc,
-                                                                   depth_scale, depth_max);
-    else
-        o3v::IntegrateCPU<uint16_t, uint8_t, float, uint16_t, uint16_t>(d, c, idx, keys, vm, K_tensor(dK), K_tensor(cK),
-                                                                        E_tensor(E), resolution, voxel_size, sdf_trunc,
-                                                                        depth_scale, depth_max);
+    integrate_layout<uint16_t>(depth, color, inputs_f32, rows, cols, buf_indices, n_blocks, block_keys, capacity, tsdf, weight,
+                               color_buf, dK, cK, E, resolution, voxel_size, sdf_trunc, depth_scale, depth_max);
+}
+void ref_integrate_f32_values(const void* depth, const void* color, int inputs_f32, int rows, int cols,
+                              const int32_t* buf_indices, int64_t n_blocks, const int32_t* block_keys, int64_t capacity,
+                              float* tsdf, float* weight, float* color_buf, const double dK[9], const double cK[9],
+                              const double E[16], int resolution, float voxel_size, float sdf_trunc, float depth_scale,
+                              float depth_max) {
+    integrate_layout<float>(depth, color, inputs_f32, rows, cols, buf_indices, n_blocks, block_keys, capacity, tsdf, weight,
+                            color_buf, dK, cK, E, resolution, voxel_size, sdf_trunc, depth_scale, depth_max);
 }
 
 // EstimateRangeCPU (VoxelBlockGridImpl.h:310-555).  frag_capacity <= 0: upstream's own heuristic allocation.

@@ -59,24 +59,38 @@ static const Dtype UInt64 = Dtype::UInt64;
 class Device {
 public:
     Device() {}
-    explicit Device(const std::string&) {}
-    bool operator==(const Device&) const { return true; }
-    bool IsCPU() const { return true; }
-    bool IsCUDA() const { return false; }
+    explicit Device(const std::string& s) : cuda_(s.rfind("CUDA", 0) == 0) {}
+    bool operator==(const Device& o) const { return cuda_ == o.cuda_; }
+    bool IsCPU() const { return !cuda_; }
+    bool IsCUDA() const { return cuda_; }
     bool IsSYCL() const { return false; }
-    std::string ToString() const { return "CPU:0"; }
+    std::string ToString() const { return cuda_ ? "CUDA:0" : "CPU:0"; }
+private:
+    bool cuda_ = false;   // only integration/ (built with O3DB_STUB_TENSOR_CUDA) ever creates CUDA stub tensors
 };
 
 class Tensor {
 public:
     Tensor() : ptr_(nullptr) {}
-    // non-owning view of caller memory
-    Tensor(void* ptr, SizeVector shape, Dtype dtype) : ptr_(ptr), shape_(shape), dtype_(dtype) {}
+    // non-owning view of caller memory (host, or device memory when `device` says so)
+    Tensor(void* ptr, SizeVector shape, Dtype dtype, const Device& device = Device())
+        : ptr_(ptr), shape_(shape), dtype_(dtype), device_(device) {}
     // owning, zero-initialised (upstream: uninitialised)
-    Tensor(const SizeVector& shape, Dtype dtype, const Device& = Device()) : shape_(shape), dtype_(dtype) {
+    Tensor(const SizeVector& shape, Dtype dtype, const Device& device = Device()) : shape_(shape), dtype_(dtype), device_(device) {
         int64_t n = 1;
         for (auto s : shape_) n *= s;
-        own_ = std::shared_ptr<char>(new char[(size_t)(n > 0 ? n : 1) * dtype.ByteSize()](), std::default_delete<char[]>());
+        const size_t bytes = (size_t)(n > 0 ? n : 1) * dtype.ByteSize();
+#ifdef O3DB_STUB_TENSOR_CUDA
+        if (device.IsCUDA()) {   // integration/forwarder_hooks.cpp: outputs the forwarders allocate live on the device
+            void* d = nullptr;
+            if (cudaMalloc(&d, bytes) != cudaSuccess || cudaMemset(d, 0, bytes) != cudaSuccess)
+                utility::LogError("ref_shim Tensor: cudaMalloc failed");
+            own_ = std::shared_ptr<char>(static_cast<char*>(d), [](char* q) { cudaFree(q); });
+            ptr_ = d;
+            return;
+        }
+#endif
+        own_ = std::shared_ptr<char>(new char[bytes](), std::default_delete<char[]>());
         ptr_ = own_.get();
     }
     template <typename T>
@@ -102,7 +116,7 @@ public:
         return n;
     }
     Dtype GetDtype() const { return dtype_; }
-    Device GetDevice() const { return Device(); }
+    Device GetDevice() const { return device_; }
     void* GetDataPtr() { return ptr_; }
     const void* GetDataPtr() const { return ptr_; }
     template <typename T>
@@ -116,7 +130,7 @@ public:
         SizeVector sub(shape_.begin() + 1, shape_.end());
         int64_t stride = dtype_.ByteSize();
         for (auto s : sub) stride *= s;
-        Tensor t(static_cast<char*>(ptr_) + i * stride, sub, dtype_);
+        Tensor t(static_cast<char*>(ptr_) + i * stride, sub, dtype_, device_);
         t.own_ = own_;
         return t;
     }
@@ -126,7 +140,7 @@ public:
         shp[0] = stop - start;
         int64_t stride = dtype_.ByteSize();
         for (size_t k = 1; k < shape_.size(); ++k) stride *= shape_[k];
-        Tensor t(static_cast<char*>(ptr_) + start * stride, shp, dtype_);
+        Tensor t(static_cast<char*>(ptr_) + start * stride, shp, dtype_, device_);
         t.own_ = own_;
         return t;
     }
@@ -160,6 +174,7 @@ private:
     void* ptr_;
     SizeVector shape_;
     Dtype dtype_;
+    Device device_;
     std::shared_ptr<char> own_;
 };
 

@@ -127,6 +127,88 @@ int64_t orc_depth_touch(const void* depth, int is_f32, int rows, int cols,
 }
 
 /* t/geometry/kernel/VoxelBlockGridImpl.h:151-308 */
+/* VoxelBlockGridImpl.h:151-308 for one value layout (the reference instantiates weight_t / color_t as
+ * uint16_t / uint16_t and float / float, VoxelBlockGridCPU.cpp / VoxelBlockGridCUDA.cu:238-244). */
+#define ORC_DEFINE_TSDF_INTEGRATE(NAME, WEIGHT_T, COLOR_T) \
+static void NAME(const void* depth, const void* color, int inputs_f32, \
+                        int rows, int cols, const int32_t* buf_indices, \
+                        int64_t n_blocks, const int32_t* block_keys, \
+                        float* tsdf_buf, WEIGHT_T* weight_buf, \
+                        COLOR_T* color_buf, const double depth_K[9], \
+                        const double color_K[9], const double extrinsic[16], \
+                        int resolution, float voxel_size, float sdf_trunc, \
+                        float depth_scale, float depth_max) { \
+    const int res = resolution; \
+    const int res2 = res * res; \
+    const int res3 = res2 * res; \
+    xform_indexer ti, ci; \
+    xi_init(&ti, depth_K, extrinsic, voxel_size); /* :184 */ \
+    const double eye[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}; \
+    xi_init(&ci, color_K ? color_K : depth_K, eye, 1.0f); /* :185-187 */ \
+    const int integrate_color = color != NULL && color_buf != NULL; \
+    const float color_multiplier = (integrate_color && inputs_f32) ? 255.0f : 1.0f; \
+    const int64_t n = n_blocks * res3; \
+    _Pragma("omp parallel for schedule(static)") \
+    for (int64_t w = 0; w < n; ++w) { \
+        const int block_idx = buf_indices[w / res3]; \
+        const int voxel_idx = (int)(w % res3); \
+        const int32_t* key = block_keys + 3 * (int64_t)block_idx; \
+        const int xb = key[0], yb = key[1], zb = key[2]; \
+        /* GeometryIndexer.h:270-278 WorkloadToCoord (3D) */ \
+        int rem = voxel_idx; \
+        const int xv = rem % res; \
+        rem = (rem - xv) / res; \
+        const int yv = rem % res; \
+        const int zv = rem / res; \
+        const int x = xb * res + xv; \
+        const int y = yb * res + yv; \
+        const int z = zb * res + zv; \
+        float xc, yc, zc, u, v; \
+        xi_rigid(&ti, (float)x, (float)y, (float)z, &xc, &yc, &zc); \
+        xi_project(&ti, xc, yc, zc, &u, &v); \
+        if (!in_boundary(u, v, rows, cols)) continue; \
+        int ui = (int)u; \
+        int vi = (int)v; \
+        float dep; \
+        if (inputs_f32) \
+            dep = ((const float*)depth)[(int64_t)vi * cols + ui] / depth_scale; \
+        else \
+            dep = ((const uint16_t*)depth)[(int64_t)vi * cols + ui] / depth_scale; \
+        float sdf = dep - zc; \
+        if (dep <= 0 || dep > depth_max || zc <= 0 || sdf < -sdf_trunc) continue; \
+        sdf = sdf < sdf_trunc ? sdf : sdf_trunc; \
+        sdf /= sdf_trunc; \
+        const int64_t lin = (int64_t)block_idx * res3 + voxel_idx; \
+        float* tsdf_ptr = tsdf_buf + lin; \
+        WEIGHT_T* weight_ptr = weight_buf + lin; \
+        float inv_wsum = 1.0f / (*weight_ptr + 1); \
+        float weight = *weight_ptr; \
+        *tsdf_ptr = (weight * (*tsdf_ptr) + sdf) * inv_wsum; \
+        if (integrate_color) { \
+            COLOR_T* color_ptr = color_buf + 3 * lin; \
+            float px, py, pz, uf, vf; \
+            xi_unproject(&ti, (float)ui, (float)vi, 1.0f, &px, &py, &pz); \
+            xi_project(&ci, px, py, pz, &uf, &vf); \
+            if (in_boundary(uf, vf, rows, cols)) { \
+                ui = (int)roundf(uf); \
+                vi = (int)roundf(vf); \
+                const int64_t off = ((int64_t)vi * cols + ui) * 3; \
+                for (int i = 0; i < 3; ++i) { \
+                    float in = inputs_f32 ? ((const float*)color)[off + i] \
+                                          : (float)((const uint8_t*)color)[off + i]; \
+                    color_ptr[i] = (COLOR_T)((weight * color_ptr[i] + \
+                                               in * color_multiplier) * \
+                                              inv_wsum); \
+                } \
+            } \
+        } \
+        *weight_ptr = (WEIGHT_T)(weight + 1); \
+    } \
+}
+
+ORC_DEFINE_TSDF_INTEGRATE(tsdf_integrate_u16, uint16_t, uint16_t)
+ORC_DEFINE_TSDF_INTEGRATE(tsdf_integrate_f32, float, float)
+
 void orc_tsdf_integrate(const void* depth, const void* color, int inputs_f32,
                         int rows, int cols, const int32_t* buf_indices,
                         int64_t n_blocks, const int32_t* block_keys,
@@ -135,75 +217,20 @@ void orc_tsdf_integrate(const void* depth, const void* color, int inputs_f32,
                         const double color_K[9], const double extrinsic[16],
                         int resolution, float voxel_size, float sdf_trunc,
                         float depth_scale, float depth_max) {
-    const int res = resolution;
-    const int res2 = res * res;
-    const int res3 = res2 * res;
-    xform_indexer ti, ci;
-    xi_init(&ti, depth_K, extrinsic, voxel_size); /* :184 */
-    const double eye[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
-    xi_init(&ci, color_K ? color_K : depth_K, eye, 1.0f); /* :185-187 */
-    const int integrate_color = color != NULL && color_buf != NULL;
-    const float color_multiplier = (integrate_color && inputs_f32) ? 255.0f : 1.0f;
+    tsdf_integrate_u16(depth, color, inputs_f32, rows, cols, buf_indices, n_blocks, block_keys, tsdf_buf, weight_buf,
+                       color_buf, depth_K, color_K, extrinsic, resolution, voxel_size, sdf_trunc, depth_scale, depth_max);
+}
 
-    const int64_t n = n_blocks * res3;
-#pragma omp parallel for schedule(static)
-    for (int64_t w = 0; w < n; ++w) {
-        const int block_idx = buf_indices[w / res3];
-        const int voxel_idx = (int)(w % res3);
-        const int32_t* key = block_keys + 3 * (int64_t)block_idx;
-        const int xb = key[0], yb = key[1], zb = key[2];
-        /* GeometryIndexer.h:270-278 WorkloadToCoord (3D) */
-        int rem = voxel_idx;
-        const int xv = rem % res;
-        rem = (rem - xv) / res;
-        const int yv = rem % res;
-        const int zv = rem / res;
-        const int x = xb * res + xv;
-        const int y = yb * res + yv;
-        const int z = zb * res + zv;
-        float xc, yc, zc, u, v;
-        xi_rigid(&ti, (float)x, (float)y, (float)z, &xc, &yc, &zc);
-        xi_project(&ti, xc, yc, zc, &u, &v);
-        if (!in_boundary(u, v, rows, cols)) continue;
-        int ui = (int)u;
-        int vi = (int)v;
-        float dep;
-        if (inputs_f32)
-            dep = ((const float*)depth)[(int64_t)vi * cols + ui] / depth_scale;
-        else
-            dep = ((const uint16_t*)depth)[(int64_t)vi * cols + ui] / depth_scale;
-        float sdf = dep - zc;
-        if (dep <= 0 || dep > depth_max || zc <= 0 || sdf < -sdf_trunc) continue;
-        sdf = sdf < sdf_trunc ? sdf : sdf_trunc;
-        sdf /= sdf_trunc;
-
-        const int64_t lin = (int64_t)block_idx * res3 + voxel_idx;
-        float* tsdf_ptr = tsdf_buf + lin;
-        uint16_t* weight_ptr = weight_buf + lin;
-        float inv_wsum = 1.0f / (*weight_ptr + 1);
-        float weight = *weight_ptr;
-        *tsdf_ptr = (weight * (*tsdf_ptr) + sdf) * inv_wsum;
-
-        if (integrate_color) {
-            uint16_t* color_ptr = color_buf + 3 * lin;
-            float px, py, pz, uf, vf;
-            xi_unproject(&ti, (float)ui, (float)vi, 1.0f, &px, &py, &pz);
-            xi_project(&ci, px, py, pz, &uf, &vf);
-            if (in_boundary(uf, vf, rows, cols)) {
-                ui = (int)roundf(uf);
-                vi = (int)roundf(vf);
-                const int64_t off = ((int64_t)vi * cols + ui) * 3;
-                for (int i = 0; i < 3; ++i) {
-                    float in = inputs_f32 ? ((const float*)color)[off + i]
-                                          : (float)((const uint8_t*)color)[off + i];
-                    color_ptr[i] = (uint16_t)((weight * color_ptr[i] +
-                                               in * color_multiplier) *
-                                              inv_wsum);
-                }
-            }
-        }
-        *weight_ptr = (uint16_t)(weight + 1);
-    }
+void orc_tsdf_integrate_f32_values(const void* depth, const void* color, int inputs_f32,
+                                   int rows, int cols, const int32_t* buf_indices,
+                                   int64_t n_blocks, const int32_t* block_keys,
+                                   float* tsdf_buf, float* weight_buf,
+                                   float* color_buf, const double depth_K[9],
+                                   const double color_K[9], const double extrinsic[16],
+                                   int resolution, float voxel_size, float sdf_trunc,
+                                   float depth_scale, float depth_max) {
+    tsdf_integrate_f32(depth, color, inputs_f32, rows, cols, buf_indices, n_blocks, block_keys, tsdf_buf, weight_buf,
+                       color_buf, depth_K, color_K, extrinsic, resolution, voxel_size, sdf_trunc, depth_scale, depth_max);
 }
 
 /* core/hashmap/HashMap.cpp:166-197 + CPU/TBBHashBackend.h:173-227: set insert.

@@ -74,7 +74,9 @@ def main():
         np.testing.assert_allclose(per, per1, atol=1e-9)
         assert abs(fit - fit1) < 1e-12 and abs(rmse - rmse1) < 1e-9
         np.testing.assert_allclose(T, T_gt, atol=2e-3)
-        print(f"multigpu_check ok: world={world} fitness={fit:.6f} rmse={rmse:.6f} |T - T_single|max={np.abs(T - T1).max():.2e}")
+        peer = int(L.lib.o3db_comm_uses_peer_memory(comm.handle))
+        print(f"multigpu_check ok: world={world} peer_memory_exchange={peer} fitness={fit:.6f} rmse={rmse:.6f} "
+              f"|T - T_single|max={np.abs(T - T1).max():.2e}")
     # ColoredICP, same sharding: the target (with colours and gradients) is replicated, the source split
     src, tgt, nrm, T_gt = make_icp_pair(300_000, seed=6)
     sc = make_colors((np.c_[src.astype(np.float64), np.ones(len(src))] @ T_gt.T)[:, :3], 1)

@@ -257,6 +257,12 @@ def test_sharded_icp_equals_single_gpu_on_2_gpus():
     (one 30-double all-reduce per iteration inside the library) == the single-GPU run on the whole source."""
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", "29533", os.path.join(ROOT, "tests", "multigpu_check.py")]
-    out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
-    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
-    assert "multigpu_check ok" in out.stdout and "colored ok" in out.stdout
+    for no_peer in (False, True):      # both transports: in-kernel NVLink peer-memory exchange, and NCCL
+        env = dict(os.environ)
+        if no_peer:
+            env["O3DB_COMM_NO_PEER"] = "1"
+        out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900, env=env)
+        assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+        assert "multigpu_check ok" in out.stdout and "colored ok" in out.stdout
+        if no_peer:
+            assert "peer_memory_exchange=0" in out.stdout

@@ -31,6 +31,9 @@ def ref():
     L.ref_depth_touch.restype = C.c_int64
     L.ref_depth_touch.argtypes = [vp, C.c_int, C.c_int, C.c_int, f64p, f64p, C.c_int, C.c_float, C.c_float, C.c_float,
                                   C.c_float, C.c_int, i32p, C.c_int64]
+    L.ref_integrate_f32_values.restype = None
+    L.ref_integrate_f32_values.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, i32p, C.c_int64, i32p, C.c_int64, f32p, vp, vp, f64p,
+                                           f64p, f64p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float]
     L.ref_integrate.restype = None
     L.ref_integrate.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, i32p, C.c_int64, i32p, C.c_int64, f32p, vp, vp, f64p,
                                 f64p, f64p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float]
@@ -127,6 +130,31 @@ def test_integrate_float_inputs_and_depth_only(ref):
                           _p(K9, f64p), _p(K9, f64p), _p(Ef, f64p), RES, VOXEL, VOXEL * TRUNC, SCALE, DMAX)
         assert np.array_equal(ot.view(np.uint32), rt.view(np.uint32)) and np.array_equal(ow, rw)
         assert np.array_equal(oc, rcol) and (oc.any() == with_color)
+
+
+@pytest.mark.parametrize("f32_inputs", [False, True])
+def test_integrate_float32_value_layout_is_the_reference_integrate(ref, f32_inputs):
+    """The reference's other value layout — IntegrateCPU<u16,u8,f32,float,float> and <f32,f32,f32,float,float>
+    (weight Float32, colour Float32, VoxelBlockGridCPU.cpp instantiations) — over 3 fused frames: tsdf, weight and
+    colour bit for bit (the float colour is NOT truncated to an integer in this layout)."""
+    cap = 3000
+    keys = np.zeros((cap, 3), np.int32)
+    ot, ow, oc = np.zeros((cap, RES ** 3), np.float32), np.zeros((cap, RES ** 3), np.float32), np.zeros((cap, RES ** 3, 3), np.float32)
+    rt, rw, rcol = ot.copy(), ow.copy(), oc.copy()
+    size = 0
+    for fid in (300, 302, 304):
+        E, depth, color = _frame(fid, f32=f32_inputs)
+        want = oracle.depth_touch(depth, PRIMESENSE_K, E, RES, VOXEL, VOXEL * TRUNC, SCALE, DMAX, 4)
+        bi, _, size, _ = oracle.hashmap_activate(keys, size, want)
+        oracle.tsdf_integrate(depth, color, bi, keys, ot, ow, oc, PRIMESENSE_K, PRIMESENSE_K, E, RES, VOXEL, VOXEL * TRUNC, SCALE, DMAX)
+        Ef = np.ascontiguousarray(E.reshape(16))
+        bi = np.ascontiguousarray(bi, np.int32)
+        ref.ref_integrate_f32_values(depth.ctypes.data, color.ctypes.data, int(f32_inputs), 480, 640, _p(bi, i32p), len(bi),
+                                     _p(keys, i32p), cap, _p(rt, f32p), rw.ctypes.data, rcol.ctypes.data, _p(K9, f64p), _p(K9, f64p),
+                                     _p(Ef, f64p), RES, VOXEL, VOXEL * TRUNC, SCALE, DMAX)
+    assert np.array_equal(ot.view(np.uint32), rt.view(np.uint32)) and np.array_equal(ow.view(np.uint32), rw.view(np.uint32))
+    assert np.array_equal(oc.view(np.uint32), rcol.view(np.uint32))
+    assert ow.max() == 3.0 and (oc != np.floor(oc)).any()
 
 
 @pytest.mark.parametrize("down", [8, 4])

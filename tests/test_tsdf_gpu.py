@@ -208,6 +208,74 @@ def test_fused_path_grows_transparently(o3d):
     assert {tuple(k) for k in keys.tolist()} == total
 
 
+def test_frame_that_outgrows_the_map_is_dropped_whole_and_recoverable():
+    """ADVICE r1 (tsdf.cu overflow): the fused path sizes the map ahead of need from what earlier frames added; a camera
+    jump that adds far more blocks than that (here ~24 k new blocks after frames that added < 1 k) cannot fit.  The
+    reference would grow inside HashMap::Activate (HashMap.cpp:166-181); the async path instead drops that frame AND
+    every later one as a whole (every CTA takes the same decision, provisional table entries are released), reports
+    which frame it was, and after o3db_vbg_reserve the caller resubmits from there.  The recovered volume must equal
+    the oracle's, bit for bit — i.e. the dropped frames left no trace."""
+    import ctypes as C
+    import re
+    from open3d_b200 import _lib as L
+    voxel, cap0 = 0.00125, 4000
+    stream = int(torch.cuda.current_stream().cuda_stream)
+    v = C.c_void_p()
+    L.check(L.lib.o3db_vbg_create(voxel, RES, cap0, 0, stream, C.byref(v)))
+    K = np.ascontiguousarray(PRIMESENSE_K)
+    seq = [(250, 0.95), (250, 0.95), (251, 0.95), (125, DMAX), (126, DMAX), (250, 0.95), (127, DMAX)]
+    frames = []
+    for fid, dmax in seq:
+        T = camera_pose(fid)
+        frames.append((render_depth(T, device="cuda").contiguous(), np.ascontiguousarray(oracle.inverse_transformation(T)), dmax))
+
+    def submit(i):
+        d, E, dmax = frames[i]
+        return L.lib.o3db_vbg_integrate_frame(v, d.data_ptr(), L.DEPTH_U16, None, 0, 480, 640, L.dptr(K), L.dptr(E), SCALE, dmax,
+                                              TRUNC_MULT, stream)
+    i, first_dropped = 0, None
+    while i < len(frames):
+        rc = submit(i)
+        if rc == 0:
+            i += 1
+            continue
+        assert rc == L.ERR_CAPACITY and first_dropped is None, (rc, L.last_error())
+        m = re.search(r"fused frame #(\d+) needed (\d+) blocks", L.last_error())
+        assert m, L.last_error()
+        first_dropped, needed = int(m.group(1)), int(m.group(2))
+        assert first_dropped == 3 and needed > 20000           # the jump
+        L.check(L.lib.o3db_vbg_reserve(v, 2 * needed, stream))
+        i = first_dropped                                       # resubmit from the dropped frame
+    if first_dropped is None:                                   # the last frames were dropped silently so far: ask
+        size = L.lib.o3db_vbg_size(v, stream)
+        assert size == L.ERR_CAPACITY, size
+    assert first_dropped == 3
+    size = L.lib.o3db_vbg_size(v, stream)
+    cap = 40000
+    okeys, otsdf, owt = np.zeros((cap, 3), np.int32), np.zeros((cap, RES ** 3), np.float32), np.zeros((cap, RES ** 3), np.uint16)
+    osize = 0
+    for d, E, dmax in frames:
+        dh = d.cpu().numpy()
+        want = oracle.depth_touch(dh, PRIMESENSE_K, E, RES, voxel, voxel * TRUNC_MULT, SCALE, dmax, 4)
+        bi, _, osize, rc = oracle.hashmap_activate(okeys, osize, want)
+        assert rc == 0
+        oracle.tsdf_integrate(dh, None, bi, okeys, otsdf, owt, None, PRIMESENSE_K, PRIMESENSE_K, E, RES, voxel,
+                              voxel * TRUNC_MULT, SCALE, dmax)
+    assert size == osize
+    from open3d_b200.t import _libshim as _s
+    capn = int(L.lib.o3db_vbg_capacity(v))
+    torch.cuda.synchronize()
+    gkeys = _s.device_view(L.lib.o3db_vbg_key_buffer(v), (capn, 3), torch.int32)[:size]
+    gt = _s.device_view(L.lib.o3db_vbg_tsdf_buffer(v), (capn, RES ** 3), torch.float32)[:size]
+    gw = _s.device_view(L.lib.o3db_vbg_weight_buffer(v), (capn, RES ** 3), torch.uint16)[:size]
+    gkeys, gt, gw = gkeys.cpu().numpy(), gt.cpu().numpy(), gw.cpu().numpy()
+    assert np.array_equal(_sorted_keys(gkeys), _sorted_keys(okeys[:osize]))
+    lut = {tuple(k): j for j, k in enumerate(okeys[:osize].tolist())}
+    perm = np.array([lut[tuple(k)] for k in gkeys.tolist()])
+    assert np.array_equal(gw, owt[perm]) and np.array_equal(gt.view(np.uint32), otsdf[perm].view(np.uint32))
+    L.lib.o3db_vbg_destroy(v)
+
+
 def test_generic_block_resolution_vs_oracle(o3d):
     """res = 8 goes through the generic (non-vectorised) integrate path."""
     res, cap = 8, 20000
