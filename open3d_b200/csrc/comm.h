@@ -9,7 +9,7 @@
 namespace o3db {
 
 static constexpr int kMaxPeers = 16;
-static constexpr int kBoxDoubles = 32;           // 30 sums + sequence word + pad = one 256-byte slot
+static constexpr int kBoxDoubles = 64;           // one 512-byte slot: 30 sums x 2 words (32 data bits : 32-bit sequence tag)
 
 // Device-visible view of a communicator's mailboxes.  box[p] is rank p's mailbox as mapped into THIS
 // process: kBoxDoubles doubles per (parity, writer) slot, [2][world] slots.

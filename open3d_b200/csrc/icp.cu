@@ -810,6 +810,9 @@ __device__ void set_identity(double* T, float* Uf) {
     }
 }
 
+#ifndef ICP_DEFER
+#define ICP_DEFER 1   // N > 1: a lane adds the term vectors of N consecutive chunks (f32) before the warp reduces them
+#endif
 #ifndef ICP_TRANSPOSE_SMEM
 #define ICP_TRANSPOSE_SMEM 0   // 1: the per-chunk transposed reduction goes through a shared-memory tile instead of shuffles
 #endif
@@ -1052,41 +1055,43 @@ __device__ __forceinline__ void icp_accumulate_chunk_smem(float (&term)[32], boo
 }
 
 // The exchange step of the source-sharded loop, done INSIDE the iteration kernel over NVLink /
-// NVSwitch peer memory instead of kernel -> ncclAllReduce -> finalize kernel: warp 0 of each rank's last block
-// stores its 30 local sums into slot [parity][rank] of EVERY rank's mailbox (plain peer stores), publishes them
-// with a system-scope release store of the sequence number, then waits until all `world` slots of its own
-// mailbox carry that number and adds them in rank order — so every rank computes bit-identical totals and the
-// identical pose update, with no broadcast.  Two slot parities suffice: rank r reuses a slot two collectives
+// NVSwitch peer memory instead of kernel -> ncclAllReduce -> finalize kernel.  Flag-in-data protocol (what NCCL
+// calls LL): warp 0 of each rank's last block stores its 30 local sums into slot [parity][rank] of EVERY rank's
+// mailbox as 8-byte words (32 data bits : 32-bit sequence number) — an aligned 8-byte store arrives whole, so a
+// reader that sees the sequence number in a word has its data bits too, and no fence / release round trip is
+// needed: the exchange costs one NVLink one-way latency.  Each rank then waits until the `world` slots of its OWN
+// mailbox carry the sequence number and adds them in rank order, so every rank computes bit-identical totals and
+// the identical pose update, with no broadcast.  Two slot parities suffice: rank r reuses a slot two collectives
 // later, which it can only reach after every peer has published the collective in between, i.e. after every peer
-// has finished reading the older one.  All 32 lanes of the warp must call it.  Returns false on a timeout (a
-// peer died): the caller flags a communication error instead of hanging the GPU.
+// has finished reading the older one.  All 32 lanes of the warp must call it.  Returns false on a timeout (a peer
+// died): the caller flags a communication error instead of hanging the GPU.
 __device__ __forceinline__ bool peer_all_reduce(const PeerView& pv, double* s_final) {
     const int lane = threadIdx.x & 31;
     unsigned long long seq = 0;
     if (lane == 0) seq = *pv.seq + 1;
     seq = __shfl_sync(0xffffffffu, seq, 0);
+    const unsigned tag = (unsigned)seq;                       // (0 never appears: the mailboxes start zeroed)
     const size_t par = (size_t)(seq & 1ull) * pv.world;
-    const double mine = lane < kNumSums ? s_final[lane] : 0.0;
-    for (int p = 0; p < pv.world; ++p)
-        if (lane < kNumSums) pv.box[p][(par + pv.rank) * kBoxDoubles + lane] = mine;
-    __threadfence_system();
-    __syncwarp();
-    if (lane < pv.world) {
-        unsigned long long* flag = reinterpret_cast<unsigned long long*>(pv.box[lane] + (par + pv.rank) * kBoxDoubles + kNumSums);
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(seq) : "memory");
+    if (lane < kNumSums) {
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(s_final[lane]);
+        const unsigned long long w0 = ((unsigned long long)tag << 32) | (bits & 0xffffffffull);
+        const unsigned long long w1 = ((unsigned long long)tag << 32) | (bits >> 32);
+        for (int p = 0; p < pv.world; ++p) {
+            double* dst = pv.box[p] + (par + pv.rank) * kBoxDoubles + 2 * lane;
+            asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(w0), "l"(w1) : "memory");
+        }
     }
     double acc = 0.0;
     bool ok = true;
     long long t0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    for (int r = 0; r < pv.world; ++r) {
-        const double* slot = pv.box[pv.rank] + (par + r) * kBoxDoubles;
-        if (lane == 0) {
-            const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(slot + kNumSums);
-            unsigned long long seen;
+    for (int r = 0; r < pv.world && ok; ++r) {
+        if (lane < kNumSums) {
+            const double* src = pv.box[pv.rank] + (par + r) * kBoxDoubles + 2 * lane;
+            unsigned long long w0, w1;
             for (;;) {
-                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flag) : "memory");
-                if (seen == seq) break;
+                asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(src) : "memory");
+                if ((unsigned)(w0 >> 32) == tag && (unsigned)(w1 >> 32) == tag) break;
                 long long t;
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
                 if (t - t0 > 4000000000ll) {   // 4 s
@@ -1094,12 +1099,9 @@ __device__ __forceinline__ bool peer_all_reduce(const PeerView& pv, double* s_fi
                     break;
                 }
             }
+            acc += __longlong_as_double((long long)((w1 << 32) | (w0 & 0xffffffffull)));
         }
-        ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;   // (also orders the other lanes' loads after lane 0's acquire)
-        if (!ok) break;
-        double v = 0.0;
-        if (lane < kNumSums) asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(slot + lane) : "memory");
-        acc += v;
+        ok = __all_sync(0xffffffffu, ok);
     }
     if (lane < kNumSums) s_final[lane] = acc;
     if (lane == 0) *pv.seq = seq;
@@ -1302,6 +1304,11 @@ icp_iteration_kernel(const __grid_constant__ IcpArgs a) {
     };
 
     double acc64 = 0.0;      // lane l: running total of slot l over this warp's queries
+#if ICP_DEFER > 1
+    float term[32];
+    int pending = 0;
+    bool matched = false;
+#endif
     issue_a(0, first);
     issue_a(1, first + stride);
     issue_b(0, first);
@@ -1318,6 +1325,22 @@ icp_iteration_kernel(const __grid_constant__ IcpArgs a) {
         issue_b(c + 1, q0 + stride);
         // (ts / ns / cg of slot c & 1 are rewritten by issue_b(c + 2), i.e. in the NEXT trip: still valid below)
         const int i = q0 + lane;
+#if ICP_DEFER > 1
+        // the lane's terms of ICP_DEFER consecutive chunks are added in f32 first (fixed order: deterministic);
+        // the 150-instruction transposed warp reduction then runs once per ICP_DEFER chunks
+        if (pending == 0) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) term[k] = 0.f;
+        }
+        if (i < n)
+            matched |= icp_process_query<L2LOSS, MODE, COLORED>(a, s_U, i, p, jp, clear_prev, &sl.ts[lane], &sl.ns[lane],
+                                                                &sl.cg[COLORED ? lane : 0], term);
+        if (++pending == ICP_DEFER) {
+            icp_accumulate_chunk(term, matched, acc64);
+            pending = 0;
+            matched = false;
+        }
+#else
         float term[32];
 #pragma unroll
         for (int k = 0; k < 32; ++k) term[k] = 0.f;
@@ -1330,7 +1353,11 @@ icp_iteration_kernel(const __grid_constant__ IcpArgs a) {
 #else
         icp_accumulate_chunk(term, matched, acc64);
 #endif
+#endif
     }
+#if ICP_DEFER > 1
+    if (pending) icp_accumulate_chunk(term, matched, acc64);
+#endif
     if (lane < kNumSums) s_warp[w][lane] = acc64;
     icp_block_epilogue<MODE>(a, s_warp, s_final);
 }
