@@ -789,12 +789,16 @@ def bench_tsdf(args, rank, world, local_rank, L, torch, stream, barrier, max_ove
         dev = out[name].pop("_dev")
         alg = tsdf_algorithmic_bytes(mean_blocks, color)
         k_ms = dev["integrate_ms"] / max(dev["profiled_frames"], 1)
-        out[name]["roofline"] = {"bound": "hbm", "kernel": "integrate_kernel", "achieved": alg / (k_ms * 1e-3) / 1e9,
+        out[name]["roofline"] = {"bound": "hbm", "kernel": "integrate16_kernel", "achieved": alg / (k_ms * 1e-3) / 1e9,
                                  "peak": peak, "unit": "GB/s", "frac": alg / (k_ms * 1e-3) / 1e9 / peak,
                                  "traffic": ncu_traffic("integrate_kernel_color" if color else "integrate_kernel"),
                                  "algorithmic_bytes_per_launch": alg, "avg_launch_us": k_ms * 1e3,
                                  "touch_kernel_avg_us": 1e3 * dev["touch_ms"] / max(dev["profiled_frames"], 1),
                                  "mean_touched_blocks_per_frame": mean_blocks, "peak_source": peak_src,
+                                 "model_note": "algorithmic bytes = every voxel of every touched block read AND written "
+                                               "(SURVEY 8d): an upper bound, voxels behind the truncation band are read "
+                                               "but not written; `traffic` is the ncu cold-cache DRAM figure (writes still "
+                                               "in L2 at the end of a replay are not counted by ncu)",
                                  "frame_frac_end_to_end": alg / (dev["ms_per_frame"] * 1e-3) / 1e9 / peak}
     # slam::Model::SynthesizeModelFrame (EstimateRange + RayCast of the last frame's frustum, depth + colour),
     # reported beside the integration numbers, not part of `value`

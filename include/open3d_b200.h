@@ -124,6 +124,18 @@ int o3db_compute_pose_colored_icp(const float* source_dev, const float* source_c
                                   double* sums29_dev, double* pose_dev, float* residual_host,
                                   int* inlier_count_host, void* stream);
 
+/* registration::GetInformationMatrix (registration/Registration.cpp:446-485, pybind get_information_matrix): the 6x6
+ * Float64 information matrix GTG of a registration — a clone of the source is transformed, matched to the target by the
+ * hybrid search (k = 1), and the Jacobians of the matched TARGET points are reduced
+ * (kernel::ComputeInformationMatrix[CUDA], RegistrationCUDA.cu:492-573, RegistrationImpl.h:686-715).  Raises (returns
+ * O3DB_ERR_INVALID with upstream's message) when there is no correspondence.  information_host: row-major 6x6.
+ * o3db_compute_information_matrix is the kernel-level twin for a given Int64 correspondence set (-1 = none). */
+int o3db_get_information_matrix(const float* source_dev, int64_t n, const float* target_dev, int64_t m,
+                                double max_correspondence_distance, const double transformation_host[16],
+                                double information_host[36], void* stream);
+int o3db_compute_information_matrix(const float* target_dev, const int64_t* correspondences_dev, int64_t n,
+                                    double information_host[36], int64_t* num_correspondences_host, void* stream);
+
 /* kernel::PoseToTransformation (kernel/TransformationConverter.cpp:81-104,
  * TransformationConverterImpl.h:22-42); host math, f64. */
 void o3db_pose_to_transformation(const double pose_host[6], double transformation_host[16]);

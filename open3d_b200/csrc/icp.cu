@@ -717,6 +717,50 @@ pose_colored_kernel(const float* __restrict__ src, const float* __restrict__ src
     }
 }
 
+// ComputeInformationMatrixKernelCUDA (RegistrationCUDA.cu:492-533) with GetInformationJacobians (RegistrationImpl.h:686-715):
+// the 21 lower-triangle terms of GTG per matched target point (f32, upstream's expression), reduced like the pose sums
+// (f32 per thread over a few terms, then f64: deterministic, and closer to the exact sum than upstream's f32 atomics).
+// corr_i32: the hybrid search's own Int32 index column (-1 = none); corr_i64: a caller's Int64 correspondence set.
+__global__ void __launch_bounds__(kThreads)
+information_matrix_kernel(const float* __restrict__ tgt, const int32_t* __restrict__ corr_i32, const int64_t* __restrict__ corr_i64,
+                          int64_t n, double* __restrict__ partials, unsigned* ticket, double* __restrict__ sums_out) {
+    __shared__ double s_warp[kThreads / 32][kSumStride];
+    __shared__ double s_final[kSumStride];
+    for (int k = threadIdx.x; k < (kThreads / 32) * kSumStride; k += kThreads) (&s_warp[0][0])[k] = 0.0;
+    __syncthreads();
+    float acc[kNumSums];
+#pragma unroll
+    for (int k = 0; k < kNumSums; ++k) acc[k] = 0.f;
+    int since = 0;
+    for (int64_t base = (int64_t)blockIdx.x * kThreads; base < n; base += (int64_t)gridDim.x * kThreads) {
+        const int64_t i = base + threadIdx.x;
+        if (i < n) {
+            const int64_t c = corr_i32 ? (int64_t)corr_i32[i] : corr_i64[i];
+            if (c != -1) {
+                const float* p = tgt + 3 * c;
+                const float px = p[0], py = p[1], pz = p[2];
+                const float Jx[6] = {0.f, pz, -py, 1.f, 0.f, 0.f};
+                const float Jy[6] = {-pz, 0.f, px, 0.f, 1.f, 0.f};
+                const float Jz[6] = {py, -px, 0.f, 0.f, 0.f, 1.f};
+                int q = 0;
+#pragma unroll
+                for (int j = 0; j < 6; ++j)
+#pragma unroll
+                    for (int k = 0; k <= j; ++k)
+                        acc[q++] += __fadd_rn(__fadd_rn(__fmul_rn(Jx[j], Jx[k]), __fmul_rn(Jy[j], Jy[k])), __fmul_rn(Jz[j], Jz[k]));
+                acc[28] += 1.0f;
+            }
+        }
+        if (++since == kFlushEvery) {
+            flush_acc(acc, s_warp);
+            since = 0;
+        }
+    }
+    flush_acc(acc, s_warp);
+    if (!block_reduce_to_global(s_warp, partials, ticket, s_final)) return;
+    if (threadIdx.x < kNumSums) sums_out[threadIdx.x] = s_final[threadIdx.x];
+}
+
 // ------------------------------------------------------ transform kernels
 
 __global__ void transform_points_kernel(float* __restrict__ p, int64_t n, Affine T) {
@@ -810,6 +854,14 @@ __device__ void set_identity(double* T, float* Uf) {
     }
 }
 
+#ifndef ICP_STAGED_THREADS
+#define ICP_STAGED_THREADS 768   // threads per block of the staged iteration kernel: ONE fat block of 24 warps per SM (80 registers
+                                 // x 768 threads fills the register file).  Measured against 3 blocks of 256 threads per SM
+                                 // (-DICP_STAGED_THREADS=256): 53.1 vs 56.0 us per iteration at 2M points — a third of the
+                                 // per-block partial rows for the last block to add up (148 instead of 444) and a third of
+                                 // the block prologues / epilogues; the loop itself has no block-wide barrier either way.
+#endif
+static constexpr int kIcpT = ICP_STAGED_THREADS;
 #ifndef ICP_DEFER
 #define ICP_DEFER 1   // N > 1: a lane adds the term vectors of N consecutive chunks (f32) before the warp reduces them
 #endif
@@ -1111,11 +1163,11 @@ __device__ __forceinline__ bool peer_all_reduce(const PeerView& pv, double* s_fi
 
 // Block epilogue shared by both iteration kernels: block partial -> (last block) grand total, solve,
 // pose update, convergence test.
-template <int MODE>
+template <int MODE, int THREADS = kThreads>
 __device__ __forceinline__ void icp_block_epilogue(const IcpArgs& a, double (*s_warp)[kSumStride], double* s_final) {
     ICP_STAMP(2);   // this block's first warp is through its loop
     long long* stamps = (ICP_TIMING && a.dbg) ? a.dbg + (size_t)blockIdx.x * 8 + 3 : nullptr;   // [3] all warps done, [4] ticket = last
-    if (!block_reduce_to_global(s_warp, a.partials, &a.st->ticket, s_final, stamps)) return;
+    if (!block_reduce_to_global<THREADS>(s_warp, a.partials, &a.st->ticket, s_final, stamps)) return;
     ICP_STAMP(5);   // last block: grand total ready
     if (a.fuse_finalize) {
         if (threadIdx.x < 32) {
@@ -1237,25 +1289,25 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 template <bool COLORED>
 struct IcpStagedSmem {   // dynamic shared memory of icp_iteration_kernel
-    IcpStage<COLORED> stage[kThreads / 32][2];
+    IcpStage<COLORED> stage[kIcpT / 32][2];
 #if ICP_TRANSPOSE_SMEM
-    float tr[kThreads / 32][kTrFloats];
+    float tr[kIcpT / 32][kTrFloats];
 #endif
 };
 
 template <bool L2LOSS, int MODE, bool COLORED = false>
-__global__ void __launch_bounds__(kThreads, ICP_MIN_BLOCKS)
+__global__ void __launch_bounds__(kIcpT, kIcpT >= 512 ? 1 : ICP_MIN_BLOCKS)
 icp_iteration_kernel(const __grid_constant__ IcpArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     IcpStagedSmem<COLORED>& sm = *reinterpret_cast<IcpStagedSmem<COLORED>*>(smem_raw);
-    __shared__ double s_warp[kThreads / 32][kSumStride];
+    __shared__ double s_warp[kIcpT / 32][kSumStride];
     __shared__ double s_final[kSumStride];
     __shared__ float s_U[16];
     __shared__ int s_done;
-    __shared__ __align__(8) unsigned long long s_mbar[kThreads / 32][2];
+    __shared__ __align__(8) unsigned long long s_mbar[kIcpT / 32][2];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int k = threadIdx.x; k < (kThreads / 32) * kSumStride; k += kThreads) (&s_warp[0][0])[k] = 0.0;
-    if (threadIdx.x < 2 * (kThreads / 32)) mbar_init(&s_mbar[0][0] + threadIdx.x, 1);
+    for (int k = threadIdx.x; k < (kIcpT / 32) * kSumStride; k += kIcpT) (&s_warp[0][0])[k] = 0.0;
+    if (threadIdx.x < 2 * (kIcpT / 32)) mbar_init(&s_mbar[0][0] + threadIdx.x, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     // Programmatic dependent launch: this grid may become resident while the previous iteration's last
     // block is still in its serial epilogue; nothing produced by that kernel is read before the wait.
@@ -1276,8 +1328,8 @@ icp_iteration_kernel(const __grid_constant__ IcpArgs a) {
     // chunk c of this warp covers working-source positions [q0(c), q0(c) + 32); the arrays are padded to
     // a multiple of 256 entries, so a chunk that starts below n can always be copied whole
     const int n = (int)a.n;
-    const int stride = gridDim.x * kThreads;
-    const int first = blockIdx.x * kThreads + w * 32;
+    const int stride = gridDim.x * kIcpT;
+    const int first = blockIdx.x * kIcpT + w * 32;
     constexpr unsigned kBytesA = 32 * sizeof(float4) + 32 * sizeof(int) + 32 * sizeof(float);
     auto issue_a = [&](int c, int q0) {        // lane 0: TMA bulk copies of chunk c into slot c & 1
         if (lane == 0 && q0 < n) {
@@ -1359,7 +1411,7 @@ icp_iteration_kernel(const __grid_constant__ IcpArgs a) {
     if (pending) icp_accumulate_chunk(term, matched, acc64);
 #endif
     if (lane < kNumSums) s_warp[w][lane] = acc64;
-    icp_block_epilogue<MODE>(a, s_warp, s_final);
+    icp_block_epilogue<MODE, kIcpT>(a, s_warp, s_final);
 }
 
 // Multi-GPU: runs after the all-reduce of st->sums.
@@ -1431,15 +1483,16 @@ static IcpKernel icp_kernel_for(const o3db_icp* c, int mode) {
 // Launch with the programmatic-stream-serialization attribute: the kernel's griddepcontrol.wait orders it
 // after the previous kernel on the stream; everything before that wait may overlap the predecessor's tail.
 // dynamic shared memory of the handle's iteration kernels (the staged variant: stage ring + transpose tile)
+static int icp_threads(const o3db_icp* c) { return c->variant == 1 ? kThreads : kIcpT; }
 static size_t icp_smem_bytes(const o3db_icp* c, int mode) {
     if (c->variant == 1) return 0;
     return (c->colored && mode == 0) ? sizeof(IcpStagedSmem<true>) : sizeof(IcpStagedSmem<false>);
 }
 
-static cudaError_t launch_icp(IcpKernel kernel, int blocks, size_t smem, cudaStream_t st, const IcpArgs& a) {
+static cudaError_t launch_icp(IcpKernel kernel, int blocks, size_t smem, cudaStream_t st, const IcpArgs& a, int threads) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)blocks);
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3((unsigned)threads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -1722,6 +1775,74 @@ int o3db_compute_pose_colored_icp(const float* source_dev, const float* source_c
     return pose_finish(&s, sums29_dev, residual_host, inlier_count_host, st);
 }
 
+int o3db_compute_information_matrix(const float* target_dev, const int64_t* correspondences_dev, int64_t n,
+                                    double information_host[36], int64_t* num_correspondences_host, void* stream) {
+    O3DB_REQUIRE(target_dev && correspondences_dev && information_host && n > 0, "o3db_compute_information_matrix: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    PoseScratch s;
+    int rc = pose_scratch_alloc(&s, n, st);
+    if (rc) return rc;
+    information_matrix_kernel<<<s.blocks, kThreads, 0, st>>>(target_dev, nullptr, correspondences_dev, n, s.partials, s.ticket, s.sums);
+    O3DB_LAUNCH_CHECK();
+    double h[kSumStride];
+    O3DB_CUDA_CHECK(cudaMemcpyAsync(h, s.sums, sizeof(h), cudaMemcpyDeviceToHost, st));
+    O3DB_CUDA_CHECK(cudaStreamSynchronize(st));
+    O3DB_CUDA_CHECK(cudaFreeAsync(s.partials, st));
+    int q = 0;
+    for (int j = 0; j < 6; ++j)           // RegistrationCUDA.cu:565-571
+        for (int k = 0; k <= j; ++k) information_host[j * 6 + k] = information_host[k * 6 + j] = h[q++];
+    if (num_correspondences_host) *num_correspondences_host = (int64_t)h[28];
+    return O3DB_OK;
+}
+
+int o3db_get_information_matrix(const float* source_dev, int64_t n, const float* target_dev, int64_t m,
+                                double max_correspondence_distance, const double transformation_host[16],
+                                double information_host[36], void* stream) {
+    O3DB_REQUIRE(source_dev && target_dev && n > 0 && m > 0, "Source and/or Target pointcloud is empty.");   // Registration.cpp:450-452
+    O3DB_REQUIRE(transformation_host && information_host && max_correspondence_distance > 0,
+                 "o3db_get_information_matrix: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    // :460-472: transform a clone of the source, hybrid search (k = 1) on the target
+    float* moved = nullptr;
+    int32_t* idx = nullptr;
+    O3DB_CUDA_CHECK(cudaMallocAsync(&moved, (size_t)n * 3 * sizeof(float), st));
+    O3DB_CUDA_CHECK(cudaMallocAsync(&idx, (size_t)n * sizeof(int32_t), st));
+    O3DB_CUDA_CHECK(cudaMemcpyAsync(moved, source_dev, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    o3db_nns* index = nullptr;
+    int rc = o3db_transform_points(transformation_host, moved, n, stream);
+    if (rc == O3DB_OK) rc = o3db_nns_create(target_dev, m, max_correspondence_distance, stream, &index);
+    if (rc == O3DB_OK) rc = o3db_nns_hybrid_search(index, moved, n, max_correspondence_distance, 1, idx, nullptr, nullptr, stream);
+    PoseScratch s;
+    if (rc == O3DB_OK) rc = pose_scratch_alloc(&s, n, st);
+    double h[kSumStride] = {0};
+    if (rc == O3DB_OK) {
+        information_matrix_kernel<<<s.blocks, kThreads, 0, st>>>(target_dev, idx, nullptr, n, s.partials, s.ticket, s.sums);
+        count_launch();
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h, s.sums, sizeof(h), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) {
+            set_last_error("o3db_get_information_matrix: %s", cudaGetErrorString(e));
+            rc = O3DB_ERR_CUDA;
+        }
+        cudaFreeAsync(s.partials, st);
+    } else {
+        cudaStreamSynchronize(st);
+    }
+    cudaFreeAsync(moved, st);
+    cudaFreeAsync(idx, st);
+    if (index) o3db_nns_destroy(index);
+    if (rc) return rc;
+    if ((int64_t)h[28] == 0) {   // :476-480
+        set_last_error("0 correspondence present between the pointclouds. Try increasing the max_correspondence_distance parameter.");
+        return O3DB_ERR_INVALID;
+    }
+    int q = 0;
+    for (int j = 0; j < 6; ++j)
+        for (int k = 0; k <= j; ++k) information_host[j * 6 + k] = information_host[k * 6 + j] = h[q++];
+    return O3DB_OK;
+}
+
 // ------------------------------------------------------------- fused ICP API
 
 void o3db_icp_destroy(o3db_icp* c) {
@@ -1817,12 +1938,12 @@ static int icp_create_impl(const float* source_dev, int64_t n, const float* targ
     for (int mode = 0; mode < 2; ++mode)
         ICP_CUDA(cudaFuncSetAttribute(icp_kernel_for(c, mode), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)icp_smem_bytes(c, mode)));
-    ICP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, icp_kernel_for(c, 0), kThreads, icp_smem_bytes(c, 0)));
-    c->grid_blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, kThreads), (int64_t)num_sms() * std::max(occ, 1)));
+    ICP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, icp_kernel_for(c, 0), icp_threads(c), icp_smem_bytes(c, 0)));
+    c->grid_blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, icp_threads(c)), (int64_t)num_sms() * std::max(occ, 1)));
     const int64_t ncell = tiled_key_space(c->nns.g.nx, c->nns.g.ny, c->nns.g.nz);   // tile-major source keys
     c->src_keys = ncell;
     // padded to whole 256-entry chunks: the staged kernel copies 32-entry chunks with TMA bulk copies
-    c->n_pad = ceil_div(n, kThreads) * kThreads;
+    c->n_pad = ceil_div(n, 256) * 256;
     ICP_CUDA(cudaMallocAsync(&c->src4, c->n_pad * sizeof(float4), st));
     ICP_CUDA(cudaMallocAsync(&c->prev, c->n_pad * sizeof(int), st));
     ICP_CUDA(cudaMallocAsync(&c->dprev, c->n_pad * sizeof(float), st));
@@ -1941,7 +2062,7 @@ int o3db_icp_iterate(o3db_icp* c, int iterations, void* stream) {
     const int todo = std::min(iterations, c->opt.max_iteration - c->launched);
     IcpArgs a = make_args(c);
     for (int k = 0; k < todo; ++k) {
-        launch_icp(icp_kernel_for(c, 0), c->grid_blocks, icp_smem_bytes(c, 0), st, a);
+        launch_icp(icp_kernel_for(c, 0), c->grid_blocks, icp_smem_bytes(c, 0), st, a, icp_threads(c));
         O3DB_LAUNCH_CHECK();
         if (!a.fuse_finalize) {
             int rc = o3db_comm_allreduce_f64(c->comm, (double*)((char*)c->st + offsetof(IcpState, sums)), kNumSums, st);
@@ -1988,7 +2109,7 @@ int o3db_icp_finish(o3db_icp* c, o3db_icp_result* result, int64_t* correspondenc
     cudaStream_t st = (cudaStream_t)stream;
     IcpArgs a = make_args(c);
     a.corr_out = correspondences_dev;
-    launch_icp(icp_kernel_for(c, 1), c->grid_blocks, icp_smem_bytes(c, 1), st, a);
+    launch_icp(icp_kernel_for(c, 1), c->grid_blocks, icp_smem_bytes(c, 1), st, a, icp_threads(c));
     O3DB_LAUNCH_CHECK();
     if (!a.fuse_finalize) {
         int rc = o3db_comm_allreduce_f64(c->comm, (double*)((char*)c->st + offsetof(IcpState, sums)), kNumSums, st);

@@ -149,6 +149,156 @@ __global__ void filter_bilateral_kernel(const float* __restrict__ src, int rows,
     dst[i] = dvd(v_sum, w_sum);
 }
 
+
+// ------------------------------------------- fused pyramid level (the multi-scale driver's own path)
+
+// Everything RGBDOdometryMultiScalePointToPlane needs from one pyramid level (RGBDOdometry.cpp:132-163) in ONE launch
+// instead of seven: source and target vertex maps, the target normal map (bilateral filter -> vertex map of the
+// smoothed depth -> normals) and, unless this is the coarsest level, both depth images of the next level.  A block
+// owns a 32 x 8 pixel tile: the target depth tile with its 2-pixel filter apron (+1 for the normal stencil) is staged
+// in shared memory once, the smoothed depths of the 33 x 9 stencil points and their vertices live in shared memory
+// too, so the filter runs once per pixel and the normal map never reads a smoothed image back from HBM.  The
+// per-pixel arithmetic is the stand-alone kernels' (same device functions, same order): bit-identical maps.
+static constexpr int kTW = 32, kTH = 8;
+struct LevelArgs {
+    const float* src_d;      // this level's depth images (metres, NaN = invalid)
+    const float* tgt_d;
+    int rows, cols;
+    Cam ti;                  // this level's intrinsics
+    float invalid_fill;      // NaN
+    float val2, pos2;        // bilateral filter: 2 sigma_value^2, 2 sigma_position^2 (radius 2)
+    float depth_diff;        // PyrDownDepth threshold
+    float* sv;
+    float* tv;
+    float* tn;
+    float* src_next;         // nullptr on the coarsest level
+    float* tgt_next;
+};
+
+__device__ __forceinline__ float pyr_down_pixel(const float* __restrict__ img, int rows, int cols, int yd, int xd,
+                                                float depth_diff, float invalid_fill) {
+    const int yc = 2 * yd, xc = 2 * xd;
+    const float centre = img[(size_t)yc * cols + xc];
+    if (centre == invalid_fill) return invalid_fill;      // (as upstream: never true for a NaN fill)
+    const float gw[3] = {0.375f, 0.25f, 0.0625f};
+    float num = 0.f, den = 0.f;
+    for (int yk = max(0, yc - 2); yk <= min(rows - 1, yc + 2); ++yk)
+        for (int xk = max(0, xc - 2); xk <= min(cols - 1, xc + 2); ++xk) {
+            const float v = img[(size_t)yk * cols + xk];
+            if (v != invalid_fill && fabsf(sub(v, centre)) < depth_diff) {
+                const float w = mul(gw[abs(xk - xc)], gw[abs(yk - yc)]);
+                num = add(num, mul(w, v));
+                den = add(den, w);
+            }
+        }
+    return den == 0 ? invalid_fill : dvd(num, den);
+}
+
+__global__ void __launch_bounds__(kTW* kTH) pyramid_level_kernel(LevelArgs a) {
+    __shared__ float s_depth[kTH + 5][kTW + 5];       // target depth, rows y0-2 .. y0+kTH+2, cols x0-2 .. x0+kTW+2 (clamped)
+    __shared__ float s_vert[kTH + 1][kTW + 1][3];     // vertices of the smoothed depth at the normal stencil points
+    pdl_grid_wait();
+    pdl_grid_launch_dependents();
+    const int tx = threadIdx.x % kTW, ty = threadIdx.x / kTW;
+    const int x0 = blockIdx.x * kTW, y0 = blockIdx.y * kTH;
+    const int x = x0 + tx, y = y0 + ty;
+    for (int k = threadIdx.x; k < (kTH + 5) * (kTW + 5); k += kTW * kTH) {
+        const int ly = k / (kTW + 5), lx = k % (kTW + 5);
+        const int gy = min(max(y0 + ly - 2, 0), a.rows - 1), gx = min(max(x0 + lx - 2, 0), a.cols - 1);   // replicated border
+        s_depth[ly][lx] = a.tgt_d[(size_t)gy * a.cols + gx];
+    }
+    __syncthreads();
+    // bilateral filter (radius 2) + vertex of the smoothed depth at every stencil point of the tile
+    for (int k = threadIdx.x; k < (kTH + 1) * (kTW + 1); k += kTW * kTH) {
+        const int ly = k / (kTW + 1), lx = k % (kTW + 1);
+        const int gy = y0 + ly, gx = x0 + lx;
+        float vx = a.invalid_fill, vy = a.invalid_fill, vz = a.invalid_fill;
+        if (gy < a.rows && gx < a.cols) {
+            const float vc = s_depth[ly + 2][lx + 2];
+            float num = 0.f, den = 0.f;
+            for (int dy = -2; dy <= 2; ++dy)
+                for (int dx = -2; dx <= 2; ++dx) {
+                    // the apron was loaded with clamped coordinates; inside the image clamping (gy + dy) equals indexing it
+                    const int cy = min(max(gy + dy, 0), a.rows - 1) - (y0 - 2), cx = min(max(gx + dx, 0), a.cols - 1) - (x0 - 2);
+                    const float v = s_depth[cy][cx];
+                    const float dv = sub(v, vc);
+                    const float w = mul(expf(dvd(-((float)(dx * dx + dy * dy)), a.pos2)), expf(dvd(-mul(dv, dv), a.val2)));
+                    num = add(num, mul(w, v));
+                    den = add(den, w);
+                }
+            const float smooth = dvd(num, den);
+            if (!is_invalid(smooth, a.invalid_fill)) unproject(a.ti, (float)gx, (float)gy, smooth, vx, vy, vz);
+        }
+        s_vert[ly][lx][0] = vx;
+        s_vert[ly][lx][1] = vy;
+        s_vert[ly][lx][2] = vz;
+    }
+    __syncthreads();
+    if (y < a.rows && x < a.cols) {
+        const size_t i = (size_t)y * a.cols + x;
+        // source / target vertex maps (ImageImpl.h:200-248)
+        const float ds = a.src_d[i], dt = s_depth[ty + 2][tx + 2];
+        float v[3] = {a.invalid_fill, a.invalid_fill, a.invalid_fill};
+        if (!is_invalid(ds, a.invalid_fill)) unproject(a.ti, (float)x, (float)y, ds, v[0], v[1], v[2]);
+        a.sv[3 * i] = v[0];
+        a.sv[3 * i + 1] = v[1];
+        a.sv[3 * i + 2] = v[2];
+        v[0] = v[1] = v[2] = a.invalid_fill;
+        if (!is_invalid(dt, a.invalid_fill)) unproject(a.ti, (float)x, (float)y, dt, v[0], v[1], v[2]);
+        a.tv[3 * i] = v[0];
+        a.tv[3 * i + 1] = v[1];
+        a.tv[3 * i + 2] = v[2];
+        // target normal map from the smoothed vertices (ImageImpl.h:249-315)
+        float n0 = a.invalid_fill, n1 = a.invalid_fill, n2 = a.invalid_fill;
+        if (y < a.rows - 1 && x < a.cols - 1) {
+            const float* v00 = s_vert[ty][tx];
+            const float* v10 = s_vert[ty][tx + 1];
+            const float* v01 = s_vert[ty + 1][tx];
+            const float f = a.invalid_fill;
+            const bool bad = (v00[0] == f && v00[1] == f && v00[2] == f) || (v01[0] == f && v01[1] == f && v01[2] == f) ||
+                             (v10[0] == f && v10[1] == f && v10[2] == f);
+            if (!bad) {
+                const float ax = sub(v01[0], v00[0]), ay = sub(v01[1], v00[1]), az = sub(v01[2], v00[2]);
+                const float bx = sub(v10[0], v00[0]), by = sub(v10[1], v00[1]), bz = sub(v10[2], v00[2]);
+                n0 = sub(mul(ay, bz), mul(az, by));
+                n1 = sub(mul(az, bx), mul(ax, bz));
+                n2 = sub(mul(ax, by), mul(ay, bx));
+                const float norm = fmaxf(__fsqrt_rn(add(add(mul(n0, n0), mul(n1, n1)), mul(n2, n2))), 1e-5f);
+                n0 = dvd(n0, norm);
+                n1 = dvd(n1, norm);
+                n2 = dvd(n2, norm);
+            }
+        }
+        a.tn[3 * i] = n0;
+        a.tn[3 * i + 1] = n1;
+        a.tn[3 * i + 2] = n2;
+    }
+    // next level's depth images (ImageImpl.h:122-198): the 16 x 4 half-resolution pixels under this tile, both images
+    if (a.src_next && threadIdx.x < 2 * (kTW / 2) * (kTH / 2)) {
+        const int which = threadIdx.x / ((kTW / 2) * (kTH / 2)), k = threadIdx.x % ((kTW / 2) * (kTH / 2));
+        const int xd = x0 / 2 + k % (kTW / 2), yd = y0 / 2 + k / (kTW / 2);
+        if (yd < a.rows / 2 && xd < a.cols / 2) {
+            const float out = pyr_down_pixel(which ? a.tgt_d : a.src_d, a.rows, a.cols, yd, xd, a.depth_diff, a.invalid_fill);
+            (which ? a.tgt_next : a.src_next)[(size_t)yd * (a.cols / 2) + xd] = out;
+        }
+    }
+}
+
+// ClipTransform of both frames in one launch (blockIdx.y selects the image).
+template <typename s_t, typename t_t>
+__global__ void clip_transform_pair_kernel(const s_t* __restrict__ src, const t_t* __restrict__ tgt, int64_t n, float scale,
+                                           float min_value, float max_value, float clip_fill, float* __restrict__ src_out,
+                                           float* __restrict__ tgt_out) {
+    pdl_grid_wait();
+    pdl_grid_launch_dependents();
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float out = blockIdx.y == 0 ? dvd((float)src[i], scale) : dvd((float)tgt[i], scale);   // ImageImpl.h:112-116
+    out = out <= min_value ? clip_fill : out;
+    out = out >= max_value ? clip_fill : out;
+    (blockIdx.y == 0 ? src_out : tgt_out)[i] = out;
+}
+
 // ------------------------------------------------------ per-pixel Jacobian
 
 // RGBDOdometryJacobianImpl.h:29-37.  Sign() takes an int (GeometryMacros.h:92): the residual is truncated first.
@@ -236,13 +386,20 @@ struct OdoArgs {
     double* delta_out;            // standalone: 16 doubles (delta transformation)
 };
 
-__device__ void odometry_finalize(const OdoArgs& a, const double* s_final) {
+// Host part of one Gauss-Newton step (RGBDOdometry.cpp:165-191, 441-462), run by warp 0 of the last block: the 6x6
+// solve is warp-parallel (reduce.cuh), lane 0 keeps the books.  `scratch`: >= 96 doubles of shared memory.
+__device__ void odometry_finalize(const OdoArgs& a, const double* s_final, double* scratch) {
     OdoState* st = a.st;
-    double s[29], pose[6];
+    const int lane = threadIdx.x & 31;
+    double* s = scratch;            // [29] the sums as DecodeAndSolve6x6 receives them
+    double* pose = scratch + 32;    // [6]
     // the 29 sums reach DecodeAndSolve6x6 as a Float32 tensor (RGBDOdometryCUDA.cu:112-124)
-    for (int k = 0; k < 29; ++k) s[k] = (double)(float)s_final[k];
+    if (lane < 29) s[lane] = (double)(float)s_final[lane];
+    __syncwarp();
     const int count = (int)s[28];
-    if (!solve6x6(s, pose)) {     // TransformationConverter.cpp:215-225
+    const bool solved = solve6x6_warp(s, scratch + 40, pose);   // TransformationConverter.cpp:215-225
+    if (lane != 0) return;
+    if (!solved) {
         st->status = 1;
         return;
     }
@@ -287,6 +444,8 @@ __global__ void __launch_bounds__(kThreads) odometry_iteration_kernel(OdoArgs a)
     __shared__ double s_final[kSumStride];
     __shared__ Cam s_cam;
     __shared__ int s_skip;
+    pdl_grid_wait();                 // the previous iteration's T / flags, the pyramid kernels' maps
+    pdl_grid_launch_dependents();
     if (threadIdx.x == 0) s_skip = (*(volatile int*)&a.st->level_done[a.level]) | (*(volatile int*)&a.st->status);
     if (threadIdx.x < 12) s_cam.e[threadIdx.x / 4][threadIdx.x % 4] = (float)a.st->T[threadIdx.x];   // TransformIndexer: f32
     if (threadIdx.x == 12) {
@@ -320,7 +479,7 @@ __global__ void __launch_bounds__(kThreads) odometry_iteration_kernel(OdoArgs a)
     flush_acc(acc, s_warp);
     if (!block_reduce_to_global(s_warp, a.partials, &a.st->ticket, s_final)) return;
     if (threadIdx.x < 29) a.st->sums[threadIdx.x] = s_final[threadIdx.x];
-    if (threadIdx.x == 0) odometry_finalize(a, s_final);
+    if (threadIdx.x < 32) odometry_finalize(a, s_final, &s_warp[0][0]);   // (s_warp is dead: reused as scratch)
 }
 
 // ------------------------------------------------------------- host side
@@ -578,15 +737,41 @@ int o3db_rgbd_odometry_multi_scale_point_to_plane(const void* source_depth_dev, 
     do {                               \
         if (rc == O3DB_OK) rc = (expr); \
     } while (0)
-    // RGBDOdometry.cpp:84-88 ClipTransform(depth_scale, 0, depth_max, NAN)
-    ODO_TRY(clip_transform(source_depth_dev, source_dtype, rows, cols, depth_scale, 0.0f, depth_max, nanf_, src_d, st));
-    ODO_TRY(clip_transform(target_depth_dev, target_dtype, rows, cols, depth_scale, 0.0f, depth_max, nanf_, tgt_d, st));
+    // RGBDOdometry.cpp:84-88 ClipTransform(depth_scale, 0, depth_max, NAN), both frames in one launch
+    if (rc == O3DB_OK) {
+        const int64_t npx = (int64_t)rows * cols;
+        const dim3 grid((unsigned)launch_image_1d(npx), 2);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(kOT);
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t e;
+        const bool su = source_dtype == O3DB_DEPTH_U16, tu = target_dtype == O3DB_DEPTH_U16;
+#define ODO_CLIP(S, T)                                                                                                   \
+    e = cudaLaunchKernelEx(&cfg, clip_transform_pair_kernel<S, T>, (const S*)source_depth_dev, (const T*)target_depth_dev, npx, \
+                           depth_scale, 0.0f, depth_max, nanf_, src_d, tgt_d)
+        if (su && tu) ODO_CLIP(uint16_t, uint16_t);
+        else if (su) ODO_CLIP(uint16_t, float);
+        else if (tu) ODO_CLIP(float, uint16_t);
+        else ODO_CLIP(float, float);
+#undef ODO_CLIP
+        count_launch();
+        if (e != cudaSuccess) {
+            set_last_error("clip_transform_pair_kernel launch failed: %s", cudaGetErrorString(e));
+            rc = O3DB_ERR_CUDA;
+        }
+    }
     double Kp[9];
     memcpy(Kp, K, sizeof(Kp));
     {
         float* cursor = pool;
         int r = rows, c = cols;
-        for (int i = 0; i < num_levels && rc == O3DB_OK; ++i) {   // :132-163
+        for (int i = 0; i < num_levels && rc == O3DB_OK; ++i) {   // :132-163, one fused launch per level
             Level& L = lv[num_levels - 1 - i];
             L.rows = r;
             L.cols = c;
@@ -595,16 +780,42 @@ int o3db_rgbd_odometry_multi_scale_point_to_plane(const void* source_depth_dev, 
             L.tv = cursor + (size_t)r * c * 3;
             L.tn = cursor + (size_t)r * c * 6;
             cursor += (size_t)r * c * 9;
-            ODO_TRY(o3db_image_create_vertex_map(src_d, r, c, Kp, nanf_, L.sv, st));
-            ODO_TRY(o3db_image_create_vertex_map(tgt_d, r, c, Kp, nanf_, L.tv, st));
-            ODO_TRY(o3db_image_filter_bilateral(tgt_d, r, c, 5, 5.0f, 10.0f, smooth, st));
-            ODO_TRY(o3db_image_create_vertex_map(smooth, r, c, Kp, nanf_, tsm, st));
-            ODO_TRY(o3db_image_create_normal_map(tsm, r, c, nanf_, L.tn, st));
-            if (i != num_levels - 1) {
-                ODO_TRY(o3db_image_pyr_down_depth(src_d, r, c, depth_outlier_trunc * 2, nanf_, tmp, st));
+            const bool last = i == num_levels - 1;
+            LevelArgs la{};
+            la.src_d = src_d;
+            la.tgt_d = tgt_d;
+            la.rows = r;
+            la.cols = c;
+            const double eye[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+            la.ti = make_cam(Kp, eye, 1.0f);
+            la.invalid_fill = nanf_;
+            la.val2 = 2.0f * 5.0f * 5.0f;            // FilterBilateral(5, 5, 10): as o3db_image_filter_bilateral
+            la.pos2 = 2.0f * 10.0f * 10.0f;
+            la.depth_diff = depth_outlier_trunc * 2;
+            la.sv = L.sv;
+            la.tv = L.tv;
+            la.tn = L.tn;
+            // the next level's images go to the two spare buffers (tmp, smooth), then the roles swap
+            la.src_next = last ? nullptr : tmp;
+            la.tgt_next = last ? nullptr : smooth;
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3((unsigned)ceil_div(c, kTW), (unsigned)ceil_div(r, kTH));
+            cfg.blockDim = dim3(kTW * kTH);
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            const cudaError_t e = cudaLaunchKernelEx(&cfg, pyramid_level_kernel, la);
+            count_launch();
+            if (e != cudaSuccess) {
+                set_last_error("pyramid_level_kernel launch failed: %s", cudaGetErrorString(e));
+                rc = O3DB_ERR_CUDA;
+            }
+            if (!last) {
                 std::swap(src_d, tmp);
-                ODO_TRY(o3db_image_pyr_down_depth(tgt_d, r, c, depth_outlier_trunc * 2, nanf_, tmp, st));
-                std::swap(tgt_d, tmp);
+                std::swap(tgt_d, smooth);
                 r /= 2;
                 c /= 2;
                 for (int k = 0; k < 9; ++k) Kp[k] /= 2;   // :159-160
@@ -633,11 +844,11 @@ int o3db_rgbd_odometry_multi_scale_point_to_plane(const void* source_depth_dev, 
         a.st = s.st;
         a.per_iter = s.per_iter;
         const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div((int64_t)a.rows * a.cols, kThreads), s.blocks));
-        for (int it = 0; it < criteria[i].max_iteration; ++it) {
-            odometry_iteration_kernel<<<blocks, kThreads, 0, st>>>(a);
+        cudaError_t e = cudaSuccess;
+        for (int it = 0; it < criteria[i].max_iteration && e == cudaSuccess; ++it) {
+            e = launch_pdl_ex(odometry_iteration_kernel, (unsigned)blocks, (unsigned)kThreads, 0, st, a);
             count_launch();
         }
-        cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) {
             set_last_error("odometry_iteration_kernel launch failed: %s", cudaGetErrorString(e));
             rc = O3DB_ERR_CUDA;

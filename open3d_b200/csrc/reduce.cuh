@@ -65,6 +65,7 @@ __device__ __forceinline__ void reduce_fence() {
 
 // Block epilogue: per-warp slots -> block partial -> (last block) grand total in
 // block-index order.  Returns true in the last block, with s_final[] filled.
+template <int THREADS = kThreads>
 __device__ __forceinline__ bool block_reduce_to_global(double (*s_warp)[kSumStride], double* __restrict__ partials,
                                                        unsigned* ticket, double* s_final,
                                                        long long* stamps = nullptr) {
@@ -74,7 +75,7 @@ __device__ __forceinline__ bool block_reduce_to_global(double (*s_warp)[kSumStri
     if (threadIdx.x < kNumSums) {
         double v = 0;
 #pragma unroll
-        for (int w = 0; w < kThreads / 32; ++w) v += s_warp[w][threadIdx.x];
+        for (int w = 0; w < THREADS / 32; ++w) v += s_warp[w][threadIdx.x];
         partials[(size_t)blockIdx.x * kSumStride + threadIdx.x] = v;
     }
     reduce_fence();
@@ -89,27 +90,28 @@ __device__ __forceinline__ bool block_reduce_to_global(double (*s_warp)[kSumStri
     // b = w, w + 8, ... for all 30 columns (lane = column, 256-byte coalesced rows, 8 loads in flight),
     // then thread k adds the 8 per-warp totals in warp order.  The association is fixed by the launch
     // shape, so the result is still deterministic for a given grid.
-    __shared__ double s_part[kThreads / 32][kSumStride];
+    __shared__ double s_part[THREADS / 32][kSumStride];
     {
         const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-        constexpr int kW = kThreads / 32, kU = 8;
+        constexpr int kW = THREADS / 32, kU = 8;
         double v = 0;
-        unsigned b = w;
-        for (; b + (kU - 1) * kW < gridDim.x; b += kU * kW) {
+        for (unsigned b = w; b < gridDim.x; b += kU * kW) {   // kU loads in flight, also in the last (partial) batch
             double t[kU];
 #pragma unroll
-            for (int u = 0; u < kU; ++u) t[u] = __ldcg(&partials[(size_t)(b + u * kW) * kSumStride + lane]);
+            for (int u = 0; u < kU; ++u) {
+                const unsigned bb = b + u * kW;
+                t[u] = bb < gridDim.x ? __ldcg(&partials[(size_t)bb * kSumStride + lane]) : 0.0;
+            }
 #pragma unroll
             for (int u = 0; u < kU; ++u) v += t[u];
         }
-        for (; b < gridDim.x; b += kW) v += __ldcg(&partials[(size_t)b * kSumStride + lane]);
         s_part[w][lane] = v;
     }
     __syncthreads();
     if (threadIdx.x < kNumSums) {
         double v = 0;
 #pragma unroll
-        for (int w = 0; w < kThreads / 32; ++w) v += s_part[w][threadIdx.x];
+        for (int w = 0; w < THREADS / 32; ++w) v += s_part[w][threadIdx.x];
         s_final[threadIdx.x] = v;
     }
     if (threadIdx.x == 0) *ticket = 0;

@@ -12,6 +12,7 @@
 // No CPU fallback: every entry point needs a CUDA device.
 #include <cuda.h>   // CUtensorMap (types only: the encoder is resolved through cudaGetDriverEntryPoint)
 
+#include <chrono>
 #include <climits>
 #include <cmath>
 #include <cstdlib>
@@ -28,6 +29,7 @@ static constexpr int kT = 256;
 static constexpr int kStepSize = 3;                 // VoxelBlockGridCUDA.cu:125 step_size
 static constexpr int kSamples = kStepSize + 1;      // est_multipler_factor
 static constexpr int kStride = 4;                   // VoxelBlockGrid.cpp:221 down_factor
+static constexpr int kPinnedInts = 16 + 8 * 16;     // o3db_vbg::h_pinned: [0..15] synchronous read-back, then a ring of 8 x 16
 
 // Programmatic dependent launch (both frame kernels are launched with the attribute): the grid may become
 // resident while its predecessor on the stream drains; nothing the predecessor wrote is read before the wait.
@@ -285,6 +287,8 @@ struct IntegrateArgs {
     int* frame_count;
     int* max_new;            // running max of blocks first seen in one frame
     int* dropped;            // [0] capacity the first dropped frame needed, [1] its frame index + 1 (0 = none)
+    int* host_status;        // pinned host memory, ring of 8 x 16 ints: the frame's status, written by the last CTA
+    int* work;               // fused mode: dynamic work-unit counter (re-armed by the last CTA); null = static striding
     int frame_id;
     int frame_index;         // 0-based index of the fused frame (reported when a frame is dropped)
     int capacity;
@@ -296,6 +300,26 @@ struct IntegrateArgs {
     int same_k;              // colour intrinsics == depth intrinsics: interior pixels map to themselves (see below)
     int use_tile;            // the depth image has a TMA descriptor: stage the projected tile in shared memory
 };
+
+
+// The last CTA of a fused frame publishes the frame's status straight into pinned HOST memory (a posted write over
+// PCIe): slot frame_index & 7 of a ring, sequence tag last.  The host therefore learns sizes without a
+// device-to-host copy or an event in the stream — the frame's two kernels stay adjacent, which programmatic
+// dependent launch needs.
+__device__ __forceinline__ void publish_status(const IntegrateArgs& a, int size_after, int n_new, int overflow,
+                                               int frame_count, int max_new) {
+    if (!a.host_status) return;
+    volatile int* hs = a.host_status + 16 * (a.frame_index & 7);
+    hs[0] = size_after;
+    hs[5] = n_new;
+    hs[6] = overflow;
+    hs[8] = frame_count;
+    hs[9] = max_new;
+    hs[10] = a.dropped[0];
+    hs[11] = a.dropped[1];
+    __threadfence_system();
+    hs[15] = a.frame_index + 1;
+}
 
 // VoxelBlockGridImpl.h:226-303 for one voxel.  Returns false if the voxel is not updated.
 template <typename depth_t>
@@ -508,6 +532,7 @@ __global__ void __launch_bounds__(kT) integrate_kernel(IntegrateArgs a) {
             a.counters[0] = 0;
             a.counters[1] = 0;
             a.counters[3] = 0;
+            publish_status(a, drop ? size0 : size0 + n_new, n_new, drop ? 1 : 0, drop ? 0 : n_total, *a.max_new);
             // counters[2] (overflow) is sticky until the host reads it
         }
     }
@@ -555,6 +580,7 @@ __global__ void __launch_bounds__(kT) integrate16_kernel(const __grid_constant__
     __shared__ __align__(8) unsigned long long s_mbar;
     __shared__ int s_meta[2][4];   // slot, block key
     __shared__ int s_rect[4];      // x0, y0 of the staged rectangle, staged?
+    __shared__ int s_wu[2];        // work unit of this / the next trip (-1 = none left)
     __shared__ bool s_last;
     constexpr int kTileCols = kTileRowBytes / (int)sizeof(depth_t);
     const int tid = threadIdx.x;
@@ -614,11 +640,19 @@ __global__ void __launch_bounds__(kT) integrate16_kernel(const __grid_constant__
         s_meta[buf][2] = k[1];
         s_meta[buf][3] = k[2];
     };
-    if (tid == 32 && (int)blockIdx.x < n_units) fetch(blockIdx.x, 0);
+    // Work units are handed out dynamically after the first one per CTA (units differ a lot in cost: a quarter block
+    // behind the surface leaves at the truncation test), so the grid drains evenly instead of waiting for the CTAs
+    // that drew one unit more.
+    if (tid == 32) {
+        const int first = (int)blockIdx.x < n_units ? (int)blockIdx.x : -1;
+        s_wu[0] = first;
+        if (first >= 0) fetch(first, 0);
+    }
 
-    int it = 0;
-    for (int wu = blockIdx.x; wu < n_units; wu += gridDim.x, ++it) {
-        __syncthreads();   // metadata of this unit published; every thread is done with the previous tile / rect
+    for (int it = 0;; ++it) {
+        __syncthreads();   // unit + metadata published; every thread is done with the previous tile / rect
+        const int wu = s_wu[it & 1];
+        if (wu < 0) break;
         const int slot = s_meta[it & 1][0];
         const int xb = s_meta[it & 1][1], yb = s_meta[it & 1][2], zb = s_meta[it & 1][3];
         const int unit = wu & 3;
@@ -672,8 +706,10 @@ __global__ void __launch_bounds__(kT) integrate16_kernel(const __grid_constant__
                 }
             }
         } else if (tid == 32) {
-            const int next = wu + (int)gridDim.x;
-            if (next < n_units) fetch(next, (it + 1) & 1);
+            int next = a.work ? (int)gridDim.x + atomicAdd(a.work, 1) : wu + (int)gridDim.x;
+            if (next >= n_units) next = -1;
+            s_wu[(it + 1) & 1] = next;
+            if (next >= 0) fetch(next, (it + 1) & 1);
         }
         // VoxelBlockGridImpl.h:226-247: voxel -> camera -> pixel, uncontracted, reference order; the y / z
         // products are shared by the thread's 4 voxels
@@ -794,6 +830,8 @@ __global__ void __launch_bounds__(kT) integrate16_kernel(const __grid_constant__
             a.counters[0] = 0;
             a.counters[1] = 0;
             a.counters[3] = 0;
+            if (a.work) *a.work = 0;
+            publish_status(a, drop ? size0 : size0 + n_new, n_new, drop ? 1 : 0, drop ? 0 : n_total, *a.max_new);
         }
     }
 }
@@ -1151,7 +1189,7 @@ int o3db_vbg_create(float voxel_size, int block_resolution, int64_t block_count,
     if (rc == O3DB_OK) e = cudaMallocAsync(&v->size_dev, 16 * sizeof(int), st);
     if (rc == O3DB_OK && e == cudaSuccess) e = cudaMemsetAsync(v->size_dev, 0, 16 * sizeof(int), st);
     if (rc == O3DB_OK && e == cudaSuccess) {
-        v->h_pinned = (int*)pinned_acquire(48 * sizeof(int));
+        v->h_pinned = (int*)pinned_acquire(kPinnedInts * sizeof(int));
         if (!v->h_pinned) e = cudaErrorMemoryAllocation;
     }
     if (rc == O3DB_OK && e == cudaSuccess) e = cudaEventCreateWithFlags(&v->ev[0], cudaEventDisableTiming);
@@ -1166,7 +1204,7 @@ int o3db_vbg_create(float voxel_size, int block_resolution, int64_t block_count,
     }
     v->counters = v->size_dev + 4;
     v->frame_count = v->size_dev + 8;
-    memset(v->h_pinned, 0, 48 * sizeof(int));
+    memset(v->h_pinned, 0, kPinnedInts * sizeof(int));
     v->inv_w = inv_weight_table();
     if (!v->inv_w) {
         set_last_error("o3db_vbg_create: could not build the weight table: %s", cudaGetErrorString(cudaGetLastError()));
@@ -1218,7 +1256,7 @@ int o3db_vbg_reserve(o3db_vbg* v, int64_t capacity, void* stream) {
     O3DB_CUDA_CHECK(cudaStreamSynchronize(st));
     O3DB_CUDA_CHECK(cudaMemsetAsync(v->counters + 2, 0, sizeof(int), st));
     O3DB_CUDA_CHECK(cudaMemsetAsync(v->size_dev + 10, 0, 2 * sizeof(int), st));
-    for (int i = 0; i < 48; ++i)
+    for (int i = 0; i < kPinnedInts; ++i)
         if (i % 16 == 6 || i % 16 == 10 || i % 16 == 11) v->h_pinned[i] = 0;
     v->sync_next_frame = true;
     return O3DB_OK;
@@ -1523,10 +1561,25 @@ int o3db_vbg_integrate_frame(o3db_vbg* v, const void* depth_dev, int depth_dtype
     // calls ago (normally long finished), read the size it published, and grow ahead of
     // need (HashMap.cpp:166-181 grows when size + n > capacity).  Three frames (two in
     // flight + this one) may add blocks the host has not seen yet.
-    const int slot = (int)(v->frames & 1);
     if (v->frames >= 2) {
-        O3DB_CUDA_CHECK(cudaEventSynchronize(v->ev[slot]));
-        rc = absorb_status(v, v->h_pinned + 16 + 16 * slot);
+        // the status frame (frames - 2) published into pinned memory; normally long there — the wait only bounds how
+        // far the host may run ahead of the device (two frames)
+        const int64_t f = v->frames - 2;
+        volatile int* hs = v->h_pinned + 16 + 16 * (int)(f & 7);
+        if (hs[15] != (int)(f + 1)) {
+            const auto t0 = std::chrono::steady_clock::now();
+            while (hs[15] != (int)(f + 1)) {
+                if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(20)) {
+                    const cudaError_t e = cudaStreamQuery(st);
+                    set_last_error("fused frame #%lld never reported its status (%s)", (long long)f,
+                                   e == cudaSuccess || e == cudaErrorNotReady ? "timeout" : cudaGetErrorString(e));
+                    return O3DB_ERR_CUDA;
+                }
+            }
+        }
+        int h[16];
+        for (int i = 0; i < 16; ++i) h[i] = hs[i];
+        rc = absorb_status(v, h);
         if (rc) return rc;
     }
     const int64_t per_frame = std::max<int64_t>(2 * v->max_new_seen, 2048);
@@ -1598,14 +1651,14 @@ int o3db_vbg_integrate_frame(o3db_vbg* v, const void* depth_dev, int depth_dtype
     a.max_new = v->size_dev + 9;
     a.frame_id = v->frame_id;
     a.frame_index = (int)v->frames;
+    a.host_status = v->h_pinned + 16;
+    a.work = v->size_dev + 12;
     rc = launch_integrate(v, a, depth_dtype, color_dtype, has_color, integrate_grid(), st);
     if (rc) return rc;
     if (prof) {
         cudaEventRecord(v->prof_ev[3 * v->prof_frames + 2], st);
         v->prof_frames += 1;
     }
-    O3DB_CUDA_CHECK(cudaMemcpyAsync(v->h_pinned + 16 + 16 * slot, v->size_dev, 16 * sizeof(int), cudaMemcpyDeviceToHost, st));
-    O3DB_CUDA_CHECK(cudaEventRecord(v->ev[slot], st));
     v->frames += 1;
     return O3DB_OK;
 }

@@ -320,6 +320,19 @@ def evaluate_registration(source, target, max_correspondence_distance, transform
     return res
 
 
+def get_information_matrix(source, target, max_correspondence_distance, transformation):
+    """GetInformationMatrix (Registration.cpp:446-485; pybind registration.get_information_matrix): 6x6 Float64 GTG
+    of the target points matched by the transformed source, on the host like upstream."""
+    if not target.has_point_positions() or not source.has_point_positions():
+        raise RuntimeError("Source and/or Target pointcloud is empty.")
+    T = as_host_f64_4x4(transformation, "transformation")
+    s, t = source.point["positions"], target.point["positions"]
+    info = np.zeros((6, 6), np.float64)
+    check(lib.o3db_get_information_matrix(s.data_ptr(), s.shape[0], t.data_ptr(), t.shape[0],
+                                          float(max_correspondence_distance), dptr(T), dptr(info), current_stream_ptr()))
+    return info
+
+
 def icp(source, target, max_correspondence_distance, init_source_to_target=None,
         estimation_method=None, criteria=None, voxel_size=-1.0, callback_after_iteration=None, comm=None):
     """ICP() (Registration.cpp:93-106) == MultiScaleICP with one scale."""

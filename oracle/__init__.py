@@ -163,6 +163,8 @@ def _declare(L):
     L.orc_svd3x3_f32.argtypes = [_f32p, _f32p, _f32p, _f32p]
     L.orc_solve_svd3x3_f32.restype = None
     L.orc_solve_svd3x3_f32.argtypes = [_f32p, _f32p, _f32p]
+    L.orc_information_matrix_f32.restype = None
+    L.orc_information_matrix_f32.argtypes = [_f32p, _i64p, C.c_int64, _f64p]
     L.orc_solve_sym3x3_pinv.restype = None
     L.orc_solve_sym3x3_pinv.argtypes = [_f64p, _f64p, _f64p]
     L.orc_icp_colored_f32.restype = C.c_int
@@ -551,6 +553,26 @@ def voxel_down_sample(positions, voxel_size, normals=None, colors=None):
 
 
 GRADIENT_SOLVERS = {"reference": 0, "exact": 1}
+
+
+def information_matrix(target, corr) -> np.ndarray:
+    """kernel::ComputeInformationMatrix: 6x6 f64 GTG over the matched target points."""
+    t = _arr(target, np.float32).reshape(-1, 3)
+    c = _arr(corr, np.int64).reshape(-1)
+    out = np.zeros(36, np.float64)
+    lib().orc_information_matrix_f32(_p(t, _f32p), _p(c, _i64p), c.shape[0], _p(out, _f64p))
+    return out.reshape(6, 6)
+
+
+def get_information_matrix(source, target, max_correspondence_distance, transformation) -> np.ndarray:
+    """registration::GetInformationMatrix (Registration.cpp:446-485): transform a clone of the source, hybrid search
+    (k = 1) on the target, GTG over the matched target points; raises when there is no correspondence."""
+    moved = transform_points(transformation, source)
+    idx, _, cnt = hybrid_search(target, moved, max_correspondence_distance, 1)
+    if int(cnt.sum()) == 0:
+        raise RuntimeError("0 correspondence present between the pointclouds. Try increasing the "
+                           "max_correspondence_distance parameter.")
+    return information_matrix(target, idx[:, 0].astype(np.int64))
 
 
 def estimate_color_gradients(points, normals, colors, radius, max_nn=30, solver="reference") -> np.ndarray:

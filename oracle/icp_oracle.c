@@ -887,6 +887,36 @@ int64_t orc_voxel_down_sample_f32(const float* pos, const float* nrm, const floa
     return m;
 }
 
+/* ------------------------------------------------- GetInformationMatrix */
+
+/* kernel::ComputeInformationMatrix (kernel/Registration.cpp:406-436, RegistrationCPU.cpp:655-735) with
+ * GetInformationJacobians (RegistrationImpl.h:686-715): GTG = sum over matched target points of
+ * Jx Jx^T + Jy Jy^T + Jz Jz^T, the 21 lower-triangle terms evaluated in f32 exactly as upstream writes them
+ * (J_x[j] * J_x[k] + J_y[j] * J_y[k] + J_z[j] * J_z[k]) and accumulated here in f64 (upstream: f32 partial sums). */
+void orc_information_matrix_f32(const float* tgt, const int64_t* corr, int64_t n, double info36[36]) {
+    double sum[21] = {0};
+#pragma omp parallel
+    {
+        double loc[21] = {0};
+#pragma omp for schedule(static) nowait
+        for (int64_t w = 0; w < n; ++w) {
+            if (corr[w] == -1) continue;
+            const float* p = tgt + 3 * corr[w];
+            const float Jx[6] = {0.f, p[2], -p[1], 1.f, 0.f, 0.f};
+            const float Jy[6] = {-p[2], 0.f, p[0], 0.f, 1.f, 0.f};
+            const float Jz[6] = {p[1], -p[0], 0.f, 0.f, 0.f, 1.f};
+            int i = 0;
+            for (int j = 0; j < 6; ++j)
+                for (int k = 0; k <= j; ++k) loc[i++] += (double)(Jx[j] * Jx[k] + Jy[j] * Jy[k] + Jz[j] * Jz[k]);
+        }
+#pragma omp critical
+        for (int i = 0; i < 21; ++i) sum[i] += loc[i];
+    }
+    int i = 0;
+    for (int j = 0; j < 6; ++j)
+        for (int k = 0; k <= j; ++k) info36[j * 6 + k] = info36[k * 6 + j] = sum[i++];
+}
+
 /* ------------------------------------------------------------ ColoredICP */
 
 void orc_solve_sym3x3_pinv(const double Ain[9], const double b[3], double x[3]) {

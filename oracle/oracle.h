@@ -159,6 +159,10 @@ int orc_icp_p2plane_f32(const float* source, int64_t n, const float* target,
                         orc_icp_result* result, double* per_iter,
                         int64_t* corr_out);
 
+/* registration::GetInformationMatrix's reduction (Registration.cpp:446-485 -> kernel::ComputeInformationMatrix):
+ * 6x6 f64 GTG over the target points matched by `corr` ([n] int64, -1 = none). */
+void orc_information_matrix_f32(const float* tgt, const int64_t* corr, int64_t n, double info36[36]);
+
 /* ------------------------------------------------------------ ColoredICP */
 
 /* t/geometry/kernel/PointCloudImpl.h:1066-1165 EstimatePointWiseColorGradientKernel driven by

@@ -97,4 +97,10 @@ void ref_color_gradient_point_f32(const float* points, const float* normals, con
                                                                                           indices, count, gradients);
 }
 
+// ComputeInformationMatrixCPU (RegistrationCPU.cpp:655-735), Float32 clouds: 6x6 Float64 GTG over the matched target points
+void ref_information_matrix_f32(const float* tgt, int64_t m, const int64_t* corr, int64_t n, double info36[36]) {
+    o3c::Tensor t((void*)tgt, {m, 3}, o3c::Float32), c((void*)corr, {n}, o3c::Int64), info(info36, {6, 6}, o3c::Float64);
+    open3d::t::pipelines::kernel::ComputeInformationMatrixCPU(t, c, info, o3c::Float32, o3c::Device());
+}
+
 }  // extern "C"

@@ -146,7 +146,14 @@ public:
     }
     // ---- members that only have to COMPILE (ComputeRtPointToPointCPU etc. are never run in the shim)
     Tensor To(const Dtype&) const { unsupported(); }
-    Tensor To(const Device&, const Dtype& = Dtype()) const {   // dtype conversion f32 -> f64 is what the kernels ask for
+    Tensor To(const Device&, const Dtype& dtype = Dtype()) const {
+        if (dtype == Dtype::Float64 && dtype_ == Dtype::Float32) {   // the one conversion the compiled kernels ask for
+            Tensor t(shape_, Dtype::Float64);
+            const float* in = static_cast<const float*>(ptr_);
+            double* out = static_cast<double*>(t.ptr_);
+            for (int64_t i = 0; i < NumElements(); ++i) out[i] = in[i];
+            return t;
+        }
         return *this;
     }
     std::tuple<Tensor, Tensor, Tensor> SVD() const { unsupported(); }

@@ -570,3 +570,21 @@ def test_colored_icp_argument_errors(o3d):
     # (the stand-alone pose kernel and the fused loop add the same f32 terms in different association orders)
     np.testing.assert_allclose(T, one.transformation, atol=1e-7)
     assert est.compute_rmse(s, t, torch.from_numpy(idx[:, 0].astype(np.int64))) > 0
+
+
+def test_get_information_matrix_vs_oracle(o3d):
+    """registration.get_information_matrix (Registration.cpp:446-485): transform, hybrid search k = 1, GTG of the matched
+    target points.  Same correspondences as the oracle (bit-exact search) => the 21 sums agree to f32-term rounding."""
+    reg = o3d.t.pipelines.registration
+    src, tgt, nrm, T_gt = make_icp_pair(60000, seed=12)
+    s, t = o3d.t.geometry.PointCloud(src), o3d.t.geometry.PointCloud(tgt)
+    for T, r in ((T_gt, 0.03), (np.eye(4), 0.05)):
+        info = reg.get_information_matrix(s, t, r, T)
+        want = oracle.get_information_matrix(src, tgt, r, T)
+        assert info.shape == (6, 6) and info.dtype == np.float64 and np.array_equal(info, info.T)
+        assert info[3, 3] == want[3, 3] > 1000              # number of correspondences
+        np.testing.assert_allclose(info, want, rtol=1e-6, atol=1e-6 * np.abs(want).max())
+    far = np.eye(4)
+    far[:3, 3] = 100.0
+    with pytest.raises(RuntimeError, match="0 correspondence"):
+        reg.get_information_matrix(s, t, 0.05, far)

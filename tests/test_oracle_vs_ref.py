@@ -485,3 +485,32 @@ def test_color_gradient_kernel_bit_exact_vs_reference_kernel(ref):
     row = np.int32([0, 1, 2])
     ref.ref_color_gradient_point_f32(_p(pts, f32p), _p(nrm, f32p), _p(col, f32p), 0, _p(row, i32p), 3, _p(want, f32p))
     assert not want[0].any() and not oracle.estimate_color_gradients(pts, nrm, col, 1.0, 30).any()
+
+
+def test_information_matrix_matches_reference_cpu_kernel(ref):
+    """ComputeInformationMatrixCPU (t/pipelines/kernel/RegistrationCPU.cpp:655-735, compiled unmodified; its
+    tbb::parallel_reduce runs as one serial f32 pass in the shim) vs the oracle's GTG (same f32 terms, f64 sums):
+    equal to the rounding noise of the reference's own f32 accumulation, unmatched points (-1) skipped on both sides."""
+    from tests.synth import make_icp_pair
+    ref.ref_information_matrix_f32.argtypes = [f32p, C.c_int64, i64p, C.c_int64, f64p]
+    src, tgt, _, T = make_icp_pair(6000, seed=3)
+    idx, _, _ = oracle.hybrid_search(tgt, oracle.transform_points(T, src), 0.05, 1)
+    corr = np.ascontiguousarray(idx[:, 0], np.int64)
+    corr[::7] = -1
+    want = np.zeros(36)
+    ref.ref_information_matrix_f32(_p(tgt, f32p), len(tgt), _p(corr, i64p), len(corr), _p(want, f64p))
+    want = want.reshape(6, 6)
+    got = oracle.information_matrix(tgt, corr)
+    assert np.array_equal(got, got.T) and np.array_equal(want, want.T)
+    n_valid = int((corr >= 0).sum())
+    assert got[3, 3] == got[4, 4] == got[5, 5] == n_valid and want[3, 3] == n_valid       # sum of 1 * 1
+    # every slot within 2e-5 of the sum of |terms| (~5 k f32 terms summed serially upstream)
+    p = tgt[corr[corr >= 0]].astype(np.float64)
+    scale = np.abs(p).max() ** 2 * n_valid
+    assert np.abs(got - want).max() <= 2e-5 * scale, np.abs(got - want).max() / scale
+    # and against an independent f64 evaluation of sum J^T J
+    J = np.zeros((n_valid, 3, 6))
+    J[:, 0, 1], J[:, 0, 2], J[:, 0, 3] = p[:, 2], -p[:, 1], 1
+    J[:, 1, 0], J[:, 1, 2], J[:, 1, 4] = -p[:, 2], p[:, 0], 1
+    J[:, 2, 0], J[:, 2, 1], J[:, 2, 5] = p[:, 1], -p[:, 0], 1
+    np.testing.assert_allclose(got, np.einsum("nij,nik->jk", J, J), rtol=1e-6, atol=1e-6 * scale)
