@@ -62,6 +62,8 @@ __device__ __forceinline__ int probe(const Table& t, const int* __restrict__ can
             v = old;
         }
         if (v == kTomb) continue;
+        if (v < 0 && cand_keys == nullptr) continue;   // a provisional entry seen by a reader without the candidate array
+                                                       // (ray cast / find): not a committed key — keep probing
         const int* kk = v >= 0 ? t.keys + 3 * (size_t)v : cand_keys + 3 * (size_t)(-(v + 2));
         if (__ldcg(kk) == kx && __ldcg(kk + 1) == ky && __ldcg(kk + 2) == kz) return v >= 0 ? v : kResDuplicate;
     }

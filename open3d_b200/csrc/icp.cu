@@ -167,6 +167,40 @@ static int canonical_ranks(int64_t n, const unsigned* start, const unsigned* key
     return O3DB_OK;
 }
 
+// Working source, CHUNK-BLOCKED: chunk c (32 consecutive sorted positions) is one 768-byte record
+//   [32 x float4 point (.w = original index) | 32 x int seed | 32 x float clearance]
+// so that everything a warp needs to start a chunk arrives with ONE bulk copy (it took three with separate arrays: 44
+// issue slots per chunk).  24 B per point, as before.
+static constexpr int kSrcChunkBytes = 32 * 16 + 32 * 4 + 32 * 4;
+struct SrcBlocked {
+    char* base;
+    __host__ __device__ static size_t bytes(int64_t n_pad) { return (size_t)(n_pad / 32) * kSrcChunkBytes; }
+    __device__ __forceinline__ char* chunk(int i) const { return base + (size_t)(i >> 5) * kSrcChunkBytes; }
+    __device__ __forceinline__ float4* point(int i) const { return reinterpret_cast<float4*>(chunk(i)) + (i & 31); }
+    __device__ __forceinline__ int* seed(int i) const { return reinterpret_cast<int*>(chunk(i) + 512) + (i & 31); }
+    __device__ __forceinline__ float* clearance(int i) const { return reinterpret_cast<float*>(chunk(i) + 640) + (i & 31); }
+};
+
+// no seeds, no clearances (and zeroed padding points)
+__global__ void src_blocked_init_kernel(SrcBlocked sb, int64_t n, int64_t n_pad, bool clear_points) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n_pad) return;
+    *sb.seed((int)i) = -1;
+    *sb.clearance((int)i) = 0.f;
+    if (clear_points && i >= n) *sb.point((int)i) = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// scatter of the caller's source into the blocked working copy (clone + initial transform)
+__global__ void scatter_source_kernel(const float* __restrict__ pts, int64_t n, Affine T, const unsigned* __restrict__ start,
+                                      const unsigned* __restrict__ key, const unsigned* __restrict__ rank, SrcBlocked sb) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float x = pts[3 * i], y = pts[3 * i + 1], z = pts[3 * i + 2];
+    apply_transform(T.m, x, y, z);
+    const unsigned p = start[key[i]] + rank[i];
+    *sb.point((int)p) = make_float4(x, y, z, __int_as_float((int)i));
+}
+
 template <bool TRANSFORM>
 __global__ void scatter_kernel(const float* __restrict__ pts, const float* __restrict__ nrm, int64_t n,
                                Affine T, const unsigned* __restrict__ start,
@@ -791,11 +825,11 @@ __global__ void pack_target_color_kernel(const float4* __restrict__ pts4, const 
     tcg[j] = make_float4(grad[o], grad[o + 1], grad[o + 2], color_intensity(col[o], col[o + 1], col[o + 2]));
 }
 
-__global__ void pack_source_intensity_kernel(const float4* __restrict__ src4, const float* __restrict__ col,
+__global__ void pack_source_intensity_kernel(SrcBlocked sb, const float* __restrict__ col,
                                              int64_t n, float* __restrict__ sint) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const int64_t o = 3 * (int64_t)__float_as_int(src4[i].w);
+    const int64_t o = 3 * (int64_t)__float_as_int(sb.point((int)i)->w);
     sint[i] = color_intensity(col[o], col[o + 1], col[o + 2]);
 }
 
@@ -820,10 +854,9 @@ struct IcpArgs {
     const float4* tgt;
     const float4* nrm;
     const unsigned* cs;
-    float4* src;          // working source, sorted, .w = original index bits
-    int* prev;            // per working source point: sorted target position of its last winner, -1 = none
-    float* dprev;         // per working source point: clearance of that winner (lower bound on the distance to every OTHER
-                          // target point, minus the motion since it was established); 0 = unknown
+    SrcBlocked src;       // working source, sorted, chunk-blocked: point (.w = original index bits), seed = sorted target
+                          // position of its last winner (-1 = none), clearance of that winner (lower bound on the distance
+                          // to every OTHER target point, minus the motion since it was established; 0 = unknown)
     int64_t n;            // local source points
     double n_total;       // source points over all ranks (fitness denominator)
     float rr, thr;
@@ -1013,7 +1046,7 @@ __device__ __forceinline__ bool icp_process_query(const IcpArgs& a, const float*
                                                   const float4* seed_cg, float (&acc)[32]) {
     const float ox = p.x, oy = p.y, oz = p.z;
     apply_transform(s_U, p.x, p.y, p.z);
-    a.src[i] = p;
+    *a.src.point(i) = p;
     unsigned bj = kNoPoint;
     bool handled = false;
     float clear_new = 0.f;      // what is known about the distance to every point other than the winner
@@ -1047,8 +1080,8 @@ __device__ __forceinline__ bool icp_process_query(const IcpArgs& a, const float*
         clear_new = 0.f;
     }
     if (kSeeded) {
-        if ((int)bj != jp) a.prev[i] = (int)bj;
-        a.dprev[i] = clear_new;
+        if ((int)bj != jp) *a.src.seed(i) = (int)bj;
+        *a.src.clearance(i) = clear_new;
     }
     int widx = -1;
     if (bj != kNoPoint) {
@@ -1223,9 +1256,9 @@ icp_iteration_direct_kernel(const __grid_constant__ IcpArgs a) {
         for (int k = 0; k < 32; ++k) term[k] = 0.f;
         bool matched = false;
         if (i < n) {
-            const float4 p = a.src[i];
-            const int jp = kSeeded ? a.prev[i] : -1;
-            const float clear_prev = kSeeded ? a.dprev[i] : 0.f;
+            const float4 p = *a.src.point(i);
+            const int jp = kSeeded ? *a.src.seed(i) : -1;
+            const float clear_prev = kSeeded ? *a.src.clearance(i) : 0.f;
             matched = icp_process_query<L2LOSS, MODE, COLORED>(a, s_U, i, p, jp, clear_prev, a.tgt + max(jp, 0), a.nrm + max(jp, 0),
                                                                COLORED ? a.tcg + max(jp, 0) : nullptr, term);
         }
@@ -1250,12 +1283,14 @@ icp_iteration_direct_kernel(const __grid_constant__ IcpArgs a) {
 // hands a consumed slot back), accumulator flushes are warp-local.
 template <bool COLORED>
 struct __align__(16) IcpStage {
-    float4 p[32];      // A: working source points
-    float4 ts[32];     // B: the seeds' target points
-    float4 ns[32];     // B: their normals
-    float4 cg[COLORED ? 32 : 1];   // B: their colour rows
-    int jp[32];        // A: seeds
-    float d2[32];      // A: clearances
+    // A: one chunk record of the working source (SrcBlocked): 768 contiguous bytes, ONE bulk copy
+    float4 p[32];      // working source points
+    int jp[32];        // seeds
+    float d2[32];      // clearances
+    // B: gathered per lane from the seeds
+    float4 ts[32];     // the seeds' target points
+    float4 ns[32];     // their normals
+    float4 cg[COLORED ? 32 : 1];   // their colour rows
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -1330,15 +1365,14 @@ icp_iteration_kernel(const __grid_constant__ IcpArgs a) {
     const int n = (int)a.n;
     const int stride = gridDim.x * kIcpT;
     const int first = blockIdx.x * kIcpT + w * 32;
-    constexpr unsigned kBytesA = 32 * sizeof(float4) + 32 * sizeof(int) + 32 * sizeof(float);
-    auto issue_a = [&](int c, int q0) {        // lane 0: TMA bulk copies of chunk c into slot c & 1
+    constexpr unsigned kBytesA = kSrcChunkBytes;
+    static_assert(offsetof(IcpStage<COLORED>, jp) == 512 && offsetof(IcpStage<COLORED>, d2) == 640, "stage A mirrors a chunk record");
+    auto issue_a = [&](int c, int q0) {        // lane 0: ONE TMA bulk copy of chunk c's record into slot c & 1
         if (lane == 0 && q0 < n) {
             IcpStage<COLORED>& sl = sm.stage[w][c & 1];
             unsigned long long* mb = &s_mbar[w][c & 1];
             mbar_expect_tx(mb, kBytesA);
-            bulk_g2s(sl.p, a.src + q0, 32 * sizeof(float4), mb);
-            bulk_g2s(sl.jp, a.prev + q0, 32 * sizeof(int), mb);
-            bulk_g2s(sl.d2, a.dprev + q0, 32 * sizeof(float), mb);
+            bulk_g2s(sl.p, a.src.chunk(q0), kBytesA, mb);
         }
     };
     auto issue_b = [&](int c, int q0) {        // every lane: gather its seed's rows of chunk c (needs A(c))
@@ -1440,9 +1474,7 @@ struct o3db_icp {
     int64_t n_pad = 0;               // n rounded up to whole 256-entry chunks (allocation size of src4 / prev)
     double n_total = 0;
     double init_T[16];
-    float4* src4 = nullptr;
-    int* prev = nullptr;             // search seeds (see IcpArgs::prev)
-    float* dprev = nullptr;          // dist^2 to the seed (see IcpArgs::dprev)
+    char* src_blk = nullptr;         // chunk-blocked working source: points, seeds, clearances (SrcBlocked)
     long long* dbg = nullptr;        // ICP_TIMING builds only
     unsigned* src_key = nullptr;     // cell key of every source point (sort order)
     unsigned* src_rank = nullptr;
@@ -1508,9 +1540,7 @@ static IcpArgs make_args(o3db_icp* c) {
     a.tgt = c->nns.pts4;
     a.nrm = c->nns.nrm4;
     a.cs = c->nns.cell_start;
-    a.src = c->src4;
-    a.prev = c->prev;
-    a.dprev = c->dprev;
+    a.src = SrcBlocked{c->src_blk};
     a.dbg = c->dbg;
     a.n = c->n;
     a.n_total = c->n_total;
@@ -1549,8 +1579,9 @@ static int icp_init_state(o3db_icp* c, cudaStream_t st) {
     }
     memcpy(c->h_st, &h, sizeof(h));
     O3DB_CUDA_CHECK(cudaMemcpyAsync(c->st, c->h_st, sizeof(IcpState), cudaMemcpyHostToDevice, st));
-    O3DB_CUDA_CHECK(cudaMemsetAsync(c->prev, 0xff, (size_t)c->n_pad * sizeof(int), st));   // no seeds yet
-    O3DB_CUDA_CHECK(cudaMemsetAsync(c->dprev, 0, (size_t)c->n_pad * sizeof(float), st));     // no clearance known
+    src_blocked_init_kernel<<<(unsigned)ceil_div(c->n_pad, kThreads), kThreads, 0, st>>>(SrcBlocked{c->src_blk}, c->n, c->n_pad,
+                                                                                         false);   // no seeds, no clearances
+    O3DB_LAUNCH_CHECK();
     c->launched = 0;
     return O3DB_OK;
 }
@@ -1559,8 +1590,8 @@ static int icp_gather_source(o3db_icp* c, cudaStream_t st) {
     Affine T0;
     for (int i = 0; i < 16; ++i) T0.m[i] = (float)c->init_T[i];   // Transform.cpp:29-31: T cast to the point dtype
     if (c->n == 0) return O3DB_OK;
-    scatter_kernel<true><<<(unsigned)ceil_div(c->n, kThreads), kThreads, 0, st>>>(
-            c->src_user, nullptr, c->n, T0, c->src_start, c->src_key, c->src_rank, c->src4, nullptr);
+    scatter_source_kernel<<<(unsigned)ceil_div(c->n, kThreads), kThreads, 0, st>>>(c->src_user, c->n, T0, c->src_start,
+                                                                                  c->src_key, c->src_rank, SrcBlocked{c->src_blk});
     O3DB_LAUNCH_CHECK();
     return O3DB_OK;
 }
@@ -1852,9 +1883,7 @@ void o3db_icp_destroy(o3db_icp* c) {
     cudaStream_t st = c->stream;
     cudaStreamSynchronize(st);
     nns_free(&c->nns, st);
-    if (c->src4) cudaFreeAsync(c->src4, st);
-    if (c->prev) cudaFreeAsync(c->prev, st);
-    if (c->dprev) cudaFreeAsync(c->dprev, st);
+    if (c->src_blk) cudaFreeAsync(c->src_blk, st);
     if (c->dbg) cudaFreeAsync(c->dbg, st);
     if (c->src_key) cudaFreeAsync(c->src_key, st);
     if (c->src_rank) cudaFreeAsync(c->src_rank, st);
@@ -1881,7 +1910,8 @@ struct ColoredInputs {   // all device pointers; null source_colors = plain poin
 
 static int icp_create_impl(const float* source_dev, int64_t n, const float* target_dev, const float* target_normals_dev,
                            int64_t m, const double init_T[16], const o3db_icp_options* options, o3db_comm* comm,
-                           const o3db::ColoredInputs& col, void* stream, o3db_icp** out) {
+                           const o3db::ColoredInputs& col, void* stream, o3db_icp** out,
+                           cudaEvent_t source_ready = nullptr) {
     O3DB_REQUIRE(out != nullptr, "o3db_icp_create: out is null");
     *out = nullptr;
     O3DB_REQUIRE(options != nullptr && init_T != nullptr, "o3db_icp_create: null options / init");
@@ -1944,10 +1974,10 @@ static int icp_create_impl(const float* source_dev, int64_t n, const float* targ
     c->src_keys = ncell;
     // padded to whole 256-entry chunks: the staged kernel copies 32-entry chunks with TMA bulk copies
     c->n_pad = ceil_div(n, 256) * 256;
-    ICP_CUDA(cudaMallocAsync(&c->src4, c->n_pad * sizeof(float4), st));
-    ICP_CUDA(cudaMallocAsync(&c->prev, c->n_pad * sizeof(int), st));
-    ICP_CUDA(cudaMallocAsync(&c->dprev, c->n_pad * sizeof(float), st));
-    ICP_CUDA(cudaMemsetAsync(c->src4 + n, 0, (c->n_pad - n) * sizeof(float4), st));
+    ICP_CUDA(cudaMallocAsync(&c->src_blk, SrcBlocked::bytes(c->n_pad), st));
+    src_blocked_init_kernel<<<(unsigned)ceil_div(c->n_pad, kThreads), kThreads, 0, st>>>(SrcBlocked{c->src_blk}, n, c->n_pad, true);
+    count_launch();
+    ICP_CUDA(cudaGetLastError());
     ICP_CUDA(cudaMallocAsync(&c->src_key, n * sizeof(unsigned), st));
     ICP_CUDA(cudaMallocAsync(&c->src_rank, n * sizeof(unsigned), st));
     ICP_CUDA(cudaMallocAsync(&c->src_start, (ncell + 1) * sizeof(unsigned), st));
@@ -1973,6 +2003,8 @@ static int icp_create_impl(const float* source_dev, int64_t n, const float* targ
     ICP_CUDA(cudaMemsetAsync(c->src_start, 0, (ncell + 1) * sizeof(unsigned), st));
     Affine T0;
     for (int i = 0; i < 16; ++i) T0.m[i] = (float)init_T[i];
+    // (host-buffer entry point: the source is still arriving on a copy stream while the target index is built)
+    if (source_ready) ICP_CUDA(cudaStreamWaitEvent(st, source_ready, 0));
     count_kernel<true><<<(unsigned)ceil_div(n, kThreads), kThreads, 0, st>>>(source_dev, n, c->nns.g, T0, c->src_start,
                                                                             c->src_key, c->src_rank);
     count_launch();
@@ -1989,7 +2021,7 @@ static int icp_create_impl(const float* source_dev, int64_t n, const float* targ
         count_launch();
         ICP_CUDA(cudaGetLastError());
         // the source sort order is fixed at creation (o3db_icp_reset re-gathers into the same slots)
-        pack_source_intensity_kernel<<<(unsigned)ceil_div(n, kThreads), kThreads, 0, st>>>(c->src4, col.source_colors, n,
+        pack_source_intensity_kernel<<<(unsigned)ceil_div(n, kThreads), kThreads, 0, st>>>(SrcBlocked{c->src_blk}, col.source_colors, n,
                                                                                           c->sint);
         count_launch();
         ICP_CUDA(cudaGetLastError());
@@ -2162,18 +2194,38 @@ int o3db_icp_point_to_plane_host(const float* source_host, int64_t n, const floa
                                  int64_t* correspondences_host, double* per_iteration_host) {
     O3DB_REQUIRE(source_host && target_host && n > 0 && m > 0, "Source and/or Target pointcloud is empty.");
     O3DB_REQUIRE(target_normals_host != nullptr, "Target pointcloud missing normals attribute.");
+    O3DB_REQUIRE(options != nullptr && result != nullptr, "o3db_icp_point_to_plane_host: null options / result");
     configure_memory_pool();
     cudaStream_t st = 0;
+    // Copy order = need order: target and normals first (the index build starts as soon as they are in), the source
+    // on a second stream so that its transfer overlaps the target's bounding box / count / scan / scatter; the source
+    // sort waits on the copy's event.  The 72 MB over PCIe remain the floor of this entry point.
+    static cudaStream_t copy_stream = nullptr;
+    static cudaEvent_t source_ready = nullptr, buffers_ready = nullptr;
+    if (!copy_stream) {
+        O3DB_CUDA_CHECK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+        O3DB_CUDA_CHECK(cudaEventCreateWithFlags(&source_ready, cudaEventDisableTiming));
+        O3DB_CUDA_CHECK(cudaEventCreateWithFlags(&buffers_ready, cudaEventDisableTiming));
+    }
     float *d_src = nullptr, *d_tgt = nullptr, *d_nrm = nullptr;
     int64_t* d_corr = nullptr;
     O3DB_CUDA_CHECK(cudaMallocAsync(&d_src, n * 3 * sizeof(float), st));
     O3DB_CUDA_CHECK(cudaMallocAsync(&d_tgt, m * 3 * sizeof(float), st));
     O3DB_CUDA_CHECK(cudaMallocAsync(&d_nrm, m * 3 * sizeof(float), st));
     if (correspondences_host) O3DB_CUDA_CHECK(cudaMallocAsync(&d_corr, n * sizeof(int64_t), st));
-    O3DB_CUDA_CHECK(cudaMemcpyAsync(d_src, source_host, n * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+    O3DB_CUDA_CHECK(cudaEventRecord(buffers_ready, st));
     O3DB_CUDA_CHECK(cudaMemcpyAsync(d_tgt, target_host, m * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
     O3DB_CUDA_CHECK(cudaMemcpyAsync(d_nrm, target_normals_host, m * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
-    int rc = o3db_icp_point_to_plane(d_src, n, d_tgt, d_nrm, m, init_T, options, result, d_corr, per_iteration_host, st);
+    O3DB_CUDA_CHECK(cudaStreamWaitEvent(copy_stream, buffers_ready, 0));      // d_src exists (stream-ordered allocation)
+    O3DB_CUDA_CHECK(cudaMemcpyAsync(d_src, source_host, n * 3 * sizeof(float), cudaMemcpyHostToDevice, copy_stream));
+    O3DB_CUDA_CHECK(cudaEventRecord(source_ready, copy_stream));
+    o3db_icp* c = nullptr;
+    int rc = icp_create_impl(d_src, n, d_tgt, d_nrm, m, init_T, options, nullptr, o3db::ColoredInputs{}, st, &c, source_ready);
+    if (rc == O3DB_OK) rc = o3db_icp_iterate(c, options->max_iteration, st);
+    if (rc == O3DB_OK) rc = o3db_icp_finish(c, result, d_corr, per_iteration_host, st);
+    cudaStreamSynchronize(st);
+    cudaStreamSynchronize(copy_stream);
+    if (c) o3db_icp_destroy(c);
     if (rc == O3DB_OK && correspondences_host) {
         cudaError_t e = cudaMemcpyAsync(correspondences_host, d_corr, n * sizeof(int64_t), cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
