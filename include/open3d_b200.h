@@ -275,6 +275,10 @@ int o3db_icp_point_to_plane_host(const float* source_host, int64_t n, const floa
  * Multi-GPU: one process per GPU; NCCL is dlopen()ed at run time
  * (libnccl.so.2 — torch's bundled copy if torch is loaded, else the system one).
  * The reference has no collective layer.
+ * o3db_comm_create is collective (every rank must call it): besides ncclCommInitRank it allocates a 1 KB-per-rank
+ * mailbox on every GPU, exchanges CUDA IPC handles (one ncclAllGather) and maps every peer's mailbox, so that the
+ * sharded ICP loop can exchange its 30-double system inside the iteration kernel over NVLink;
+ * if any rank cannot map any peer, all ranks agree to use ncclAllReduce instead.
  * ---------------------------------------------------------------------- */
 #define O3DB_UNIQUE_ID_BYTES 128
 int o3db_comm_get_unique_id(uint8_t id_out[O3DB_UNIQUE_ID_BYTES]);

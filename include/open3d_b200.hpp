@@ -45,10 +45,14 @@ struct PointCloud {
 
     /// PointCloud::EstimateColorGradients (t/geometry/PointCloud.cpp:723-767, hybrid search) into a
     /// caller-owned [N,3] device buffer, which becomes this cloud's color_gradients attribute.
-    void EstimateColorGradients(float* gradients_dev, int max_nn = 30, double radius = 0.0, void* stream = nullptr) {
+    /// exact_solver = false (default): upstream's solve_svd3x3<float>, bit for bit; true: exact pseudo-inverse (extension).
+    void EstimateColorGradients(float* gradients_dev, int max_nn = 30, double radius = 0.0, void* stream = nullptr,
+                                bool exact_solver = false) {
         if (!HasPointColors()) throw std::runtime_error("PointCloud must have colors attribute to estimate color gradients.");
         if (!HasPointNormals()) throw std::runtime_error("PointCloud must have normals attribute to estimate color gradients.");
-        Check(o3db_estimate_color_gradients(positions, normals, colors, num_points, radius, max_nn, gradients_dev, stream));
+        Check(o3db_estimate_color_gradients_solver(positions, normals, colors, num_points, radius, max_nn,
+                                                   exact_solver ? O3DB_GRADIENT_SOLVER_EXACT : O3DB_GRADIENT_SOLVER_REFERENCE,
+                                                   gradients_dev, stream));
         color_gradients = gradients_dev;
     }
 };
@@ -228,6 +232,18 @@ inline RegistrationResult ICP(const geometry::PointCloud& source, const geometry
         if (callback_after_iteration) callback_after_iteration(k, per[2 * k], per[2 * k + 1]);
     }
     return out;
+}
+
+/// registration::GetInformationMatrix (Registration.cpp:446-485): row-major 6x6 Float64 GTG on the host.
+inline std::array<double, 36> GetInformationMatrix(const geometry::PointCloud& source, const geometry::PointCloud& target,
+                                                   double max_correspondence_distance,
+                                                   const std::array<double, 16>& transformation, void* stream = nullptr) {
+    if (!target.HasPointPositions() || !source.HasPointPositions())
+        throw std::runtime_error("Source and/or Target pointcloud is empty.");
+    std::array<double, 36> info{};
+    Check(o3db_get_information_matrix(source.positions, source.num_points, target.positions, target.num_points,
+                                      max_correspondence_distance, transformation.data(), info.data(), stream));
+    return info;
 }
 
 }  // namespace registration

@@ -2,8 +2,8 @@
 # 8 GPUs: sharded == single at 8 ranks (peer exchange), full bench N=8 (weak + strong + configs[3] + TSDF replicas)
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 tests/multigpu_check.py 2>&1 | grep -E "multigpu|Error|error" | head -8 | tee gpurun_out/r02_multigpu23.log
-timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 8 --steps 10 --warmup 3 > gpurun_out/r02_bench23_n8.json 2> gpurun_out/r02_bench23_n8.err; python - <<'PY'
+timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 tests/multigpu_check.py 2>&1 | grep -E "multigpu|Error|error" | head -8 | tee gpurun_out/r02_multigpu23.log
+timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 8 --steps 10 --warmup 3 > gpurun_out/r02_bench23_n8.json 2> gpurun_out/r02_bench23_n8.err; python - <<'PY'
 import json
 d=json.loads(open('gpurun_out/r02_bench23_n8.json').read().strip().splitlines()[-1])
 m=d['multi_gpu']

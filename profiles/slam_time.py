@@ -12,15 +12,19 @@ import open3d_b200  # noqa: E402
 from tests.synth import PRIMESENSE_K, camera_pose, render_depth  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 100
+start = int(os.environ.get("SLAM_START", 0))      # first frame of the segment (bench.py gives rank r the frames 100 r ...)
+if "LOCAL_RANK" in os.environ:                     # under torchrun: one segment per rank, as bench.py does
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    start = 100 * int(os.environ["LOCAL_RANK"])
 slam = open3d_b200.t.pipelines.slam
 frames = []
 for i in range(n):
-    d, c = render_depth(camera_pose(i), device="cuda", with_color=True)
+    d, c = render_depth(camera_pose(start + i), device="cuda", with_color=True)
     frames.append((d.contiguous(), c.contiguous()))
 
 
 def loop(k, parts=None):
-    T0 = camera_pose(0)
+    T0 = camera_pose(start)
     model = slam.Model(0.008, 16, 40000, T0)
     pose = T0.copy()
     rc = slam.Frame(480, 640, PRIMESENSE_K)
@@ -50,5 +54,6 @@ dt = time.perf_counter() - t0
 parts = []
 loop(n, parts)
 p = np.array(parts[1:]) * 1e3
-print(f"slam ms/frame {1e3 * dt / n:.4f}  (track {p[:, 0].mean():.4f} ms, integrate+raycast synced {p[:, 1].mean():.4f} ms)  "
-      f"drift mm {1e3 * np.linalg.norm(pose[:3, 3] - camera_pose(n - 1)[:3, 3]):.2f}")
+worst = int(np.argmax(p.sum(1)))
+print(f"start {start} slam ms/frame {1e3 * dt / n:.4f}  (track {p[:, 0].mean():.4f} ms, integrate+raycast synced {p[:, 1].mean():.4f} ms)  "
+      f"worst frame {worst + 1}: {p[worst, 0]:.3f} + {p[worst, 1]:.3f} ms  drift mm {1e3 * np.linalg.norm(pose[:3, 3] - camera_pose(start + n - 1)[:3, 3]):.2f}")

@@ -43,6 +43,16 @@ def test_input_validation_errors():
         reg.multi_scale_icp(src, tgt, [-1, -1], [reg.ICPConvergenceCriteria()], [0.1, 0.1], np.eye(4), est)
     with pytest.raises(RuntimeError, match="decreasing"):
         reg.multi_scale_icp(src, tgt, [0.01, 0.02], [reg.ICPConvergenceCriteria()] * 2, [0.1, 0.1], np.eye(4), est)
+    with pytest.raises(RuntimeError, match="strictly decreasing"):      # Registration.cpp:190-200: equal sizes are rejected too
+        reg.multi_scale_icp(src, tgt, [0.02, 0.02], [reg.ICPConvergenceCriteria()] * 2, [0.1, 0.1], np.eye(4), est)
+    with pytest.raises(RuntimeError, match="in scale: 1"):              # the message names the offending scale
+        reg.multi_scale_icp(src, tgt, [0.04, 0.02], [reg.ICPConvergenceCriteria()] * 2, [0.1, 0.0], np.eye(4), est)
+    with pytest.raises(RuntimeError, match="empty"):
+        reg.get_information_matrix(o3d.t.geometry.PointCloud(), tgt, 0.1, np.eye(4))
+    tgt_c = o3d.t.geometry.PointCloud(tgt.point["positions"]).set_point_normals(tgt.point["normals"])
+    tgt_c.set_point_colors(np.zeros((64, 3), np.float32))
+    with pytest.raises(ValueError, match="solver"):
+        tgt_c.estimate_color_gradients(30, 0.1, solver="fast")
     with pytest.raises(RuntimeError, match=r"\[4, 4\]"):
         reg.icp(src, tgt, 0.1, np.eye(3), est)
     with pytest.raises(RuntimeError, match="Float32"):
