@@ -722,6 +722,7 @@ def bench_tsdf(args, rank, world, local_rank, L, torch, stream, barrier, max_ove
         results = {}
         for mode in ("device", "host"):
             tot_ms, launches, touch_ms, integ_ms, nfr, blocks = 0.0, 0, 0.0, 0.0, 0, 0
+            exec_ms, exec_launches = 0.0, 0
             # device mode runs one extra, untimed pass with per-kernel CUDA events (they perturb the
             # pipeline, so the pass that feeds `value` runs without them)
             n_pass = warmup + steps + (1 if mode == "device" else 0)
@@ -750,6 +751,11 @@ def bench_tsdf(args, rank, world, local_rank, L, torch, stream, barrier, max_ove
                     tot_ms += a.elapsed_time(b) if mode == "device" else wall
                     launches += L.launch_count() - l0
                     blocks = int(size)
+                    if mode == "device":       # device-timer duration of the integrate launches of the TIMED passes
+                        em, el = C.c_double(0), C.c_int64(0)
+                        L.check(L.lib.o3db_vbg_exec_stats(v, C.byref(em), C.byref(el), 1, stream))
+                        exec_ms += em.value
+                        exec_launches += el.value
                 if profiled:
                     if True:
                         tm, im, nf = C.c_double(0), C.c_double(0), C.c_int64(0)
@@ -761,7 +767,8 @@ def bench_tsdf(args, rank, world, local_rank, L, torch, stream, barrier, max_ove
             tot_ms = max_over_ranks(tot_ms)
             results[mode] = {"frames_per_sec": F * steps / (tot_ms * 1e-3),
                              "ms_per_frame": tot_ms / (len(mine) * steps), "launches": launches, "blocks_total": blocks,
-                             "touch_ms": touch_ms, "integrate_ms": integ_ms, "profiled_frames": nfr}
+                             "touch_ms": touch_ms, "integrate_ms": integ_ms, "profiled_frames": nfr,
+                             "exec_ms": exec_ms, "exec_launches": exec_launches}
         dev, host = results["device"], results["host"]
         entry = {"value": dev["frames_per_sec"], "unit": "frames/s", "ms_per_frame": dev["ms_per_frame"],
                  "gpu_launches": dev["launches"], "blocks_in_volume_after_sequence": dev["blocks_total"],
@@ -789,8 +796,16 @@ def bench_tsdf(args, rank, world, local_rank, L, torch, stream, barrier, max_ove
         dev = out[name].pop("_dev")
         alg = tsdf_algorithmic_bytes(mean_blocks, color)
         k_ms = dev["integrate_ms"] / max(dev["profiled_frames"], 1)
+        x_ms = dev["exec_ms"] / max(dev["exec_launches"], 1)
         out[name]["roofline"] = {"bound": "hbm", "kernel": "integrate16_kernel", "achieved": alg / (k_ms * 1e-3) / 1e9,
                                  "peak": peak, "unit": "GB/s", "frac": alg / (k_ms * 1e-3) / 1e9 / peak,
+                                 "avg_exec_us_device_timer": x_ms * 1e3,
+                                 "frac_device_timer": (alg / (x_ms * 1e-3) / 1e9 / peak) if x_ms > 0 else None,
+                                 "timing_note": "avg_launch_us / frac: CUDA events around every kernel in an extra, untimed pass "
+                                                "(the events sit between the frame's two kernels and disable their programmatic "
+                                                "overlap, so each interval also contains an un-hidden launch latency); "
+                                                "avg_exec_us_device_timer: %globaltimer of the last CTA's end minus the earliest "
+                                                "CTA's start, accumulated by the kernel itself during the TIMED passes",
                                  "traffic": ncu_traffic("integrate_kernel_color" if color else "integrate_kernel"),
                                  "algorithmic_bytes_per_launch": alg, "avg_launch_us": k_ms * 1e3,
                                  "touch_kernel_avg_us": 1e3 * dev["touch_ms"] / max(dev["profiled_frames"], 1),

@@ -415,6 +415,12 @@ int o3db_vbg_integrate_sequence(o3db_vbg* vbg, int64_t n_frames, const void* con
                                 const double* extrinsics_host, float depth_scale, float depth_max,
                                 float trunc_voxel_multiplier, int host_images, void* stream);
 
+/* Device-side execution time of the fused integrate launches since the last reset: per launch, %globaltimer of the last
+ * CTA's end minus the earliest CTA's start (after its griddepcontrol.wait), summed.  Unlike CUDA events between the two
+ * frame kernels this does not disable their programmatic overlap, so it is the kernel's duration inside an undisturbed
+ * frame stream.  Synchronises the stream. */
+int o3db_vbg_exec_stats(o3db_vbg* vbg, double* integrate_exec_ms, int64_t* launches, int reset, void* stream);
+
 /* Block keys of the last integrated frame (Model::frustum_block_coords_): copies
  * up to max_blocks keys, returns the count (stream synchronise). */
 int64_t o3db_vbg_last_frustum_blocks(o3db_vbg* vbg, int32_t* block_coords_dev, int64_t max_blocks,

@@ -106,6 +106,7 @@ _SIGS = {
     "o3db_vbg_create": (_i, [_f, _i, _i64, _i, _vp, C.POINTER(_vp)]),
     "o3db_vbg_destroy": (None, [_vp]),
     "o3db_vbg_size": (_i64, [_vp, _vp]),
+    "o3db_vbg_exec_stats": (_i, [_vp, _dp, C.POINTER(_i64), _i, _vp]),
     "o3db_depth_touch": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _f, _f, _f, _f, _i, _vp, _i64, _vp, _vp]),
     "o3db_integrate_blocks": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _i64, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _f, _f,
                                    _f, _f, _vp]),

@@ -1170,21 +1170,40 @@ __device__ __forceinline__ bool peer_all_reduce(const PeerView& pv, double* s_fi
     bool ok = true;
     long long t0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    for (int r = 0; r < pv.world && ok; ++r) {
+    // collect in batches of 8 ranks: all loads of a batch are in flight together (one memory round trip per batch when
+    // the peers have already published, instead of one per rank), the sum stays in rank order
+    constexpr int kBatch = 8;
+    for (int r0 = 0; r0 < pv.world && ok; r0 += kBatch) {
+        unsigned long long w0[kBatch], w1[kBatch];
         if (lane < kNumSums) {
-            const double* src = pv.box[pv.rank] + (par + r) * kBoxDoubles + 2 * lane;
-            unsigned long long w0, w1;
-            for (;;) {
-                asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(src) : "memory");
-                if ((unsigned)(w0 >> 32) == tag && (unsigned)(w1 >> 32) == tag) break;
-                long long t;
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-                if (t - t0 > 4000000000ll) {   // 4 s
-                    ok = false;
-                    break;
+            unsigned pending = 0;
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u)
+                if (r0 + u < pv.world) pending |= 1u << u;
+            while (pending) {
+#pragma unroll
+                for (int u = 0; u < kBatch; ++u)
+                    if (pending & (1u << u)) {
+                        const double* src = pv.box[pv.rank] + (par + r0 + u) * kBoxDoubles + 2 * lane;
+                        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0[u]), "=l"(w1[u]) : "l"(src) : "memory");
+                    }
+#pragma unroll
+                for (int u = 0; u < kBatch; ++u)
+                    if ((pending & (1u << u)) && (unsigned)(w0[u] >> 32) == tag && (unsigned)(w1[u] >> 32) == tag) pending &= ~(1u << u);
+                if (pending) {
+                    long long t;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                    if (t - t0 > 4000000000ll) {   // 4 s
+                        ok = false;
+                        break;
+                    }
                 }
             }
-            acc += __longlong_as_double((long long)((w1 << 32) | (w0 & 0xffffffffull)));
+            if (ok) {
+#pragma unroll
+                for (int u = 0; u < kBatch; ++u)
+                    if (r0 + u < pv.world) acc += __longlong_as_double((long long)((w1[u] << 32) | (w0[u] & 0xffffffffull)));
+            }
         }
         ok = __all_sync(0xffffffffu, ok);
     }

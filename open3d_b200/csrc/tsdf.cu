@@ -289,6 +289,8 @@ struct IntegrateArgs {
     int* dropped;            // [0] capacity the first dropped frame needed, [1] its frame index + 1 (0 = none)
     int* host_status;        // pinned host memory, ring of 8 x 16 ints: the frame's status, written by the last CTA
     int* work;               // fused mode: dynamic work-unit counter (re-armed by the last CTA); null = static striding
+    unsigned long long* exec_ns;   // fused mode: [0] earliest CTA start of this launch (re-armed by the last CTA), [1] sum over
+                                   // launches of (last CTA end - earliest start), [2] launches — %globaltimer, unperturbed by events
     int frame_id;
     int frame_index;         // 0-based index of the fused frame (reported when a frame is dropped)
     int capacity;
@@ -590,6 +592,11 @@ __global__ void __launch_bounds__(kT) integrate16_kernel(const __grid_constant__
     }
     pdl_wait();                 // the touch kernel's lists / counters, the previous frame's size
     pdl_launch_dependents();
+    if (a.exec_ns && tid == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        atomicMin(&a.exec_ns[0], now);
+    }
     const bool fused = a.counters != nullptr;
     int n_exist = 0, n_new = 0, n_total = a.n_blocks, size0 = 0;
     bool drop = false;
@@ -831,6 +838,13 @@ __global__ void __launch_bounds__(kT) integrate16_kernel(const __grid_constant__
             a.counters[1] = 0;
             a.counters[3] = 0;
             if (a.work) *a.work = 0;
+            if (a.exec_ns) {
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                a.exec_ns[1] += now - a.exec_ns[0];
+                a.exec_ns[2] += 1;
+                a.exec_ns[0] = ~0ull;
+            }
             publish_status(a, drop ? size0 : size0 + n_new, n_new, drop ? 1 : 0, drop ? 0 : n_total, *a.max_new);
         }
     }
@@ -1205,6 +1219,13 @@ int o3db_vbg_create(float voxel_size, int block_resolution, int64_t block_count,
     v->counters = v->size_dev + 4;
     v->frame_count = v->size_dev + 8;
     memset(v->h_pinned, 0, kPinnedInts * sizeof(int));
+    if (cudaMalloc(&v->exec_ns, 3 * sizeof(unsigned long long)) == cudaSuccess) {
+        const unsigned long long init[3] = {~0ull, 0ull, 0ull};
+        cudaMemcpy(v->exec_ns, init, sizeof(init), cudaMemcpyHostToDevice);
+    } else {
+        v->exec_ns = nullptr;
+        (void)cudaGetLastError();
+    }
     v->inv_w = inv_weight_table();
     if (!v->inv_w) {
         set_last_error("o3db_vbg_create: could not build the weight table: %s", cudaGetErrorString(cudaGetLastError()));
@@ -1219,7 +1240,7 @@ void o3db_vbg_destroy(o3db_vbg* v) {
     if (!v) return;
     cudaDeviceSynchronize();
     void* ptrs[] = {v->table, v->keys, v->stamp, v->size_dev, v->tsdf, v->weight, v->color, v->cand_keys,
-                    v->exist_list, v->new_list, v->frame_slots, v->ftable, v->d_depth[0], v->d_depth[1],
+                    v->exist_list, v->new_list, v->frame_slots, v->ftable, v->exec_ns, v->d_depth[0], v->d_depth[1],
                     v->d_color[0], v->d_color[1]};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -1653,6 +1674,7 @@ int o3db_vbg_integrate_frame(o3db_vbg* v, const void* depth_dev, int depth_dtype
     a.frame_index = (int)v->frames;
     a.host_status = v->h_pinned + 16;
     a.work = v->size_dev + 12;
+    a.exec_ns = v->exec_ns;
     rc = launch_integrate(v, a, depth_dtype, color_dtype, has_color, integrate_grid(), st);
     if (rc) return rc;
     if (prof) {
@@ -1721,6 +1743,22 @@ int o3db_vbg_integrate_sequence(o3db_vbg* v, int64_t n_frames, const void* const
                                                               stream);
         if (rc != O3DB_OK) return rc;
     }
+    return O3DB_OK;
+}
+
+int o3db_vbg_exec_stats(o3db_vbg* v, double* integrate_exec_ms, int64_t* launches, int reset, void* stream) {
+    O3DB_REQUIRE(v != nullptr, "o3db_vbg_exec_stats: null handle");
+    unsigned long long h[3] = {0, 0, 0};
+    if (v->exec_ns) {
+        O3DB_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+        O3DB_CUDA_CHECK(cudaMemcpy(h, v->exec_ns, sizeof(h), cudaMemcpyDeviceToHost));
+        if (reset) {
+            const unsigned long long init[3] = {~0ull, 0ull, 0ull};
+            O3DB_CUDA_CHECK(cudaMemcpy(v->exec_ns, init, sizeof(init), cudaMemcpyHostToDevice));
+        }
+    }
+    if (integrate_exec_ms) *integrate_exec_ms = 1e-6 * (double)h[1];
+    if (launches) *launches = (int64_t)h[2];
     return O3DB_OK;
 }
 

@@ -97,6 +97,7 @@ struct o3db_vbg {
     int2* new_list = nullptr;
     int* frame_slots = nullptr;
     int* frame_count = nullptr;
+    unsigned long long* exec_ns = nullptr;   // device-timer statistics of the fused integrate launches (o3db_vbg_exec_stats)
     const float* inv_w = nullptr;  // [65536] 1 / (w + 1) per u16 weight (integrate16_kernel); per-device table, not owned
     float checked_scale = 0.f;     // depth_scale the 3-FMA u16 division was last verified for ...
     bool checked_scale_ok = false; // ... and whether it reproduces d / scale for all 65536 u16 values
