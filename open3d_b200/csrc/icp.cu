@@ -2219,13 +2219,22 @@ int o3db_icp_point_to_plane_host(const float* source_host, int64_t n, const floa
     // Copy order = need order: target and normals first (the index build starts as soon as they are in), the source
     // on a second stream so that its transfer overlaps the target's bounding box / count / scan / scatter; the source
     // sort waits on the copy's event.  The 72 MB over PCIe remain the floor of this entry point.
-    static cudaStream_t copy_stream = nullptr;
-    static cudaEvent_t source_ready = nullptr, buffers_ready = nullptr;
-    if (!copy_stream) {
-        O3DB_CUDA_CHECK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
-        O3DB_CUDA_CHECK(cudaEventCreateWithFlags(&source_ready, cudaEventDisableTiming));
-        O3DB_CUDA_CHECK(cudaEventCreateWithFlags(&buffers_ready, cudaEventDisableTiming));
+    struct CopyLane {      // one per device, created on first use (streams and events belong to a device)
+        cudaStream_t stream = nullptr;
+        cudaEvent_t source_ready = nullptr, buffers_ready = nullptr;
+    };
+    static CopyLane lanes[64];
+    int dev = 0;
+    O3DB_CUDA_CHECK(cudaGetDevice(&dev));
+    O3DB_REQUIRE(dev >= 0 && dev < 64, "o3db_icp_point_to_plane_host: device index out of range");
+    CopyLane& lane = lanes[dev];
+    if (!lane.stream) {
+        O3DB_CUDA_CHECK(cudaStreamCreateWithFlags(&lane.stream, cudaStreamNonBlocking));
+        O3DB_CUDA_CHECK(cudaEventCreateWithFlags(&lane.source_ready, cudaEventDisableTiming));
+        O3DB_CUDA_CHECK(cudaEventCreateWithFlags(&lane.buffers_ready, cudaEventDisableTiming));
     }
+    cudaStream_t copy_stream = lane.stream;
+    cudaEvent_t source_ready = lane.source_ready, buffers_ready = lane.buffers_ready;
     float *d_src = nullptr, *d_tgt = nullptr, *d_nrm = nullptr;
     int64_t* d_corr = nullptr;
     O3DB_CUDA_CHECK(cudaMallocAsync(&d_src, n * 3 * sizeof(float), st));
