@@ -17,11 +17,18 @@
 //
 // All pixel-selecting arithmetic (projection, roundf, residual gate) is evaluated without FMA contraction in the
 // reference's source order, as everywhere else in this library.
+#include <atomic>
+#include <chrono>
 #include <climits>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <vector>
+
+#include <cooperative_groups.h>
 
 #include "common.cuh"
 #include "reduce.cuh"
@@ -159,6 +166,18 @@ __global__ void filter_bilateral_kernel(const float* __restrict__ src, int rows,
 // in shared memory once, the smoothed depths of the 33 x 9 stencil points and their vertices live in shared memory
 // too, so the filter runs once per pixel and the normal map never reads a smoothed image back from HBM.  The
 // per-pixel arithmetic is the stand-alone kernels' (same device functions, same order): bit-identical maps.
+static constexpr int kMaxLevels = 8;
+
+struct OdoState {
+    double T[16];                 // source -> target, updated every iteration
+    double sums[kSumStride];
+    double res_rmse, res_fitness; // OdometryResult::inlier_rmse_ / fitness_ (RGBDOdometry.cpp:165, 190-191)
+    int level_done[kMaxLevels];
+    int status;                   // 0 ok, 1 singular 6x6, 2 inlier_count <= 0
+    int executed;
+    unsigned ticket;
+};
+
 static constexpr int kTW = 32, kTH = 8;
 struct LevelArgs {
     const float* src_d;      // this level's depth images (metres, NaN = invalid)
@@ -173,6 +192,8 @@ struct LevelArgs {
     float* tn;
     float* src_next;         // nullptr on the coarsest level
     float* tgt_next;
+    OdoState* init_state;    // first launch of a track: the state the iterations start from (no copy / memset on the stream)
+    double init_T[16];
 };
 
 __device__ __forceinline__ float pyr_down_pixel(const float* __restrict__ img, int rows, int cols, int yd, int xd,
@@ -199,6 +220,14 @@ __global__ void __launch_bounds__(kTW* kTH) pyramid_level_kernel(LevelArgs a) {
     __shared__ float s_vert[kTH + 1][kTW + 1][3];     // vertices of the smoothed depth at the normal stencil points
     pdl_grid_wait();
     pdl_grid_launch_dependents();
+    if (a.init_state && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+        // RGBDOdometry.cpp:165 OdometryResult(trans, /*prev rmse*/ 0.0, /*prev fitness*/ 1.0); the iteration kernels read
+        // it after their griddepcontrol.wait, i.e. after every pyramid launch has completed
+        OdoState z{};
+        for (int i = 0; i < 16; ++i) z.T[i] = a.init_T[i];
+        z.res_fitness = 1.0;
+        *a.init_state = z;
+    }
     const int tx = threadIdx.x % kTW, ty = threadIdx.x / kTW;
     const int x0 = blockIdx.x * kTW, y0 = blockIdx.y * kTH;
     const int x = x0 + tx, y = y0 + ty;
@@ -344,7 +373,8 @@ __device__ __forceinline__ bool jacobian_p2plane(int x, int y, float trunc, cons
     return true;
 }
 
-__device__ __forceinline__ void accumulate_odometry(float (&acc)[kNumSums], const float (&J)[6], float r, float delta) {
+template <int N>
+__device__ __forceinline__ void accumulate_odometry(float (&acc)[N], const float (&J)[6], float r, float delta) {
     const float d_huber = huber_deriv(r, delta), r_huber = huber_loss(r, delta);
     int s = 0;
 #pragma unroll
@@ -359,18 +389,6 @@ __device__ __forceinline__ void accumulate_odometry(float (&acc)[kNumSums], cons
 
 // ----------------------------------------------------------- fused loop
 
-static constexpr int kMaxLevels = 8;
-
-struct OdoState {
-    double T[16];                 // source -> target, updated every iteration
-    double sums[kSumStride];
-    double res_rmse, res_fitness; // OdometryResult::inlier_rmse_ / fitness_ (RGBDOdometry.cpp:165, 190-191)
-    int level_done[kMaxLevels];
-    int status;                   // 0 ok, 1 singular 6x6, 2 inlier_count <= 0
-    int executed;
-    unsigned ticket;
-};
-
 struct OdoArgs {
     const float* sv;
     const float* tv;
@@ -384,50 +402,76 @@ struct OdoArgs {
     double* per_iter;             // optional device log: (inlier_rmse, fitness) per executed iteration
     int standalone;               // 1: ComputeOdometryResultPointToPlane seam (T is not updated, delta -> st->sums[..])
     double* delta_out;            // standalone: 16 doubles (delta transformation)
+    unsigned long long* host_out; // last launch of a track: pinned host block that receives the final state + token
+    unsigned long long host_token;
 };
 
-// Host part of one Gauss-Newton step (RGBDOdometry.cpp:165-191, 441-462), run by warp 0 of the last block: the 6x6
-// solve is warp-parallel (reduce.cuh), lane 0 keeps the books.  `scratch`: >= 96 doubles of shared memory.
-__device__ void odometry_finalize(const OdoArgs& a, const double* s_final, double* scratch) {
-    OdoState* st = a.st;
+static constexpr int kStateWords = (int)(sizeof(OdoState) / sizeof(unsigned long long));
+static_assert(sizeof(OdoState) % sizeof(unsigned long long) == 0, "OdoState is copied as 8-byte words");
+static constexpr int kHostTokenWord = 64;   // the token lands behind the state: the host that sees it has the state
+
+// Final state -> pinned host memory, by the first kStateWords threads of one block (all of the block's threads must
+// call it): every writer orders its stores system-wide, then one thread stores the token the host spins on — no
+// device-to-host copy and no stream synchronisation at the end of a track.
+__device__ __forceinline__ void publish_state(const OdoArgs& a, const OdoState* from) {
+    if (!a.host_out) return;
+    if (threadIdx.x < kStateWords) {
+        reinterpret_cast<volatile unsigned long long*>(a.host_out)[threadIdx.x] =
+            reinterpret_cast<const volatile unsigned long long*>(from)[threadIdx.x];
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) reinterpret_cast<volatile unsigned long long*>(a.host_out)[kHostTokenWord] = a.host_token;
+}
+
+// Host part of one Gauss-Newton step (RGBDOdometry.cpp:165-191, 441-462), run by ONE WARP (all 32 lanes must call
+// it): the 6x6 solve is warp-parallel (reduce.cuh), the six sin / cos of the pose and the sixteen entries of
+// T <- dT T are spread over lanes (as icp_finalize_iteration does), lane 0 keeps the books.  `st` is the state the
+// step updates — the global one for the per-iteration kernel, a shared-memory copy for the level-resident kernel —
+// `per_iter` the optional log.  `scratch`: >= 96 doubles of shared memory.
+__device__ void odometry_finalize(const OdoArgs& a, OdoState* st, double* per_iter, const double* s_final, double* scratch) {
     const int lane = threadIdx.x & 31;
     double* s = scratch;            // [29] the sums as DecodeAndSolve6x6 receives them
     double* pose = scratch + 32;    // [6]
+    double* trig = scratch + 40;    // [6] cos a, cos b, cos g, sin a, sin b, sin g (aliases the solve's matrix: dead by then)
+    double* dT = scratch + 48;      // [16]
     // the 29 sums reach DecodeAndSolve6x6 as a Float32 tensor (RGBDOdometryCUDA.cu:112-124)
     if (lane < 29) s[lane] = (double)(float)s_final[lane];
     __syncwarp();
     const int count = (int)s[28];
     const bool solved = solve6x6_warp(s, scratch + 40, pose);   // TransformationConverter.cpp:215-225
-    if (lane != 0) return;
-    if (!solved) {
-        st->status = 1;
+    if (!solved || count <= 0) {    // singular system; RGBDOdometry.cpp:449-452 inlier_count <= 0
+        if (lane == 0) st->status = !solved ? 1 : 2;
         return;
     }
-    if (count <= 0) {             // RGBDOdometry.cpp:449-452
-        st->status = 2;
-        return;
-    }
-    double dT[16];
-    pose_to_T(pose, dT);
+    __syncwarp();
+    if (lane < 3) trig[lane] = cos(pose[lane]);
+    else if (lane < 6) trig[lane] = sin(pose[lane - 3]);
+    __syncwarp();
+    if (lane == 0) pose_to_T_trig(pose, trig[0], trig[3], trig[1], trig[4], trig[2], trig[5], dT);
+    __syncwarp();
     const double d_rmse = (double)((float)s[27] / (float)count);   // float inlier_residual / int (:455)
     const double d_fit = (double)count / (double)((int64_t)a.rows * a.cols);
     if (a.standalone) {
-        for (int i = 0; i < 16; ++i) a.delta_out[i] = dT[i];
-        st->res_rmse = d_rmse;
-        st->res_fitness = d_fit;
+        if (lane < 16) a.delta_out[lane] = dT[lane];
+        if (lane == 0) {
+            st->res_rmse = d_rmse;
+            st->res_fitness = d_fit;
+        }
         return;
     }
-    double R[16];
-    for (int i = 0; i < 4; ++i)   // :175-176 result.transformation_ = delta.transformation_.Matmul(result.transformation_)
-        for (int j = 0; j < 4; ++j) {
-            double v = 0;
-            for (int k = 0; k < 4; ++k) v += dT[i * 4 + k] * st->T[k * 4 + j];
-            R[i * 4 + j] = v;
-        }
-    for (int i = 0; i < 16; ++i) st->T[i] = R[i];
-    if (a.per_iter) {
-        a.per_iter[2 * st->executed] = d_rmse;
-        a.per_iter[2 * st->executed + 1] = d_fit;
+    if (lane < 16) {   // :175-176 result.transformation_ = delta.transformation_.Matmul(result.transformation_)
+        const int i = lane >> 2, j = lane & 3;
+        double v = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v += dT[i * 4 + k] * st->T[k * 4 + j];
+        __syncwarp(0xffffu);        // every lane has read the old T
+        st->T[lane] = v;
+    }
+    if (lane != 0) return;
+    if (per_iter) {
+        per_iter[2 * st->executed] = d_rmse;
+        per_iter[2 * st->executed + 1] = d_fit;
     }
     st->executed += 1;
     if (fabs(st->res_fitness - d_fit) / st->res_fitness < a.rel_fitness &&
@@ -457,7 +501,10 @@ __global__ void __launch_bounds__(kThreads) odometry_iteration_kernel(OdoArgs a)
     }
     for (int k = threadIdx.x; k < (kThreads / 32) * kSumStride; k += kThreads) (&s_warp[0][0])[k] = 0.0;
     __syncthreads();
-    if (s_skip) return;
+    if (s_skip) {
+        if (blockIdx.x == 0) publish_state(a, a.st);   // (the state is final: the previous launch completed)
+        return;
+    }
     const Cam ti = s_cam;
     float acc[kNumSums];
 #pragma unroll
@@ -479,7 +526,121 @@ __global__ void __launch_bounds__(kThreads) odometry_iteration_kernel(OdoArgs a)
     flush_acc(acc, s_warp);
     if (!block_reduce_to_global(s_warp, a.partials, &a.st->ticket, s_final)) return;
     if (threadIdx.x < 29) a.st->sums[threadIdx.x] = s_final[threadIdx.x];
-    if (threadIdx.x < 32) odometry_finalize(a, s_final, &s_warp[0][0]);   // (s_warp is dead: reused as scratch)
+    if (threadIdx.x < 32) odometry_finalize(a, a.st, a.per_iter, s_final, &s_warp[0][0]);   // (s_warp is dead: reused as scratch)
+    if (a.host_out) {
+        __threadfence();             // warp 0's updates of the state, before the block reads it back
+        __syncthreads();
+        publish_state(a, a.st);
+    }
+}
+
+// ------------------------------------------------ level-resident iterations
+//
+// A coarse pyramid level is a few thousand pixels: its iteration is over in a couple of microseconds of work, and
+// what the per-iteration kernel above spends is the fixed part — launch + drain of the predecessor, partial rows to
+// global memory, the ticket, the last block's grand total.  For those levels ONE thread-block cluster runs ALL the
+// iterations of the level in one launch: the pixels are strided over the cluster's CTAs, a CTA's 29 sums go through
+// the transposed warp reduction (reduce.cuh) into one shared-memory row, the rows are exchanged through distributed
+// shared memory behind one hardware cluster barrier per iteration, and EVERY CTA adds them in rank order and runs the
+// same f64 solve / pose update on its own shared-memory copy of the state — bit-identical everywhere, so nothing is
+// broadcast and the next iteration starts after a __syncthreads.  Rank 0 writes the state back at the end.
+// The sums are those of the per-iteration kernel up to the association of the additions (f32 per thread and across
+// the warp — at most kLevelFlush + 5 roundings deep — then f64), far inside the reference's own all-f32 reduction.
+static constexpr int kLevelThreads = 512;
+static constexpr int kMaxCluster = 16;
+static constexpr int kLevelFlush = 16;       // f32 terms per thread between two warp reductions
+
+__global__ void __launch_bounds__(kLevelThreads, 1) odometry_level_kernel(OdoArgs a, int max_iteration) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned crank = cluster.block_rank(), csize = cluster.num_blocks();
+    __shared__ double s_warp[kLevelThreads / 32][kSumStride];
+    __shared__ double s_part[2][kSumStride];     // this CTA's sums, double-buffered by iteration parity (see below)
+    __shared__ double s_final[kSumStride];
+    __shared__ double s_scratch[96];
+    __shared__ OdoState s_st;
+    __shared__ Cam s_cam;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    pdl_grid_wait();                 // the previous level's T / flags, the pyramid kernels' maps
+    pdl_grid_launch_dependents();
+    for (int k = threadIdx.x; k < kStateWords; k += kLevelThreads)
+        reinterpret_cast<unsigned long long*>(&s_st)[k] = reinterpret_cast<const unsigned long long*>(a.st)[k];
+    __syncthreads();
+    // (every CTA of the cluster read the same state: the decision is uniform, no peer is left waiting)
+    if (s_st.status | s_st.level_done[a.level]) {
+        if (crank == 0) publish_state(a, &s_st);
+        return;
+    }
+    double* per_iter = crank == 0 ? a.per_iter : nullptr;
+    const int n = a.rows * a.cols;
+    const int stride = (int)csize * kLevelThreads;
+    for (int it = 0; it < max_iteration; ++it) {
+        if (threadIdx.x < 12) s_cam.e[threadIdx.x / 4][threadIdx.x % 4] = (float)s_st.T[threadIdx.x];   // TransformIndexer: f32
+        if (threadIdx.x == 12) {
+            s_cam.fx = a.fx;
+            s_cam.fy = a.fy;
+            s_cam.cx = a.cx;
+            s_cam.cy = a.cy;
+            s_cam.scale = 1.0f;
+        }
+        __syncthreads();
+        const Cam ti = s_cam;
+        float acc[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) acc[k] = 0.f;
+        double total = 0.0;          // lane l: sum l of this warp
+        int since = 0;
+        for (int base = (int)crank * kLevelThreads; base < n; base += stride) {   // (block-uniform trip count)
+            const int i = base + threadIdx.x;
+            if (i < n) {
+                float J[6], r;
+                if (jacobian_p2plane(i % a.cols, i / a.cols, a.trunc, a.sv, a.tv, a.tn, a.rows, a.cols, ti, J, r))
+                    accumulate_odometry(acc, J, r, a.huber_delta);
+            }
+            if (++since == kLevelFlush) {
+                total += (double)warp_transpose_sum32(acc);
+#pragma unroll
+                for (int k = 0; k < 32; ++k) acc[k] = 0.f;
+                since = 0;
+            }
+        }
+        total += (double)warp_transpose_sum32(acc);
+        s_warp[w][lane] = total;
+        __syncthreads();
+        // Parity double buffer: a CTA refills s_part[p] two iterations later, which it can only reach after every
+        // peer passed the barrier of the iteration in between — i.e. after every peer finished reading s_part[p].
+        const int par = it & 1;
+        if (threadIdx.x < 32) {
+            double v = 0;
+#pragma unroll
+            for (int k = 0; k < kLevelThreads / 32; ++k) v += s_warp[k][lane];
+            s_part[par][lane] = v;
+        }
+        cluster.sync();              // barrier.cluster arrive.release / wait.acquire: the rows are visible cluster-wide
+        if (threadIdx.x < 32) {
+            double t[kMaxCluster];   // all the peers' rows in flight, then added in rank order
+#pragma unroll
+            for (unsigned r = 0; r < kMaxCluster; ++r) {
+                const double x = cluster.map_shared_rank(&s_part[par][0], r < csize ? r : crank)[lane];   // (always a valid rank)
+                t[r] = r < csize ? x : 0.0;
+            }
+            double v = 0;
+#pragma unroll
+            for (unsigned r = 0; r < kMaxCluster; ++r) v += t[r];
+            s_final[lane] = v;
+            if (lane < 29) s_st.sums[lane] = v;
+            __syncwarp();
+            odometry_finalize(a, &s_st, per_iter, s_final, s_scratch);
+        }
+        __syncthreads();
+        if (s_st.status | s_st.level_done[a.level]) break;   // identical in every CTA
+    }
+    cluster.sync();                  // nobody leaves while a peer may still read its shared memory
+    if (crank == 0) {
+        for (int k = threadIdx.x; k < kStateWords; k += kLevelThreads)
+            reinterpret_cast<unsigned long long*>(a.st)[k] = reinterpret_cast<const unsigned long long*>(&s_st)[k];
+        publish_state(a, &s_st);
+    }
 }
 
 // ------------------------------------------------------------- host side
@@ -589,8 +750,10 @@ struct OdoScratch {
     int blocks = 1;
 };
 
-static void odo_scratch_free(OdoScratch* s, cudaStream_t st) {
-    if (s->h_st) cudaStreamSynchronize(st);   // the pinned block may still feed / receive an async copy
+static void odo_scratch_free(OdoScratch* s, cudaStream_t st, bool pinned_idle = false) {
+    // the pinned block may still feed / receive an async copy (not when the result arrived by publish_state: its
+    // token is the last store the device makes to the block)
+    if (s->h_st && !pinned_idle) cudaStreamSynchronize(st);
     if (s->st) cudaFreeAsync(s->st, st);
     if (s->partials) cudaFreeAsync(s->partials, st);
     if (s->per_iter) cudaFreeAsync(s->per_iter, st);
@@ -599,10 +762,14 @@ static void odo_scratch_free(OdoScratch* s, cudaStream_t st) {
     *s = OdoScratch{};
 }
 
-static int odo_scratch_alloc(OdoScratch* s, int64_t pixels, int log_entries, const double* T, cudaStream_t st) {
+// device_init: the first pyramid launch writes the initial state (LevelArgs::init_state) and every launch overwrites
+// its own partial rows before reading them, so nothing has to be copied or cleared on the stream.
+static int odo_scratch_alloc(OdoScratch* s, int64_t pixels, int log_entries, const double* T, cudaStream_t st,
+                             bool device_init = false) {
     configure_memory_pool();
     s->blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(pixels, kThreads), (int64_t)num_sms() * ODO_BLOCKS_PER_SM));
-    static_assert(sizeof(OdoState) <= 4096, "OdoState must fit a pinned block");
+    static_assert(sizeof(OdoState) <= 4096 - 64, "OdoState and the token must fit a pinned block");
+    static_assert(kStateWords <= kHostTokenWord && (kHostTokenWord + 1) * sizeof(unsigned long long) <= 4096, "token placement");
     O3DB_CUDA_CHECK(cudaMallocAsync(&s->st, sizeof(OdoState), st));
     O3DB_CUDA_CHECK(cudaMallocAsync(&s->partials, (size_t)s->blocks * kSumStride * sizeof(double), st));
     O3DB_CUDA_CHECK(cudaMallocAsync(&s->per_iter, (size_t)std::max(1, log_entries) * 2 * sizeof(double), st));
@@ -612,6 +779,7 @@ static int odo_scratch_alloc(OdoScratch* s, int64_t pixels, int log_entries, con
         set_last_error("pinned host allocation failed");
         return O3DB_ERR_CUDA;
     }
+    if (device_init) return O3DB_OK;
     OdoState h{};
     for (int i = 0; i < 16; ++i) h.T[i] = T[i];
     h.res_rmse = 0.0;       // RGBDOdometry.cpp:165 OdometryResult(trans, /*prev rmse*/ 0.0, /*prev fitness*/ 1.0)
@@ -632,6 +800,82 @@ static int odo_status_to_rc(int status) {
         return O3DB_ERR_NO_INLIERS;
     }
     return O3DB_OK;
+}
+
+// Cluster size the level-resident kernel runs with on the current device: 16 CTAs (non-portable size, one GPC) when
+// the device can co-schedule such a cluster, else 8, else 0 = the per-iteration kernel everywhere.  Decided once per
+// device.  O3DB_ODO_LEVEL_CLUSTER = 0 | 8 | 16 caps it (measurements, fallback).
+static int level_cluster_size() {
+    static std::mutex mu;
+    static int cached[64];
+    static bool known[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+    std::lock_guard<std::mutex> lk(mu);
+    if (known[dev]) return cached[dev];
+    int cap = 16;
+    if (const char* e = getenv("O3DB_ODO_LEVEL_CLUSTER")) cap = atoi(e);
+    int chosen = 0;
+    for (int c : {16, 8}) {
+        if (c > cap) continue;
+        if (c > 8 && cudaFuncSetAttribute(odometry_level_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+            cudaGetLastError();
+            continue;
+        }
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)c);
+        cfg.blockDim = dim3(kLevelThreads);
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)c;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        int clusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&clusters, odometry_level_kernel, &cfg) == cudaSuccess && clusters >= 1) {
+            chosen = c;
+            break;
+        }
+        cudaGetLastError();
+    }
+    cached[dev] = chosen;
+    known[dev] = true;
+    if (getenv("O3DB_ODO_VERBOSE")) fprintf(stderr, "[o3db] odometry level-resident kernel: cluster of %d CTAs on device %d\n", chosen, dev);
+    return chosen;
+}
+
+// Pixels per thread up to which a level runs in the level-resident kernel: beyond that the cluster's 8 - 16 SMs are
+// slower at the pixel loop than the whole GPU is at the per-iteration kernel's fixed cost.
+static int level_pixels_per_thread() {
+    static const int v = [] {
+        const char* e = getenv("O3DB_ODO_LEVEL_PX_PER_THREAD");
+        return e ? atoi(e) : 12;
+    }();
+    return v;
+}
+
+// O3DB_ODO_NO_ZERO_COPY=1: read the result back with a copy + stream synchronisation (measurements, fallback)
+static bool zero_copy_result() {
+    static const bool v = getenv("O3DB_ODO_NO_ZERO_COPY") == nullptr;
+    return v;
+}
+
+static cudaError_t launch_level(const OdoArgs& a, int max_iteration, int cluster, cudaStream_t st) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)cluster);
+    cfg.blockDim = dim3(kLevelThreads);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = (unsigned)cluster;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 2;
+    return cudaLaunchKernelEx(&cfg, odometry_level_kernel, a, max_iteration);
 }
 
 }  // namespace o3db
@@ -730,13 +974,13 @@ int o3db_rgbd_odometry_multi_scale_point_to_plane(const void* source_depth_dev, 
     float* tgt_d = src_d + full;
     float* tmp = tgt_d + full;
     float* smooth = tmp + full;
-    float* tsm = smooth + full;            // [full * 3]
     OdoScratch s;
     int rc = O3DB_OK;
 #define ODO_TRY(expr)                  \
     do {                               \
         if (rc == O3DB_OK) rc = (expr); \
     } while (0)
+    ODO_TRY(odo_scratch_alloc(&s, full, total_iters, init_source_to_target, st, /*device_init=*/true));
     // RGBDOdometry.cpp:84-88 ClipTransform(depth_scale, 0, depth_max, NAN), both frames in one launch
     if (rc == O3DB_OK) {
         const int64_t npx = (int64_t)rows * cols;
@@ -798,6 +1042,8 @@ int o3db_rgbd_odometry_multi_scale_point_to_plane(const void* source_depth_dev, 
             // the next level's images go to the two spare buffers (tmp, smooth), then the roles swap
             la.src_next = last ? nullptr : tmp;
             la.tgt_next = last ? nullptr : smooth;
+            la.init_state = i == 0 ? s.st : nullptr;
+            for (int k = 0; k < 16; ++k) la.init_T[k] = init_source_to_target[k];
             cudaLaunchConfig_t cfg{};
             cfg.gridDim = dim3((unsigned)ceil_div(c, kTW), (unsigned)ceil_div(r, kTH));
             cfg.blockDim = dim3(kTW * kTH);
@@ -823,7 +1069,15 @@ int o3db_rgbd_odometry_multi_scale_point_to_plane(const void* source_depth_dev, 
             }
         }
     }
-    ODO_TRY(odo_scratch_alloc(&s, full, total_iters, init_source_to_target, st));
+    // which launch is the last one of the track (it publishes the result into pinned host memory)
+    int final_level = -1;
+    for (int i = 0; i < num_levels; ++i)
+        if (criteria[i].max_iteration > 0) final_level = i;
+    static std::atomic<unsigned long long> g_token{0};
+    const unsigned long long token = ++g_token;
+    volatile unsigned long long* h_words = reinterpret_cast<volatile unsigned long long*>(s.h_st);
+    const bool zero_copy = zero_copy_result() && final_level >= 0 && rc == O3DB_OK;
+    if (zero_copy) h_words[kHostTokenWord] = 0;
     for (int i = 0; i < num_levels && rc == O3DB_OK; ++i) {
         OdoArgs a{};
         a.sv = lv[i].sv;
@@ -843,21 +1097,69 @@ int o3db_rgbd_odometry_multi_scale_point_to_plane(const void* source_depth_dev, 
         a.partials = s.partials;
         a.st = s.st;
         a.per_iter = s.per_iter;
-        const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div((int64_t)a.rows * a.cols, kThreads), s.blocks));
+        const int64_t pixels = (int64_t)a.rows * a.cols;
+        const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(pixels, kThreads), s.blocks));
+        const int cluster = level_cluster_size();
         cudaError_t e = cudaSuccess;
-        for (int it = 0; it < criteria[i].max_iteration && e == cudaSuccess; ++it) {
-            e = launch_pdl_ex(odometry_iteration_kernel, (unsigned)blocks, (unsigned)kThreads, 0, st, a);
+        if (cluster > 0 && criteria[i].max_iteration >= 2 &&
+            pixels <= (int64_t)cluster * kLevelThreads * level_pixels_per_thread()) {
+            // a coarse level: all its iterations in one launch of one thread-block cluster
+            if (zero_copy && i == final_level) {
+                a.host_out = const_cast<unsigned long long*>(h_words);
+                a.host_token = token;
+            }
+            e = launch_level(a, criteria[i].max_iteration, cluster, st);
             count_launch();
+        } else {
+            for (int it = 0; it < criteria[i].max_iteration && e == cudaSuccess; ++it) {
+                if (zero_copy && i == final_level && it == criteria[i].max_iteration - 1) {
+                    a.host_out = const_cast<unsigned long long*>(h_words);
+                    a.host_token = token;
+                }
+                e = launch_pdl_ex(odometry_iteration_kernel, (unsigned)blocks, (unsigned)kThreads, 0, st, a);
+                count_launch();
+            }
         }
         if (e != cudaSuccess) {
-            set_last_error("odometry_iteration_kernel launch failed: %s", cudaGetErrorString(e));
+            set_last_error("odometry iteration kernel launch failed: %s", cudaGetErrorString(e));
             rc = O3DB_ERR_CUDA;
         }
     }
+    bool published = false;
     if (rc == O3DB_OK) {
-        cudaError_t e = cudaMemcpyAsync(s.h_st, s.st, sizeof(OdoState), cudaMemcpyDeviceToHost, st);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-        if (e == cudaSuccess && per_iteration_host && s.h_st->executed > 0) {
+        cudaError_t e = cudaSuccess;
+        if (zero_copy) {
+            // the last launch stores the final state and then the token into the pinned block: spin on it instead of
+            // a device-to-host copy + stream synchronisation; the stream is queried now and then so that a failed
+            // launch (or a kernel that never published) ends the wait
+            const auto t0 = std::chrono::steady_clock::now();
+            for (unsigned spins = 1;; ++spins) {
+                if (h_words[kHostTokenWord] == token) {
+                    published = true;
+                    break;
+                }
+                if ((spins & 0x3fffu) == 0) {
+                    e = cudaStreamQuery(st);
+                    if (e == cudaSuccess) {
+                        published = h_words[kHostTokenWord] == token;
+                        break;
+                    }
+                    if (e != cudaErrorNotReady) break;
+                    e = cudaSuccess;
+                    if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(30)) {
+                        set_last_error("o3db_rgbd_odometry_multi_scale_point_to_plane: the device never published its result");
+                        rc = O3DB_ERR_CUDA;
+                        break;
+                    }
+                }
+            }
+            std::atomic_thread_fence(std::memory_order_acquire);
+        }
+        if (rc == O3DB_OK && e == cudaSuccess && !published) {
+            e = cudaMemcpyAsync(s.h_st, s.st, sizeof(OdoState), cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        }
+        if (rc == O3DB_OK && e == cudaSuccess && per_iteration_host && s.h_st->executed > 0) {
             e = cudaMemcpyAsync(per_iteration_host, s.per_iter, (size_t)s.h_st->executed * 2 * sizeof(double),
                                 cudaMemcpyDeviceToHost, st);
             if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -865,7 +1167,7 @@ int o3db_rgbd_odometry_multi_scale_point_to_plane(const void* source_depth_dev, 
         if (e != cudaSuccess) {
             set_last_error("o3db_rgbd_odometry_multi_scale_point_to_plane: %s", cudaGetErrorString(e));
             rc = O3DB_ERR_CUDA;
-        } else {
+        } else if (rc == O3DB_OK) {
             memcpy(result_host->transformation, s.h_st->T, sizeof(s.h_st->T));
             result_host->inlier_rmse = s.h_st->res_rmse;
             result_host->fitness = s.h_st->res_fitness;
@@ -875,7 +1177,7 @@ int o3db_rgbd_odometry_multi_scale_point_to_plane(const void* source_depth_dev, 
         }
     }
 #undef ODO_TRY
-    odo_scratch_free(&s, st);
+    odo_scratch_free(&s, st, /*pinned_idle=*/published);
     cudaFreeAsync(pool, st);
     return rc;
 }

@@ -224,11 +224,13 @@ __device__ __forceinline__ bool solve6x6_warp(const double* __restrict__ A, doub
     return ok;
 }
 
-// TransformationConverterImpl.h:22-42 + TransformationConverter.cpp:81-104.
-__device__ __host__ inline void pose_to_T(const double* p, double* T) {
+// TransformationConverterImpl.h:22-42 + TransformationConverter.cpp:81-104.  The trigonometric values come in as
+// arguments so that a warp can evaluate the six sin / cos calls on six lanes (odometry.cu) and still run the very
+// same expressions as the single-thread path.
+__device__ __host__ inline void pose_to_T_trig(const double* p, double ca, double sa, double cb, double sb, double cg,
+                                               double sg, double* T) {
     for (int i = 0; i < 16; ++i) T[i] = 0.0;
     T[15] = 1.0;
-    const double ca = cos(p[0]), sa = sin(p[0]), cb = cos(p[1]), sb = sin(p[1]), cg = cos(p[2]), sg = sin(p[2]);
     T[0] = cg * cb;
     T[1] = -1 * sg * ca + cg * sb * sa;
     T[2] = sg * sa + cg * sb * ca;
@@ -241,6 +243,10 @@ __device__ __host__ inline void pose_to_T(const double* p, double* T) {
     T[3] = p[3];
     T[7] = p[4];
     T[11] = p[5];
+}
+
+__device__ __host__ inline void pose_to_T(const double* p, double* T) {
+    pose_to_T_trig(p, cos(p[0]), sin(p[0]), cos(p[1]), sin(p[1]), cos(p[2]), sin(p[2]), T);
 }
 
 }  // namespace o3db

@@ -7,12 +7,14 @@
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 
 import numpy as np
 import torch
 
 from .. import _libshim as _s
-from ..._lib import (COLOR_F32, COLOR_NONE, COLOR_U8, DEPTH_F32, DEPTH_U16, check, dptr, lib)
+from ..._lib import (COLOR_F32, COLOR_NONE, COLOR_U8, DEPTH_F32, DEPTH_U16, ERR_CAPACITY, O3DBError, check, dptr, lib)
+from ._replay import FrameReplay
 from ...core import as_device_f32_points, as_host_f64_4x4, current_stream_ptr
 
 
@@ -264,7 +266,7 @@ class _BlockHashMap:
         self._v = vbg
 
     def size(self):
-        return int(check(lib.o3db_vbg_size(self._v._h, current_stream_ptr())))
+        return self._v._replay.guard(lambda: int(check(lib.o3db_vbg_size(self._v._h, current_stream_ptr()))))
 
     def capacity(self):
         return int(lib.o3db_vbg_capacity(self._v._h))
@@ -332,6 +334,21 @@ class VoxelBlockGrid:
         check(lib.o3db_vbg_create(self.voxel_size, self.block_resolution, int(block_count), int(self._with_color),
                                   current_stream_ptr(), C.byref(h)))
         self._h = h
+        # HashMap::Activate grows the map on demand (HashMap.cpp:166-181); the fused path reports a frame that did
+        # not fit instead, and this puts the reference's behaviour back (see _replay.py).  auto_grow = False hands
+        # the O3DB_ERR_CAPACITY error to the caller.
+        me = weakref.proxy(self)             # no reference cycle: __del__ frees the device buffers promptly
+        self._replay = FrameReplay(lambda *frame: me._submit_frame(*frame), lambda n: me.hashmap().reserve(n),
+                                   lambda: me.hashmap().capacity(),
+                                   lambda e: isinstance(e, O3DBError) and e.code == ERR_CAPACITY)
+
+    @property
+    def auto_grow(self):
+        return self._replay.enabled
+
+    @auto_grow.setter
+    def auto_grow(self, on):
+        self._replay.enabled = bool(on)
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -393,26 +410,22 @@ class VoxelBlockGrid:
     # fused path used by slam.Model.integrate
     def integrate_frame(self, depth, color, intrinsic, extrinsic, depth_scale=1000.0, depth_max=3.0,
                         trunc_voxel_multiplier=8.0):
-        K, E = _k9(intrinsic), as_host_f64_4x4(extrinsic, "extrinsic")
+        K, E = _k9(intrinsic), as_host_f64_4x4(extrinsic, "extrinsic").copy()
         host = (isinstance(depth, torch.Tensor) and not depth.is_cuda) or isinstance(depth, np.ndarray)
         if host:
             d = torch.from_numpy(np.ascontiguousarray(depth)) if isinstance(depth, np.ndarray) else depth.contiguous()
             c = None
             if color is not None and (not isinstance(color, torch.Tensor) or color.numel() > 0):
                 c = torch.from_numpy(np.ascontiguousarray(color)) if isinstance(color, np.ndarray) else color.contiguous()
-            rows, cols = int(d.shape[0]), int(d.shape[1])
-            check(lib.o3db_vbg_integrate_frame_host(self._h, d.data_ptr(), _depth_dtype(d),
-                                                    None if c is None else c.data_ptr(), _color_dtype(c), rows, cols,
-                                                    dptr(K), dptr(E), float(depth_scale), float(depth_max),
-                                                    float(trunc_voxel_multiplier), current_stream_ptr()))
-            return
-        d = _image_tensor(depth)
-        c = _image_tensor(color)
+        else:
+            d, c = _image_tensor(depth), _image_tensor(color)
+        self._replay.submit(host, d, c, K, E, float(depth_scale), float(depth_max), float(trunc_voxel_multiplier))
+
+    def _submit_frame(self, host, d, c, K, E, depth_scale, depth_max, trunc_voxel_multiplier):
         rows, cols = int(d.shape[0]), int(d.shape[1])
-        check(lib.o3db_vbg_integrate_frame(self._h, d.data_ptr(), _depth_dtype(d),
-                                           None if c is None else c.data_ptr(), _color_dtype(c), rows, cols, dptr(K),
-                                           dptr(E), float(depth_scale), float(depth_max),
-                                           float(trunc_voxel_multiplier), current_stream_ptr()))
+        fn = lib.o3db_vbg_integrate_frame_host if host else lib.o3db_vbg_integrate_frame
+        check(fn(self._h, d.data_ptr(), _depth_dtype(d), None if c is None else c.data_ptr(), _color_dtype(c), rows,
+                 cols, dptr(K), dptr(E), depth_scale, depth_max, trunc_voxel_multiplier, current_stream_ptr()))
 
     _RAYCAST_ATTRS = {"vertex": (3, torch.float32), "normal": (3, torch.float32), "depth": (1, torch.float32),
                       "color": (3, torch.float32), "index": (8, torch.int64), "mask": (8, torch.bool),
@@ -439,17 +452,18 @@ class VoxelBlockGrid:
         rng = torch.empty((max(height // max(down, 1), 0), max(width // max(down, 1), 0), 2), dtype=torch.float32,
                           device="cuda")
         bc = None if block_coords is None else self.hashmap()._keys_arg(block_coords)
-        check(lib.o3db_vbg_ray_cast(self._h, None if bc is None else bc.data_ptr(), 0 if bc is None else bc.shape[0],
-                                    dptr(K), dptr(E), width, height, C.byref(ptrs), float(depth_scale),
-                                    float(depth_min), float(depth_max), float(weight_threshold),
-                                    float(trunc_voxel_multiplier), down, rng.data_ptr(), current_stream_ptr()))
+        self._replay.guard(lambda: check(lib.o3db_vbg_ray_cast(
+            self._h, None if bc is None else bc.data_ptr(), 0 if bc is None else bc.shape[0], dptr(K), dptr(E), width,
+            height, C.byref(ptrs), float(depth_scale), float(depth_min), float(depth_max), float(weight_threshold),
+            float(trunc_voxel_multiplier), down, rng.data_ptr(), current_stream_ptr())))
         out["range"] = rng
         return out
 
     def last_frustum_block_coordinates(self):
         cap = 76800
         out = torch.empty((cap, 3), dtype=torch.int32, device="cuda")
-        n = int(check(lib.o3db_vbg_last_frustum_blocks(self._h, out.data_ptr(), cap, current_stream_ptr())))
+        n = int(self._replay.guard(
+            lambda: check(lib.o3db_vbg_last_frustum_blocks(self._h, out.data_ptr(), cap, current_stream_ptr()))))
         if n > cap:
             out = torch.empty((n, 3), dtype=torch.int32, device="cuda")
             check(lib.o3db_vbg_last_frustum_blocks(self._h, out.data_ptr(), n, current_stream_ptr()))

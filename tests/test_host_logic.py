@@ -138,3 +138,107 @@ def test_no_cpu_fallback_new_entry_points():
                                                              L.dptr(K), L.dptr(T), 1.0, 3.0, crit, 1, 0.07, 0.05,
                                                              C.byref(res), None, None)
     assert rc == L.ERR_CUDA
+
+
+class _FakeFusedVolume:
+    """Stand-in for the o3db_vbg_integrate_frame contract (include/open3d_b200.h): the host runs two frames ahead; a
+    frame whose blocks do not fit is dropped with every later one; the error surfaces when frame F-2's status is read
+    at the submission of frame F, or at a size() call; reserve() re-arms; the first frame after a reserve is sized
+    synchronously."""
+
+    class CapacityError(RuntimeError):
+        pass
+
+    def __init__(self, capacity):
+        self.capacity, self.size, self.frames = capacity, 0, 0
+        self.integrated = []          # frame tags that reached the volume, in order
+        self.submitted = []           # (library index, tag, dropped?)
+        self.dropped_from = None
+        self.sync_next = True
+        self.reserves = []
+
+    def _raise_if_visible(self, upto):
+        if self.dropped_from is not None and self.dropped_from[0] <= upto:
+            k, need = self.dropped_from
+            raise self.CapacityError(f"voxel block hash map capacity ({self.capacity} blocks) exceeded: fused frame "
+                                     f"#{k} needed {need} blocks; that frame and all later ones were dropped")
+
+    def submit(self, tag, blocks):
+        self._raise_if_visible(self.frames - 2)
+        if self.sync_next:
+            self.sync_next = False
+            self.capacity = max(self.capacity, self.size + blocks)
+        dropped = self.dropped_from is not None or self.size + blocks > self.capacity
+        if dropped and self.dropped_from is None:
+            self.dropped_from = (self.frames, self.size + blocks)
+        if not dropped:
+            self.size += blocks
+            self.integrated.append(tag)
+        self.submitted.append((self.frames, tag, dropped))
+        self.frames += 1
+
+    def get_size(self):
+        self._raise_if_visible(self.frames)
+        return self.size
+
+    def reserve(self, n):
+        self.reserves.append(n)
+        self.capacity = max(self.capacity, n)
+        self.dropped_from = None
+        self.sync_next = True
+
+
+def _replay_for(vol):
+    from open3d_b200.t.geometry._replay import FrameReplay
+    return FrameReplay(vol.submit, vol.reserve, lambda: vol.capacity, lambda e: isinstance(e, vol.CapacityError))
+
+
+def test_frame_replay_restores_hashmap_activate_growth():
+    """HashMap::Activate grows on demand (HashMap.cpp:166-181): through FrameReplay the caller never sees the fused
+    path's dropped-frame error, every frame is integrated exactly once and in order."""
+    from open3d_b200.t.geometry._replay import parse_dropped_frame
+    assert parse_dropped_frame("... fused frame #12 needed 3456 blocks; that frame") == (12, 3456)
+    assert parse_dropped_frame("singular 6x6") is None
+    vol = _FakeFusedVolume(1000)
+    rp = _replay_for(vol)
+    blocks = [800, 50, 50, 5000, 40, 30, 20000, 10, 10]     # two jumps that do not fit
+    for tag, b in enumerate(blocks):
+        rp.submit(tag, b)
+    assert rp.guard(vol.get_size) == sum(blocks)
+    assert vol.integrated == list(range(len(blocks)))
+    assert rp.recoveries == 2 and len(vol.reserves) == 2
+    assert vol.reserves[0] >= 5900 + 2048 and vol.reserves[1] >= 2 * vol.reserves[0]
+    # a drop of the very last frames is only visible to the guarded call
+    vol = _FakeFusedVolume(1000)
+    rp = _replay_for(vol)
+    for tag, b in enumerate([500, 100, 9000]):
+        rp.submit(tag, b)
+    assert vol.integrated == [0, 1]
+    assert rp.guard(vol.get_size) == 9600 and vol.integrated == [0, 1, 2]
+
+
+def test_frame_replay_hands_over_what_it_cannot_recover():
+    vol = _FakeFusedVolume(1000)
+    rp = _replay_for(vol)
+    rp.enabled = False
+    with pytest.raises(_FakeFusedVolume.CapacityError, match="fused frame #1 needed 5500 blocks"):
+        for tag, b in enumerate([500, 5000, 10, 10, 10]):
+            rp.submit(tag, b)
+    # other errors pass through untouched, and the failed frame is not remembered
+    from open3d_b200.t.geometry._replay import FrameReplay
+
+    def boom(*_):
+        raise ValueError("bad image")
+    rp = FrameReplay(boom, lambda n: None, lambda: 0, lambda e: False)
+    with pytest.raises(ValueError, match="bad image"):
+        rp.submit(0, 1)
+    assert len(rp._ring) == 0 and rp._next == 0
+    # a dropped frame older than the ring cannot be resubmitted from here
+    vol = _FakeFusedVolume(1000)
+    rp = _replay_for(vol)
+    for tag in range(3):
+        rp.submit(tag, 10)
+    rp._ring.clear()
+    vol.dropped_from = (1, 4000)
+    with pytest.raises(_FakeFusedVolume.CapacityError):
+        rp.guard(vol.get_size)

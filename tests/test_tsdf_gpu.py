@@ -276,6 +276,47 @@ def test_frame_that_outgrows_the_map_is_dropped_whole_and_recoverable():
     L.lib.o3db_vbg_destroy(v)
 
 
+def test_voxel_block_grid_grows_like_hashmap_activate_after_a_dropped_frame(o3d):
+    """The same camera jump through the Python mirror: VoxelBlockGrid.integrate_frame must behave like the reference,
+    whose HashMap::Activate grows the map on demand (HashMap.cpp:166-181) — no error reaches the caller, and the
+    volume equals the oracle's bit for bit (the dropped frames were resubmitted in order, once)."""
+    voxel, cap0 = 0.00125, 4000
+    vbg = o3d.t.geometry.VoxelBlockGrid(("tsdf", "weight"), (torch.float32, torch.uint16), ((1,), (1,)), voxel, RES, cap0)
+    seq = [(250, 0.95), (250, 0.95), (251, 0.95), (125, DMAX), (126, DMAX), (250, 0.95), (127, DMAX)]
+    cap = 40000
+    okeys, otsdf, owt = np.zeros((cap, 3), np.int32), np.zeros((cap, RES ** 3), np.float32), np.zeros((cap, RES ** 3), np.uint16)
+    osize = 0
+    for fid, dmax in seq:
+        T = camera_pose(fid)
+        d = render_depth(T, device="cuda").contiguous()
+        E = np.ascontiguousarray(oracle.inverse_transformation(T))
+        vbg.integrate_frame(d, None, PRIMESENSE_K, E, SCALE, dmax, TRUNC_MULT)
+        dh = d.cpu().numpy()
+        want = oracle.depth_touch(dh, PRIMESENSE_K, E, RES, voxel, voxel * TRUNC_MULT, SCALE, dmax, 4)
+        bi, _, osize, rc = oracle.hashmap_activate(okeys, osize, want)
+        assert rc == 0
+        oracle.tsdf_integrate(dh, None, bi, okeys, otsdf, owt, None, PRIMESENSE_K, PRIMESENSE_K, E, RES, voxel,
+                              voxel * TRUNC_MULT, SCALE, dmax)
+    hm = vbg.hashmap()
+    assert hm.size() == osize                      # also the call that surfaces a drop of the very last frames
+    assert vbg._replay.recoveries >= 1 and hm.capacity() > cap0
+    gkeys = hm.key_tensor().cpu().numpy()[:osize]
+    lut = {tuple(k): j for j, k in enumerate(okeys[:osize].tolist())}
+    perm = np.array([lut[tuple(k)] for k in gkeys.tolist()])
+    gt = vbg.attribute("tsdf").cpu().numpy().reshape(-1, RES ** 3)[:osize]
+    gw = vbg.attribute("weight").cpu().numpy().reshape(-1, RES ** 3)[:osize]
+    assert np.array_equal(gw, owt[perm]) and np.array_equal(gt.view(np.uint32), otsdf[perm].view(np.uint32))
+    # auto_grow = False hands the documented error to the caller instead
+    vbg2 = o3d.t.geometry.VoxelBlockGrid(("tsdf", "weight"), (torch.float32, torch.uint16), ((1,), (1,)), voxel, RES, cap0)
+    vbg2.auto_grow = False
+    with pytest.raises(RuntimeError, match=r"fused frame #3 needed \d+ blocks"):
+        for fid, dmax in seq:
+            T = camera_pose(fid)
+            vbg2.integrate_frame(render_depth(T, device="cuda").contiguous(), None, PRIMESENSE_K,
+                                 np.ascontiguousarray(oracle.inverse_transformation(T)), SCALE, dmax, TRUNC_MULT)
+        vbg2.hashmap().size()
+
+
 def test_generic_block_resolution_vs_oracle(o3d):
     """res = 8 goes through the generic (non-vectorised) integrate path."""
     res, cap = 8, 20000
