@@ -61,7 +61,7 @@ _i64 = C.c_int64
 _dbl = C.c_double
 _f = C.c_float
 _i = C.c_int
-_dp = C.POINTER(C.c_double)
+_dp = C.c_void_p   # double* parameters: a plain address (see dptr) — ctypes also accepts POINTER(c_double) objects here
 
 _SIGS = {
     "o3db_last_error": (C.c_char_p, []),
@@ -171,8 +171,8 @@ def check(rc: int) -> int:
 
 
 def dptr(arr):
-    """double[...] pointer of a contiguous float64 numpy array."""
-    return arr.ctypes.data_as(_dp)
+    """Address of a contiguous float64 numpy array, for the double* parameters (the caller keeps the array alive)."""
+    return arr.ctypes.data
 
 
 def launch_count() -> int:

@@ -8,9 +8,18 @@ import numpy as np
 import torch
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)   # what torch.cuda.current_stream() wraps; ~10x cheaper
+_has_cuda = None
+
+
 def current_stream_ptr() -> int:
-    if not torch.cuda.is_available():
+    global _has_cuda
+    if _has_cuda is None:
+        _has_cuda = bool(torch.cuda.is_available())
+    if not _has_cuda:
         return 0   # the C ABI call that follows fails with O3DB_ERR_CUDA (no CPU fallback)
+    if _raw_stream is not None:
+        return int(_raw_stream(torch.cuda.current_device()))
     return int(torch.cuda.current_stream().cuda_stream)
 
 

@@ -55,15 +55,25 @@ class FrameReplay:
         self._next += 1
 
     def submit(self, *frame):
-        self._run(("frame", frame))
+        try:                                 # the common case costs one call and one append
+            self._submit_one(frame)
+        except Exception as err:  # noqa: BLE001
+            self._run(("frame", frame), err)
 
     def guard(self, fn):
-        return self._run(("call", fn))
+        try:
+            return fn()
+        except Exception as err:  # noqa: BLE001
+            return self._run(("call", fn), err)
 
-    def _run(self, last):
-        queue = deque([last])
+    def _run(self, last, err):
+        """`last` just failed with `err`: recover if that is the documented capacity error, then finish `last`."""
+        replay = self._recover(err) if self.enabled else None
+        if replay is None:
+            raise err
+        queue = deque([("frame", f) for f in replay] + [last])
         result = None
-        budget = MAX_RECOVERIES
+        budget = MAX_RECOVERIES - 1
         while queue:
             kind, item = queue[0]
             try:

@@ -66,6 +66,27 @@ def _criteria_list(criteria_list):
     return out
 
 
+_criteria_cache = {}
+
+
+def _c_criteria(criteria_list):
+    """(C array, levels, total iterations) of a criteria list; the frame loop passes the same tuple of ints every
+    frame, so that case is cached."""
+    key = None
+    if isinstance(criteria_list, tuple) and all(type(c) is int for c in criteria_list):
+        key = criteria_list
+        hit = _criteria_cache.get(key)
+        if hit is not None:
+            return hit
+    crit = _criteria_list(criteria_list)
+    arr = (_CCriteria * len(crit))(*[_CCriteria(int(c.max_iteration), float(c.relative_rmse),
+                                                float(c.relative_fitness)) for c in crit])
+    out = (arr, len(crit), sum(int(c.max_iteration) for c in crit))
+    if key is not None and len(_criteria_cache) < 64:
+        _criteria_cache[key] = out
+    return out
+
+
 def _raise(rc):
     if rc == ERR_SINGULAR:
         raise O3DBError(rc, "Singular 6x6 linear system detected, tracking failed.")
@@ -94,17 +115,16 @@ def rgbd_odometry_multi_scale(source, target, intrinsics, init_source_to_target=
     K = _k9(intrinsics)
     T0 = as_host_f64_4x4(np.eye(4) if init_source_to_target is None else init_source_to_target,
                          "init_source_to_target")
-    crit = _criteria_list(criteria_list)
-    arr = (_CCriteria * len(crit))(*[_CCriteria(int(c.max_iteration), float(c.relative_rmse),
-                                                float(c.relative_fitness)) for c in crit])
+    arr, n_levels, total_iterations = _c_criteria(criteria_list)
     res = _CResult()
-    per = np.zeros((max(sum(int(c.max_iteration) for c in crit), 1), 2))
+    # the per-iteration log costs a device-to-host copy + stream synchronisation at the end of the track: only on request
+    per = np.zeros((max(total_iterations, 1), 2)) if return_log else None
     rc = lib.o3db_rgbd_odometry_multi_scale_point_to_plane(
         sd.data_ptr(), _depth_dtype(sd), td.data_ptr(), _depth_dtype(td), rows, cols, dptr(K), dptr(T0),
-        float(depth_scale), float(depth_max), arr, len(crit), float(params.depth_outlier_trunc),
-        float(params.depth_huber_delta), C.byref(res), dptr(per), current_stream_ptr())
+        float(depth_scale), float(depth_max), arr, n_levels, float(params.depth_outlier_trunc),
+        float(params.depth_huber_delta), C.byref(res), None if per is None else dptr(per), current_stream_ptr())
     _raise(rc)
-    out = OdometryResult(np.array(res.transformation, np.float64).reshape(4, 4), float(res.inlier_rmse),
+    out = OdometryResult(np.array(res.transformation[:], np.float64).reshape(4, 4), float(res.inlier_rmse),
                          float(res.fitness))
     return (out, per[: int(res.iterations)].copy()) if return_log else out
 

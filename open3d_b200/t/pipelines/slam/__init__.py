@@ -40,7 +40,8 @@ class Frame:
         self._data[name] = data
 
     def get_data(self, name):
-        return self._data.get(name, torch.empty(0))
+        d = self._data.get(name)
+        return torch.empty(0) if d is None else d
 
     def set_data_from_image(self, name, image):
         self._data[name] = image.as_tensor() if isinstance(image, Image) else image
@@ -49,15 +50,18 @@ class Frame:
         return Image(self.get_data(name))
 
 
+_IDENTITY = np.eye(4)   # TrackFrameToModel's initial guess (read only)
+
+
 def _inverse_transformation(T):
-    """t::geometry::InverseTransformation (t/geometry/Utility.h:77-115), f64 on the host"""
-    E = np.eye(4)
-    R, t = T[:3, :3], T[:3, 3]
-    E[:3, :3] = R.T
-    E[0, 3] = -(E[0, 0] * t[0] + E[0, 1] * t[1] + E[0, 2] * t[2])
-    E[1, 3] = -(E[1, 0] * t[0] + E[1, 1] * t[1] + E[1, 2] * t[2])
-    E[2, 3] = -(E[2, 0] * t[0] + E[2, 1] * t[1] + E[2, 2] * t[2])
-    return E
+    """t::geometry::InverseTransformation (t/geometry/Utility.h:77-115), f64 on the host: R^T and -R^T t, the
+    translation summed in the reference's order (plain Python floats are IEEE doubles: same results as the numpy
+    expression, a fraction of its cost on the frame loop's critical path)."""
+    (r00, r01, r02, t0), (r10, r11, r12, t1), (r20, r21, r22, t2) = T[0].tolist(), T[1].tolist(), T[2].tolist()
+    return np.array([[r00, r10, r20, -(r00 * t0 + r10 * t1 + r20 * t2)],
+                     [r01, r11, r21, -(r01 * t0 + r11 * t1 + r21 * t2)],
+                     [r02, r12, r22, -(r02 * t0 + r12 * t1 + r22 * t2)],
+                     [0.0, 0.0, 0.0, 1.0]])
 
 
 class Model:
@@ -70,6 +74,7 @@ class Model:
                                          (torch.float32, torch.uint16, torch.uint16), ((1,), (1,), (3,)),
                                          voxel_size, block_resolution, block_count, device)
         self.transformation_frame_to_world = as_host_f64_4x4(np.eye(4) if transformation is None else transformation)
+        self._extrinsic_of = None            # (pose bytes, its inverse): integrate and ray cast use the same one
         self.frame_id = -1
         self._frustum_dirty = False
 
@@ -87,13 +92,19 @@ class Model:
         """Model::Integrate (slam/Model.cpp:91-106)."""
         depth = input_frame.get_data("depth")
         color = input_frame.get_data("color")
-        T = self.transformation_frame_to_world
-        E = _inverse_transformation(T)
+        E = self._extrinsic()
         if isinstance(color, torch.Tensor) and color.numel() == 0:
             color = None
         self.voxel_grid.integrate_frame(depth, color, input_frame.get_intrinsics(), E, depth_scale, depth_max,
                                         trunc_voxel_multiplier)
         self._frustum_dirty = True
+
+    def _extrinsic(self):
+        """world -> frame of the current pose (InverseTransformation), computed once per pose."""
+        key = self.transformation_frame_to_world.tobytes()   # by value: the pose array may be updated in place
+        if self._extrinsic_of is None or self._extrinsic_of[0] != key:
+            self._extrinsic_of = (key, _inverse_transformation(self.transformation_frame_to_world))
+        return self._extrinsic_of[1]
 
     @property
     def frustum_block_coords(self):
@@ -112,7 +123,7 @@ class Model:
         return odometry.rgbd_odometry_multi_scale(
             RGBDImage(input_frame.get_data_as_image("color"), input_frame.get_data_as_image("depth")),
             RGBDImage(model_frame.get_data_as_image("color"), model_frame.get_data_as_image("depth")),
-            model_frame.get_intrinsics(), np.eye(4), depth_scale, depth_max, criteria, method,
+            model_frame.get_intrinsics(), _IDENTITY, depth_scale, depth_max, criteria, method,
             odometry.OdometryLossParams(depth_diff))
 
     def synthesize_model_frame(self, raycast_frame, depth_scale=1000.0, depth_min=0.1, depth_max=3.0,
@@ -121,11 +132,10 @@ class Model:
         frame from the current pose into raycast_frame's "depth" (and "color")."""
         if weight_threshold < 0:
             weight_threshold = min(self.frame_id * 1.0, 3.0)
-        T = self.transformation_frame_to_world
         # upstream always renders {"depth", "color"} and drops the colour when !enable_color (Model.cpp:49-55);
         # the depth map does not depend on it, so the colour pass (8-corner trilinear gather) is skipped here
         attrs = ("depth", "color") if enable_color else ("depth",)
-        res = self.voxel_grid.ray_cast(None, raycast_frame.get_intrinsics(), _inverse_transformation(T),
+        res = self.voxel_grid.ray_cast(None, raycast_frame.get_intrinsics(), self._extrinsic(),
                                        raycast_frame.width(), raycast_frame.height(), attrs, depth_scale,
                                        depth_min, depth_max, weight_threshold, trunc_voxel_multiplier)
         raycast_frame.set_data("depth", res["depth"])
