@@ -215,9 +215,12 @@ __device__ __forceinline__ float pyr_down_pixel(const float* __restrict__ img, i
     return den == 0 ? invalid_fill : dvd(num, den);
 }
 
+// kUnrollRows: the 5 x 5 tap loop fully unrolled (64 registers, 4 blocks per SM) or by rows (48 registers, 5 blocks).
+template <bool kUnrollRows>
 __global__ void __launch_bounds__(kTW* kTH) pyramid_level_kernel(LevelArgs a) {
     __shared__ float s_depth[kTH + 5][kTW + 5];       // target depth, rows y0-2 .. y0+kTH+2, cols x0-2 .. x0+kTW+2 (clamped)
     __shared__ float s_vert[kTH + 1][kTW + 1][3];     // vertices of the smoothed depth at the normal stencil points
+    __shared__ float s_wpos[5][5];                    // the filter's spatial weights: one division + expf each, once per block
     pdl_grid_wait();
     pdl_grid_launch_dependents();
     if (a.init_state && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
@@ -236,6 +239,10 @@ __global__ void __launch_bounds__(kTW* kTH) pyramid_level_kernel(LevelArgs a) {
         const int gy = min(max(y0 + ly - 2, 0), a.rows - 1), gx = min(max(x0 + lx - 2, 0), a.cols - 1);   // replicated border
         s_depth[ly][lx] = a.tgt_d[(size_t)gy * a.cols + gx];
     }
+    if (threadIdx.x < 25) {   // the very expression the per-tap code evaluated (and filter_bilateral_kernel evaluates): same bits
+        const int dy = (int)threadIdx.x / 5 - 2, dx = (int)threadIdx.x % 5 - 2;
+        s_wpos[dy + 2][dx + 2] = expf(dvd(-((float)(dx * dx + dy * dy)), a.pos2));
+    }
     __syncthreads();
     // bilateral filter (radius 2) + vertex of the smoothed depth at every stencil point of the tile
     for (int k = threadIdx.x; k < (kTH + 1) * (kTW + 1); k += kTW * kTH) {
@@ -245,16 +252,30 @@ __global__ void __launch_bounds__(kTW* kTH) pyramid_level_kernel(LevelArgs a) {
         if (gy < a.rows && gx < a.cols) {
             const float vc = s_depth[ly + 2][lx + 2];
             float num = 0.f, den = 0.f;
-            for (int dy = -2; dy <= 2; ++dy)
-                for (int dx = -2; dx <= 2; ++dx) {
-                    // the apron was loaded with clamped coordinates; inside the image clamping (gy + dy) equals indexing it
-                    const int cy = min(max(gy + dy, 0), a.rows - 1) - (y0 - 2), cx = min(max(gx + dx, 0), a.cols - 1) - (x0 - 2);
-                    const float v = s_depth[cy][cx];
+            // the apron was loaded with clamped coordinates; inside the image clamping (gy + dy) equals indexing it
+            int cy[5], cx[5];
+#pragma unroll
+            for (int d = 0; d < 5; ++d) {
+                cy[d] = min(max(gy + d - 2, 0), a.rows - 1) - (y0 - 2);
+                cx[d] = min(max(gx + d - 2, 0), a.cols - 1) - (x0 - 2);
+            }
+            auto taps_of_row = [&](int dy) {
+#pragma unroll
+                for (int dx = 0; dx < 5; ++dx) {
+                    const float v = s_depth[cy[dy]][cx[dx]];
                     const float dv = sub(v, vc);
-                    const float w = mul(expf(dvd(-((float)(dx * dx + dy * dy)), a.pos2)), expf(dvd(-mul(dv, dv), a.val2)));
+                    const float w = mul(s_wpos[dy][dx], expf(dvd(-mul(dv, dv), a.val2)));
                     num = add(num, mul(w, v));
                     den = add(den, w);
                 }
+            };
+            if constexpr (kUnrollRows) {
+#pragma unroll
+                for (int dy = 0; dy < 5; ++dy) taps_of_row(dy);
+            } else {
+#pragma unroll 1
+                for (int dy = 0; dy < 5; ++dy) taps_of_row(dy);
+            }
             const float smooth = dvd(num, den);
             if (!is_invalid(smooth, a.invalid_fill)) unproject(a.ti, (float)gx, (float)gy, smooth, vx, vy, vz);
         }
@@ -343,25 +364,25 @@ __device__ __forceinline__ float huber_loss(float r, float delta) {
                          : (float)__dsub_rn((double)mul(delta, abs_r), __dmul_rn(__dmul_rn(0.5, (double)delta), (double)delta));
 }
 
-// RGBDOdometryJacobianImpl.h:106-160
-__device__ __forceinline__ bool jacobian_p2plane(int x, int y, float trunc, const float* __restrict__ sv_map,
-                                                 const float* __restrict__ tv_map, const float* __restrict__ tn_map,
-                                                 int rows, int cols, const Cam& ti, float (&J)[6], float& r) {
-    const float* sv = sv_map + 3 * ((size_t)y * cols + x);
-    const float s0 = sv[0];
+// RGBDOdometryJacobianImpl.h:106-160 in two phases, so that a thread can keep several pixels' loads in flight
+// (odometry_level_kernel); jacobian_p2plane below is the two of them back to back.
+// Phase 1: transformed source vertex and the target pixel it projects to; false = rejected.
+__device__ __forceinline__ bool probe_source(float s0, float s1, float s2, int rows, int cols, const Cam& ti, float& p0,
+                                             float& p1, float& p2, int& target_index) {
     if (isnan(s0)) return false;
-    float p0, p1, p2, u, v;
-    rigid(ti, s0, sv[1], sv[2], p0, p1, p2);
+    float u, v;
+    rigid(ti, s0, s1, s2, p0, p1, p2);
     project(ti, p0, p1, p2, u, v);
     u = roundf(u);
     v = roundf(v);
     if (p2 < 0 || !in_boundary(u, v, rows, cols)) return false;
-    const int ui = (int)u, vi = (int)v;
-    const float* tv = tv_map + 3 * ((size_t)vi * cols + ui);
-    const float* tn = tn_map + 3 * ((size_t)vi * cols + ui);
-    const float t0 = tv[0], n0 = tn[0];
+    target_index = (int)v * cols + (int)u;
+    return true;
+}
+// Phase 2: residual gate and Jacobian from the target vertex t and normal n at that pixel.
+__device__ __forceinline__ bool residual_jacobian(float p0, float p1, float p2, float t0, float t1, float t2, float n0,
+                                                  float n1, float n2, float trunc, float (&J)[6], float& r) {
     if (isnan(t0) || isnan(n0)) return false;
-    const float t1 = tv[1], t2 = tv[2], n1 = tn[1], n2 = tn[2];
     r = add(add(mul(sub(p0, t0), n0), mul(sub(p1, t1), n1)), mul(sub(p2, t2), n2));
     if (fabsf(r) > trunc) return false;
     J[0] = add(mul(-p2, n1), mul(p1, n2));
@@ -371,6 +392,18 @@ __device__ __forceinline__ bool jacobian_p2plane(int x, int y, float trunc, cons
     J[4] = n1;
     J[5] = n2;
     return true;
+}
+
+__device__ __forceinline__ bool jacobian_p2plane(int x, int y, float trunc, const float* __restrict__ sv_map,
+                                                 const float* __restrict__ tv_map, const float* __restrict__ tn_map,
+                                                 int rows, int cols, const Cam& ti, float (&J)[6], float& r) {
+    const float* sv = sv_map + 3 * ((size_t)y * cols + x);
+    float p0, p1, p2;
+    int ti_idx;
+    if (!probe_source(sv[0], sv[1], sv[2], rows, cols, ti, p0, p1, p2, ti_idx)) return false;
+    const float* tv = tv_map + 3 * (size_t)ti_idx;
+    const float* tn = tn_map + 3 * (size_t)ti_idx;
+    return residual_jacobian(p0, p1, p2, tv[0], tv[1], tv[2], tn[0], tn[1], tn[2], trunc, J, r);
 }
 
 template <int N>
@@ -545,11 +578,13 @@ __global__ void __launch_bounds__(kThreads) odometry_iteration_kernel(OdoArgs a)
 // same f64 solve / pose update on its own shared-memory copy of the state — bit-identical everywhere, so nothing is
 // broadcast and the next iteration starts after a __syncthreads.  Rank 0 writes the state back at the end.
 // The sums are those of the per-iteration kernel up to the association of the additions (f32 per thread and across
-// the warp — at most kLevelFlush + 5 roundings deep — then f64), far inside the reference's own all-f32 reduction.
+// the warp — at most kLevelFlush + kLevelBatch + 4 roundings deep — then f64), far inside the reference's own all-f32 reduction.
 static constexpr int kLevelThreads = 512;
 static constexpr int kMaxCluster = 16;
-static constexpr int kLevelFlush = 16;       // f32 terms per thread between two warp reductions
+static constexpr int kLevelFlush = 16;       // f32 terms per thread between two warp reductions (at most kLevelFlush + kLevelBatch - 1)
 
+// kLevelBatch: pixels a thread has in flight.
+template <int kLevelBatch>
 __global__ void __launch_bounds__(kLevelThreads, 1) odometry_level_kernel(OdoArgs a, int max_iteration) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
@@ -590,14 +625,57 @@ __global__ void __launch_bounds__(kLevelThreads, 1) odometry_level_kernel(OdoArg
         for (int k = 0; k < 32; ++k) acc[k] = 0.f;
         double total = 0.0;          // lane l: sum l of this warp
         int since = 0;
-        for (int base = (int)crank * kLevelThreads; base < n; base += stride) {   // (block-uniform trip count)
-            const int i = base + threadIdx.x;
-            if (i < n) {
+        // kLevelBatch pixels per thread and round: all their source vertices are requested first, then all the target
+        // vertices / normals — two dependent L2 round trips per round instead of two per pixel (the level is latency
+        // bound: 2 - 10 pixels per thread).  The pixels are accumulated in index order, as a one-by-one loop would.
+        for (int base = (int)crank * kLevelThreads; base < n; base += kLevelBatch * stride) {   // (block-uniform trip count)
+            float p[kLevelBatch][3];
+            int tix[kLevelBatch];
+#pragma unroll
+            for (int u = 0; u < kLevelBatch; ++u) {
+                const int i = base + u * stride + (int)threadIdx.x;
+                p[u][0] = __int_as_float(0x7fc00000);   // beyond the image: rejected like an invalid vertex
+                p[u][1] = p[u][2] = 0.f;
+                if (i < n) {
+                    const float* sv = a.sv + 3 * (size_t)i;
+                    p[u][0] = sv[0];
+                    p[u][1] = sv[1];
+                    p[u][2] = sv[2];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kLevelBatch; ++u) {
+                float q0, q1, q2;
+                int t_index;
+                if (probe_source(p[u][0], p[u][1], p[u][2], a.rows, a.cols, ti, q0, q1, q2, t_index)) {
+                    p[u][0] = q0;
+                    p[u][1] = q1;
+                    p[u][2] = q2;
+                    tix[u] = t_index;
+                } else {
+                    tix[u] = -1;
+                }
+            }
+            float tv[kLevelBatch][3], tn[kLevelBatch][3];
+#pragma unroll
+            for (int u = 0; u < kLevelBatch; ++u) {
+                const size_t o = 3 * (size_t)(tix[u] < 0 ? 0 : tix[u]);   // (a rejected pixel reads pixel 0 and ignores it)
+                tv[u][0] = a.tv[o];
+                tv[u][1] = a.tv[o + 1];
+                tv[u][2] = a.tv[o + 2];
+                tn[u][0] = a.tn[o];
+                tn[u][1] = a.tn[o + 1];
+                tn[u][2] = a.tn[o + 2];
+            }
+#pragma unroll
+            for (int u = 0; u < kLevelBatch; ++u) {
                 float J[6], r;
-                if (jacobian_p2plane(i % a.cols, i / a.cols, a.trunc, a.sv, a.tv, a.tn, a.rows, a.cols, ti, J, r))
+                if (tix[u] >= 0 && residual_jacobian(p[u][0], p[u][1], p[u][2], tv[u][0], tv[u][1], tv[u][2], tn[u][0],
+                                                     tn[u][1], tn[u][2], a.trunc, J, r))
                     accumulate_odometry(acc, J, r, a.huber_delta);
             }
-            if (++since == kLevelFlush) {
+            since += kLevelBatch;
+            if (since >= kLevelFlush) {
                 total += (double)warp_transpose_sum32(acc);
 #pragma unroll
                 for (int k = 0; k < 32; ++k) acc[k] = 0.f;
@@ -818,7 +896,9 @@ static int level_cluster_size() {
     int chosen = 0;
     for (int c : {16, 8}) {
         if (c > cap) continue;
-        if (c > 8 && cudaFuncSetAttribute(odometry_level_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+        if (c > 8 && (cudaFuncSetAttribute(odometry_level_kernel<1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
+                      cudaFuncSetAttribute(odometry_level_kernel<3>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
+                      cudaFuncSetAttribute(odometry_level_kernel<4>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess)) {
             cudaGetLastError();
             continue;
         }
@@ -833,7 +913,7 @@ static int level_cluster_size() {
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         int clusters = 0;
-        if (cudaOccupancyMaxActiveClusters(&clusters, odometry_level_kernel, &cfg) == cudaSuccess && clusters >= 1) {
+        if (cudaOccupancyMaxActiveClusters(&clusters, odometry_level_kernel<4>, &cfg) == cudaSuccess && clusters >= 1) {
             chosen = c;
             break;
         }
@@ -875,7 +955,13 @@ static cudaError_t launch_level(const OdoArgs& a, int max_iteration, int cluster
     attr[1].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 2;
-    return cudaLaunchKernelEx(&cfg, odometry_level_kernel, a, max_iteration);
+    static const int batch = [] {       // pixels in flight per thread (O3DB_ODO_LEVEL_BATCH = 1 | 3 | 4: measurements)
+        const char* v = getenv("O3DB_ODO_LEVEL_BATCH");
+        return v ? atoi(v) : 3;
+    }();
+    if (batch <= 1) return cudaLaunchKernelEx(&cfg, odometry_level_kernel<1>, a, max_iteration);
+    if (batch >= 4) return cudaLaunchKernelEx(&cfg, odometry_level_kernel<4>, a, max_iteration);
+    return cudaLaunchKernelEx(&cfg, odometry_level_kernel<3>, a, max_iteration);
 }
 
 }  // namespace o3db
@@ -1053,7 +1139,12 @@ int o3db_rgbd_odometry_multi_scale_point_to_plane(const void* source_depth_dev, 
             attr[0].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = attr;
             cfg.numAttrs = 1;
-            const cudaError_t e = cudaLaunchKernelEx(&cfg, pyramid_level_kernel, la);
+            static const bool unroll_rows = [] {
+                const char* v = getenv("O3DB_ODO_PYR_UNROLL");
+                return v ? atoi(v) != 0 : false;
+            }();
+            const cudaError_t e = unroll_rows ? cudaLaunchKernelEx(&cfg, pyramid_level_kernel<true>, la)
+                                              : cudaLaunchKernelEx(&cfg, pyramid_level_kernel<false>, la);
             count_launch();
             if (e != cudaSuccess) {
                 set_last_error("pyramid_level_kernel launch failed: %s", cudaGetErrorString(e));
