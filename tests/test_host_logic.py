@@ -242,3 +242,27 @@ def test_frame_replay_hands_over_what_it_cannot_recover():
     vol.dropped_from = (1, 4000)
     with pytest.raises(_FakeFusedVolume.CapacityError):
         rp.guard(vol.get_size)
+
+
+def test_frame_loop_helpers_of_the_python_mirror():
+    """Small host-side pieces on the dense-SLAM loop's critical path: they must stay exact while being cheap."""
+    import oracle
+    from open3d_b200.t.pipelines import odometry, slam
+    # InverseTransformation (t/geometry/Utility.h:77-115): bit-identical to the oracle's restatement
+    rng = np.random.default_rng(7)
+    for _ in range(50):
+        T = np.eye(4)
+        T[:3, :3] = np.linalg.qr(rng.normal(size=(3, 3)))[0]
+        T[:3, 3] = rng.normal(size=3) * 3
+        assert np.array_equal(slam._inverse_transformation(T).view(np.uint64), oracle.inverse_transformation(T).view(np.uint64))
+    # Frame.get_data: an absent name is an empty tensor (Frame.h), a present one the very object
+    f = slam.Frame(4, 4, np.eye(3))
+    d = torch.zeros((4, 4), dtype=torch.uint16)
+    f.set_data("depth", d)
+    assert f.get_data("depth") is d and f.get_data("color").numel() == 0
+    # criteria lists: ints convert like vector<OdometryConvergenceCriteria>{6, 3, 1}; the tuple-of-ints case is cached
+    a1, n1, it1 = odometry._c_criteria((6, 3, 1))
+    a2, n2, it2 = odometry._c_criteria((6, 3, 1))
+    assert a1 is a2 and (n1, it1) == (3, 10) and [a1[i].max_iteration for i in range(3)] == [6, 3, 1]
+    a3, n3, it3 = odometry._c_criteria([odometry.OdometryConvergenceCriteria(4, 1e-3, 1e-3), 2])
+    assert (n3, it3) == (2, 6) and a3[0].relative_rmse == 1e-3 and a3[1].max_iteration == 2
