@@ -56,3 +56,39 @@ def test_product_does_not_import_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", src, flags=re.M), f
                 assert "liboracle" not in src and "orc_" not in src, f
+
+
+def test_shipped_library_carries_the_blackwell_instructions_the_design_claims():
+    """SASS of the in-tree libo3db200.so (sm_100a cubins): the TMA bulk copy of the ICP chunk ring (UBLKCP), the tiled
+    TMA load of the integrate kernel (UTMALDG.2D), mbarrier transactions (SYNCS), programmatic dependent launch
+    (ACQBULK / PREEXIT) and the cluster barrier of the level-resident odometry kernel (UCGABAR) — DESIGN.md §4,
+    profiles/r02_sass_excerpts.md.  A build that silently lost one of them (a knob left on, an #if) fails here."""
+    import shutil
+    import subprocess
+    from open3d_b200 import _lib
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(tool):
+        pytest.skip("cuobjdump not available")
+    elfs = subprocess.run([tool, "-lelf", _lib.LIB_PATH], capture_output=True, text=True, timeout=120).stdout
+    assert "sm_100a" in elfs
+    sass = subprocess.run([tool, "-sass", _lib.LIB_PATH], capture_output=True, text=True, timeout=300).stdout
+    current, per_kernel = None, {}
+    for line in sass.splitlines():
+        if "Function :" in line:
+            current = line.split("Function :")[1].strip()
+            per_kernel[current] = set()
+        elif current is not None:
+            for m in ("UBLKCP", "UTMALDG.2D", "SYNCS.ARRIVE.TRANS64", "ACQBULK", "PREEXIT", "UCGABAR_ARV", "UCGABAR_WAIT",
+                      "LDGSTS"):
+                if m in line:
+                    per_kernel[current].add(m)
+
+    def has(kernel_substring, *mnemonics):
+        hits = [k for k, v in per_kernel.items() if kernel_substring in k and all(m in v for m in mnemonics)]
+        assert hits, (kernel_substring, mnemonics)
+
+    has("icp_iteration_kernel", "UBLKCP", "SYNCS.ARRIVE.TRANS64", "LDGSTS", "ACQBULK", "PREEXIT")
+    has("integrate16_kernel", "UTMALDG.2D", "ACQBULK")
+    has("touch_kernel", "ACQBULK")
+    has("odometry_level_kernel", "UCGABAR_ARV", "UCGABAR_WAIT", "ACQBULK", "PREEXIT")
+    has("pyramid_level_kernel", "ACQBULK", "PREEXIT")
